@@ -1,0 +1,140 @@
+/*
+ * niw_b200.h -- C ABI of the B200-native NeRF ray-render path for the invertible-warp BARF
+ * codebase (sfchng/neural_invertible_warp).
+ *
+ * The reference has NO native boundary (it is eager PyTorch); each entry point below replaces a
+ * chain of ATen ops inside one reference Python function, cited as reference file:line.  The
+ * Python mirror of the reference's Graph/NeRF API (neural_invertible_warp_b200/*.py) binds these
+ * symbols with ctypes and calls them from torch.autograd.Function.forward/backward; see
+ * INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a contiguous row-major fp32 array unless noted;
+ *   - the caller owns and allocates every buffer, including workspaces (sizes are queried);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - return value 0 = success; >0 = a cudaError_t; <0 = NIW_E_* argument error.  Nothing throws.
+ *     niw_error_string() turns a code into text.
+ *   - no hidden state apart from idempotent function attributes (max dynamic shared memory).
+ *   - B = images, P = rays per image, R = B*P rays, N = samples per ray, S = R*N samples.
+ */
+#ifndef NIW_B200_H_
+#define NIW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIW_ABI_VERSION 1
+
+#define NIW_E_BADARG   (-1)  /* null pointer / non-positive size */
+#define NIW_E_UNSUPP   (-2)  /* shape or option outside what the kernels implement */
+#define NIW_E_WORKSPACE (-3) /* workspace too small */
+
+/* precision of the MLP GEMMs */
+#define NIW_PREC_FP32 0 /* CUDA-core fp32 (parity / high-precision path)          */
+#define NIW_PREC_BF16 1 /* tcgen05 BF16 operands, FP32 accumulate in TMEM (fast)  */
+
+int niw_abi_version(void);
+const char* niw_error_string(int code);
+
+/* ---- (a1) camera.get_center_and_ray + [:, ray_idx]   camera.py:419-443, model/nerf.py:298-300
+ * pose [B,3,4] world->camera, intr [B,3,3].  Pixel p -> ((p%W)+.5, (p/W)+.5, 1).  If ray_idx is
+ * NULL the P pixels idx_start .. idx_start+P-1 are used (render_by_slices, model/nerf.py:326-327).
+ * Backward produces d_pose [B,3,4] (overwritten) from d_center / d_ray (either may be NULL). */
+int niw_raygen_pose_fwd(const float* pose, const float* intr, const int64_t* ray_idx, int64_t idx_start,
+                        int B, int P, int H, int W, float* center, float* ray, void* stream);
+int niw_raygen_pose_bwd(const float* pose, const float* intr, const int64_t* ray_idx, int64_t idx_start,
+                        int B, int P, int H, int W, const float* d_center, const float* d_ray,
+                        float* d_pose, void* stream);
+
+/* ---- (a2) camera.get_unwarped_center_and_ray   camera.py:359-390
+ * Writes pts [B,2P,3] = [P grid rows ; P centre rows] in the camera frame, or in the world frame
+ * of pose_init [B,3,4] when it is non-NULL (the layout barf_inn_llff.py:348 concatenates). */
+int niw_raygen_unwarped(const float* intr, const float* pose_init, const int64_t* ray_idx, int64_t idx_start,
+                        int B, int P, int H, int W, float* pts, void* stream);
+
+/* ---- (a3) DeformNetwork.forward   model/nvp/nvp_ndr.py:365-468, model/nvp/embedder.py:41-50
+ * 3 coupling blocks, hidden 128, 6 frequency bands, Softplus(beta=100), including the reference's
+ * point-index annealing quirk.  `wpack` holds the EFFECTIVE (weight-norm resolved) weights,
+ * NIW_NVP_BLOCK_FLOATS floats per block in the order
+ *     W1a[128][26], W2a[128], b2a[1], W1b[128][13], W2b[3][128], b2b[3]
+ * (W1* = the columns of lin{b}_{a,b}_0 that multiply the embedded coordinates).  `code_bias`
+ * [3][2][B][128] holds, per block / part / image, lin_0.bias + W_0[:, emb:] . code_b where
+ * code_b = lin{b}_c(code)+code -- a B-sized product done by the host in PyTorch.
+ * pts/out are [B,Pt,3].  Backward overwrites d_wpack (same layout) and d_code_bias. */
+#define NIW_NVP_HIDDEN 128
+#define NIW_NVP_FREQS 6
+#define NIW_NVP_BLOCKS 3
+#define NIW_NVP_BLOCK_FLOATS (128 * 26 + 128 + 1 + 128 * 13 + 3 * 128 + 3)
+int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
+                     int B, int Pt, float* out, void* stream);
+int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
+                     int B, int Pt, const float* d_out, float* d_wpack, float* d_code_bias, void* stream);
+
+/* ---- (a4) Graph.sample_depth   model/nerf.py:334-344
+ * depth[r,k] = ((u+k)/N)*scale + dmin, optionally 1/(.+1e-8); evaluated with the reference's
+ * rounding sequence (no FMA contraction).  u [n_rays*N] or NULL (=0.5, un-stratified). */
+int niw_sample_stratified(const float* u, int64_t n_rays, int N, float scale, float dmin, int inverse,
+                          float* depth, void* stream);
+
+/* ---- (a5) Graph.sample_depth_from_pdf + cat + sort   model/nerf.py:346-365, :313-315
+ * pdf [R,N]; unif [Nf] = 0.5*(grid[:-1]+grid[1:]); bins [N+1] = linspace(dmin,dmax,N+1) (both made
+ * by the host with torch so they carry the reference's fp32 rounding).  The CDF is accumulated
+ * sequentially in fp64 and rounded per element (what torch.cumsum does on CPU), searchsorted is
+ * right=True.  Outputs (each may be NULL): fine [R,Nf], idx [R,Nf] int64, merged [R,N+Nf] =
+ * ascending sort of depth_coarse [R,N] ++ fine. */
+int niw_sample_pdf_merge(const float* pdf, const float* depth_coarse, const float* unif, const float* bins,
+                         int64_t R, int N, int Nf, float* fine, int64_t* idx, float* merged, void* stream);
+
+/* ---- (a9) NeRF.composite   model/nerf.py:458-474
+ * ray [R,3], rgb_s [R,N,3], sigma [R,N], depth_s [R,N] -> rgb [R,3], depth [R], opacity [R],
+ * prob [R,N], trans [R,N] (transmittance, saved for backward).  bg < 0 disables setbg_opaque.
+ * Backward: d_rgb_s [R,N,3], d_sigma [R,N], d_ray [R,3] (through ||ray||), all overwritten. */
+int niw_composite_fwd(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                      int64_t R, int N, float bg, float* rgb, float* depth, float* opacity,
+                      float* prob, float* trans, void* stream);
+int niw_composite_bwd(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                      const float* prob, const float* trans, int64_t R, int N, float bg,
+                      const float* d_rgb, const float* d_depth, const float* d_opacity,
+                      float* d_rgb_s, float* d_sigma, float* d_ray, void* stream);
+
+/* ---- (a6+a7+a8) NeRF.forward_samples   model/nerf.py:416-456, model/barf.py:256-268, camera.py:517-521
+ * x = center + depth*ray, view = normalize(ray), BARF-weighted positional encoding (L=10 / 4),
+ * 8x256 MLP with skip at layer 4, softplus density from pre-ReLU column 0 of layer 7, ReLU on the
+ * other 256, RGB head (256+27)->128->3, sigmoid.
+ * `params` is the flat fp32 parameter vector in reference state_dict order
+ *     mlp_feat.0.weight [256,63], .bias, ..., mlp_feat.7.weight [257,256], .bias,
+ *     mlp_rgb.0.weight [128,283], .bias, mlp_rgb.1.weight [3,128], .bias      (NIW_NERF_PARAMS floats; the BARF `progress` scalar is not part of it)
+ * band_w3 [10] / band_wv [4] are the coarse-to-fine band weights (all ones without barf_c2f); these two
+ * are HOST pointers (the only ones in this ABI): 14 floats the host derives from `progress`.
+ * center/ray [R,3], depth [R,N] -> rgb [R,N,3], sigma [R,N].  `workspace` keeps what backward
+ * needs (niw_nerf_workspace_bytes; `training`=0 allows a smaller, forward-only workspace).
+ * Backward ADDS into d_params (caller zeroes it once per step) and overwrites d_center, d_ray. */
+#define NIW_NERF_PARAMS 530052
+size_t niw_nerf_workspace_bytes(int64_t R, int N, int precision, int training);
+int niw_nerf_fwd(const float* params, const float* center, const float* ray, const float* depth,
+                 int64_t R, int N, const float* band_w3, const float* band_wv, int precision, int training,
+                 void* workspace, size_t workspace_bytes, float* rgb, float* sigma, void* stream);
+int niw_nerf_bwd(const float* params, const float* center, const float* ray, const float* depth,
+                 int64_t R, int N, const float* band_w3, const float* band_wv, int precision,
+                 void* workspace, size_t workspace_bytes, const float* d_rgb, const float* d_sigma,
+                 float* d_params, float* d_center, float* d_ray, void* stream);
+
+/* ---- loss head: image gather + MSE   model/nerf.py:276-288, model/base.py:209-211
+ * image [B,3,H,W], rgb [B,P,3]; loss += scale * sum((rgb - image[:, :, pix])^2) (scale = 1/(B*P*3)
+ * for the mean); d_rgb = 2*scale*(rgb - target) is written when non-NULL.  loss is a device scalar
+ * that the caller zeroes. */
+int niw_mse_gather(const float* image, const float* rgb, const int64_t* ray_idx, int64_t idx_start,
+                   int B, int P, int H, int W, float scale, float* loss, float* d_rgb, void* stream);
+
+/* ---- tcgen05 self-test: D[128,N] = A[128,K] . B[N,K]^T with BF16 operands staged exactly as the
+ * MLP kernel stages them.  variant selects the operand form under test (see csrc/mlp_tc.cu). */
+int niw_tc_selftest(const float* A, const float* Bm, int N, int K, int variant, float* D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIW_B200_H_ */

@@ -1,0 +1,75 @@
+"""ctypes binding of csrc/libniw_b200.so (the C ABI declared in include/niw_b200.h).
+
+There is deliberately no CPU or PyTorch fallback: if the library cannot be loaded the import of
+any op raises, and every op refuses non-CUDA tensors.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_c = ctypes
+_P = _c.c_void_p
+_LIB = None
+
+NIW_PREC_FP32 = 0
+NIW_PREC_BF16 = 1
+NIW_NERF_PARAMS = 530052
+NIW_NVP_BLOCK_FLOATS = 128 * 26 + 128 + 1 + 128 * 13 + 3 * 128 + 3
+ABI_VERSION = 1
+
+# name -> (restype, argtypes); mirrors include/niw_b200.h one to one
+SIGNATURES = {
+    "niw_abi_version": (_c.c_int, []),
+    "niw_error_string": (_c.c_char_p, [_c.c_int]),
+    "niw_raygen_pose_fwd": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
+    "niw_raygen_pose_bwd": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
+    "niw_raygen_unwarped": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
+    "niw_nvp_warp_fwd": (_c.c_int, [_P, _P, _P, _c.c_float, _c.c_int, _c.c_int, _P, _P]),
+    "niw_nvp_warp_bwd": (_c.c_int, [_P, _P, _P, _c.c_float, _c.c_int, _c.c_int, _P, _P, _P, _P]),
+    "niw_sample_stratified": (_c.c_int, [_P, _c.c_int64, _c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P]),
+    "niw_sample_pdf_merge": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _P, _P, _P]),
+    "niw_composite_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P, _P]),
+    "niw_composite_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "niw_nerf_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
+    "niw_nerf_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _P, _P, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _P, _P]),
+    "niw_nerf_bwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _P, _P, _c.c_int, _P, _c.c_size_t, _P, _P, _P, _P, _P, _P]),
+    "niw_mse_gather": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),
+    "niw_tc_selftest": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
+}
+
+
+def library_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load (building first if the sources are newer and nvcc is available) and type the library."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if build_if_missing:
+        try:
+            if _build.needs_build():
+                _build.build()
+        except Exception as e:  # no nvcc on this box: fall through to the prebuilt file
+            if not os.path.exists(path):
+                raise RuntimeError("libniw_b200.so is missing and could not be built: %s" % e)
+    if not os.path.exists(path):
+        raise RuntimeError("libniw_b200.so not found at %s -- run `python -m neural_invertible_warp_b200.build`; "
+                           "there is no CPU fallback" % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError = ABI mismatch, loud on purpose
+        fn.restype = res
+        fn.argtypes = args
+    if lib.niw_abi_version() != ABI_VERSION:
+        raise RuntimeError("libniw_b200.so ABI version %d != %d" % (lib.niw_abi_version(), ABI_VERSION))
+    _LIB = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        raise RuntimeError("niw_b200: %s (code %d)" % (load().niw_error_string(code).decode(), code))

@@ -1,0 +1,96 @@
+// C-ABI glue: dispatch of the NeRF MLP entry points by precision, the loss head, error strings.
+#include "common.cuh"
+#include "mlp_shared.cuh"
+#include <string.h>
+
+using namespace niw;
+
+extern "C" int niw_abi_version(void) { return NIW_ABI_VERSION; }
+
+extern "C" const char* niw_error_string(int code) {
+    if (code == 0) return "success";
+    if (code == NIW_E_BADARG) return "niw: bad argument (null pointer or non-positive size)";
+    if (code == NIW_E_UNSUPP) return "niw: unsupported shape or option";
+    if (code == NIW_E_WORKSPACE) return "niw: workspace too small";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "niw: unknown error";
+}
+
+extern "C" size_t niw_nerf_workspace_bytes(int64_t R, int N, int precision, int training) {
+    if (R <= 0 || N <= 0) return 0;
+    return precision == NIW_PREC_BF16 ? tc_workspace_bytes(R, N, training) : fp32_workspace_bytes(R, N, training);
+}
+
+// NOTE band_w3 / band_wv are HOST pointers (10 + 4 floats computed by the host from `progress`,
+// model/barf.py:260-264); they are passed to the kernels by value.
+extern "C" int niw_nerf_fwd(const float* params, const float* center, const float* ray, const float* depth, int64_t R,
+                            int N, const float* band_w3, const float* band_wv, int precision, int training,
+                            void* workspace, size_t workspace_bytes, float* rgb, float* sigma, void* stream) {
+    NIW_CHECK_ARG(params && center && ray && depth && band_w3 && band_wv && workspace && rgb && sigma && R > 0 && N > 0);
+    Bands3 b3; BandsV bv;
+    memcpy(b3.w, band_w3, sizeof(b3.w)); memcpy(bv.w, band_wv, sizeof(bv.w));
+    if (precision == NIW_PREC_FP32)
+        return fp32_fwd(params, center, ray, depth, R, N, b3, bv, training, workspace, workspace_bytes, rgb, sigma,
+                        niw_stream(stream));
+    if (precision == NIW_PREC_BF16)
+        return tc_fwd(params, center, ray, depth, R, N, b3, bv, training, workspace, workspace_bytes, rgb, sigma,
+                      niw_stream(stream));
+    return NIW_E_UNSUPP;
+}
+
+extern "C" int niw_nerf_bwd(const float* params, const float* center, const float* ray, const float* depth, int64_t R,
+                            int N, const float* band_w3, const float* band_wv, int precision, void* workspace,
+                            size_t workspace_bytes, const float* d_rgb, const float* d_sigma, float* d_params,
+                            float* d_center, float* d_ray, void* stream) {
+    NIW_CHECK_ARG(params && center && ray && depth && band_w3 && band_wv && workspace && d_rgb && d_sigma && d_params &&
+                  d_center && d_ray && R > 0 && N > 0);
+    Bands3 b3; BandsV bv;
+    memcpy(b3.w, band_w3, sizeof(b3.w)); memcpy(bv.w, band_wv, sizeof(bv.w));
+    if (precision == NIW_PREC_FP32)
+        return fp32_bwd(params, center, ray, depth, R, N, b3, bv, workspace, workspace_bytes, d_rgb, d_sigma, d_params,
+                        d_center, d_ray, niw_stream(stream));
+    if (precision == NIW_PREC_BF16)
+        return tc_bwd(params, center, ray, depth, R, N, b3, bv, workspace, workspace_bytes, d_rgb, d_sigma, d_params,
+                      d_center, d_ray, niw_stream(stream));
+    return NIW_E_UNSUPP;
+}
+
+// ---- loss head: pixel gather + squared error  (model/nerf.py:276-288, model/base.py:209-211) ----
+namespace {
+__global__ void mse_gather_kernel(const float* __restrict__ image, const float* __restrict__ rgb,
+                                  const int64_t* __restrict__ ray_idx, int64_t idx_start, int B, int P, int HW,
+                                  float scale, float* __restrict__ loss, float* __restrict__ d_rgb) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    if (t < (int64_t)B * P) {
+        int b = (int)(t / P), p = (int)(t % P);
+        int64_t pix = ray_idx ? ray_idx[p] : idx_start + p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float diff = rgb[t * 3 + c] - image[((int64_t)b * 3 + c) * HW + pix];
+            acc += diff * diff;
+            if (d_rgb) d_rgb[t * 3 + c] = 2.f * scale * diff;
+        }
+    }
+    acc = warp_sum(acc);
+    __shared__ float red[8];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+        atomicAdd(loss, v * scale);
+    }
+}
+}  // namespace
+
+extern "C" int niw_mse_gather(const float* image, const float* rgb, const int64_t* ray_idx, int64_t idx_start, int B,
+                              int P, int H, int W, float scale, float* loss, float* d_rgb, void* stream) {
+    NIW_CHECK_ARG(image && rgb && loss && B > 0 && P > 0 && H > 0 && W > 0);
+    int64_t n = (int64_t)B * P;
+    mse_gather_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(image, rgb, ray_idx, idx_start, B, P, H * W,
+                                                                         scale, loss, d_rgb);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,58 @@
+// Shared helpers for the niw_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/niw_b200.h"
+
+#define NIW_SM_COUNT_FALLBACK 148
+
+#define NIW_CHECK_ARG(cond) do { if (!(cond)) return NIW_E_BADARG; } while (0)
+#define NIW_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
+#define NIW_LAUNCH_CHECK() do { cudaError_t e__ = cudaPeekAtLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+static inline cudaStream_t niw_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int niw_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = NIW_SM_COUNT_FALLBACK;
+    }
+    return n;
+}
+
+static inline unsigned niw_blocks(int64_t work, int per_block) {
+    int64_t b = (work + per_block - 1) / per_block;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// pixel index -> camera-frame grid point K^-1 (x+.5, y+.5, 1)   (camera.py:430-436)
+struct Mat3 { float m[9]; };
+
+__device__ __forceinline__ Mat3 inverse3x3(const float* __restrict__ K) {
+    // general adjugate inverse; the reference calls torch.inverse (camera.py:342)
+    float a = K[0], b = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], h = K[7], i = K[8];
+    float A = e * i - f * h, Bc = -(d * i - f * g), C = d * h - e * g;
+    float det = a * A + b * Bc + c * C;
+    float r = 1.0f / det;
+    Mat3 o;
+    o.m[0] = A * r;  o.m[1] = -(b * i - c * h) * r; o.m[2] = (b * f - c * e) * r;
+    o.m[3] = Bc * r; o.m[4] = (a * i - c * g) * r;  o.m[5] = -(a * f - c * d) * r;
+    o.m[6] = C * r;  o.m[7] = -(a * h - b * g) * r; o.m[8] = (a * e - b * d) * r;
+    return o;
+}
+
+__device__ __forceinline__ void pixel_to_cam(const Mat3& Ki, int64_t pix, int W, float g[3]) {
+    float x = (float)(pix % W) + 0.5f, y = (float)(pix / W) + 0.5f;
+    g[0] = Ki.m[0] * x + Ki.m[1] * y + Ki.m[2];
+    g[1] = Ki.m[3] * x + Ki.m[4] * y + Ki.m[5];
+    g[2] = Ki.m[6] * x + Ki.m[7] * y + Ki.m[8];
+}

@@ -1,0 +1,149 @@
+// Volume compositing.  reference model/nerf.py:458-474.
+// One warp per ray; samples are visited 32 at a time (coalesced), with a warp-shuffle inclusive
+// scan of sigma*delta per chunk and a running carry, so transmittance never leaves registers.
+// The backward pass walks the chunks in reverse with a suffix scan and reuses the saved
+// transmittance and weights (no exp in backward).  HBM-bound: 24 B/sample fwd, 40 B/sample bwd.
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARPS = 8;
+
+__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ float warp_suffix_incl_scan(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+composite_fwd_kernel(const float* __restrict__ ray, const float* __restrict__ rgb_s, const float* __restrict__ sigma,
+                     const float* __restrict__ depth_s, int64_t R, int N, float bg, float* __restrict__ rgb,
+                     float* __restrict__ depth, float* __restrict__ opacity, float* __restrict__ prob,
+                     float* __restrict__ trans) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
+        float rx = ray[r * 3], ry = ray[r * 3 + 1], rz = ray[r * 3 + 2];
+        float len = sqrtf(rx * rx + ry * ry + rz * rz);
+        const float* sg = sigma + r * N;
+        const float* dp = depth_s + r * N;
+        const float* cs = rgb_s + r * N * 3;
+        float carry = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_o = 0.f;
+        for (int base = 0; base < N; base += 32) {
+            int i = base + lane;
+            bool ok = i < N;
+            float d = ok ? dp[i] : 0.f;
+            float dn = (i + 1 < N) ? dp[i + 1] : 0.f;
+            float intv = (i + 1 < N) ? (dn - d) : 1e10f;           // last interval = 1e10 (nerf.py:461)
+            float sd = ok ? sg[i] * (intv * len) : 0.f;           // sigma * (intv * ray_length)
+            float incl = warp_incl_scan(sd, lane);
+            float T = expf(-((incl - sd) + carry));
+            float w = T * (1.f - expf(-sd));
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+            if (ok) {
+                if (prob) prob[r * N + i] = w;
+                if (trans) trans[r * N + i] = T;
+                a_r += w * cs[i * 3]; a_g += w * cs[i * 3 + 1]; a_b += w * cs[i * 3 + 2];
+                a_d += w * d; a_o += w;
+            }
+        }
+        a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b); a_d = warp_sum(a_d); a_o = warp_sum(a_o);
+        if (lane == 0) {
+            if (bg >= 0.f) { float k = bg * (1.f - a_o); a_r += k; a_g += k; a_b += k; }
+            rgb[r * 3] = a_r; rgb[r * 3 + 1] = a_g; rgb[r * 3 + 2] = a_b;
+            depth[r] = a_d; opacity[r] = a_o;
+        }
+    }
+}
+
+// dL/d(sd_i) = T_{i+1} v_i - sum_{j>i} w_j v_j,  v_i = g_rgb.c_i + g_depth d_i + g_op,  T_{i+1} = T_i - w_i
+__global__ void __launch_bounds__(WARPS * 32)
+composite_bwd_kernel(const float* __restrict__ ray, const float* __restrict__ rgb_s, const float* __restrict__ sigma,
+                     const float* __restrict__ depth_s, const float* __restrict__ prob,
+                     const float* __restrict__ trans, int64_t R, int N, float bg, const float* __restrict__ d_rgb,
+                     const float* __restrict__ d_depth, const float* __restrict__ d_opacity,
+                     float* __restrict__ d_rgb_s, float* __restrict__ d_sigma, float* __restrict__ d_ray) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
+        float rx = ray[r * 3], ry = ray[r * 3 + 1], rz = ray[r * 3 + 2];
+        float len = sqrtf(rx * rx + ry * ry + rz * rz);
+        float gr = d_rgb ? d_rgb[r * 3] : 0.f, gg = d_rgb ? d_rgb[r * 3 + 1] : 0.f, gb = d_rgb ? d_rgb[r * 3 + 2] : 0.f;
+        float gd = d_depth ? d_depth[r] : 0.f;
+        float go = d_opacity ? d_opacity[r] : 0.f;
+        if (bg >= 0.f) go -= bg * (gr + gg + gb);
+        const float* sg = sigma + r * N;
+        const float* dp = depth_s + r * N;
+        const float* cs = rgb_s + r * N * 3;
+        float carry = 0.f, dlen = 0.f;
+        int nchunks = (N + 31) / 32;
+        for (int c = nchunks - 1; c >= 0; --c) {
+            int i = c * 32 + lane;
+            bool ok = i < N;
+            float d = ok ? dp[i] : 0.f;
+            float dn = (i + 1 < N) ? dp[i + 1] : 0.f;
+            float intv = (i + 1 < N) ? (dn - d) : 1e10f;
+            float w = ok ? prob[r * N + i] : 0.f;
+            float T = ok ? trans[r * N + i] : 0.f;
+            float c0 = ok ? cs[i * 3] : 0.f, c1 = ok ? cs[i * 3 + 1] : 0.f, c2 = ok ? cs[i * 3 + 2] : 0.f;
+            float v = gr * c0 + gg * c1 + gb * c2 + gd * d + go;
+            float wv = w * v;
+            float sfx = warp_suffix_incl_scan(wv, lane);          // sum_{j>=i} within chunk
+            float after = (sfx - wv) + carry;                    // sum_{j>i} over the whole ray
+            carry += __shfl_sync(0xffffffffu, sfx, 0);
+            float dsd = (T - w) * v - after;
+            if (ok) {
+                float s = sg[i];
+                d_sigma[r * N + i] = dsd * (intv * len);
+                dlen += dsd * s * intv;
+                d_rgb_s[(r * N + i) * 3] = w * gr;
+                d_rgb_s[(r * N + i) * 3 + 1] = w * gg;
+                d_rgb_s[(r * N + i) * 3 + 2] = w * gb;
+            }
+        }
+        dlen = warp_sum(dlen);
+        if (lane == 0 && d_ray) {
+            float k = len > 0.f ? dlen / len : 0.f;               // d||ray||/dray = ray/||ray||
+            d_ray[r * 3] = k * rx; d_ray[r * 3 + 1] = k * ry; d_ray[r * 3 + 2] = k * rz;
+        }
+    }
+}
+
+inline unsigned grid_for(int64_t R) {
+    int64_t blocks = (R + WARPS - 1) / WARPS;
+    int64_t cap = (int64_t)niw_num_sms() * 8;   // 8 x 256 threads = 64 warps / SM resident
+    return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+extern "C" int niw_composite_fwd(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                                 int64_t R, int N, float bg, float* rgb, float* depth, float* opacity, float* prob,
+                                 float* trans, void* stream) {
+    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && rgb && depth && opacity && R > 0 && N > 0);
+    composite_fwd_kernel<<<grid_for(R), WARPS * 32, 0, niw_stream(stream)>>>(ray, rgb_s, sigma, depth_s, R, N, bg, rgb,
+                                                                            depth, opacity, prob, trans);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int niw_composite_bwd(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                                 const float* prob, const float* trans, int64_t R, int N, float bg,
+                                 const float* d_rgb, const float* d_depth, const float* d_opacity, float* d_rgb_s,
+                                 float* d_sigma, float* d_ray, void* stream) {
+    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && prob && trans && d_rgb_s && d_sigma && R > 0 && N > 0);
+    composite_bwd_kernel<<<grid_for(R), WARPS * 32, 0, niw_stream(stream)>>>(
+        ray, rgb_s, sigma, depth_s, prob, trans, R, N, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma, d_ray);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,161 @@
+// Ray generation.
+//   a1  camera.get_center_and_ray + sub-selection   reference camera.py:419-443, model/nerf.py:298-300
+//   a2  camera.get_unwarped_center_and_ray          reference camera.py:359-390
+// The reference materialises the full B x HW grid and then indexes it; here only the requested
+// pixels are ever generated (one thread per ray), and the pose gradient is reduced per image.
+#include "common.cuh"
+
+namespace {
+
+// world-frame quantities of one pose: Rinv = R^T, tinv = -R^T t   (camera.py:89-95)
+struct PoseInv { float R[9]; float t[3]; float tinv[3]; };
+
+__device__ __forceinline__ PoseInv load_pose(const float* __restrict__ p) {
+    PoseInv q;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) q.R[i * 3 + j] = p[i * 4 + j];
+        q.t[i] = p[i * 4 + 3];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        q.tinv[j] = -(q.R[0 * 3 + j] * q.t[0] + q.R[1 * 3 + j] * q.t[1] + q.R[2 * 3 + j] * q.t[2]);
+    return q;
+}
+
+__device__ __forceinline__ void cam_to_world(const PoseInv& q, const float g[3], float out[3]) {
+    // X_hom @ pose_inv^T  (camera.py:343-346)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        out[j] = q.R[0 * 3 + j] * g[0] + q.R[1 * 3 + j] * g[1] + q.R[2 * 3 + j] * g[2] + q.tinv[j];
+}
+
+__global__ void raygen_pose_fwd_kernel(const float* __restrict__ pose, const float* __restrict__ intr,
+                                       const int64_t* __restrict__ ray_idx, int64_t idx_start, int B, int P, int W,
+                                       float* __restrict__ center, float* __restrict__ ray) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * P) return;
+    int b = (int)(t / P), p = (int)(t % P);
+    int64_t pix = ray_idx ? ray_idx[p] : idx_start + p;
+    Mat3 Ki = inverse3x3(intr + b * 9);
+    PoseInv q = load_pose(pose + b * 12);
+    float g[3], gw[3];
+    pixel_to_cam(Ki, pix, W, g);
+    cam_to_world(q, g, gw);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        center[t * 3 + j] = q.tinv[j];
+        ray[t * 3 + j] = gw[j] - q.tinv[j];  // grid_3D - center_3D  (camera.py:442)
+    }
+}
+
+// d_pose[b] = sum over rays.  ray_j = sum_i R[i][j] g_i, center_j = -sum_i R[i][j] t_i, so
+//   dR[i][j] = sum g_i d_ray_j - t_i * sum d_center_j ,  dt_i = -sum_j R[i][j] sum d_center_j.
+__global__ void raygen_pose_bwd_kernel(const float* __restrict__ pose, const float* __restrict__ intr,
+                                       const int64_t* __restrict__ ray_idx, int64_t idx_start, int B, int P, int W,
+                                       const float* __restrict__ d_center, const float* __restrict__ d_ray,
+                                       float* __restrict__ d_pose) {
+    int b = blockIdx.y;
+    Mat3 Ki = inverse3x3(intr + b * 9);
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        int64_t t = (int64_t)b * P + p;
+        int64_t pix = ray_idx ? ray_idx[p] : idx_start + p;
+        float g[3];
+        pixel_to_cam(Ki, pix, W, g);
+        if (d_ray) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[i * 3 + j] += g[i] * d_ray[t * 3 + j];
+        }
+        if (d_center) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[9 + j] += d_center[t * 3 + j];
+        }
+    }
+    __shared__ float red[12][8];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        float v = warp_sum(acc[i]);
+        if (lane == 0) red[i][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+        red[threadIdx.x][0] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const float* pb = pose + b * 12;
+        int i = threadIdx.x / 4, j = threadIdx.x % 4;
+        float out;
+        if (j < 3) out = red[i * 3 + j][0] - pb[i * 4 + 3] * red[9 + j][0];
+        else out = -(pb[i * 4 + 0] * red[9][0] + pb[i * 4 + 1] * red[10][0] + pb[i * 4 + 2] * red[11][0]);
+        atomicAdd(d_pose + b * 12 + threadIdx.x, out);
+    }
+}
+
+__global__ void raygen_unwarped_kernel(const float* __restrict__ intr, const float* __restrict__ pose_init,
+                                       const int64_t* __restrict__ ray_idx, int64_t idx_start, int B, int P, int W,
+                                       float* __restrict__ pts) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * P) return;
+    int b = (int)(t / P), p = (int)(t % P);
+    int64_t pix = ray_idx ? ray_idx[p] : idx_start + p;
+    Mat3 Ki = inverse3x3(intr + b * 9);
+    float g[3], c[3] = {0.f, 0.f, 0.f};
+    pixel_to_cam(Ki, pix, W, g);
+    if (pose_init) {
+        PoseInv q = load_pose(pose_init + b * 12);
+        float gw[3];
+        cam_to_world(q, g, gw);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { g[j] = gw[j]; c[j] = q.tinv[j]; }
+    }
+    float* grid_row = pts + ((int64_t)b * 2 * P + p) * 3;
+    float* cen_row = pts + ((int64_t)b * 2 * P + P + p) * 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { grid_row[j] = g[j]; cen_row[j] = c[j]; }
+}
+
+}  // namespace
+
+extern "C" int niw_raygen_pose_fwd(const float* pose, const float* intr, const int64_t* ray_idx, int64_t idx_start,
+                                   int B, int P, int H, int W, float* center, float* ray, void* stream) {
+    NIW_CHECK_ARG(pose && intr && center && ray && B > 0 && P > 0 && H > 0 && W > 0);
+    int64_t n = (int64_t)B * P;
+    raygen_pose_fwd_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, B, P, W,
+                                                                              center, ray);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int niw_raygen_pose_bwd(const float* pose, const float* intr, const int64_t* ray_idx, int64_t idx_start,
+                                   int B, int P, int H, int W, const float* d_center, const float* d_ray,
+                                   float* d_pose, void* stream) {
+    NIW_CHECK_ARG(pose && intr && d_pose && (d_center || d_ray) && B > 0 && P > 0 && H > 0 && W > 0);
+    NIW_CUDA(cudaMemsetAsync(d_pose, 0, sizeof(float) * 12 * B, niw_stream(stream)));
+    int bx = (P + 255) / 256;
+    if (bx > 64) bx = 64;
+    dim3 grid(bx, B);
+    raygen_pose_bwd_kernel<<<grid, 256, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, B, P, W, d_center,
+                                                               d_ray, d_pose);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int niw_raygen_unwarped(const float* intr, const float* pose_init, const int64_t* ray_idx,
+                                   int64_t idx_start, int B, int P, int H, int W, float* pts, void* stream) {
+    NIW_CHECK_ARG(intr && pts && B > 0 && P > 0 && H > 0 && W > 0);
+    int64_t n = (int64_t)B * P;
+    raygen_unwarped_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(intr, pose_init, ray_idx, idx_start, B,
+                                                                              P, W, pts);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,349 @@
+"""Operator layer: torch.autograd.Functions over the C ABI (include/niw_b200.h).
+
+Each function mirrors one reference operation (file:line in the docstrings) on CUDA tensors.
+PyTorch is used for device memory, streams and autograd bookkeeping only; all arithmetic on the
+ray/sample axes happens in the library.  Non-CUDA inputs raise: there is no CPU fallback.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import NIW_PREC_BF16, NIW_PREC_FP32, NIW_NERF_PARAMS, NIW_NVP_BLOCK_FLOATS  # noqa: F401
+
+_c = ctypes
+
+
+def _p(t):
+    return None if t is None else _c.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return _c.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("niw_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("niw_b200: %s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _idx(ray_idx, device):
+    if ray_idx is None:
+        return None
+    if not ray_idx.is_cuda:
+        ray_idx = ray_idx.to(device)
+    return ray_idx.to(torch.int64).contiguous()
+
+
+PRECISIONS = {"fp32": NIW_PREC_FP32, "bf16": NIW_PREC_BF16}
+
+
+def precision_code(p):
+    if isinstance(p, int):
+        return p
+    try:
+        return PRECISIONS[str(p).lower()]
+    except KeyError:
+        raise RuntimeError("niw_b200: unknown arch.mlp_precision %r (fp32 | bf16)" % (p,))
+
+
+# --------------------------------------------------------------------------------------------
+# ray generation
+# --------------------------------------------------------------------------------------------
+
+class _RaygenPose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose, intr, ray_idx, idx_start, P, H, W):
+        lib = _lib.load()
+        pose, intr = _f32(pose, "pose"), _f32(intr, "intr")
+        B = pose.shape[0]
+        center = torch.empty(B, P, 3, device=pose.device, dtype=torch.float32)
+        ray = torch.empty_like(center)
+        _lib.check(lib.niw_raygen_pose_fwd(_p(pose), _p(intr), _p(ray_idx), idx_start, B, P, H, W, _p(center),
+                                           _p(ray), _stream()))
+        ctx.save_for_backward(pose, intr, ray_idx)
+        ctx.dims = (idx_start, B, P, H, W)
+        return center, ray
+
+    @staticmethod
+    def backward(ctx, d_center, d_ray):
+        pose, intr, ray_idx = ctx.saved_tensors
+        idx_start, B, P, H, W = ctx.dims
+        d_pose = torch.empty_like(pose)
+        dc = None if d_center is None else d_center.contiguous()
+        dr = None if d_ray is None else d_ray.contiguous()
+        _lib.check(_lib.load().niw_raygen_pose_bwd(_p(pose), _p(intr), _p(ray_idx), idx_start, B, P, H, W, _p(dc),
+                                                   _p(dr), _p(d_pose), _stream()))
+        return d_pose, None, None, None, None, None, None
+
+
+def raygen_pose(pose, intr, H, W, ray_idx=None, idx_start=0, num=None):
+    """camera.get_center_and_ray followed by ``[:, ray_idx]`` (camera.py:419-443,
+    model/nerf.py:298-300).  pose [B,3,4], intr [B,3,3] -> center, ray [B,P,3].  With
+    ``ray_idx=None`` pixels ``idx_start .. idx_start+num-1`` (default: the whole frame)."""
+    ray_idx = _idx(ray_idx, pose.device)
+    P = int(ray_idx.numel()) if ray_idx is not None else int(num if num is not None else H * W - idx_start)
+    return _RaygenPose.apply(pose, intr, ray_idx, int(idx_start), P, int(H), int(W))
+
+
+def raygen_unwarped(intr, H, W, ray_idx=None, pose_init=None, idx_start=0, num=None):
+    """camera.get_unwarped_center_and_ray (camera.py:359-390) -> pts [B,2P,3] = [grid ; centre]."""
+    lib = _lib.load()
+    intr = _f32(intr, "intr")
+    pose_init = _f32(pose_init, "pose_init")
+    ray_idx = _idx(ray_idx, intr.device)
+    P = int(ray_idx.numel()) if ray_idx is not None else int(num if num is not None else H * W - idx_start)
+    B = intr.shape[0]
+    pts = torch.empty(B, 2 * P, 3, device=intr.device, dtype=torch.float32)
+    _lib.check(lib.niw_raygen_unwarped(_p(intr), _p(pose_init), _p(ray_idx), int(idx_start), B, P, int(H), int(W),
+                                       _p(pts), _stream()))
+    return pts
+
+
+# --------------------------------------------------------------------------------------------
+# NVP warp
+# --------------------------------------------------------------------------------------------
+
+class _NvpWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wpack, code_bias, pts, alpha_ratio):
+        lib = _lib.load()
+        wpack, code_bias, pts = _f32(wpack, "wpack"), _f32(code_bias, "code_bias"), _f32(pts, "pts")
+        B, Pt = pts.shape[0], pts.shape[1]
+        if wpack.numel() != 3 * NIW_NVP_BLOCK_FLOATS or tuple(code_bias.shape) != (3, 2, B, 128):
+            raise RuntimeError("niw_b200: NVP warp supports 3 blocks x hidden 128 x 6 bands only")
+        out = torch.empty_like(pts)
+        _lib.check(lib.niw_nvp_warp_fwd(_p(wpack), _p(code_bias), _p(pts), float(alpha_ratio), B, Pt, _p(out), _stream()))
+        ctx.save_for_backward(wpack, code_bias, pts)
+        ctx.alpha = float(alpha_ratio)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        wpack, code_bias, pts = ctx.saved_tensors
+        B, Pt = pts.shape[0], pts.shape[1]
+        d_w = torch.empty_like(wpack)
+        d_cb = torch.empty_like(code_bias)
+        _lib.check(_lib.load().niw_nvp_warp_bwd(_p(wpack), _p(code_bias), _p(pts), ctx.alpha, B, Pt,
+                                                _p(d_out.contiguous()), _p(d_w), _p(d_cb), _stream()))
+        return d_w, d_cb, None, None
+
+
+def nvp_warp(wpack, code_bias, pts, alpha_ratio):
+    """DeformNetwork.forward on packed effective weights (model/nvp/nvp_ndr.py:365-468).
+    pts [B,Pt,3] (no gradient: the reference detaches them, barf_inn_llff.py:328-330)."""
+    return _NvpWarp.apply(wpack, code_bias, pts, alpha_ratio)
+
+
+# --------------------------------------------------------------------------------------------
+# depth sampling
+# --------------------------------------------------------------------------------------------
+
+def sample_stratified(u, n_rays, N, depth_range, param, device=None):
+    """Graph.sample_depth (model/nerf.py:334-344).  u: [n_rays*N] uniforms or None (0.5).
+    Returns depth [n_rays, N].  Bit-exact with the reference's fp32 CPU evaluation."""
+    lib = _lib.load()
+    dmin, dmax = float(depth_range[0]), float(depth_range[1])
+    u = _f32(u, "u")
+    device = u.device if u is not None else device
+    if u is not None and u.numel() != n_rays * N:
+        raise RuntimeError("niw_b200: uniforms have %d elements, expected %d" % (u.numel(), n_rays * N))
+    if param not in ("metric", "inverse"):
+        raise KeyError(param)
+    depth = torch.empty(n_rays, N, device=device, dtype=torch.float32)
+    _lib.check(lib.niw_sample_stratified(_p(u), n_rays, N, dmax - dmin, dmin, int(param == "inverse"), _p(depth),
+                                         _stream()))
+    return depth
+
+
+_TABLES = {}
+
+
+def _pdf_tables(N, Nf, depth_range, device):
+    """unif = 0.5*(grid[:-1]+grid[1:]) and bins = linspace(dmin,dmax,N+1) evaluated by torch on the
+    CPU in fp32, exactly as the reference does (model/nerf.py:352-356), cached per configuration."""
+    key = (N, Nf, float(depth_range[0]), float(depth_range[1]), str(device))
+    if key not in _TABLES:
+        grid = torch.linspace(0, 1, Nf + 1)
+        unif = 0.5 * (grid[:-1] + grid[1:])
+        bins = torch.linspace(float(depth_range[0]), float(depth_range[1]), N + 1)
+        _TABLES[key] = (unif.to(device), bins.to(device))
+    return _TABLES[key]
+
+
+def sample_pdf_merge(pdf, depth_coarse, Nf, depth_range, want_idx=False, want_fine=True, want_merged=True):
+    """Graph.sample_depth_from_pdf (model/nerf.py:346-365) fused with the cat+sort of
+    model/nerf.py:313-315.  pdf, depth_coarse [R,N] -> (fine [R,Nf], idx [R,Nf] int64, merged [R,N+Nf])."""
+    lib = _lib.load()
+    pdf = _f32(pdf, "pdf")
+    R, N = pdf.shape
+    depth_coarse = _f32(depth_coarse, "depth_coarse")
+    unif, bins = _pdf_tables(N, Nf, depth_range, pdf.device)
+    fine = torch.empty(R, Nf, device=pdf.device, dtype=torch.float32) if want_fine else None
+    idx = torch.empty(R, Nf, device=pdf.device, dtype=torch.int64) if want_idx else None
+    merged = torch.empty(R, N + Nf, device=pdf.device, dtype=torch.float32) if want_merged else None
+    _lib.check(lib.niw_sample_pdf_merge(_p(pdf), _p(depth_coarse), _p(unif), _p(bins), R, N, Nf, _p(fine), _p(idx),
+                                        _p(merged), _stream()))
+    return fine, idx, merged
+
+
+# --------------------------------------------------------------------------------------------
+# compositing
+# --------------------------------------------------------------------------------------------
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ray, rgb_s, sigma, depth_s, bg):
+        lib = _lib.load()
+        ray, rgb_s, sigma, depth_s = _f32(ray, "ray"), _f32(rgb_s, "rgb_samples"), _f32(sigma, "density_samples"), \
+            _f32(depth_s, "depth_samples")
+        R, N = sigma.shape
+        dev = ray.device
+        rgb = torch.empty(R, 3, device=dev)
+        depth = torch.empty(R, device=dev)
+        opacity = torch.empty(R, device=dev)
+        prob = torch.empty(R, N, device=dev)
+        trans = torch.empty(R, N, device=dev)
+        _lib.check(lib.niw_composite_fwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), R, N, float(bg), _p(rgb),
+                                         _p(depth), _p(opacity), _p(prob), _p(trans), _stream()))
+        ctx.save_for_backward(ray, rgb_s, sigma, depth_s, prob, trans)
+        ctx.bg = float(bg)
+        ctx.mark_non_differentiable(prob)
+        return rgb, depth, opacity, prob
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_depth, d_opacity, _d_prob):
+        ray, rgb_s, sigma, depth_s, prob, trans = ctx.saved_tensors
+        R, N = sigma.shape
+        d_rgb_s = torch.empty_like(rgb_s)
+        d_sigma = torch.empty_like(sigma)
+        d_ray = torch.empty_like(ray)
+        c = lambda t: None if t is None else t.contiguous()
+        _lib.check(_lib.load().niw_composite_bwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), _p(prob), _p(trans), R, N,
+                                                 ctx.bg, _p(c(d_rgb)), _p(c(d_depth)), _p(c(d_opacity)),
+                                                 _p(d_rgb_s), _p(d_sigma), _p(d_ray), _stream()))
+        return d_ray, d_rgb_s, d_sigma, None, None
+
+
+def composite(ray, rgb_samples, density_samples, depth_samples, bgcolor=None):
+    """NeRF.composite (model/nerf.py:458-474) on flattened rays: ray [R,3], rgb_samples [R,N,3],
+    density_samples [R,N], depth_samples [R,N] -> rgb [R,3], depth [R], opacity [R], prob [R,N].
+    No gradient flows to depth_samples (they come from torch.rand / no_grad in the reference)."""
+    bg = -1.0 if bgcolor is None else float(bgcolor)
+    return _Composite.apply(ray, rgb_samples, density_samples, depth_samples, bg)
+
+
+# --------------------------------------------------------------------------------------------
+# positional encoding + MLP
+# --------------------------------------------------------------------------------------------
+
+def band_weights(progress, c2f, L):
+    """BARF coarse-to-fine weights (model/barf.py:260-264) as a host list of L floats (fp32 math
+    mirrors the reference: alpha, clamp, *pi, cos in fp32)."""
+    if c2f is None:
+        return [1.0] * L
+    start, end = c2f
+    alpha = (torch.tensor(float(progress), dtype=torch.float32) - start) / (end - start) * L
+    k = torch.arange(L, dtype=torch.float32)
+    w = (1 - ((alpha - k).clamp(min=0, max=1) * math.pi).cos()) / 2
+    return [float(x) for x in w]
+
+
+class _NerfSamples(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, params, center, ray, depth, bw3, bwv, precision, training):
+        lib = _lib.load()
+        params, center, ray, depth = _f32(params, "params"), _f32(center, "center"), _f32(ray, "ray"), _f32(depth, "depth")
+        if params.numel() != NIW_NERF_PARAMS:
+            raise RuntimeError("niw_b200: the MLP kernels implement the 8x256/skip-4/128-RGB architecture "
+                               "(%d parameters); got %d" % (NIW_NERF_PARAMS, params.numel()))
+        R, N = depth.shape
+        nbytes = lib.niw_nerf_workspace_bytes(R, N, precision, int(training))
+        if nbytes == 0:
+            raise RuntimeError("niw_b200: MLP precision %d is not available in this build" % precision)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=depth.device)
+        rgb = torch.empty(R, N, 3, device=depth.device)
+        sigma = torch.empty(R, N, device=depth.device)
+        b3 = (_c.c_float * 10)(*bw3)
+        bv = (_c.c_float * 4)(*bwv)
+        _lib.check(lib.niw_nerf_fwd(_p(params), _p(center), _p(ray), _p(depth), R, N, b3, bv, precision, int(training),
+                                    _p(ws), nbytes, _p(rgb), _p(sigma), _stream()))
+        if training:
+            ctx.save_for_backward(params, center, ray, depth, ws)
+            ctx.cfg = (tuple(bw3), tuple(bwv), precision, nbytes)
+        return rgb, sigma
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_sigma):
+        params, center, ray, depth, ws = ctx.saved_tensors
+        bw3, bwv, precision, nbytes = ctx.cfg
+        R, N = depth.shape
+        d_params = torch.zeros_like(params)
+        d_center = torch.empty_like(center)
+        d_ray = torch.empty_like(ray)
+        if d_rgb is None:
+            d_rgb = torch.zeros(R, N, 3, device=depth.device)
+        if d_sigma is None:
+            d_sigma = torch.zeros(R, N, device=depth.device)
+        b3 = (_c.c_float * 10)(*bw3)
+        bv = (_c.c_float * 4)(*bwv)
+        _lib.check(_lib.load().niw_nerf_bwd(_p(params), _p(center), _p(ray), _p(depth), R, N, b3, bv, precision, _p(ws),
+                                            nbytes, _p(d_rgb.contiguous()), _p(d_sigma.contiguous()), _p(d_params),
+                                            _p(d_center), _p(d_ray), _stream()))
+        return d_params, d_center, d_ray, None, None, None, None, None
+
+
+def nerf_forward_samples(params, center, ray, depth, bw3, bwv, precision=NIW_PREC_FP32, training=None):
+    """NeRF.forward_samples (model/nerf.py:449-456 -> :416-447, with camera.py:517-521 and the BARF
+    encoding model/barf.py:256-268).  params: flat [530052] fp32; center/ray [R,3]; depth [R,N]
+    -> rgb [R,N,3], sigma [R,N]."""
+    if training is None:
+        training = torch.is_grad_enabled() and (params.requires_grad or center.requires_grad or ray.requires_grad)
+    return _NerfSamples.apply(params, center, ray, depth, list(bw3), list(bwv), precision_code(precision), bool(training))
+
+
+# --------------------------------------------------------------------------------------------
+# loss head
+# --------------------------------------------------------------------------------------------
+
+class _MseGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, image, ray_idx, idx_start):
+        lib = _lib.load()
+        rgb, image = _f32(rgb, "rgb"), _f32(image, "image")
+        B, P = rgb.shape[0], rgb.shape[1]
+        H, W = image.shape[-2:]
+        loss = torch.zeros((), device=rgb.device)
+        d_rgb = torch.empty_like(rgb)
+        scale = 1.0 / (B * P * 3)
+        _lib.check(lib.niw_mse_gather(_p(image), _p(rgb), _p(ray_idx), idx_start, B, P, H, W, scale, _p(loss), _p(d_rgb),
+                                      _stream()))
+        ctx.save_for_backward(d_rgb)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_rgb,) = ctx.saved_tensors
+        return d_rgb * g, None, None, None
+
+
+def mse_gather(rgb, image, ray_idx=None, idx_start=0):
+    """MSE between rendered rgb [B,P,3] and image[:, :, ray_idx] (model/nerf.py:276-283,
+    model/base.py:209-211), without materialising the gathered pixels."""
+    return _MseGather.apply(rgb, image, _idx(ray_idx, rgb.device), int(idx_start))
+
+
+def tc_selftest(A, Bm, variant=0):
+    """D = A . Bm^T through the tcgen05 staging used by the MLP kernel (A [128,K], Bm [N,K])."""
+    lib = _lib.load()
+    A, Bm = _f32(A, "A"), _f32(Bm, "B")
+    N, K = Bm.shape
+    D = torch.zeros(128, N, device=A.device)
+    _lib.check(lib.niw_tc_selftest(_p(A), _p(Bm), N, K, int(variant), _p(D), _stream()))
+    return D

@@ -1,0 +1,283 @@
+"""GPU parity: every C-ABI operator against the CPU oracle (oracle/reference_port.py) and against
+the golden vectors minted from the executed reference (tests/golden)."""
+import math
+
+import pytest
+import torch
+
+from neural_invertible_warp_b200 import synthetic as syn
+from oracle import reference_port as ora
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def F():
+    from neural_invertible_warp_b200 import functional
+    return functional
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def flat_params(p):
+    return torch.cat([p[k].reshape(-1) for k in nerf_keys()])
+
+
+def nerf_keys():
+    keys = []
+    for i in range(8):
+        keys += [f"mlp_feat.{i}.weight", f"mlp_feat.{i}.bias"]
+    for i in range(2):
+        keys += [f"mlp_rgb.{i}.weight", f"mlp_rgb.{i}.bias"]
+    return keys
+
+
+def unflatten(flat, like):
+    out, off = {}, 0
+    for k in nerf_keys():
+        n = like[k].numel()
+        out[k] = flat[off:off + n].view_as(like[k])
+        off += n
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+
+def test_raygen_pose_golden(F, golden):
+    g = golden("camera")
+    H, W = g["H"], g["W"]
+    pose = g["pose"].to(DEV).requires_grad_(True)
+    intr = g["intr"].to(DEV)
+    c, r = F.raygen_pose(pose, intr, H, W)
+    torch.testing.assert_close(c.cpu(), g["center"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(r.cpu(), g["ray"], rtol=1e-5, atol=1e-5)
+    wc = (syn.uniforms(g["wc_seed"], *c.shape) - 0.5).to(DEV)
+    wr = (syn.uniforms(g["wr_seed"], *r.shape) - 0.5).to(DEV)
+    ((c * wc).sum() + (r * wr).sum()).backward()
+    assert rel_l2(pose.grad, g["pose_grad"]) < 1e-4
+    c2, r2 = F.raygen_pose(pose.detach(), intr, H, W, ray_idx=g["ray_idx"].to(DEV))
+    torch.testing.assert_close(c2.cpu(), g["center"][:, g["ray_idx"]], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(r2.cpu(), g["ray"][:, g["ray_idx"]], rtol=1e-5, atol=1e-5)
+    c3, r3 = F.raygen_pose(pose.detach(), intr, H, W, idx_start=7, num=13)
+    torch.testing.assert_close(r3.cpu(), g["ray"][:, 7:20], rtol=1e-5, atol=1e-5)
+
+
+def test_raygen_unwarped_golden(F, golden):
+    g = golden("camera")
+    H, W = g["H"], g["W"]
+    idx = g["ray_idx"].to(DEV)
+    P = idx.numel()
+    pts = F.raygen_unwarped(g["intr"].to(DEV), H, W, ray_idx=idx).cpu()
+    torch.testing.assert_close(pts[:, :P], g["grid_cam"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(pts[:, P:], g["center_cam"], rtol=0, atol=0)
+    pts = F.raygen_unwarped(g["intr"].to(DEV), H, W, ray_idx=idx, pose_init=g["pose"].to(DEV)).cpu()
+    torch.testing.assert_close(pts[:, :P], g["grid_w"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(pts[:, P:], g["center_w"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["llff", "dtu"])
+def test_sampler_bit_exact_golden(F, golden, tag):
+    g = golden("sampler")[tag]
+    B, R, N = g["u"].shape[:3]
+    d = F.sample_stratified(g["u"].to(DEV).reshape(-1), B * R, N, g["range"], g["param"])
+    assert torch.equal(d.cpu().view(B, R, N, 1), g["depth"]), "stratified depths must be bit-exact"
+    fine, idx, merged = F.sample_pdf_merge(g["pdf"].to(DEV).view(B * R, N), d, g["Nf"], g["range"], want_idx=True)
+    assert torch.equal(idx.cpu().view(B, R, -1), g["idx"]), "importance-sampling bins must be bit-exact"
+    assert torch.equal(fine.cpu().view(B, R, -1, 1), g["fine"])
+    assert torch.equal(merged.cpu().view(B, R, -1, 1), g["merged"])
+
+
+def test_sampler_unstratified_and_ragged(F):
+    d = F.sample_stratified(None, 5, 7, [2.0, 6.0], "metric", device=DEV)
+    ref = ora.stratified_depth(0.5, 7, [2.0, 6.0], "metric").expand(1, 5, 7, 1)
+    assert torch.equal(d.cpu().view(1, 5, 7, 1), ref.contiguous())
+
+
+@pytest.mark.parametrize("R,N,Nf", [(1000, 64, 128), (257, 128, 64), (33, 48, 80)])
+def test_pdf_sampler_vs_oracle_random(F, R, N, Nf):
+    gen = torch.Generator().manual_seed(R + N)
+    pdf = torch.rand(1, R, N, generator=gen) ** 4
+    pdf = pdf / pdf.sum(-1, keepdim=True) * torch.rand(1, R, 1, generator=gen)
+    pdf[0, ::7, : N // 3] = 0
+    u = torch.rand(1, R, N, 1, generator=gen)
+    rng = [1.2, 5.2]
+    coarse = ora.stratified_depth(u, N, rng, "metric")
+    fine_ref, idx_ref = ora.pdf_depth(pdf, N, Nf, rng, return_idx=True)
+    merged_ref = ora.merge_depth(coarse, fine_ref)
+    fine, idx, merged = F.sample_pdf_merge(pdf[0].to(DEV), coarse[0, ..., 0].to(DEV), Nf, rng, want_idx=True)
+    assert torch.equal(idx.cpu(), idx_ref[0])
+    assert torch.equal(fine.cpu(), fine_ref[0, ..., 0])
+    assert torch.equal(merged.cpu(), merged_ref[0, ..., 0])
+    assert bool((merged[:, 1:] >= merged[:, :-1]).all())
+
+
+def test_composite_golden(F, golden):
+    g = golden("composite")
+    B, R, N = g["sigma"].shape
+    ins = [g[k].to(DEV).reshape(B * R, *g[k].shape[2:]).requires_grad_(True) for k in ("ray", "rgb_samples", "sigma")]
+    depth_s = g["depth_samples"].to(DEV).reshape(B * R, N)
+    rgb, d, op, prob = F.composite(ins[0], ins[1], ins[2], depth_s)
+    torch.testing.assert_close(rgb.cpu().view(B, R, 3), g["rgb"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(d.cpu().view(B, R, 1), g["depth"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(op.cpu().view(B, R, 1), g["opacity"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(prob.cpu().view(B, R, N, 1), g["prob"], rtol=1e-5, atol=1e-7)
+    w = [(syn.uniforms(s, *t.shape) - 0.5).to(DEV) for s, t in zip(g["w_seeds"], (g["rgb"], g["depth"], g["opacity"]))]
+    ((rgb.view(B, R, 3) * w[0]).sum() + (d.view(B, R, 1) * w[1]).sum() + (op.view(B, R, 1) * w[2]).sum()).backward()
+    assert rel_l2(ins[0].grad.view(B, R, 3), g["d_ray"]) < 1e-4
+    assert rel_l2(ins[1].grad.view(B, R, N, 3), g["d_rgb_samples"]) < 1e-5
+    assert rel_l2(ins[2].grad.view(B, R, N), g["d_sigma"]) < 1e-4
+
+
+@pytest.mark.parametrize("R,N", [(300, 128), (77, 50), (5, 1), (64, 192)])
+def test_composite_vs_oracle(F, R, N):
+    gen = torch.Generator().manual_seed(R * N)
+    ray = torch.randn(1, R, 3, generator=gen)
+    rgb_s = torch.rand(1, R, N, 3, generator=gen)
+    sig = torch.rand(1, R, N, generator=gen) * 4
+    depth = (torch.rand(1, R, N, 1, generator=gen) + torch.arange(N)[None, None, :, None]) / N * 4 + 1
+    ins_ref = [t.clone().requires_grad_(True) for t in (ray, rgb_s, sig)]
+    ref = ora.composite(ins_ref[0], ins_ref[1], ins_ref[2], depth, bgcolor=1.0)
+    ins = [t[0].to(DEV).requires_grad_(True) for t in (ray, rgb_s, sig)]
+    out = F.composite(ins[0], ins[1], ins[2], depth[0, ..., 0].to(DEV), bgcolor=1.0)
+    for a, b in zip(out, ref):
+        torch.testing.assert_close(a.cpu().reshape(-1), b.detach().reshape(-1), rtol=2e-5, atol=2e-6)
+    gw = [torch.rand(t.shape, generator=gen) - 0.5 for t in ref[:3]]
+    sum((a * w).sum() for a, w in zip(ref[:3], gw)).backward()
+    sum((a.reshape(w[0].shape) * w[0].to(DEV)).sum() for a, w in zip(out[:3], gw)).backward()
+    for a, b in zip(ins, ins_ref):
+        assert rel_l2(a.grad, b.grad[0]) < 2e-4
+
+
+def _nvp_pack(p, code):
+    from neural_invertible_warp_b200.nvp import pack_effective
+    return pack_effective(p, code)
+
+
+@pytest.mark.parametrize("alpha", [0.05, 0.4, 1.0])
+def test_nvp_golden(F, golden, alpha):
+    g = golden("nvp")
+    case = g["cases"][alpha]
+    p = {k: v.to(DEV).requires_grad_(True) for k, v in syn.nvp_params(g["param_seed"]).items()}
+    code = syn.latent_codes(g["code_seed"], 2).to(DEV).requires_grad_(True)
+    wpack, code_bias = _nvp_pack(p, code)
+    pts = g["pts"].to(DEV)[:, :, 0]
+    out = F.nvp_warp(wpack, code_bias, pts, alpha)
+    torch.testing.assert_close(out.cpu(), case["out"][:, :, 0], rtol=1e-5, atol=5e-6)
+    w = (syn.uniforms(g["w_seed"], *case["out"].shape) - 0.5)[:, :, 0].to(DEV)
+    (out * w).sum().backward()
+    assert rel_l2(code.grad, case["d_code"]) < 2e-3
+    assert rel_l2(p["lin0_a_1.weight"].grad, case["d_a1w"]) < 2e-3
+    assert rel_l2(p["lin2_b_1.weight"].grad, case["d_b1w"]) < 2e-3
+    for k, d in case["grads"].items():
+        gk = p[k].grad.double().cpu().flatten()
+        assert abs(gk.norm().item() - d["l2"]) <= 5e-3 * max(d["l2"], 1e-12), k
+        assert abs(gk.sum().item() - d["sum"]) <= 5e-3 * max(d["abssum"], 1e-12), k
+
+
+def test_nvp_vs_oracle_large(F):
+    B, Pt = 3, 700            # crosses CTA and image boundaries (128 points per CTA)
+    p_cpu = syn.nvp_params(5)
+    code_cpu = syn.latent_codes(6, B)
+    pts_cpu = torch.randn(B, Pt, 1, 3, generator=torch.Generator().manual_seed(7)) * 0.7
+    q = {k: v.clone().requires_grad_(True) for k, v in p_cpu.items()}
+    cg = code_cpu.clone().requires_grad_(True)
+    ref = ora.nvp_warp(q, cg, pts_cpu, 0.3)
+    w = torch.rand(ref.shape, generator=torch.Generator().manual_seed(8)) - 0.5
+    (ref * w).sum().backward()
+    p = {k: v.to(DEV).requires_grad_(True) for k, v in p_cpu.items()}
+    code = code_cpu.to(DEV).requires_grad_(True)
+    wpack, code_bias = _nvp_pack(p, code)
+    out = F.nvp_warp(wpack, code_bias, pts_cpu[:, :, 0].to(DEV), 0.3)
+    torch.testing.assert_close(out.cpu(), ref.detach()[:, :, 0], rtol=1e-5, atol=5e-6)
+    (out * w[:, :, 0].to(DEV)).sum().backward()
+    assert rel_l2(code.grad, cg.grad) < 2e-3
+    for k in q:
+        assert rel_l2(p[k].grad, q[k].grad) < 3e-3, k
+
+
+@pytest.mark.parametrize("progress", [0.2, 0.3, 1.0])
+def test_nerf_mlp_fp32_golden(F, golden, progress):
+    """NeRF.forward on the golden points: centre = point, zero depth, ray = view direction."""
+    g = golden("nerf_mlp")
+    case = g["cases"][progress]
+    p_cpu = syn.nerf_params(g["param_seed"])
+    flat = flat_params(p_cpu).to(DEV).requires_grad_(True)
+    pts = g["points"].reshape(-1, 3).to(DEV).requires_grad_(True)
+    unit = g["ray_unit"].reshape(-1, 3).to(DEV).requires_grad_(True)
+    depth = torch.zeros(pts.shape[0], 1, device=DEV)
+    bw3, bwv = F.band_weights(progress, g["c2f"], 10), F.band_weights(progress, g["c2f"], 4)
+    rgb, sigma = F.nerf_forward_samples(flat, pts, unit, depth, bw3, bwv, "fp32", training=True)
+    shp = g["points"].shape[:-1]
+    torch.testing.assert_close(rgb.cpu().view(*shp, 3), case["rgb"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(sigma.cpu().view(*shp), case["density"], rtol=1e-4, atol=1e-5)
+    wr = (syn.uniforms(g["wr_seed"], *case["rgb"].shape) - 0.5).to(DEV)
+    wd = (syn.uniforms(g["wd_seed"], *case["density"].shape) - 0.5).to(DEV)
+    ((rgb.view(*shp, 3) * wr).sum() + (sigma.view(*shp) * wd).sum()).backward()
+    assert rel_l2(pts.grad.view(*shp, 3), case["d_points"]) < 2e-3
+    grads = unflatten(flat.grad.cpu(), p_cpu)
+    for k, d in case["grads"].items():
+        gk = grads[k].double().flatten()
+        assert abs(gk.norm().item() - d["l2"]) <= 2e-3 * max(d["l2"], 1e-12), k
+        assert abs(gk.sum().item() - d["sum"]) <= 2e-3 * max(d["abssum"], 1e-12), k
+
+
+@pytest.mark.parametrize("R,N", [(48, 16), (10, 128), (3, 37)])
+def test_nerf_fp32_vs_oracle_with_ray_grads(F, R, N):
+    """forward_samples incl. all three gradient routes into ray and the centre route."""
+    gen = torch.Generator().manual_seed(R + 31 * N)
+    p_cpu = syn.nerf_params(3)
+    center = torch.randn(1, R, 3, generator=gen) * 0.1
+    ray = torch.randn(1, R, 3, generator=gen) * 0.5 + torch.tensor([0., 0., 1.])
+    u = torch.rand(1, R, N, 1, generator=gen)
+    depth = ora.stratified_depth(u, N, [1.2, 5.2], "metric")
+    q = {k: v.clone().requires_grad_(True) for k, v in p_cpu.items()}
+    c_ref, r_ref = center.clone().requires_grad_(True), ray.clone().requires_grad_(True)
+    pts, unit = ora.sample_points(c_ref, r_ref, depth)
+    rgb_ref, sig_ref = ora.nerf_mlp(q, pts, unit, progress=0.3, c2f=[0.1, 0.5])
+    out_ref = ora.composite(r_ref, rgb_ref, sig_ref, depth)
+    tgt = torch.rand(1, R, 3, generator=gen)
+    loss_ref = ora.mse(out_ref[0], tgt) + 0.1 * out_ref[1].mean()
+    loss_ref.backward()
+
+    flat = flat_params(p_cpu).to(DEV).requires_grad_(True)
+    c, r = center[0].to(DEV).requires_grad_(True), ray[0].to(DEV).requires_grad_(True)
+    d = depth[0, ..., 0].to(DEV)
+    bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
+    rgb_s, sig_s = F.nerf_forward_samples(flat, c, r, d, bw3, bwv, "fp32")
+    torch.testing.assert_close(rgb_s.cpu(), rgb_ref.detach()[0], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(sig_s.cpu(), sig_ref.detach()[0], rtol=1e-4, atol=2e-5)
+    rgb, dep, op, _ = F.composite(r, rgb_s, sig_s, d)
+    assert (rgb.cpu() - out_ref[0].detach()[0]).abs().max() < 1e-3     # north_star forward tolerance
+    assert (dep.cpu() - out_ref[1].detach()[0, :, 0]).abs().max() < 1e-3
+    assert (op.cpu() - out_ref[2].detach()[0, :, 0]).abs().max() < 1e-3
+    loss = ((rgb - tgt[0].to(DEV)) ** 2).mean() + 0.1 * dep.mean()
+    loss.backward()
+    assert rel_l2(c.grad, c_ref.grad[0]) < 1e-2
+    assert rel_l2(r.grad, r_ref.grad[0]) < 1e-2
+    grads = unflatten(flat.grad.cpu(), p_cpu)
+    for k in q:
+        assert rel_l2(grads[k], q[k].grad) < 5e-3, k
+
+
+def test_mse_gather(F):
+    gen = torch.Generator().manual_seed(0)
+    B, P, H, W = 3, 50, 12, 16
+    image = torch.rand(B, 3, H, W, generator=gen)
+    rgb = torch.rand(B, P, 3, generator=gen).requires_grad_(True)
+    idx = torch.randperm(H * W, generator=gen)[:P]
+    ref = ora.mse(rgb, ora.gather_pixels(image, idx))
+    ref.backward()
+    x = rgb.detach().to(DEV).requires_grad_(True)
+    loss = F.mse_gather(x, image.to(DEV), idx.to(DEV))
+    torch.testing.assert_close(loss.cpu(), ref.detach(), rtol=1e-5, atol=1e-7)
+    (loss * 3).backward()
+    torch.testing.assert_close(x.grad.cpu(), rgb.grad * 3, rtol=1e-5, atol=1e-8)
+
+
+def test_ops_refuse_cpu_tensors(F):
+    with pytest.raises(RuntimeError):
+        F.composite(torch.zeros(2, 3), torch.zeros(2, 4, 3), torch.zeros(2, 4), torch.zeros(2, 4))
