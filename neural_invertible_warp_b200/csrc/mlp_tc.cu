@@ -1,9 +1,444 @@
-// placeholder until the tcgen05 path lands
+// Fused positional-encoding + 8x256 NeRF MLP on the 5th-generation tensor cores (tcgen05, sm_100a).
+// SURVEY.md section 8 rows a6+a7+a8; reference model/nerf.py:416-456, model/barf.py:256-268.
+//
+// Forward (tc_fwd_kernel): persistent, one CTA per SM, 384 threads.
+//   warp 0      producer: streams the pre-packed BF16 weights (1.03 MB / pass) from L2 into a
+//               3-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256|128, K=16) with the
+//               activation tile as A (shared memory, K-major, no swizzle) and the weight chunk as B
+//   warp 2      TMEM allocator (2 x 256 fp32 columns = all 512 columns)
+//   warp 3      loads biases / head weights into shared memory
+//   warps 4-7   epilogue of tile slot 0,  warps 8-11 epilogue of tile slot 1: one thread per
+//               sample row; TMEM -> registers -> +bias, ReLU -> BF16 -> next layer's A tile in
+//               shared memory (and to HBM for the backward pass).  The density head (row 0 of
+//               layer 7) and the 128->3 RGB layer are folded into the epilogues as FP32 dot
+//               products, the positional encoding is computed straight into the A tile.
+// Two 128-sample tiles share every weight chunk, so weights cross L2->SMEM once per 256 samples.
+//
+// Shared-memory operand layout (both operands, all layers): [K/8 chunks][rows][8 bf16], i.e. the
+// canonical no-swizzle K-major UMMA layout with 128 B core matrices, SBO = 128 B (8-row groups are
+// contiguous) and LBO = rows*16 B.  Epilogue thread r writes 16 B at chunk*rows*16 + r*16: a warp
+// writes 512 contiguous bytes (bank-conflict free).  The same image, stored per tile in HBM, is
+// the MN-major operand of the weight-gradient GEMM in the backward pass (K = samples).
 #include "common.cuh"
 #include "mlp_shared.cuh"
+#include "tc_ptx.cuh"
+
 namespace niw {
-size_t tc_workspace_bytes(int64_t, int, int) { return 0; }
-int tc_fwd(const float*, const float*, const float*, const float*, int64_t, int, const Bands3&, const BandsV&, int, void*, size_t, float*, float*, cudaStream_t) { return NIW_E_UNSUPP; }
-int tc_bwd(const float*, const float*, const float*, const float*, int64_t, int, const Bands3&, const BandsV&, void*, size_t, const float*, const float*, float*, float*, float*, cudaStream_t) { return NIW_E_UNSUPP; }
+
+namespace tc {
+
+constexpr int TILE = 128;                         // samples per tile (UMMA M)
+constexpr int NLAYER = 9;                         // 8 feature layers + rgb0
+constexpr int CHUNK_K = 32;                       // K extent of one streamed weight chunk
+constexpr int NSTAGE = 3;
+constexpr int ACT_BYTES = TILE * WIDTH * 2;       // 65536
+constexpr int ENC_BYTES = TILE * ENC3_PAD * 2;    // 16384
+constexpr int STAGE_BYTES = WIDTH * CHUNK_K * 2;  // 16384
+constexpr int KROW = TILE * 16;                   // 2048: byte stride between K-chunks (8 elems) of an A tile
+
+__host__ __device__ constexpr int layer_chunks(int l) { return l == 0 ? 2 : (l == 4 ? 10 : (l == 8 ? 9 : 8)); }
+__host__ __device__ constexpr int layer_rows(int l) { return l == 8 ? RGBW : WIDTH; }
+__host__ __device__ constexpr int layer_in(int l) { return l == 8 ? WIDTH + ENCV : feat_in(l); }
+__host__ __device__ constexpr int64_t layer_woff(int l) { return l == 8 ? RGB0_W : feat_w_off(l); }
+__host__ __device__ constexpr int64_t layer_boff(int l) { return l == 8 ? RGB0_B : feat_b_off(l); }
+__host__ __device__ constexpr int layer_rowoff(int l) { return l == 7 ? 1 : 0; }   // layer 7: row 0 is the density head
+__host__ __device__ constexpr int64_t stream_off(int l) {                        // byte offset of layer l in the stream
+    int64_t o = 0;
+    for (int i = 0; i < l; ++i) o += (int64_t)layer_chunks(i) * layer_rows(i) * CHUNK_K * 2;
+    return o;
 }
-extern "C" int niw_tc_selftest(const float*, const float*, int, int, int, float*, void*) { return NIW_E_UNSUPP; }
+constexpr int64_t STREAM_BYTES = stream_off(NLAYER);
+static_assert(STREAM_BYTES == 1056768, "weight stream size");
+
+// fp32 constants kept in shared memory
+constexpr int C_BIAS = 0;                         // [9][256]
+constexpr int C_W7R0 = C_BIAS + NLAYER * WIDTH;   // [256]  density row of layer 7
+constexpr int C_WRGB1 = C_W7R0 + WIDTH;           // [3][128]
+constexpr int C_MISC = C_WRGB1 + 3 * RGBW;        // b7[0], brgb1[0..2]
+constexpr int C_FLOATS = C_MISC + 4;
+
+// per-tile activation image saved for backward: h0..h7 (64 KB each) + hr (32 KB)
+constexpr int64_t SAVE_TILE_BYTES = 8 * (int64_t)ACT_BYTES + TILE * RGBW * 2;
+
+// shared memory map of the forward kernel
+constexpr int SM_ACT = 0;
+constexpr int SM_ENC = SM_ACT + 2 * ACT_BYTES;
+constexpr int SM_RING = SM_ENC + 2 * ENC_BYTES;
+constexpr int SM_CONST = SM_RING + NSTAGE * STAGE_BYTES;
+constexpr int SM_BAR = SM_CONST + ((C_FLOATS * 4 + 15) / 16) * 16;
+constexpr int SM_TOTAL = SM_BAR + 128;
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+
+struct Workspace {
+    uint8_t* wstream;     // forward weight stream (bf16)
+    uint8_t* wstream_t;   // backward (transposed) weight stream
+    float* consts;        // C_FLOATS
+    float* sig_pre;       // [S]
+    float* rgb_keep;      // [S,3]
+    uint8_t* save;        // [tiles] x SAVE_TILE_BYTES
+    size_t bytes;
+};
+
+inline Workspace carve(void* base, int64_t S, bool training) {
+    Workspace w;
+    size_t off = 0;
+    auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += (n + 255) & ~size_t(255); return p; };
+    int64_t tiles = (S + TILE - 1) / TILE;
+    w.wstream = take(STREAM_BYTES);
+    w.wstream_t = take(STREAM_BYTES + 65536);
+    w.consts = (float*)take(C_FLOATS * 4);
+    w.sig_pre = (float*)take(training ? S * 4 : 0);
+    w.rgb_keep = (float*)take(training ? S * 12 : 0);
+    w.save = take(training ? tiles * SAVE_TILE_BYTES : 0);
+    w.bytes = off;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: fp32 parameters -> BF16 chunk stream in MMA consumption order + fp32 constants
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ stream, float* __restrict__ consts) {
+    // one thread per 16-byte group (8 consecutive k of one row)
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ngroups = STREAM_BYTES / 16;
+    if (gid < ngroups) {
+        int64_t byte = gid * 16;
+        int l = 0;
+#pragma unroll
+        for (int i = 1; i < NLAYER; ++i) if (byte >= stream_off(i)) l = i;
+        const int rows = layer_rows(l);
+        int64_t rel = byte - stream_off(l);
+        int chunk = (int)(rel / ((int64_t)rows * CHUNK_K * 2));
+        int64_t in_chunk = rel % ((int64_t)rows * CHUNK_K * 2);
+        int kc = (int)(in_chunk / (rows * 16));          // which 8-wide k group inside the chunk
+        int n = (int)((in_chunk % (rows * 16)) / 16);
+        int k0 = chunk * CHUNK_K + kc * 8;
+        const int in_dim = layer_in(l);
+        const float* Wl = P + layer_woff(l) + (int64_t)(n + layer_rowoff(l)) * in_dim;
+        uint32_t out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int ka = k0 + 2 * j, kb = ka + 1;
+            out[j] = ptx::pack_bf16(ka < in_dim ? Wl[ka] : 0.f, kb < in_dim ? Wl[kb] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(stream + byte) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    if (gid < C_FLOATS) {
+        int i = (int)gid;
+        float v;
+        if (i < C_W7R0) {
+            int l = i / WIDTH, n = i % WIDTH;
+            v = n < layer_rows(l) ? P[layer_boff(l) + n + layer_rowoff(l)] : 0.f;
+        } else if (i < C_WRGB1) {
+            v = P[feat_w_off(7) + (i - C_W7R0)];
+        } else if (i < C_MISC) {
+            v = P[RGB1_W + (i - C_WRGB1)];
+        } else {
+            int j = i - C_MISC;
+            v = j == 0 ? P[feat_b_off(7)] : P[RGB1_B + (j - 1)];
+        }
+        consts[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+
+// sin / cos of an fp32 argument that may be huge (inverse-depth samples reach |x| ~ 1e8): exact
+// range reduction of the *rounded fp32 argument* in fp64 (so the value matches the reference's
+// sin(fp32(x*freq)) rather than the mathematically exact sin(2^k pi x)), then MUFU on |r| <= pi/2.
+__device__ __forceinline__ void sincos_reduced(float arg, float& s, float& c) {
+    double t = (double)arg * 0.31830988618379067154;
+    long long n = __double2ll_rn(t);
+    float fr = (float)(t - (double)n) * PI_F;
+    s = __sinf(fr); c = __cosf(fr);
+    if (n & 1) { s = -s; c = -c; }
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(__expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// write the 64-wide encoded position of one row into an A-tile image ([8 chunks][128 rows][8 bf16])
+__device__ __forceinline__ void write_enc_row(uint8_t* enc_tile, int row, const float x[3], const Bands3& bw, bool valid) {
+    float e[ENC3_PAD];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        e[c] = valid ? x[c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < L3; ++k) {
+            float sn, cs;
+            sincos_reduced(x[c] * ((float)(1 << k) * PI_F), sn, cs);
+            e[3 + c * 2 * L3 + k] = valid ? bw.w[k] * sn : 0.f;
+            e[3 + c * 2 * L3 + L3 + k] = valid ? bw.w[k] * cs : 0.f;
+        }
+    }
+    e[ENC3] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < ENC3_PAD / 8; ++ch) {
+        uint4 v = make_uint4(ptx::pack_bf16(e[ch * 8], e[ch * 8 + 1]), ptx::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]),
+                             ptx::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]), ptx::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
+        *reinterpret_cast<uint4*>(enc_tile + ch * KROW + row * 16) = v;
+    }
+}
+
+// write the 32-wide encoded view direction (27 + zero pad) of one row into chunks 0..3 of an enc tile
+__device__ __forceinline__ void write_venc_row(uint8_t* enc_tile, int row, const float v3[3], const BandsV& bw, bool valid) {
+    float e[ENCV_PAD];
+    float inv = 1.f / fmaxf(sqrtf(v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2]), 1e-12f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float x = v3[c] * inv;
+        e[c] = valid ? x : 0.f;
+#pragma unroll
+        for (int k = 0; k < LV; ++k) {
+            float sn, cs;
+            sincos_reduced(x * ((float)(1 << k) * PI_F), sn, cs);
+            e[3 + c * 2 * LV + k] = valid ? bw.w[k] * sn : 0.f;
+            e[3 + c * 2 * LV + LV + k] = valid ? bw.w[k] * cs : 0.f;
+        }
+    }
+#pragma unroll
+    for (int i = ENCV; i < ENCV_PAD; ++i) e[i] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < ENCV_PAD / 8; ++ch) {
+        uint4 v = make_uint4(ptx::pack_bf16(e[ch * 8], e[ch * 8 + 1]), ptx::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]),
+                             ptx::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]), ptx::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
+        *reinterpret_cast<uint4*>(enc_tile + ch * KROW + row * 16) = v;
+    }
+}
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+// ------------------------------------------------------------------------------------------
+// fused forward kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(384, 1)
+tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ consts_g, const float* __restrict__ center,
+              const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N, Bands3 bw3, BandsV bwv,
+              float* __restrict__ rgb_out, float* __restrict__ sigma_out, float* __restrict__ sig_pre,
+              float* __restrict__ rgb_keep, uint8_t* __restrict__ save) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    uint64_t* w_full = bars;                 // [NSTAGE]
+    uint64_t* w_empty = bars + NSTAGE;       // [NSTAGE]
+    uint64_t* a_ready = bars + 2 * NSTAGE;   // [2]
+    uint64_t* acc_full = a_ready + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    float* cst = reinterpret_cast<float*>(smem + SM_CONST);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (S + TILE - 1) / TILE;
+    const int64_t npairs = (ntiles + 1) / 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], TILE); ptx::mbar_init(&acc_full[i], 1); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+    if (warp == 3) for (int i = lane; i < C_FLOATS; i += 32) cst[i] = consts_g[i];
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+                const uint8_t* src = wstream;
+                for (int l = 0; l < NLAYER; ++l) {
+                    const uint32_t bytes = (uint32_t)layer_rows(l) * CHUNK_K * 2;
+                    for (int c = 0; c < layer_chunks(l); ++c, ++it) {
+                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                        ptx::mbar_wait(&w_empty[st], ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&w_full[st], bytes);
+                        ptx::bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src, bytes, &w_full[st]);
+                        src += bytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, ready_uses = 0;
+            const uint32_t act0 = ptx::smem_addr(smem + SM_ACT), enc0 = ptx::smem_addr(smem + SM_ENC);
+            const uint32_t ring0 = ptx::smem_addr(smem + SM_RING);
+            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+                for (int l = 0; l < NLAYER; ++l, ++ready_uses) {
+                    const int rows = layer_rows(l), nch = layer_chunks(l);
+                    const uint32_t idesc = ptx::idesc_bf16(TILE, rows, 0, 0);
+                    for (int c = 0; c < nch; ++c, ++it) {
+                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                        ptx::mbar_wait(&w_full[st], ph);
+                        ptx::tc_fence_after();
+                        // which A tile region does this chunk multiply?
+                        const bool from_enc = (l == 0) || (c >= 8);
+                        const int kc0 = (l == 0 ? c : (c >= 8 ? c - 8 : c)) * (CHUNK_K / 8);
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            if (c == 0) { ptx::mbar_wait(&a_ready[s], ready_uses & 1); ptx::tc_fence_after(); }
+                            const uint32_t a_base = (from_enc ? enc0 + s * ENC_BYTES : act0 + s * ACT_BYTES) + kc0 * KROW;
+                            const uint32_t b_base = ring0 + st * STAGE_BYTES;
+#pragma unroll
+                            for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
+                                uint64_t ad = ptx::smem_desc(a_base + ks * 2 * KROW, KROW, 128);
+                                uint64_t bd = ptx::smem_desc(b_base + ks * 2 * rows * 16, rows * 16, 128);
+                                ptx::mma_bf16(tmem_base + s * WIDTH, ad, bd, idesc, (c | ks) != 0);
+                            }
+                            if (c == nch - 1) ptx::mma_commit(&acc_full[s]);
+                        }
+                        ptx::mma_commit(&w_empty[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue warpgroups (one thread per sample row) =================
+        const int slot = (warp - 4) >> 2;
+        const int row = ((warp & 3) << 5) | lane;
+        uint8_t* act = smem + SM_ACT + slot * ACT_BYTES;
+        uint8_t* enc = smem + SM_ENC + slot * ENC_BYTES;
+        const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * WIDTH;
+        uint32_t full_uses = 0;
+        for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+            const int64_t tile = pair * 2 + slot;
+            const int64_t g = tile * TILE + row;
+            const bool valid = tile < ntiles && g < S;
+            float v3[3] = {0.f, 0.f, 1.f};
+            {
+                float x[3] = {0.f, 0.f, 0.f};
+                if (valid) {
+                    const int64_t r = g / N;
+                    const float d = depth[g];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        v3[c] = ray[r * 3 + c];
+                        x[c] = __fadd_rn(center[r * 3 + c], __fmul_rn(v3[c], d));
+                    }
+                }
+                write_enc_row(enc, row, x, bw3, valid);
+            }
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&a_ready[slot]);
+            uint8_t* save_tile = save ? save + tile * SAVE_TILE_BYTES : nullptr;
+            for (int l = 0; l < NLAYER; ++l, ++full_uses) {
+                ptx::mbar_wait(&acc_full[slot], full_uses & 1);
+                ptx::tc_fence_after();
+                const float* bias = cst + C_BIAS + l * WIDTH;
+                if (l < 8) {
+                    float sig_acc = 0.f;
+#pragma unroll 1
+                    for (int cc = 0; cc < WIDTH / 32; ++cc) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(tacc + cc * 32, v);
+                        ptx::tmem_ld_wait();
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = fmaxf(__uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j], 0.f);
+                            float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1], 0.f);
+                            pk[j] = ptx::pack_bf16(a, b);
+                            if (l == 6) {   // density head: row 0 of layer 7 applied to h6 (nerf.py:427)
+                                __nv_bfloat162 q = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+                                sig_acc += cst[C_W7R0 + cc * 32 + 2 * j] * __low2float(q) +
+                                           cst[C_W7R0 + cc * 32 + 2 * j + 1] * __high2float(q);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                            *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
+                            if (save_tile && tile < ntiles)
+                                *reinterpret_cast<uint4*>(save_tile + (int64_t)l * ACT_BYTES + (cc * 4 + q) * KROW + row * 16) = o;
+                        }
+                    }
+                    if (l == 6 && valid) {
+                        float pre = sig_acc + cst[C_MISC];
+                        sigma_out[g] = softplus_f(pre);
+                        if (sig_pre) sig_pre[g] = pre;
+                    }
+                    if (l == 7) write_venc_row(enc, row, v3, bwv, valid);   // A columns 256..287 of rgb0
+                    ptx::tc_fence_before();
+                    ptx::fence_proxy_async();
+                    ptx::mbar_arrive(&a_ready[slot]);
+                } else {
+                    // rgb0 epilogue: hr = relu(.), rgb = sigmoid(W_rgb1 hr + b)   (nerf.py:442-446)
+                    float o0 = cst[C_MISC + 1], o1 = cst[C_MISC + 2], o2 = cst[C_MISC + 3];
+#pragma unroll 1
+                    for (int cc = 0; cc < RGBW / 32; ++cc) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(tacc + cc * 32, v);
+                        ptx::tmem_ld_wait();
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = fmaxf(__uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j], 0.f);
+                            float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1], 0.f);
+                            pk[j] = ptx::pack_bf16(a, b);
+                            __nv_bfloat162 q = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+                            float ra = __low2float(q), rb = __high2float(q);
+                            const int col = cc * 32 + 2 * j;
+                            o0 += cst[C_WRGB1 + col] * ra + cst[C_WRGB1 + col + 1] * rb;
+                            o1 += cst[C_WRGB1 + RGBW + col] * ra + cst[C_WRGB1 + RGBW + col + 1] * rb;
+                            o2 += cst[C_WRGB1 + 2 * RGBW + col] * ra + cst[C_WRGB1 + 2 * RGBW + col + 1] * rb;
+                        }
+                        if (save_tile && tile < ntiles) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                *reinterpret_cast<uint4*>(save_tile + 8 * (int64_t)ACT_BYTES + (cc * 4 + q) * KROW + row * 16) =
+                                    make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                        }
+                    }
+                    if (valid) {
+                        float r0 = sigmoid_f(o0), r1 = sigmoid_f(o1), r2 = sigmoid_f(o2);
+                        rgb_out[g * 3] = r0; rgb_out[g * 3 + 1] = r1; rgb_out[g * 3 + 2] = r2;
+                        if (rgb_keep) { rgb_keep[g * 3] = r0; rgb_keep[g * 3 + 1] = r1; rgb_keep[g * 3 + 2] = r2; }
+                    }
+                    ptx::tc_fence_before();   // TMEM reads done before the next pass overwrites the accumulator
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------
+// host entry points
+// ------------------------------------------------------------------------------------------
+
+size_t tc_workspace_bytes(int64_t R, int N, int training) { return tc::carve(nullptr, R * (int64_t)N, training != 0).bytes; }
+
+int tc_fwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N, const Bands3& b3,
+           const BandsV& bv, int training, void* ws, size_t ws_bytes, float* rgb, float* sigma, cudaStream_t st) {
+    using namespace tc;
+    const int64_t S = R * (int64_t)N;
+    Workspace w = carve(ws, S, training != 0);
+    if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
+    const int64_t groups = STREAM_BYTES / 16;
+    pack_weights_kernel<<<niw_blocks(groups, 256), 256, 0, st>>>(P, w.wstream, w.consts);
+    NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    const int64_t npairs = ((S + TILE - 1) / TILE + 1) / 2;
+    int grid = niw_num_sms();
+    if (grid > npairs) grid = (int)npairs;
+    tc_fwd_kernel<<<grid, 384, SM_TOTAL, st>>>(w.wstream, w.consts, center, ray, depth, S, N, b3, bv, rgb, sigma,
+                                             training ? w.sig_pre : nullptr, training ? w.rgb_keep : nullptr,
+                                             training ? w.save : nullptr);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+int tc_bwd(const float*, const float*, const float*, const float*, int64_t, int, const Bands3&, const BandsV&, void*,
+           size_t, const float*, const float*, float*, float*, float*, cudaStream_t) {
+    return NIW_E_UNSUPP;
+}
+
+}  // namespace niw

@@ -1,0 +1,88 @@
+"""tcgen05 path: descriptor self-test, then the fused BF16 MLP forward against the FP32 CUDA path
+and the CPU oracle."""
+import pytest
+import torch
+
+from neural_invertible_warp_b200 import synthetic as syn
+from oracle import reference_port as ora
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def F():
+    from neural_invertible_warp_b200 import functional
+    return functional
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("N,K", [(256, 256), (128, 64), (64, 32)])
+def test_tc_selftest_variants(F, variant, N, K):
+    """Variants 0 (K-major) and 2 (MN-major) must be exact BF16 GEMMs; 1 and 3 are the same with
+    LBO/SBO exchanged and are reported (xfail) so the descriptor semantics are on record."""
+    gen = torch.Generator().manual_seed(N + K)
+    A = torch.randn(128, K, generator=gen)
+    Bm = torch.randn(N, K, generator=gen)
+    ref = _bf16(A).double() @ _bf16(Bm).double().t()
+    D = F.tc_selftest(A.to(DEV), Bm.to(DEV), variant).cpu().double()
+    err = (D - ref).abs().max().item()
+    print("tc_selftest variant %d N=%d K=%d max err %.3e" % (variant, N, K, err))
+    if variant in (1, 3):
+        if err > 1e-3:
+            pytest.xfail("swapped LBO/SBO is (as expected) not the hardware convention: err %.3e" % err)
+    assert err < 1e-3, "tcgen05 descriptor convention mismatch (variant %d): %.3e" % (variant, err)
+
+
+def _flat(p):
+    keys = []
+    for i in range(8):
+        keys += [f"mlp_feat.{i}.weight", f"mlp_feat.{i}.bias"]
+    for i in range(2):
+        keys += [f"mlp_rgb.{i}.weight", f"mlp_rgb.{i}.bias"]
+    return torch.cat([p[k].reshape(-1) for k in keys])
+
+
+@pytest.mark.parametrize("R,N", [(4, 128), (37, 16), (64, 192), (1024, 128)])
+def test_tc_forward_vs_fp32(F, R, N):
+    gen = torch.Generator().manual_seed(R + N)
+    flat = _flat(syn.nerf_params(11)).to(DEV)
+    center = (torch.randn(R, 3, generator=gen) * 0.1).to(DEV)
+    ray = (torch.randn(R, 3, generator=gen) * 0.3 + torch.tensor([0., 0., 1.])).to(DEV)
+    u = torch.rand(1, R, N, 1, generator=gen)
+    depth = ora.stratified_depth(u, N, [1.2, 5.2], "metric")[0, ..., 0].to(DEV)
+    bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
+    rgb32, sig32 = F.nerf_forward_samples(flat, center, ray, depth, bw3, bwv, "fp32", training=False)
+    rgb16, sig16 = F.nerf_forward_samples(flat, center, ray, depth, bw3, bwv, "bf16", training=False)
+    torch.cuda.synchronize()
+    e_rgb = (rgb16 - rgb32).abs().max().item()
+    e_sig = ((sig16 - sig32).abs() / (1 + sig32.abs())).max().item()
+    print("bf16 vs fp32 per-sample: rgb %.3e sigma(rel) %.3e" % (e_rgb, e_sig))
+    assert e_rgb < 3e-2 and e_sig < 3e-2
+    out32 = F.composite(ray, rgb32, sig32, depth)
+    out16 = F.composite(ray, rgb16, sig16, depth)
+    for a, b, name in zip(out16[:3], out32[:3], ("rgb", "depth", "opacity")):
+        print("composited %s max abs diff %.3e" % (name, (a - b).abs().max().item()))
+    assert (out16[0] - out32[0]).abs().max() < 1e-2
+    assert (out16[2] - out32[2]).abs().max() < 1e-2
+
+
+def test_tc_forward_inverse_depth_far_samples(F):
+    """LLFF inverse-depth sampling puts the last samples at |x| up to 1e8: composited outputs must
+    still agree (transmittance is ~0 there)."""
+    R, N = 256, 128
+    gen = torch.Generator().manual_seed(5)
+    flat = _flat(syn.nerf_params(12)).to(DEV)
+    center = (torch.randn(R, 3, generator=gen) * 0.05).to(DEV)
+    ray = (torch.randn(R, 3, generator=gen) * 0.2 + torch.tensor([0., 0., 1.])).to(DEV)
+    u = torch.rand(1, R, N, 1, generator=gen)
+    depth = ora.stratified_depth(u, N, [1, 0], "inverse")[0, ..., 0].to(DEV)
+    bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
+    o32 = F.composite(ray, *F.nerf_forward_samples(flat, center, ray, depth, bw3, bwv, "fp32", training=False), depth)
+    o16 = F.composite(ray, *F.nerf_forward_samples(flat, center, ray, depth, bw3, bwv, "bf16", training=False), depth)
+    assert (o16[0] - o32[0]).abs().max() < 1e-2
+    assert (o16[2] - o32[2]).abs().max() < 1e-2
