@@ -48,7 +48,10 @@ composite_fwd_kernel(const float* __restrict__ ray, const float* __restrict__ rg
             float intv = (i + 1 < N) ? (dn - d) : 1e10f;           // last interval = 1e10 (nerf.py:461)
             float sd = ok ? sg[i] * (intv * len) : 0.f;           // sigma * (intv * ray_length)
             float incl = warp_incl_scan(sd, lane);
-            float T = expf(-((incl - sd) + carry));
+            // exclusive prefix by shifting (incl - sd would cancel against the 1e10 last interval)
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 0.f;
+            float T = expf(-(excl + carry));
             float w = T * (1.f - expf(-sd));
             carry += __shfl_sync(0xffffffffu, incl, 31);
             if (ok) {
@@ -99,7 +102,9 @@ composite_bwd_kernel(const float* __restrict__ ray, const float* __restrict__ rg
             float v = gr * c0 + gg * c1 + gb * c2 + gd * d + go;
             float wv = w * v;
             float sfx = warp_suffix_incl_scan(wv, lane);          // sum_{j>=i} within chunk
-            float after = (sfx - wv) + carry;                    // sum_{j>i} over the whole ray
+            float nxt = __shfl_down_sync(0xffffffffu, sfx, 1);
+            if (lane == 31) nxt = 0.f;
+            float after = nxt + carry;                           // sum_{j>i} over the whole ray
             carry += __shfl_sync(0xffffffffu, sfx, 0);
             float dsd = (T - w) * v - after;
             if (ok) {

@@ -20,11 +20,12 @@ def _bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("N,K", [(256, 256), (128, 64), (64, 32)])
 def test_tc_selftest_variants(F, variant, N, K):
-    """Variants 0 (K-major) and 2 (MN-major) must be exact BF16 GEMMs; 1 and 3 are the same with
-    LBO/SBO exchanged and are reported (xfail) so the descriptor semantics are on record."""
+    """Variants 0 (K-major) and 2 (MN-major) must be exact BF16 GEMMs.  (Variants 1 / 3 -- LBO and
+    SBO exchanged -- were run once on a B200: they fault with an illegal address, which settles
+    the descriptor convention; they are not run here because the fault poisons the CUDA context.)"""
     gen = torch.Generator().manual_seed(N + K)
     A = torch.randn(128, K, generator=gen)
     Bm = torch.randn(N, K, generator=gen)
@@ -32,9 +33,6 @@ def test_tc_selftest_variants(F, variant, N, K):
     D = F.tc_selftest(A.to(DEV), Bm.to(DEV), variant).cpu().double()
     err = (D - ref).abs().max().item()
     print("tc_selftest variant %d N=%d K=%d max err %.3e" % (variant, N, K, err))
-    if variant in (1, 3):
-        if err > 1e-3:
-            pytest.xfail("swapped LBO/SBO is (as expected) not the hardware convention: err %.3e" % err)
     assert err < 1e-3, "tcgen05 descriptor convention mismatch (variant %d): %.3e" % (variant, err)
 
 
