@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native NeRF ray-render hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rays R] [--precision bf16|fp32]
+
+Workload (BASELINE.json configs[1], "C2"): one ``barf_inn_llff`` train step -- NVP-warped ray
+generation, stratified sampling, fused positional encoding + 8x256 MLP, compositing, MSE, full
+backward, Adam -- on 1 024 rays x 128 samples per GPU (16 synthetic 480x640 LLFF-shaped images,
+64 rays each, random-init weights).  With N GPUs every rank renders its own 1/N slice of a global
+batch of N x 1 024 rays (weak scaling) and the gradients are all-reduced once per step.
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every field):
+  value        train rays/s, inputs resident in HBM, device RNG, per-step CUDA events (max over ranks)
+  e2e          same metric through the public API with the step's host-side inputs (camera batch,
+               host-drawn ray indices and stratified uniforms) copied from pinned memory every step
+               and the loss read back
+  roofline     the MLP kernels (the dominant kernels): algorithmic FLOP / CUDA-event time vs the
+               measured dense-BF16 peak in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (oracle/reference_port.py, a restatement of the reference's PyTorch
+               code pinned to goldens from the executed reference) on the host cores, bounded sample
+``--impl reference`` times that CPU implementation alone (all host threads) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MLP_FLOP_FWD = 2 * 527872              # per sample (un-padded dims)
+MLP_FLOP_TRAIN = 3 * MLP_FLOP_FWD      # fwd + dX + dW
+N_SAMPLES = 128
+IMAGES = 16
+H, W = 480, 640
+METRIC = "train rays/sec (fwd+bwd, 128 samp/ray)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step (C2: 1024; C5: 8192)")
+    ap.add_argument("--precision", default=None, help="MLP operand precision: bf16 (tcgen05) or fp32 (CUDA cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------
+# the CPU implementation (oracle port of the reference path)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_train_step_factory(rays, seed=0):
+    """C2 on the host: returns (step_fn, n_rays).  Everything inside is oracle/reference_port.py."""
+    from neural_invertible_warp_b200 import synthetic as syn
+    from oracle import reference_port as ora
+    B, P = IMAGES, rays // IMAGES
+    p = {k: v.requires_grad_(True) for k, v in syn.nerf_params(seed).items()}
+    q = {k: v.requires_grad_(True) for k, v in syn.nvp_params(seed + 1).items()}
+    code = syn.latent_codes(seed + 2, B).requires_grad_(True)
+    intr = syn.intrinsics(B, H, W, 0.81)
+    image = syn.images(seed + 3, B, H, W)
+    cfg = dict(N=N_SAMPLES, Nf=None, range=[1, 0], param="inverse", L_3D=10, L_view=4, skip=(4,), c2f=[0.1, 0.5])
+    opt_a = torch.optim.Adam(list(p.values()), lr=1e-3)
+    opt_b = torch.optim.Adam(list(q.values()) + [code], lr=5e-4)
+
+    def step():
+        opt_a.zero_grad(); opt_b.zero_grad()
+        ray_idx = torch.randperm(H * W)[:P]
+        u = torch.rand(B, P, N_SAMPLES, 1)
+        ray, center, *_ = ora.warped_rays(q, code, H, W, intr, ray_idx, 0.05)
+        out = ora.render_rays(p, center, ray, u, cfg, progress=0.3)
+        loss = ora.mse(out["rgb"], ora.gather_pixels(image, ray_idx))
+        loss.backward()
+        opt_a.step(); opt_b.step()
+        return float(loss)
+    return step, B * P
+
+
+def time_cpu(rays, steps, warmup):
+    step, n = cpu_train_step_factory(rays)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: the
+    reference is pure Python, it cannot be compiled into oracle/_ref, and /root/reference does not
+    exist on the GPU box), all host threads, bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.manual_seed(0)
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    rate, dt = time_cpu(args.rays, steps, warm)
+    cores = torch.get_num_threads()
+    line = dict(impl="reference", metric=METRIC, value=rate, unit="rays/s", n_gpus=args.gpus, steps=steps, warmup=warm,
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
+                data="synthetic", config=workload_config(args, "fp32"),
+                cpu_baseline=dict(value=rate, unit="rays/s", cores=cores, kind="port",
+                                  sample="%d steps of %d rays x %d samples (the full C2 step), torch CPU fp32, %d threads of %d host cores"
+                                         % (steps, args.rays, N_SAMPLES, cores, os.cpu_count() or 0)),
+                e2e=dict(value=rate, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def workload_config(args, precision):
+    return dict(workload="barf_inn_llff train step (C2): NVP-warped raygen + stratified sampling + PE + 8x256 MLP + "
+                         "composite + MSE, fwd+bwd + Adam; %d rays/GPU x %d samples, %d synthetic %dx%d images"
+                         % (args.rays, N_SAMPLES, IMAGES, H, W),
+                rays_per_gpu=args.rays, samples_per_ray=N_SAMPLES, images=IMAGES, mlp_precision=precision,
+                parallelism="dp%d (rays sharded, one gradient all-reduce)" % args.gpus,
+                l2="256 MiB memset between steps, outside the per-step CUDA-event pairs")
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch.distributed as dist
+    from neural_invertible_warp_b200 import _lib, config as cfgmod, engine, synthetic as syn
+    from neural_invertible_warp_b200 import functional as F
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    _lib.load()
+    precision = args.precision or "bf16"
+    if _lib.load().niw_nerf_workspace_bytes(1, 1, F.precision_code(precision), 1) == 0:
+        raise SystemExit("precision %s unavailable" % precision)
+
+    rays_global = args.rays * world
+    opt = cfgmod.builtin_options("barf_inn_llff", barf_c2f=[0.1, 0.5], device=dev,
+                                 nerf=dict(rand_rays=rays_global, sample_intvs=N_SAMPLES),
+                                 arch=dict(mlp_precision=precision))
+    torch.manual_seed(0)
+    graph = engine.build_graph(opt, IMAGES)
+    # reference init leaves the warp at the identity (zero-init output layers): perturb like the
+    # parity tests do so that every gradient path carries signal
+    sd = {k: v.to(dev) for k, v in syn.nvp_params(1).items()}
+    graph.warp_mlp.load_state_dict(sd)
+    graph.warp_latent.weight.data = syn.latent_codes(2, IMAGES).to(dev)
+    graph.nerf.progress.data.fill_(0.3)
+    var_dev = engine.synthetic_var(opt, IMAGES, seed=3)
+    bucket = engine.GradBucket(graph)
+    optim = torch.optim.Adam([dict(params=graph.nerf.parameters(), lr=1e-3)], fused=True)
+    optim_pose = torch.optim.Adam([dict(params=list(graph.warp_mlp.parameters()) + list(graph.warp_latent.parameters()),
+                                        lr=5e-4)], fused=True)
+    it = 5000
+    P_local = (rays_global // IMAGES + world - 1) // world
+    rays_local = P_local * IMAGES
+
+    def step_device():
+        v = cfgmod.AttrDict(var_dev)
+        loss = engine.train_step(opt, graph, v, it, bucket=bucket, rank=rank, world=world)
+        optim.step(); optim_pose.step()
+        return loss
+
+    # ---- host-side inputs of the e2e leg (pinned) ----
+    gen = torch.Generator().manual_seed(1234 + rank)
+    pin = dict(idx=torch.arange(IMAGES).pin_memory(), intr=var_dev.intr.cpu().pin_memory(),
+               pose=var_dev.pose.cpu().pin_memory(),
+               ray_idx=torch.empty(P_local, dtype=torch.int64).pin_memory(),
+               u=torch.empty(IMAGES, P_local, N_SAMPLES, 1).pin_memory())
+    h2d = sum(t.numel() * t.element_size() for t in pin.values())
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        pin["ray_idx"].copy_(torch.randperm(H * W, generator=gen)[:P_local])
+        pin["u"].copy_(torch.rand(IMAGES, P_local, N_SAMPLES, 1, generator=gen))
+        v = cfgmod.AttrDict(idx=pin["idx"].to(dev, non_blocking=True), intr=pin["intr"].to(dev, non_blocking=True),
+                            pose=pin["pose"].to(dev, non_blocking=True), image=var_dev.image)
+        ridx = pin["ray_idx"].to(dev, non_blocking=True)
+        u = pin["u"].to(dev, non_blocking=True)
+        bucket.zero()
+        with engine.feed_draws(ray_idx=ridx, u=u):
+            v = graph.forward(opt, v, mode="train", iter=it)
+        loss = engine.summarize_loss(opt, graph.compute_loss(opt, v, mode="train"))
+        (loss.all * (1.0 / world)).backward()
+        if world > 1:
+            bucket.allreduce()
+        optim.step(); optim_pose.step()
+        loss_host.copy_(loss.all.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the user reads the loss
+        return float(loss_host)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, with_events=True):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between."""
+        evs = []
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step_fn(); b.record()
+            evs.append((a, b))
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return ms, wall
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    step_e2e()
+    barrier()
+
+    # ---- value: device-resident ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = _lib.launch_count()
+    with F.KernelTimer() as kt:
+        ms_total, _ = timed(step_device, args.steps)
+        kernel_ms = kt.totals()
+    launches = _lib.launch_count() - n0
+    ms_total = max_over_ranks(ms_total)
+    # ---- e2e: host buffers in, loss out (wall clock around synchronised steps) ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop() if rank == 0 else None
+
+    ms_per_step = ms_total / args.steps
+    rays_per_step = rays_local * world
+    value = rays_per_step / (ms_per_step * 1e-3)
+    e2e_value = rays_per_step * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernels (the MLP) ----
+    pk = peaks()
+    mlp_calls = kernel_ms.get("nerf_fwd", (0, 0.0))[0]
+    mlp_ms = kernel_ms.get("nerf_fwd", (0, 0.0))[1] + kernel_ms.get("nerf_bwd", (0, 0.0))[1]
+    flop_per_step = MLP_FLOP_TRAIN * rays_local * N_SAMPLES
+    achieved = flop_per_step * mlp_calls / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    comp_ms = kernel_ms.get("composite_fwd", (0, 0.0))[1] + kernel_ms.get("composite_bwd", (0, 0.0))[1]
+    roof = dict(bound="tensor", kernel="niw_nerf_fwd + niw_nerf_bwd (fused PE + 8x256 MLP, fwd + dX + dW)",
+                achieved=achieved, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                frac=achieved / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
+                flop_per_launch_pair=flop_per_step, mlp_ms_per_step=mlp_ms / max(mlp_calls, 1),
+                mlp_share_of_step=mlp_ms / ms_total if ms_total > 0 else None,
+                composite_ms_per_step=comp_ms / max(mlp_calls, 1))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        torch.manual_seed(0)
+        rate, dt = time_cpu(args.rays, 3, 1)
+        cpu = dict(value=rate, unit="rays/s", cores=torch.get_num_threads(), kind="port",
+                   sample="3 steps (after 1 warm-up) of the same C2 step, %d rays x %d samples, oracle/reference_port.py on "
+                          "torch CPU fp32, %.2f s/step" % (args.rays, N_SAMPLES, dt))
+
+    line = dict(metric=METRIC, value=value, unit="rays/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=("bf16" if precision == "bf16" else "fp32"), data="synthetic",
+                config=workload_config(args, precision), mlp_evals_per_s=value * N_SAMPLES,
+                e2e=dict(value=e2e_value, unit="rays/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                         ms_per_step=e2e_s / args.steps * 1e3),
+                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, clocks=clk)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -39,6 +39,8 @@ extern "C" {
 
 int niw_abi_version(void);
 const char* niw_error_string(int code);
+/* number of kernels this library has launched since it was loaded (monotonic; all streams) */
+unsigned long long niw_launch_count(void);
 
 /* ---- (a1) camera.get_center_and_ray + [:, ray_idx]   camera.py:419-443, model/nerf.py:298-300
  * pose [B,3,4] world->camera, intr [B,3,3].  Pixel p -> ((p%W)+.5, (p/W)+.5, 1).  If ray_idx is

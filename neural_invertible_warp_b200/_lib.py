@@ -22,6 +22,7 @@ ABI_VERSION = 1
 SIGNATURES = {
     "niw_abi_version": (_c.c_int, []),
     "niw_error_string": (_c.c_char_p, [_c.c_int]),
+    "niw_launch_count": (_c.c_ulonglong, []),
     "niw_raygen_pose_fwd": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
     "niw_raygen_pose_bwd": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     "niw_raygen_unwarped": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
@@ -68,6 +69,11 @@ def load(build_if_missing=True):
         raise RuntimeError("libniw_b200.so ABI version %d != %d" % (lib.niw_abi_version(), ABI_VERSION))
     _LIB = lib
     return lib
+
+
+def launch_count():
+    """Kernels launched by the library so far (bench.py: ``gpu_launches``)."""
+    return int(load().niw_launch_count())
 
 
 def check(code):

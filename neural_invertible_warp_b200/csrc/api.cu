@@ -5,7 +5,12 @@
 
 using namespace niw;
 
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+namespace niw { void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); } }
+
 extern "C" int niw_abi_version(void) { return NIW_ABI_VERSION; }
+extern "C" unsigned long long niw_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* niw_error_string(int code) {
     if (code == 0) return "success";
@@ -89,7 +94,7 @@ extern "C" int niw_mse_gather(const float* image, const float* rgb, const int64_
                               int P, int H, int W, float scale, float* loss, float* d_rgb, void* stream) {
     NIW_CHECK_ARG(image && rgb && loss && B > 0 && P > 0 && H > 0 && W > 0);
     int64_t n = (int64_t)B * P;
-    mse_gather_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(image, rgb, ray_idx, idx_start, B, P, H * W,
+    niw::note_launch(), mse_gather_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(image, rgb, ray_idx, idx_start, B, P, H * W,
                                                                          scale, loss, d_rgb);
     NIW_LAUNCH_CHECK();
     return 0;

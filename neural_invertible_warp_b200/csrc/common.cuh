@@ -10,6 +10,10 @@
 #define NIW_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
 #define NIW_LAUNCH_CHECK() do { cudaError_t e__ = cudaPeekAtLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
+// every kernel launch of the library is counted (niw_launch_count): bench.py reports the number
+// of launches inside its timed region, and tests use it to prove the CUDA path is the one running
+namespace niw { void note_launch(); }
+
 static inline cudaStream_t niw_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int niw_num_sms() {

@@ -136,7 +136,7 @@ extern "C" int niw_composite_fwd(const float* ray, const float* rgb_s, const flo
                                  int64_t R, int N, float bg, float* rgb, float* depth, float* opacity, float* prob,
                                  float* trans, void* stream) {
     NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && rgb && depth && opacity && R > 0 && N > 0);
-    composite_fwd_kernel<<<grid_for(R), WARPS * 32, 0, niw_stream(stream)>>>(ray, rgb_s, sigma, depth_s, R, N, bg, rgb,
+    niw::note_launch(), composite_fwd_kernel<<<grid_for(R), WARPS * 32, 0, niw_stream(stream)>>>(ray, rgb_s, sigma, depth_s, R, N, bg, rgb,
                                                                             depth, opacity, prob, trans);
     NIW_LAUNCH_CHECK();
     return 0;
@@ -147,7 +147,7 @@ extern "C" int niw_composite_bwd(const float* ray, const float* rgb_s, const flo
                                  const float* d_rgb, const float* d_depth, const float* d_opacity, float* d_rgb_s,
                                  float* d_sigma, float* d_ray, void* stream) {
     NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && prob && trans && d_rgb_s && d_sigma && R > 0 && N > 0);
-    composite_bwd_kernel<<<grid_for(R), WARPS * 32, 0, niw_stream(stream)>>>(
+    niw::note_launch(), composite_bwd_kernel<<<grid_for(R), WARPS * 32, 0, niw_stream(stream)>>>(
         ray, rgb_s, sigma, depth_s, prob, trans, R, N, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma, d_ray);
     NIW_LAUNCH_CHECK();
     return 0;

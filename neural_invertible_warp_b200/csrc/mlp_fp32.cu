@@ -392,13 +392,13 @@ void launch_dw(const float* G, int ldg, int Nout, const float* X, int ldx, int x
     if (m_per < 256) m_per = 256;
     unsigned z = (unsigned)((M + m_per - 1) / m_per);
     dim3 grid((Nout + BM - 1) / BM, (K + BN - 1) / BN, z);
-    linear_bwd_dw_kernel<<<grid, 256, 0, st>>>(G, ldg, Nout, X, ldx, x_div, K, M, m_per, dW, ldw);
+    niw::note_launch(), linear_bwd_dw_kernel<<<grid, 256, 0, st>>>(G, ldg, Nout, X, ldx, x_div, K, M, m_per, dW, ldw);
 }
 
 void launch_colsum(const float* G, int ldg, int Nout, int64_t M, float* db, cudaStream_t st) {
     int64_t m_per = 4096;
     dim3 grid((Nout + 31) / 32, (unsigned)((M + m_per - 1) / m_per));
-    colsum_kernel<<<grid, 256, 0, st>>>(G, ldg, Nout, M, m_per, db);
+    niw::note_launch(), colsum_kernel<<<grid, 256, 0, st>>>(G, ldg, Nout, M, m_per, db);
 }
 
 }  // namespace
@@ -418,8 +418,8 @@ static int fp32_fwd_chunk(const float* P, const float* center, const float* ray,
     const int64_t S = R * N;
     Fp32Workspace w;
     carve(&w, wsbase, S, R, training);
-    encode_points_kernel<<<niw_blocks(S, 128), 128, 0, st>>>(center, ray, depth, S, N, b3, w.enc);
-    encode_view_kernel<<<niw_blocks(R, 128), 128, 0, st>>>(ray, R, bv, w.venc);
+    niw::note_launch(), encode_points_kernel<<<niw_blocks(S, 128), 128, 0, st>>>(center, ray, depth, S, N, b3, w.enc);
+    niw::note_launch(), encode_view_kernel<<<niw_blocks(R, 128), 128, 0, st>>>(ray, R, bv, w.venc);
     for (int l = 0; l < NFEAT; ++l) {
         const float* Wl = P + feat_w_off(l);
         const float* bl = P + feat_b_off(l);
@@ -428,18 +428,18 @@ static int fp32_fwd_chunk(const float* P, const float* center, const float* ray,
         const float* A2 = l == SKIP ? w.enc : nullptr;
         int K2 = l == SKIP ? ENC3 : 0;
         if (l < NFEAT - 1)
-            linear_fwd_kernel<EPI_RELU><<<grid_mn(S, WIDTH), 256, 0, st>>>(A1, lda1, K1, A2, ENC3_PAD, K2, 1, Wl,
+            niw::note_launch(), linear_fwd_kernel<EPI_RELU><<<grid_mn(S, WIDTH), 256, 0, st>>>(A1, lda1, K1, A2, ENC3_PAD, K2, 1, Wl,
                                                                          feat_in(l), bl, S, WIDTH, w.h[l], WIDTH,
                                                                          nullptr, nullptr);
         else
-            linear_fwd_kernel<EPI_LAYER7><<<grid_mn(S, WIDTH + 1), 256, 0, st>>>(A1, lda1, K1, nullptr, 0, 0, 1, Wl,
+            niw::note_launch(), linear_fwd_kernel<EPI_LAYER7><<<grid_mn(S, WIDTH + 1), 256, 0, st>>>(A1, lda1, K1, nullptr, 0, 0, 1, Wl,
                                                                                feat_in(l), bl, S, WIDTH + 1, w.h[l],
                                                                                WIDTH, w.sig_pre, sigma);
     }
-    linear_fwd_kernel<EPI_RELU><<<grid_mn(S, RGBW), 256, 0, st>>>(w.h[NFEAT - 1], WIDTH, WIDTH, w.venc, ENCV_PAD, ENCV, N,
+    niw::note_launch(), linear_fwd_kernel<EPI_RELU><<<grid_mn(S, RGBW), 256, 0, st>>>(w.h[NFEAT - 1], WIDTH, WIDTH, w.venc, ENCV_PAD, ENCV, N,
                                                                 P + RGB0_W, WIDTH + ENCV, P + RGB0_B, S, RGBW, w.hr,
                                                                 RGBW, nullptr, nullptr);
-    linear_fwd_kernel<EPI_SIGMOID><<<grid_mn(S, 3), 256, 0, st>>>(w.hr, RGBW, RGBW, nullptr, 0, 0, 1, P + RGB1_W, RGBW,
+    niw::note_launch(), linear_fwd_kernel<EPI_SIGMOID><<<grid_mn(S, 3), 256, 0, st>>>(w.hr, RGBW, RGBW, nullptr, 0, 0, 1, P + RGB1_W, RGBW,
                                                                P + RGB1_B, S, 3, rgb, 3, nullptr, nullptr);
     if (training) cudaMemcpyAsync(w.rgb_keep, rgb, sizeof(float) * S * 3, cudaMemcpyDeviceToDevice, st);
     return (int)cudaPeekAtLastError();
@@ -468,22 +468,22 @@ int fp32_bwd(const float* P, const float* center, const float* ray, const float*
     Fp32Workspace w;
     carve(&w, (float*)ws, S, R, true);
     // RGB head
-    rgb_sigmoid_bwd_kernel<<<niw_blocks(S * 3, 256), 256, 0, st>>>(d_rgb, w.rgb_keep, S * 3, w.g3);
+    niw::note_launch(), rgb_sigmoid_bwd_kernel<<<niw_blocks(S * 3, 256), 256, 0, st>>>(d_rgb, w.rgb_keep, S * 3, w.g3);
     launch_dw(w.g3, 3, 3, w.hr, RGBW, 1, RGBW, S, dP + RGB1_W, RGBW, st);
     launch_colsum(w.g3, 3, 3, S, dP + RGB1_B, st);
-    linear_bwd_dx_kernel<<<grid_mn(S, RGBW), 256, 0, st>>>(w.g3, 3, 3, P + RGB1_W, RGBW, RGBW, nullptr, nullptr, w.hr,
+    niw::note_launch(), linear_bwd_dx_kernel<<<grid_mn(S, RGBW), 256, 0, st>>>(w.g3, 3, 3, P + RGB1_W, RGBW, RGBW, nullptr, nullptr, w.hr,
                                                          RGBW, S, w.g_hr, RGBW, 0);
     launch_dw(w.g_hr, RGBW, RGBW, w.h[NFEAT - 1], WIDTH, 1, WIDTH, S, dP + RGB0_W, WIDTH + ENCV, st);
     launch_dw(w.g_hr, RGBW, RGBW, w.venc, ENCV_PAD, N, ENCV, S, dP + RGB0_W + WIDTH, WIDTH + ENCV, st);
     launch_colsum(w.g_hr, RGBW, RGBW, S, dP + RGB0_B, st);
     float* g = w.gA;       // gradient wrt the current layer's post-activation output (already masked)
     float* gn = w.gB;
-    linear_bwd_dx_kernel<<<grid_mn(S, WIDTH), 256, 0, st>>>(w.g_hr, RGBW, RGBW, P + RGB0_W, WIDTH + ENCV, WIDTH, nullptr,
+    niw::note_launch(), linear_bwd_dx_kernel<<<grid_mn(S, WIDTH), 256, 0, st>>>(w.g_hr, RGBW, RGBW, P + RGB0_W, WIDTH + ENCV, WIDTH, nullptr,
                                                           nullptr, w.h[NFEAT - 1], WIDTH, S, g, WIDTH, 0);
     cudaMemsetAsync(w.g_venc, 0, sizeof(float) * S * ENCV_PAD, st);
-    linear_bwd_dx_kernel<<<grid_mn(S, ENCV), 256, 0, st>>>(w.g_hr, RGBW, RGBW, P + RGB0_W + WIDTH, WIDTH + ENCV, ENCV,
+    niw::note_launch(), linear_bwd_dx_kernel<<<grid_mn(S, ENCV), 256, 0, st>>>(w.g_hr, RGBW, RGBW, P + RGB0_W + WIDTH, WIDTH + ENCV, ENCV,
                                                          nullptr, nullptr, nullptr, 0, S, w.g_venc, ENCV_PAD, 0);
-    softplus_bwd_kernel<<<niw_blocks(S, 256), 256, 0, st>>>(d_sigma, w.sig_pre, S, w.gs);
+    niw::note_launch(), softplus_bwd_kernel<<<niw_blocks(S, 256), 256, 0, st>>>(d_sigma, w.sig_pre, S, w.gs);
     for (int l = NFEAT - 1; l >= 0; --l) {
         const float* Wl = P + feat_w_off(l);
         float* dWl = dP + feat_w_off(l);
@@ -497,25 +497,25 @@ int fp32_bwd(const float* P, const float* center, const float* ray, const float*
             launch_dw(w.gs, 1, 1, X, ldx, 1, Kx, S, dWl, ldw, st);
             launch_colsum(g, WIDTH, WIDTH, S, dbl + 1, st);
             launch_colsum(w.gs, 1, 1, S, dbl, st);
-            linear_bwd_dx_kernel<<<grid_mn(S, WIDTH), 256, 0, st>>>(g, WIDTH, WIDTH, Wl + ldw, ldw, WIDTH, w.gs, Wl, X,
+            niw::note_launch(), linear_bwd_dx_kernel<<<grid_mn(S, WIDTH), 256, 0, st>>>(g, WIDTH, WIDTH, Wl + ldw, ldw, WIDTH, w.gs, Wl, X,
                                                                   WIDTH, S, gn, WIDTH, 0);
         } else {
             launch_dw(g, WIDTH, WIDTH, X, ldx, 1, Kx, S, dWl, ldw, st);
             if (l == SKIP) launch_dw(g, WIDTH, WIDTH, w.enc, ENC3_PAD, 1, ENC3, S, dWl + WIDTH, ldw, st);
             launch_colsum(g, WIDTH, WIDTH, S, dbl, st);
             if (l == SKIP)   // gradient into the re-injected encoding (overwrites; layer 0 adds later)
-                linear_bwd_dx_kernel<<<grid_mn(S, ENC3), 256, 0, st>>>(g, WIDTH, WIDTH, Wl + WIDTH, ldw, ENC3, nullptr,
+                niw::note_launch(), linear_bwd_dx_kernel<<<grid_mn(S, ENC3), 256, 0, st>>>(g, WIDTH, WIDTH, Wl + WIDTH, ldw, ENC3, nullptr,
                                                                      nullptr, nullptr, 0, S, w.g_enc, ENC3_PAD, 0);
             if (l > 0)
-                linear_bwd_dx_kernel<<<grid_mn(S, WIDTH), 256, 0, st>>>(g, WIDTH, WIDTH, Wl, ldw, WIDTH, nullptr, nullptr,
+                niw::note_launch(), linear_bwd_dx_kernel<<<grid_mn(S, WIDTH), 256, 0, st>>>(g, WIDTH, WIDTH, Wl, ldw, WIDTH, nullptr, nullptr,
                                                                       X, WIDTH, S, gn, WIDTH, 0);
             else
-                linear_bwd_dx_kernel<<<grid_mn(S, ENC3), 256, 0, st>>>(g, WIDTH, WIDTH, Wl, ldw, ENC3, nullptr, nullptr,
+                niw::note_launch(), linear_bwd_dx_kernel<<<grid_mn(S, ENC3), 256, 0, st>>>(g, WIDTH, WIDTH, Wl, ldw, ENC3, nullptr, nullptr,
                                                                      nullptr, 0, S, w.g_enc, ENC3_PAD, 1);
         }
         float* t = g; g = gn; gn = t;
     }
-    encode_bwd_kernel<<<niw_blocks(R * 32, 128), 128, 0, st>>>(center, ray, depth, R, N, b3, bv, w.g_enc, ENC3_PAD,
+    niw::note_launch(), encode_bwd_kernel<<<niw_blocks(R * 32, 128), 128, 0, st>>>(center, ray, depth, R, N, b3, bv, w.g_enc, ENC3_PAD,
                                                               w.g_venc, ENCV_PAD, d_center, d_ray);
     return (int)cudaPeekAtLastError();
 }

@@ -424,12 +424,12 @@ int tc_fwd(const float* P, const float* center, const float* ray, const float* d
     Workspace w = carve(ws, S, training != 0);
     if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
     const int64_t groups = STREAM_BYTES / 16;
-    pack_weights_kernel<<<niw_blocks(groups, 256), 256, 0, st>>>(P, w.wstream, w.consts);
+    niw::note_launch(), pack_weights_kernel<<<niw_blocks(groups, 256), 256, 0, st>>>(P, w.wstream, w.consts);
     NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     const int64_t npairs = ((S + TILE - 1) / TILE + 1) / 2;
     int grid = niw_num_sms();
     if (grid > npairs) grid = (int)npairs;
-    tc_fwd_kernel<<<grid, 384, SM_TOTAL, st>>>(w.wstream, w.consts, center, ray, depth, S, N, b3, bv, rgb, sigma,
+    niw::note_launch(), tc_fwd_kernel<<<grid, 384, SM_TOTAL, st>>>(w.wstream, w.consts, center, ray, depth, S, N, b3, bv, rgb, sigma,
                                              training ? w.sig_pre : nullptr, training ? w.rgb_keep : nullptr,
                                              training ? w.save : nullptr);
     NIW_LAUNCH_CHECK();

@@ -321,7 +321,7 @@ extern "C" int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, cons
                                 int B, int Pt, float* out, void* stream) {
     NIW_CHECK_ARG(wpack && code_bias && pts && out && B > 0 && Pt > 0);
     int64_t total = (int64_t)B * Pt;
-    nvp_fwd_kernel<<<niw_blocks(total, PTS), PTS, 0, niw_stream(stream)>>>(wpack, code_bias, pts,
+    niw::note_launch(), nvp_fwd_kernel<<<niw_blocks(total, PTS), PTS, 0, niw_stream(stream)>>>(wpack, code_bias, pts,
                                                                           make_bands(alpha_ratio), B, Pt, out);
     NIW_LAUNCH_CHECK();
     return 0;
@@ -335,7 +335,7 @@ extern "C" int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, cons
     NIW_CUDA(cudaMemsetAsync(d_code_bias, 0, sizeof(float) * NIW_NVP_BLOCKS * 2 * (size_t)B * HID, st));
     NIW_CUDA(cudaFuncSetAttribute(nvp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     int64_t total = (int64_t)B * Pt;
-    nvp_bwd_kernel<<<niw_blocks(total, PTS), PTS, BWD_SMEM, st>>>(wpack, code_bias, pts, make_bands(alpha_ratio), B, Pt,
+    niw::note_launch(), nvp_bwd_kernel<<<niw_blocks(total, PTS), PTS, BWD_SMEM, st>>>(wpack, code_bias, pts, make_bands(alpha_ratio), B, Pt,
                                                                  d_out, d_wpack, d_code_bias);
     NIW_LAUNCH_CHECK();
     return 0;

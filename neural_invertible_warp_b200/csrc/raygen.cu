@@ -130,7 +130,7 @@ extern "C" int niw_raygen_pose_fwd(const float* pose, const float* intr, const i
                                    int B, int P, int H, int W, float* center, float* ray, void* stream) {
     NIW_CHECK_ARG(pose && intr && center && ray && B > 0 && P > 0 && H > 0 && W > 0);
     int64_t n = (int64_t)B * P;
-    raygen_pose_fwd_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, B, P, W,
+    niw::note_launch(), raygen_pose_fwd_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, B, P, W,
                                                                               center, ray);
     NIW_LAUNCH_CHECK();
     return 0;
@@ -144,7 +144,7 @@ extern "C" int niw_raygen_pose_bwd(const float* pose, const float* intr, const i
     int bx = (P + 255) / 256;
     if (bx > 64) bx = 64;
     dim3 grid(bx, B);
-    raygen_pose_bwd_kernel<<<grid, 256, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, B, P, W, d_center,
+    niw::note_launch(), raygen_pose_bwd_kernel<<<grid, 256, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, B, P, W, d_center,
                                                                d_ray, d_pose);
     NIW_LAUNCH_CHECK();
     return 0;
@@ -154,7 +154,7 @@ extern "C" int niw_raygen_unwarped(const float* intr, const float* pose_init, co
                                    int64_t idx_start, int B, int P, int H, int W, float* pts, void* stream) {
     NIW_CHECK_ARG(intr && pts && B > 0 && P > 0 && H > 0 && W > 0);
     int64_t n = (int64_t)B * P;
-    raygen_unwarped_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(intr, pose_init, ray_idx, idx_start, B,
+    niw::note_launch(), raygen_unwarped_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(intr, pose_init, ray_idx, idx_start, B,
                                                                               P, W, pts);
     NIW_LAUNCH_CHECK();
     return 0;

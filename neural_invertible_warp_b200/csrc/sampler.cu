@@ -111,7 +111,7 @@ extern "C" int niw_sample_stratified(const float* u, int64_t n_rays, int N, floa
                                      float* depth, void* stream) {
     NIW_CHECK_ARG(depth && n_rays > 0 && N > 0);
     int64_t total = n_rays * N;
-    stratified_kernel<<<niw_blocks((total + 3) / 4, 256), 256, 0, niw_stream(stream)>>>(u, total, N, scale, dmin,
+    niw::note_launch(), stratified_kernel<<<niw_blocks((total + 3) / 4, 256), 256, 0, niw_stream(stream)>>>(u, total, N, scale, dmin,
                                                                                        inverse, depth);
     NIW_LAUNCH_CHECK();
     return 0;
@@ -132,7 +132,7 @@ extern "C" int niw_sample_pdf_merge(const float* pdf, const float* depth_coarse,
     int64_t blocks = (R + WARPS - 1) / WARPS;
     int64_t cap = (int64_t)niw_num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    pdf_merge_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, smem, niw_stream(stream)>>>(
+    niw::note_launch(), pdf_merge_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, smem, niw_stream(stream)>>>(
         pdf, depth_coarse, unif, bins, R, N, Nf, npow2, fine, idx, merged);
     NIW_LAUNCH_CHECK();
     return 0;

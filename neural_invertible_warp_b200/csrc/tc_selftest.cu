@@ -82,7 +82,7 @@ extern "C" int niw_tc_selftest(const float* A, const float* Bm, int N, int K, in
         return NIW_E_UNSUPP;
     size_t smem = (size_t)(128 + N) * K * 2;
     NIW_CUDA(cudaFuncSetAttribute(niw::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    niw::tc_selftest_kernel<<<1, 128, smem, niw_stream(stream)>>>(A, Bm, N, K, variant, D);
+    niw::note_launch(), niw::tc_selftest_kernel<<<1, 128, smem, niw_stream(stream)>>>(A, Bm, N, K, variant, D);
     NIW_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,202 @@
+"""Host orchestration around the drop-in Graphs: what the reference's ``Model`` classes do to a
+graph between construction and ``loss.backward()``, plus the data-parallel hooks the reference
+lacks (it asserts a single GPU, options.py:103).
+
+* ``build_graph``      -- ``Model.build_networks`` for the target models (reference model/base.py:34-37,
+                          barf.py:38-44, barf_inn_llff.py:25-82, barf_inn_dtu.py:323-336): attaches
+                          ``se3_refine`` / ``warp_latent`` + ``warp_mlp`` + ``global_rigid`` / ``pose_net``.
+* ``summarize_loss``   -- model/base.py:130-142 without the NaN/Inf host syncs.
+* ``train_step``       -- ``graph.forward`` -> ``compute_loss`` -> ``backward`` (model/nerf.py:77-101 minus
+                          the optimiser), optionally over a 1/k ray shard with one gradient all-reduce.
+* ``GradBucket``       -- flat fp32 bucket of every trainable gradient: ONE NCCL all-reduce per step
+                          (SURVEY.md section 8e); rays shard, parameters replicate.
+"""
+import importlib
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import camera
+from .config import AttrDict
+from .nvp import DeformNetwork
+
+
+def build_graph(opt, n_images, initial_poses_w2c=None):
+    """Instantiate ``neural_invertible_warp_b200.model.<opt.model>.Graph`` on ``opt.device`` with
+    the sub-modules the reference's engine attaches."""
+    name = opt.model
+    mod = importlib.import_module("neural_invertible_warp_b200.model." + name)
+    dev = opt.device
+    if name == "barf_inn_dtu":
+        from .model.pose_models.inn import INNPoseParams
+        if initial_poses_w2c is None:
+            raise RuntimeError("barf_inn_dtu needs the initial world->camera poses")
+        pose_net = INNPoseParams(opt, num_poses=n_images, initial_poses_w2c=initial_poses_w2c.to(dev), device=dev)
+        return mod.Graph(opt, pose_net).to(dev)
+    graph = mod.Graph(opt).to(dev)
+    if name == "barf":
+        graph.se3_refine = nn.Embedding(n_images, 6).to(dev)
+        nn.init.zeros_(graph.se3_refine.weight)
+    elif name == "barf_inn_llff":
+        if opt.warp_latent.enc_type != "l2fbarf":
+            raise NotImplementedError("warp_latent.enc_type=%r" % (opt.warp_latent.enc_type,))
+        graph.warp_latent = nn.Embedding(n_images, opt.warp_latent.embed_dim).to(dev)
+        graph.warp_mlp = DeformNetwork(d_feature=opt.warp_latent.embed_dim, d_in=3, d_out_1=1, d_out_2=3, n_blocks=3,
+                                       d_hidden=opt.inn.real_nvp.d_hidden, n_layers=1, skip_in=[],
+                                       multires=opt.inn.real_nvp.multires, weight_norm=True, actfn=opt.inn.actfn).to(dev)
+        if opt.warp_latent.normalize:
+            graph.frame_id = (torch.linspace(1, n_images, n_images)[:, None] / n_images).to(dev)
+        pose = graph.pose_eye[None].repeat(n_images, 1, 1)
+        graph.global_rigid = nn.Embedding(n_images, 12, _weight=pose.reshape(-1, 12).clone()).to(dev)
+    return graph
+
+
+def trainable_parameters(graph):
+    """Every parameter an optimiser of the reference touches, in a fixed order (identical on all ranks)."""
+    out = []
+    for n, p in graph.named_parameters():
+        if n.endswith("progress") or n.startswith("global_rigid") or "pose_global" in n:
+            continue   # schedules / Kabsch outputs: written through .data, never optimised
+        out.append((n, p))
+    return out
+
+
+def summarize_loss(opt, loss):
+    """model/base.py:130-142: loss.all = sum_k 10**w_k loss_k."""
+    total = 0.
+    for key in list(loss.keys()):
+        if key == "all":
+            continue
+        if opt.loss_weight[key] is not None:
+            total = total + 10 ** float(opt.loss_weight[key]) * loss[key]
+    loss.update(all=total)
+    return loss
+
+
+class GradBucket:
+    """One flat fp32 buffer holding every trainable gradient.  ``attach`` points each ``p.grad`` at
+    its slice, so backward accumulates straight into the bucket and ``allreduce`` is a single
+    collective over ~0.7 M floats (latency-bound on NVLink; nothing to overlap at this size)."""
+
+    def __init__(self, graph):
+        self.params = [p for _, p in trainable_parameters(graph)]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
+        self.attach()
+
+    def attach(self):
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+
+def shard_ray_idx(ray_idx, rank, world):
+    """Contiguous 1/world slice of the per-image pixel list (same list on every rank)."""
+    n = ray_idx.numel()
+    per = (n + world - 1) // world
+    return ray_idx[rank * per:min((rank + 1) * per, n)]
+
+
+class _ShardedRandperm:
+    """Makes ``torch.randperm`` inside ``Graph.forward`` return this rank's slice of the global
+    draw: every rank consumes the same generator state (seeded identically), keeps the first
+    ``rand_rays // B`` entries as the global batch and takes its contiguous 1/k of them."""
+
+    def __init__(self, rank, world, global_per_image):
+        self.rank, self.world, self.n = rank, world, global_per_image
+        self._orig = None
+
+    def __enter__(self):
+        self._orig = torch.randperm
+        orig, rank, world, n = self._orig, self.rank, self.world, self.n
+
+        def randperm(*a, **k):
+            return shard_ray_idx(orig(*a, **k)[:n], rank, world)
+        torch.randperm = randperm
+        return self
+
+    def __exit__(self, *exc):
+        torch.randperm = self._orig
+
+
+class feed_draws:
+    """Feed host-made random draws to ``Graph.forward``: the next ``torch.randperm`` returns
+    ``ray_idx`` and the next ``torch.rand`` returns ``u`` (both already on the device).  This is
+    the parity-mode RNG path: uniforms and ray indices come from the caller's
+    generator instead of the device generator, e.g. a host data loader or a recorded reference run."""
+
+    def __init__(self, ray_idx=None, u=None):
+        self.ray_idx, self.u = ray_idx, u
+
+    def __enter__(self):
+        self._rand, self._perm = torch.rand, torch.randperm
+        me = self
+
+        def rand(*shape, **k):
+            if me.u is None:
+                return me._rand(*shape, **k)
+            u, me.u = me.u, None
+            return u.view(*shape)
+
+        def randperm(n, **k):
+            if me.ray_idx is None:
+                return me._perm(n, **k)
+            r, me.ray_idx = me.ray_idx, None
+            return r
+        torch.rand, torch.randperm = rand, randperm
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randperm = self._rand, self._perm
+
+
+def train_step(opt, graph, var, it, bucket=None, rank=0, world=1):
+    """One optimisation step minus the optimiser: forward, loss, backward (+ all-reduce).
+
+    With ``world > 1`` the rank renders a contiguous 1/world slice of the global ray batch; local
+    losses are means over the local rays, so they are scaled by ``n_local / n_global`` before the
+    summed all-reduce -- the reduced gradient equals the single-GPU gradient of the
+    same global batch.  Returns the loss dict (``all`` is the local, scaled value).
+    """
+    B = len(var.idx)
+    n_global = opt.nerf.rand_rays // B
+    takes_iter = opt.model in ("barf_inn_llff", "nerf_inn_llff", "barf_inn_dtu", "nerf_inn_dtu")
+    if bucket is not None:
+        bucket.zero()
+    else:
+        graph.zero_grad(set_to_none=True)
+    if world > 1:
+        with _ShardedRandperm(rank, world, n_global):
+            var = graph.forward(opt, var, mode="train", iter=it) if takes_iter else graph.forward(opt, var, mode="train")
+    else:
+        var = graph.forward(opt, var, mode="train", iter=it) if takes_iter else graph.forward(opt, var, mode="train")
+    loss = summarize_loss(opt, graph.compute_loss(opt, var, mode="train"))
+    scale = 1.0
+    if world > 1:
+        scale = len(var.ray_idx) / float(n_global)
+    (loss.all * scale).backward()
+    if bucket is not None and world > 1:
+        bucket.allreduce()
+    return loss
+
+
+def synthetic_var(opt, B, seed=0, dtu=False):
+    """A ``var`` batch shaped like ``train_data.all`` (data/llff.py:79-92, data/dtu.py:369-380) from
+    the deterministic generators in ``synthetic``."""
+    from . import synthetic as syn
+    dev = opt.device
+    var = AttrDict(idx=torch.arange(B, device=dev), image=syn.images(seed, B, opt.H, opt.W).to(dev),
+                   intr=syn.intrinsics(B, opt.H, opt.W, 1.8 if dtu else 0.81).to(dev),
+                   pose=(syn.dtu_poses(seed + 1, B) if dtu else syn.llff_poses(seed + 1, B)).to(dev))
+    if dtu:
+        var.depth_range = torch.tensor([[1.2, 5.2]]).repeat(B, 1).to(dev)
+    return var

@@ -44,6 +44,47 @@ def _idx(ray_idx, device):
 PRECISIONS = {"fp32": NIW_PREC_FP32, "bf16": NIW_PREC_BF16}
 
 
+class KernelTimer:
+    """CUDA-event timing of named library calls on the launching stream (bench.py's roofline leg).
+    Disabled by default (zero overhead); ``with KernelTimer() as t`` arms it; ``t.totals()`` syncs
+    and returns {name: (calls, total_ms)}."""
+    active = None
+
+    def __init__(self):
+        self.events = []
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            n, ms = out.get(name, (0, 0.0))
+            out[name] = (n + 1, ms + a.elapsed_time(b))
+        return out
+
+
+class _timed:
+    def __init__(self, name):
+        self.name, self.t = name, KernelTimer.active
+
+    def __enter__(self):
+        if self.t is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.t is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.t.events.append((self.name, self.a, b))
+
+
 def precision_code(p):
     if isinstance(p, int):
         return p
@@ -210,8 +251,9 @@ class _Composite(torch.autograd.Function):
         opacity = torch.empty(R, device=dev)
         prob = torch.empty(R, N, device=dev)
         trans = torch.empty(R, N, device=dev)
-        _lib.check(lib.niw_composite_fwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), R, N, float(bg), _p(rgb),
-                                         _p(depth), _p(opacity), _p(prob), _p(trans), _stream()))
+        with _timed("composite_fwd"):
+            _lib.check(lib.niw_composite_fwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), R, N, float(bg), _p(rgb),
+                                             _p(depth), _p(opacity), _p(prob), _p(trans), _stream()))
         ctx.save_for_backward(ray, rgb_s, sigma, depth_s, prob, trans)
         ctx.bg = float(bg)
         ctx.mark_non_differentiable(prob)
@@ -225,9 +267,11 @@ class _Composite(torch.autograd.Function):
         d_sigma = torch.empty_like(sigma)
         d_ray = torch.empty_like(ray)
         c = lambda t: None if t is None else t.contiguous()
-        _lib.check(_lib.load().niw_composite_bwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), _p(prob), _p(trans), R, N,
-                                                 ctx.bg, _p(c(d_rgb)), _p(c(d_depth)), _p(c(d_opacity)),
-                                                 _p(d_rgb_s), _p(d_sigma), _p(d_ray), _stream()))
+        d_rgb, d_depth, d_opacity = c(d_rgb), c(d_depth), c(d_opacity)
+        with _timed("composite_bwd"):
+            _lib.check(_lib.load().niw_composite_bwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), _p(prob), _p(trans), R,
+                                                     N, ctx.bg, _p(d_rgb), _p(d_depth), _p(d_opacity), _p(d_rgb_s),
+                                                     _p(d_sigma), _p(d_ray), _stream()))
         return d_ray, d_rgb_s, d_sigma, None, None
 
 
@@ -272,8 +316,9 @@ class _NerfSamples(torch.autograd.Function):
         sigma = torch.empty(R, N, device=depth.device)
         b3 = (_c.c_float * 10)(*bw3)
         bv = (_c.c_float * 4)(*bwv)
-        _lib.check(lib.niw_nerf_fwd(_p(params), _p(center), _p(ray), _p(depth), R, N, b3, bv, precision, int(training),
-                                    _p(ws), nbytes, _p(rgb), _p(sigma), _stream()))
+        with _timed("nerf_fwd"):
+            _lib.check(lib.niw_nerf_fwd(_p(params), _p(center), _p(ray), _p(depth), R, N, b3, bv, precision,
+                                        int(training), _p(ws), nbytes, _p(rgb), _p(sigma), _stream()))
         if training:
             ctx.save_for_backward(params, center, ray, depth, ws)
             ctx.cfg = (tuple(bw3), tuple(bwv), precision, nbytes)
@@ -293,9 +338,11 @@ class _NerfSamples(torch.autograd.Function):
             d_sigma = torch.zeros(R, N, device=depth.device)
         b3 = (_c.c_float * 10)(*bw3)
         bv = (_c.c_float * 4)(*bwv)
-        _lib.check(_lib.load().niw_nerf_bwd(_p(params), _p(center), _p(ray), _p(depth), R, N, b3, bv, precision, _p(ws),
-                                            nbytes, _p(d_rgb.contiguous()), _p(d_sigma.contiguous()), _p(d_params),
-                                            _p(d_center), _p(d_ray), _stream()))
+        d_rgb, d_sigma = d_rgb.contiguous(), d_sigma.contiguous()
+        with _timed("nerf_bwd"):
+            _lib.check(_lib.load().niw_nerf_bwd(_p(params), _p(center), _p(ray), _p(depth), R, N, b3, bv, precision,
+                                                _p(ws), nbytes, _p(d_rgb), _p(d_sigma), _p(d_params), _p(d_center),
+                                                _p(d_ray), _stream()))
         return d_params, d_center, d_ray, None, None, None, None, None
 
 

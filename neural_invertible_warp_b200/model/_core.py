@@ -1,0 +1,261 @@
+"""Shared implementation behind the per-model ``Graph`` / ``NeRF`` classes.
+
+The reference states the same render arithmetic four times (model/nerf.py:243-483,
+model/nerf_inn_llff.py:485-818, model/nerf_inn_dtu.py:363-680, model/nerf_gaussian.py); here it
+exists once.  ``NeRFCore`` owns the reference's parameter objects (``mlp_feat.{i}``, ``mlp_rgb.{i}``
+``nn.Linear`` -- same names, shapes and initialisation, so ``state_dict`` round-trips) and maps
+``forward_samples`` / ``composite`` onto the CUDA operators; ``RenderCore`` is the ray pipeline
+(ray generation -> stratified depths -> fused encoding+MLP -> compositing -> optional inverse-CDF
+resampling and second pass) that ``Graph.render`` / ``render_local`` / ``render_by_slices`` share.
+
+Tensors cross this layer in the reference's shapes ([B,P,3], [B,P,N,1] ...); the kernels see them
+flattened over rays.
+"""
+import math
+
+import torch
+from torch import nn
+
+from .. import camera
+from .. import functional as F
+from ..config import AttrDict
+
+edict = AttrDict   # the reference returns EasyDict; AttrDict has the same access semantics
+
+
+def get_layer_dims(layers):
+    """reference util.py (get_layer_dims): [(k_in, k_out)] of consecutive entries."""
+    return list(zip(layers[:-1], layers[1:]))
+
+
+def _arch_supported(opt):
+    a = opt.arch
+    feat = list(a.layers_feat)
+    rgb = list(a.layers_rgb)
+    ok = (len(feat) == 9 and all(w == 256 for w in feat[1:]) and list(a.skip) == [4]
+          and len(rgb) == 3 and rgb[1] == 128 and rgb[2] == 3 and a.posenc and a.posenc.L_3D == 10
+          and a.posenc.L_view == 4 and bool(opt.nerf.view_dep) and a.density_activ == "softplus")
+    return ok
+
+
+class NeRFCore(nn.Module):
+    """Parameter-compatible with reference ``model.nerf.NeRF`` (model/nerf.py:367-483)."""
+
+    has_progress = False   # BARF variants own a ``progress`` Parameter (model/barf.py:254)
+
+    def __init__(self, opt):
+        super().__init__()
+        self.define_network(opt)
+        if self.has_progress:
+            self.progress = nn.Parameter(torch.tensor(0.))
+
+    # -- construction ---------------------------------------------------------------------
+    def define_network(self, opt):
+        if not _arch_supported(opt):
+            raise RuntimeError(
+                "niw_b200: the CUDA path implements the reference architecture only (8x256 feature MLP, skip at "
+                "layer 4, 128-wide view-dependent RGB head, posenc L_3D=10 / L_view=4, softplus density); got "
+                "arch=%r -- there is no fallback" % (dict(opt.arch),))
+        d3 = 3 + 6 * opt.arch.posenc.L_3D
+        dv = 3 + 6 * opt.arch.posenc.L_view
+        self.mlp_feat = nn.ModuleList()
+        self.total_param = 0
+        dims = get_layer_dims(opt.arch.layers_feat)
+        for li, (k_in, k_out) in enumerate(dims):
+            if li == 0:
+                k_in = d3
+            if li in opt.arch.skip:
+                k_in += d3
+            if li == len(dims) - 1:
+                k_out += 1
+            lin = nn.Linear(k_in, k_out)
+            if opt.arch.tf_init:
+                self.tensorflow_init_weights(opt, lin, out="first" if li == len(dims) - 1 else None)
+            self.mlp_feat.append(lin)
+            self.total_param += lin.weight.numel()
+        self.mlp_rgb = nn.ModuleList()
+        dims = get_layer_dims(opt.arch.layers_rgb)
+        for li, (k_in, k_out) in enumerate(dims):
+            if li == 0:
+                k_in = opt.arch.layers_feat[-1] + dv
+            lin = nn.Linear(k_in, k_out)
+            if opt.arch.tf_init:
+                self.tensorflow_init_weights(opt, lin, out="all" if li == len(dims) - 1 else None)
+            self.mlp_rgb.append(lin)
+            self.total_param += lin.weight.numel()
+
+    def tensorflow_init_weights(self, opt, linear, out=None):
+        """Xavier-uniform with ReLU gain on hidden rows (model/nerf.py:404-414)."""
+        gain = math.sqrt(2.0)
+        with torch.no_grad():
+            if out == "all":
+                nn.init.xavier_uniform_(linear.weight)
+            elif out == "first":
+                nn.init.xavier_uniform_(linear.weight[:1])
+                nn.init.xavier_uniform_(linear.weight[1:], gain=gain)
+            else:
+                nn.init.xavier_uniform_(linear.weight, gain=gain)
+            nn.init.zeros_(linear.bias)
+
+    # -- helpers ----------------------------------------------------------------------------
+    def flat_parameters(self):
+        """The 530 052 MLP parameters as one fp32 vector in state_dict order (autograd splits the
+        gradient back onto the ``nn.Linear`` parameters)."""
+        ps = []
+        for lin in list(self.mlp_feat) + list(self.mlp_rgb):
+            ps += [lin.weight.reshape(-1), lin.bias]
+        return torch.cat(ps)
+
+    def band_weights(self, opt):
+        """Coarse-to-fine weights of the L_3D / L_view bands (model/barf.py:256-268): all ones
+        for plain NeRF or when ``barf_c2f`` is unset."""
+        c2f = opt.barf_c2f if (self.has_progress and opt.get("barf_c2f") is not None) else None
+        prog = float(self.progress.data) if self.has_progress else 0.0
+        return (F.band_weights(prog, c2f, opt.arch.posenc.L_3D), F.band_weights(prog, c2f, opt.arch.posenc.L_view))
+
+    @staticmethod
+    def precision(opt):
+        return opt.arch.get("mlp_precision", "bf16") if hasattr(opt.arch, "get") else "bf16"
+
+    def _check_mode(self, opt, mode):
+        if opt.nerf.density_noise_reg and mode == "train":
+            raise RuntimeError("niw_b200: nerf.density_noise_reg is not implemented in the CUDA path")
+
+    # -- reference API ----------------------------------------------------------------------
+    def forward(self, opt, points_3D, ray_unit=None, mode=None):
+        """model/nerf.py:416-447 on explicit points: each point is treated as a one-sample ray
+        (x = p + 0 * v), so the same fused kernel serves this entry point."""
+        self._check_mode(opt, mode)
+        if ray_unit is None:
+            raise AssertionError("view-dependent network: ray_unit is required")
+        shape = points_3D.shape[:-1]
+        pts = points_3D.reshape(-1, 3)
+        view = ray_unit.expand_as(points_3D).reshape(-1, 3)
+        depth = torch.zeros(pts.shape[0], 1, device=pts.device)
+        bw3, bwv = self.band_weights(opt)
+        rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), pts, view, depth, bw3, bwv, self.precision(opt))
+        return rgb.view(*shape, 3), sigma.view(*shape)
+
+    def forward_samples(self, opt, center, ray, depth_samples, mode=None):
+        """model/nerf.py:449-456: center, ray [B,P,3], depth_samples [B,P,N,1] ->
+        rgb_samples [B,P,N,3], density_samples [B,P,N]."""
+        self._check_mode(opt, mode)
+        B, P, N = depth_samples.shape[:3]
+        bw3, bwv = self.band_weights(opt)
+        rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), center.reshape(B * P, 3), ray.reshape(B * P, 3),
+                                            depth_samples.reshape(B * P, N), bw3, bwv, self.precision(opt))
+        return rgb.view(B, P, N, 3), sigma.view(B, P, N)
+
+    def composite(self, opt, ray, rgb_samples, density_samples, depth_samples):
+        """model/nerf.py:458-474 -> rgb [B,P,3], depth [B,P,1], opacity [B,P,1], prob [B,P,N,1]."""
+        B, P, N = density_samples.shape
+        bg = opt.data.bgcolor if opt.nerf.setbg_opaque else None
+        rgb, depth, opacity, prob = F.composite(ray.reshape(B * P, 3), rgb_samples.reshape(B * P, N, 3),
+                                                density_samples.reshape(B * P, N), depth_samples.reshape(B * P, N), bg)
+        return rgb.view(B, P, 3), depth.view(B, P, 1), opacity.view(B, P, 1), prob.view(B, P, N, 1)
+
+    def positional_encoding(self, opt, input, L):
+        """model/nerf.py:476-483 (+ the BARF weighting of model/barf.py:256-268 in subclasses with
+        ``progress``).  API utility in PyTorch: the render path computes the encoding inside the
+        MLP kernel and never materialises it."""
+        freq = 2 ** torch.arange(L, dtype=torch.float32, device=input.device) * math.pi
+        spectrum = input[..., None] * freq
+        enc = torch.stack([spectrum.sin(), spectrum.cos()], dim=-2).reshape(*input.shape[:-1], -1)
+        if self.has_progress and opt.get("barf_c2f") is not None:
+            w = torch.tensor(F.band_weights(float(self.progress.data), opt.barf_c2f, L), device=input.device)
+            enc = (enc.reshape(-1, L) * w).reshape(enc.shape)
+        return enc
+
+
+class RenderCore(nn.Module):
+    """Ray pipeline shared by every Graph.  Subclasses provide ``self.nerf`` (and ``nerf_fine``)."""
+
+    # -- depth sampling ---------------------------------------------------------------------
+    def sample_depth(self, opt, batch_size, num_rays=None, depth_range=None):
+        """model/nerf.py:334-344 (DTU: nerf_inn_dtu.py:524-546 takes ``depth_range``).  The uniform
+        draws come from ``torch.rand`` exactly as in the reference, so a shared seed gives shared
+        jitter; the arithmetic runs in one kernel with the reference's rounding sequence."""
+        rng = opt.nerf.depth.range if depth_range is None else depth_range
+        rng = [float(rng[0]), float(rng[1])]
+        num_rays = num_rays or opt.H * opt.W
+        N = opt.nerf.sample_intvs
+        u = torch.rand(batch_size, num_rays, N, 1, device=opt.device) if opt.nerf.sample_stratified else None
+        d = F.sample_stratified(None if u is None else u.view(-1), batch_size * num_rays, N, rng,
+                                opt.nerf.depth.param, device=opt.device)
+        return d.view(batch_size, num_rays, N, 1)
+
+    def sample_depth_from_pdf(self, opt, pdf):
+        """model/nerf.py:346-365: pdf [B,P,N] -> fine depths [B,P,Nf,1] (bit-exact bins)."""
+        B, P, N = pdf.shape
+        fine, _, _ = F.sample_pdf_merge(pdf.reshape(B * P, N), None, opt.nerf.sample_intvs_fine, opt.nerf.depth.range,
+                                        want_merged=False)
+        return fine.view(B, P, -1, 1)
+
+    # -- rays -> pixels ---------------------------------------------------------------------
+    def _render_rays(self, opt, center, ray, intr, mode, depth_range=None):
+        """Everything after ray generation in model/nerf.py:301-319."""
+        B, P = ray.shape[:2]
+        if opt.camera.ndc:
+            center, ray = camera.convert_NDC(opt, center, ray, intr=intr)
+        depth_samples = self.sample_depth(opt, B, num_rays=P, depth_range=depth_range)
+        rgb_s, sigma_s = self.nerf.forward_samples(opt, center, ray, depth_samples, mode=mode)
+        rgb, depth, opacity, prob = self.nerf.composite(opt, ray, rgb_s, sigma_s, depth_samples)
+        ret = edict(rgb=rgb, depth=depth, opacity=opacity)
+        if opt.nerf.fine_sampling:
+            N = depth_samples.shape[2]
+            with torch.no_grad():
+                # inverse-CDF resampling fused with the cat + sort of model/nerf.py:313-315
+                _, _, merged = F.sample_pdf_merge(prob.reshape(B * P, N), depth_samples.reshape(B * P, N),
+                                                  opt.nerf.sample_intvs_fine, opt.nerf.depth.range, want_fine=False)
+                depth_samples = merged.view(B, P, -1, 1)
+            rgb_s, sigma_s = self.nerf_fine.forward_samples(opt, center, ray, depth_samples, mode=mode)
+            rgb_f, depth_f, opacity_f, _ = self.nerf_fine.composite(opt, ray, rgb_s, sigma_s, depth_samples)
+            ret.update(rgb_fine=rgb_f, depth_fine=depth_f, opacity_fine=opacity_f)
+        return ret
+
+    def _render_pose(self, opt, pose, intr=None, ray_idx=None, mode=None, depth_range=None, idx_start=0, num=None):
+        """model/nerf.py:293-319.  Only the requested pixels are generated (no full-frame grid, no
+        NaN retry loop / host sync: the kernel cannot produce the NaN the reference guards against)."""
+        center, ray = camera.get_center_and_ray(opt, pose, intr=intr, ray_idx=ray_idx, idx_start=idx_start, num=num)
+        return self._render_rays(opt, center, ray, intr, mode, depth_range=depth_range)
+
+    def _render_local(self, opt, ray, center, intr=None, ray_idx=None, mode=None, depth_range=None):
+        """model/nerf_inn_llff.py:581-612 / nerf_inn_dtu.py:420-456: render given world-frame rays."""
+        if ray_idx is not None:
+            center, ray = center[:, ray_idx], ray[:, ray_idx]
+        return self._render_rays(opt, center, ray, intr, mode, depth_range=depth_range)
+
+    def _slices(self, opt, render_slice):
+        """model/nerf.py:321-332: ``rand_rays`` pixels at a time, concatenated along the ray axis."""
+        keys = ["rgb", "depth", "opacity"]
+        if opt.nerf.fine_sampling:
+            keys += ["rgb_fine", "depth_fine", "opacity_fine"]
+        parts = {k: [] for k in keys}
+        HW = opt.H * opt.W
+        for c in range(0, HW, opt.nerf.rand_rays):
+            ret = render_slice(c, min(opt.nerf.rand_rays, HW - c))
+            for k in keys:
+                parts[k].append(ret[k])
+        return edict({k: torch.cat(v, dim=1) for k, v in parts.items()})
+
+    # -- losses -----------------------------------------------------------------------------
+    def L1_loss(self, pred, label=0):
+        return (pred.contiguous() - label).abs().mean()
+
+    def MSE_loss(self, pred, label=0):
+        return ((pred.contiguous() - label) ** 2).mean()
+
+    def _image_losses(self, opt, var, mode):
+        """model/nerf.py:276-288: the pixel gather + squared error run in one kernel that never
+        materialises ``image[:, ray_idx]``."""
+        loss = edict()
+        B = len(var.idx)
+        ray_idx = var.ray_idx if (opt.nerf.rand_rays and mode in ["train", "test-optim"]) else None
+        image = var.image.view(B, 3, opt.H, opt.W)
+        if opt.loss_weight.render is not None:
+            loss.render = F.mse_gather(var.rgb, image, ray_idx)
+        if opt.loss_weight.render_fine is not None:
+            if not opt.nerf.fine_sampling:
+                raise AssertionError("loss_weight.render_fine needs nerf.fine_sampling")
+            loss.render_fine = F.mse_gather(var.rgb_fine, image, ray_idx)
+        return loss

@@ -1,0 +1,88 @@
+"""Drop-in for reference ``model/barf_inn_llff.py`` (Graph :273-424, NeRF :427-442): the per-image
+pose is an invertible NVP warp of the camera-frame pixel grid and camera centre."""
+import math
+
+import torch
+
+from .. import camera
+from . import barf, nerf_inn_llff
+from ._core import NeRFCore
+
+
+class NeRF(NeRFCore):
+    has_progress = True
+
+
+class Graph(nerf_inn_llff.Graph):
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.nerf = NeRF(opt)
+        if opt.nerf.fine_sampling:
+            self.nerf_fine = NeRF(opt)
+        self.pose_eye = torch.eye(3, 4).to(opt.device)
+
+    def _initial_pose(self, opt, var):
+        """Initial world->camera poses and whether the un-warped points live in that world frame
+        (blender) or in the camera frame (LLFF: pose_init None, barf_inn_llff.py:309-323)."""
+        if opt.data.dataset == "blender":
+            if opt.camera.noise_type == "barf":
+                var.pose_noise = self.pose_noise[var.idx]
+                pose = camera.pose.compose([var.pose_noise, var.pose])
+            elif opt.camera.noise_type == "l2g":
+                var.pose_noise = self.pose_noise[var.idx]
+                pose = camera.pose.compose([var.pose, var.pose_noise])
+            else:
+                pose = var.pose
+            return pose, pose
+        return self.pose_eye[None].repeat(len(var.idx), 1, 1), None
+
+    def get_pose_init(self, opt, var, mode=None, ind=None, iter=None):
+        """barf_inn_llff.py:282-302."""
+        if mode == "train":
+            return self._initial_pose(opt, var)[0]
+
+    def _latent(self, opt):
+        if opt.warp_latent.enc_type == "l2fbarf":
+            return self.warp_latent.weight
+        if opt.warp_latent.enc_type == "posenc":
+            return self.positional_encoding(opt, self.frame_id, opt.warp_latent.posenc.freq_len)
+        raise NotImplementedError("warp_latent.enc_type=%r" % (opt.warp_latent.enc_type,))
+
+    def get_pose(self, opt, var, mode=None, ind=None, iter=None):
+        """barf_inn_llff.py:305-399.  train: (ray, center_3D, grid_3D, alpha_ratio), each [B,P,3]."""
+        if mode == "train":
+            _, pose_init = self._initial_pose(opt, var)
+            P = len(var.ray_idx)
+            # [grid ; centre] rows for the sampled pixels only, no gradient (:325-330, :348)
+            with torch.no_grad():
+                pts = camera.unwarped_points(opt, var.intr, ray_idx=var.ray_idx, pose_init=pose_init)
+            var.grid_cam, var.center_cam = pts[:, :P], pts[:, P:]
+            if opt.inn.real_nvp.c2f == True:   # noqa: E712  (the reference compares with == True)
+                alpha_ratio = max(min(iter / opt.inn.real_nvp.max_pe_iter, 1), 0)
+            else:
+                alpha_ratio = 1
+            warped = self.warp_mlp.forward(self._latent(opt), pts.unsqueeze(2), alpha_ratio=alpha_ratio)[:, :, 0]
+            grid_3D, center_3D = warped[:, :P], warped[:, P:]
+            return grid_3D - center_3D, center_3D, grid_3D, alpha_ratio
+        if mode == "render_train":
+            # the reference's branch calls warp_mlp.forward with a wrong arity (:378, SURVEY.md A.6 iii)
+            # and has no live caller; implemented with the evident intent (image ``ind``, alpha 1).
+            with torch.no_grad():
+                pts = camera.unwarped_points(opt, var.intr[ind][None])
+            P = pts.shape[1] // 2
+            warped = self.warp_mlp.forward(self._latent(opt)[ind][None], pts.unsqueeze(2), alpha_ratio=1)[:, :, 0]
+            return warped[:, :P] - warped[:, P:], warped[:, P:]
+        if mode in ["val", "eval", "test-optim"]:
+            return barf.Graph._aligned_test_pose(self, opt, var, mode)
+        return var.pose
+
+    def positional_encoding(self, opt, input, L):
+        """barf_inn_llff.py:416-423 (un-weighted encoding of small per-image inputs)."""
+        return _plain_encoding(input, L)
+
+
+def _plain_encoding(x, L):
+    freq = 2 ** torch.arange(L, dtype=torch.float32, device=x.device) * math.pi
+    spectrum = x[..., None] * freq
+    return torch.stack([spectrum.sin(), spectrum.cos()], dim=-2).reshape(*x.shape[:-1], -1)

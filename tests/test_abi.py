@@ -1,0 +1,38 @@
+"""The C-ABI library builds for sm_100a without a GPU, loads, and exports exactly what
+include/niw_b200.h declares (no compute calls here)."""
+import ctypes
+import subprocess
+
+from neural_invertible_warp_b200 import _lib, build, header
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    declared = header.declared_symbols()
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_lib.SIGNATURES) == set(declared), set(_lib.SIGNATURES) ^ set(declared)
+    lib.niw_abi_version.restype = ctypes.c_int
+    assert lib.niw_abi_version() == _lib.ABI_VERSION
+    lib.niw_error_string.restype = ctypes.c_char_p
+    assert b"workspace" in lib.niw_error_string(-3)
+
+
+def test_library_is_blackwell_native():
+    """SASS of the fused MLP kernel holds tcgen05 MMAs (UTC*MMA), TMEM loads (LDTM) and bulk async
+    copies (UBLKCP) -- not a recompiled mma.sync path."""
+    sass = subprocess.run(["cuobjdump", "-sass", build.LIB], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass
+    assert "LDTM" in sass
+    assert "UBLKCP" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_ops_fail_loudly_without_cuda():
+    import pytest
+    import torch
+    from neural_invertible_warp_b200 import functional as F
+    with pytest.raises(RuntimeError):
+        F.composite(torch.zeros(1, 3), torch.zeros(1, 4, 3), torch.zeros(1, 4), torch.zeros(1, 4))

@@ -1,0 +1,188 @@
+"""GPU parity at the Graph level: the drop-in ``Graph.forward`` / ``compute_loss`` / ``backward``
+against golden vectors minted from the executed reference (tests/golden/graph_*.pt), with the
+reference's own uniform draws and ray indices replayed."""
+import contextlib
+import math
+
+import pytest
+import torch
+
+from neural_invertible_warp_b200 import config as cfgmod
+from neural_invertible_warp_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+def close(a, b, **kw):
+    torch.testing.assert_close(a.detach().cpu(), b, **{**TOL, **kw})
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def digest_close(named_grads, digest, rtol=2e-3):
+    for k, d in digest.items():
+        g = named_grads[k].detach().double().cpu().flatten()
+        assert g.numel() == d["numel"], k
+        assert abs(g.norm().item() - d["l2"]) <= rtol * max(d["l2"], 1e-12), (k, g.norm().item(), d["l2"])
+        assert abs(g.sum().item() - d["sum"]) <= rtol * max(d["abssum"], 1e-12), k
+        torch.testing.assert_close(g[:8].float(), d["head"], rtol=2.5 * rtol,
+                                   atol=2.5 * rtol * max(d["head"].abs().max().item(),
+                                                         3 * d["l2"] / math.sqrt(d["numel"])) + 1e-12)
+
+
+@contextlib.contextmanager
+def replay_rng(rand=(), randperm=()):
+    """Feed recorded ``torch.rand`` / ``torch.randperm`` results (the reference's draws) to the graph."""
+    rand, randperm = list(rand), list(randperm)
+    o_rand, o_perm = torch.rand, torch.randperm
+
+    def _rand(*shape, **k):
+        t = rand.pop(0)
+        assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+        return t.to(k.get("device", "cpu")).clone()
+
+    def _perm(n, **k):
+        return randperm.pop(0).to(k.get("device", "cpu"))
+
+    torch.rand, torch.randperm = _rand, _perm
+    try:
+        yield
+    finally:
+        torch.rand, torch.randperm = o_rand, o_perm
+
+
+def load_nerf(module, p):
+    sd = module.state_dict()
+    module.load_state_dict({**{k: v for k, v in sd.items() if k not in p}, **{k: v.to(DEV) for k, v in p.items()}})
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from neural_invertible_warp_b200 import engine
+    return engine
+
+
+def _step(eng, opt, graph, var, it, g):
+    with replay_rng(rand=[g["u"]], randperm=[g["ray_idx"]]):
+        loss = eng.train_step(opt, graph, var, it)
+    return loss
+
+
+def test_graph_barf_train_step(eng, golden):
+    g = golden("graph_barf")
+    B = g["B"]
+    opt = cfgmod.builtin_options("barf_llff", model="barf", barf_c2f=[0.1, 0.5], device=DEV,
+                                 data=dict(image_size=[g["H"], g["W"]]),
+                                 nerf=dict(rand_rays=g["rand_rays"], sample_intvs=g["N"]), arch=dict(mlp_precision="fp32"))
+    graph = eng.build_graph(opt, B)
+    load_nerf(graph.nerf, syn.nerf_params(g["param_seed"]))
+    graph.nerf.progress.data.fill_(g["progress"])
+    graph.se3_refine.weight.data = g["se3"].to(DEV)
+    var = eng.synthetic_var(opt, B, g["var_seed"])
+    loss = _step(eng, opt, graph, var, None, g)
+    close(var.rgb, g["rgb"]); close(var.opacity, g["opacity"]); close(var.depth, g["depth"], rtol=1e-4, atol=1e-4)
+    close(loss.all, g["loss"])
+    assert rel_l2(graph.se3_refine.weight.grad, g["d_se3"]) < 5e-3
+    digest_close({k: v.grad for k, v in graph.nerf.named_parameters() if v.grad is not None}, g["grads"])
+    # state_dict keys are the reference's (checkpoint compatibility)
+    keys = set(graph.state_dict().keys())
+    assert {"nerf.mlp_feat.0.weight", "nerf.mlp_feat.7.bias", "nerf.mlp_rgb.1.weight", "nerf.progress",
+            "se3_refine.weight"} <= keys
+
+
+@pytest.mark.parametrize("tag", ["p16", "p40"])
+def test_graph_inn_llff_train_step(eng, golden, tag):
+    g = golden("graph_inn_llff")[tag]
+    B = g["B"]
+    opt = cfgmod.builtin_options("barf_inn_llff", barf_c2f=[0.1, 0.5], device=DEV, data=dict(image_size=[g["H"], g["W"]]),
+                                 nerf=dict(rand_rays=g["rays_per_img"] * B, sample_intvs=g["N"]),
+                                 loss_weight=dict(global_alignment=2), arch=dict(mlp_precision="fp32"))
+    graph = eng.build_graph(opt, B)
+    load_nerf(graph.nerf, syn.nerf_params(g["nerf_seed"]))
+    graph.nerf.progress.data.fill_(g["progress"])
+    graph.warp_latent.weight.data = syn.latent_codes(g["code_seed"], B).to(DEV)
+    graph.warp_mlp.load_state_dict({k: v.to(DEV) for k, v in syn.nvp_params(g["nvp_seed"]).items()})
+    var = eng.synthetic_var(opt, B, g["var_seed"])
+    loss = _step(eng, opt, graph, var, g["iter"], g)
+    assert var.inn_posenc_alpha == g["alpha_ratio"]
+    close(var.grid_3D, g["grid_3D"]); close(var.center, g["center"])
+    close(var.rgb, g["rgb"]); close(var.opacity, g["opacity"]); close(var.depth, g["depth"], rtol=1e-4, atol=1e-4)
+    close(loss.render, g["loss_render"])
+    close(graph.global_rigid.weight.data, g["global_rigid"], rtol=1e-4, atol=1e-5)
+    close(loss.global_alignment, g["loss_global_alignment"], rtol=1e-4, atol=1e-7)
+    close(loss.all, g["loss"], rtol=1e-4, atol=1e-6)
+    assert rel_l2(graph.warp_latent.weight.grad, g["d_code"]) < 5e-3
+    digest_close({k: v.grad for k, v in graph.warp_mlp.named_parameters()}, g["nvp_grads"], rtol=5e-2)
+    digest_close({k: v.grad for k, v in graph.nerf.named_parameters() if v.grad is not None}, g["grads"])
+    assert {"warp_mlp.lin0_a_0.weight_g", "warp_mlp.lin2_b_1.bias", "warp_mlp.lin1_c.weight", "warp_latent.weight",
+            "global_rigid.weight"} <= set(graph.state_dict().keys())
+
+
+def test_graph_inn_dtu_train_step_hierarchical(eng, golden):
+    g = golden("graph_inn_dtu")
+    B = g["B"]
+    opt = cfgmod.builtin_options("barf_inn_dtu", barf_c2f=[0.1, 0.5], device=DEV, data=dict(image_size=[g["H"], g["W"]]),
+                                 nerf=dict(rand_rays=g["rays_per_img"] * B, sample_intvs=g["N"], fine_sampling=True,
+                                           sample_intvs_fine=g["Nf"], depth=dict(range=[1.2, 5.2])),
+                                 loss_weight=dict(render_fine=0), arch=dict(mlp_precision="fp32"))
+    var = eng.synthetic_var(opt, B, g["var_seed"], dtu=True)
+    graph = eng.build_graph(opt, B, initial_poses_w2c=var.pose.clone())
+    load_nerf(graph.nerf, syn.nerf_params(g["nerf_seed"]))
+    load_nerf(graph.nerf_fine, syn.nerf_params(g["nerf_fine_seed"]))
+    graph.nerf.progress.data.fill_(g["progress"]); graph.nerf_fine.progress.data.fill_(g["progress"])
+    graph.pose_net.pose_latent.weight.data = syn.latent_codes(g["code_seed"], B).to(DEV)
+    graph.pose_net.pose_embedding.load_state_dict({k: v.to(DEV) for k, v in syn.nvp_params(g["nvp_seed"]).items()})
+    loss = _step(eng, opt, graph, var, g["iter"], g)
+    close(var.rgb, g["rgb"]); close(var.opacity, g["opacity"]); close(var.depth, g["depth"], rtol=1e-4, atol=1e-5)
+    close(var.rgb_fine, g["rgb_fine"]); close(var.opacity_fine, g["opacity_fine"])
+    close(var.depth_fine, g["depth_fine"], rtol=1e-4, atol=1e-5)
+    close(loss.all, g["loss"])
+    close(graph.pose_net.pose_global.weight.data, g["pose_global"], rtol=1e-4, atol=1e-5)
+    assert rel_l2(graph.pose_net.pose_latent.weight.grad, g["d_code"]) < 5e-3
+    digest_close({k: v.grad for k, v in graph.pose_net.pose_embedding.named_parameters()}, g["nvp_grads"], rtol=5e-2)
+    digest_close({k: v.grad for k, v in graph.nerf.named_parameters() if v.grad is not None}, g["grads"])
+    digest_close({k: v.grad for k, v in graph.nerf_fine.named_parameters() if v.grad is not None}, g["grads_fine"])
+
+
+def test_eval_render_by_slices_matches_single_render(eng):
+    """render_by_slices (model/nerf.py:321-332) == one render over the same pixels, with
+    un-stratified sampling so the two are comparable; full frame, ragged last slice."""
+    B = 2
+    opt = cfgmod.builtin_options("barf_llff", model="barf", device=DEV, data=dict(image_size=[12, 17]),
+                                 nerf=dict(rand_rays=50, sample_intvs=16, sample_stratified=False),
+                                 arch=dict(mlp_precision="fp32"))
+    graph = eng.build_graph(opt, B)
+    load_nerf(graph.nerf, syn.nerf_params(3))
+    var = eng.synthetic_var(opt, B, 5)
+    with torch.no_grad():
+        a = graph.render_by_slices(opt, var.pose, intr=var.intr, mode="eval")
+        b = graph.render(opt, var.pose, intr=var.intr, mode="eval")
+    assert a.rgb.shape == (B, 12 * 17, 3)
+    for k in ("rgb", "depth", "opacity"):
+        torch.testing.assert_close(a[k], b[k], rtol=1e-6, atol=1e-6)
+
+
+def test_nerf_forward_points_api(eng, golden):
+    """NeRF.forward(points, ray_unit) (model/nerf.py:416-447) through the one-sample-ray mapping,
+    and the positional_encoding utility, against the CPU oracle."""
+    from oracle import reference_port as ora
+    opt = cfgmod.builtin_options("barf_inn_llff", barf_c2f=[0.1, 0.5], device=DEV, arch=dict(mlp_precision="fp32"))
+    graph = eng.build_graph(opt, 2)
+    p = syn.nerf_params(21)
+    load_nerf(graph.nerf, p)
+    graph.nerf.progress.data.fill_(0.3)
+    gen = torch.Generator().manual_seed(9)
+    pts = torch.randn(2, 5, 7, 3, generator=gen)
+    unit = torch.nn.functional.normalize(torch.randn(2, 5, 1, 3, generator=gen), dim=-1).expand(2, 5, 7, 3)
+    rgb_ref, sig_ref = ora.nerf_mlp(p, pts, unit, progress=0.3, c2f=[0.1, 0.5])
+    with torch.no_grad():
+        rgb, sig = graph.nerf.forward(opt, pts.to(DEV), ray_unit=unit.to(DEV), mode="eval")
+    close(rgb, rgb_ref, rtol=1e-4, atol=1e-5)
+    close(sig, sig_ref, rtol=1e-4, atol=1e-5)
+    enc = graph.nerf.positional_encoding(opt, pts.to(DEV), 10)
+    close(enc, ora.barf_encoding(pts, 10, 0.3, [0.1, 0.5])[..., 3:], rtol=1e-4, atol=2e-4)
