@@ -20,46 +20,13 @@
 // contiguous) and LBO = rows*16 B.  Epilogue thread r writes 16 B at chunk*rows*16 + r*16: a warp
 // writes 512 contiguous bytes (bank-conflict free).  The same image, stored per tile in HBM, is
 // the MN-major operand of the weight-gradient GEMM in the backward pass (K = samples).
-#include "common.cuh"
-#include "mlp_shared.cuh"
-#include "tc_ptx.cuh"
+#include "tc_layout.cuh"
 
 namespace niw {
 
 namespace tc {
 
-constexpr int TILE = 128;                         // samples per tile (UMMA M)
-constexpr int NLAYER = 9;                         // 8 feature layers + rgb0
-constexpr int CHUNK_K = 32;                       // K extent of one streamed weight chunk
 constexpr int NSTAGE = 3;
-constexpr int ACT_BYTES = TILE * WIDTH * 2;       // 65536
-constexpr int ENC_BYTES = TILE * ENC3_PAD * 2;    // 16384
-constexpr int STAGE_BYTES = WIDTH * CHUNK_K * 2;  // 16384
-constexpr int KROW = TILE * 16;                   // 2048: byte stride between K-chunks (8 elems) of an A tile
-
-__host__ __device__ constexpr int layer_chunks(int l) { return l == 0 ? 2 : (l == 4 ? 10 : (l == 8 ? 9 : 8)); }
-__host__ __device__ constexpr int layer_rows(int l) { return l == 8 ? RGBW : WIDTH; }
-__host__ __device__ constexpr int layer_in(int l) { return l == 8 ? WIDTH + ENCV : feat_in(l); }
-__host__ __device__ constexpr int64_t layer_woff(int l) { return l == 8 ? RGB0_W : feat_w_off(l); }
-__host__ __device__ constexpr int64_t layer_boff(int l) { return l == 8 ? RGB0_B : feat_b_off(l); }
-__host__ __device__ constexpr int layer_rowoff(int l) { return l == 7 ? 1 : 0; }   // layer 7: row 0 is the density head
-__host__ __device__ constexpr int64_t stream_off(int l) {                        // byte offset of layer l in the stream
-    int64_t o = 0;
-    for (int i = 0; i < l; ++i) o += (int64_t)layer_chunks(i) * layer_rows(i) * CHUNK_K * 2;
-    return o;
-}
-constexpr int64_t STREAM_BYTES = stream_off(NLAYER);
-static_assert(STREAM_BYTES == 1056768, "weight stream size");
-
-// fp32 constants kept in shared memory
-constexpr int C_BIAS = 0;                         // [9][256]
-constexpr int C_W7R0 = C_BIAS + NLAYER * WIDTH;   // [256]  density row of layer 7
-constexpr int C_WRGB1 = C_W7R0 + WIDTH;           // [3][128]
-constexpr int C_MISC = C_WRGB1 + 3 * RGBW;        // b7[0], brgb1[0..2]
-constexpr int C_FLOATS = C_MISC + 4;
-
-// per-tile activation image saved for backward: h0..h7 (64 KB each) + hr (32 KB)
-constexpr int64_t SAVE_TILE_BYTES = 8 * (int64_t)ACT_BYTES + TILE * RGBW * 2;
 
 // shared memory map of the forward kernel
 constexpr int SM_ACT = 0;
@@ -69,31 +36,6 @@ constexpr int SM_CONST = SM_RING + NSTAGE * STAGE_BYTES;
 constexpr int SM_BAR = SM_CONST + ((C_FLOATS * 4 + 15) / 16) * 16;
 constexpr int SM_TOTAL = SM_BAR + 128;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-
-struct Workspace {
-    uint8_t* wstream;     // forward weight stream (bf16)
-    uint8_t* wstream_t;   // backward (transposed) weight stream
-    float* consts;        // C_FLOATS
-    float* sig_pre;       // [S]
-    float* rgb_keep;      // [S,3]
-    uint8_t* save;        // [tiles] x SAVE_TILE_BYTES
-    size_t bytes;
-};
-
-inline Workspace carve(void* base, int64_t S, bool training) {
-    Workspace w;
-    size_t off = 0;
-    auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += (n + 255) & ~size_t(255); return p; };
-    int64_t tiles = (S + TILE - 1) / TILE;
-    w.wstream = take(STREAM_BYTES);
-    w.wstream_t = take(STREAM_BYTES + 65536);
-    w.consts = (float*)take(C_FLOATS * 4);
-    w.sig_pre = (float*)take(training ? S * 4 : 0);
-    w.rgb_keep = (float*)take(training ? S * 12 : 0);
-    w.save = take(training ? tiles * SAVE_TILE_BYTES : 0);
-    w.bytes = off;
-    return w;
-}
 
 // ------------------------------------------------------------------------------------------
 // weight packing: fp32 parameters -> BF16 chunk stream in MMA consumption order + fp32 constants
@@ -142,26 +84,43 @@ __global__ void pack_weights_kernel(const float* __restrict__ P, uint8_t* __rest
     }
 }
 
+// transposed stream of the dX pass: step s, chunk c holds B[n][k] = W_layer[k + rowoff][col0 + n]
+// for k in [32c, 32c+32) as [4 k-groups][N rows][8 bf16]
+__global__ void pack_weights_bwd_kernel(const float* __restrict__ P, uint8_t* __restrict__ stream) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= BSTREAM_BYTES / 16) return;
+    const int64_t byte = gid * 16;
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < NSTEP; ++i) if (byte >= bstream_off(i)) s = i;
+    const int n_rows = step_n(s);
+    const int64_t rel = byte - bstream_off(s);
+    const int chunk = (int)(rel / ((int64_t)n_rows * CHUNK_K * 2));
+    const int64_t in_chunk = rel % ((int64_t)n_rows * CHUNK_K * 2);
+    const int kg = (int)(in_chunk / (n_rows * 16));
+    const int n = (int)((in_chunk % (n_rows * 16)) / 16);
+    const int k0 = chunk * CHUNK_K + kg * 8;
+    const int l = step_layer(s);
+    const int in_dim = layer_in(l);
+    const float* Wl = P + layer_woff(l) + (int64_t)layer_rowoff(l) * in_dim + step_col0(s) + n;
+    const bool ok = n < step_nvalid(s);
+    uint32_t out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = ok ? Wl[(int64_t)(k0 + 2 * j) * in_dim] : 0.f;
+        float b = ok ? Wl[(int64_t)(k0 + 2 * j + 1) * in_dim] : 0.f;
+        out[j] = ptx::pack_bf16(a, b);
+    }
+    *reinterpret_cast<uint4*>(stream + byte) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
 
-// sin / cos of an fp32 argument that may be huge (inverse-depth samples reach |x| ~ 1e8): exact
-// range reduction of the *rounded fp32 argument* in fp64 (so the value matches the reference's
-// sin(fp32(x*freq)) rather than the mathematically exact sin(2^k pi x)), then MUFU on |r| <= pi/2.
-__device__ __forceinline__ void sincos_reduced(float arg, float& s, float& c) {
-    double t = (double)arg * 0.31830988618379067154;
-    long long n = __double2ll_rn(t);
-    float fr = (float)(t - (double)n) * PI_F;
-    s = __sinf(fr); c = __cosf(fr);
-    if (n & 1) { s = -s; c = -c; }
-}
-
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(__expf(x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
-
 // write the 64-wide encoded position of one row into an A-tile image ([8 chunks][128 rows][8 bf16])
-__device__ __forceinline__ void write_enc_row(uint8_t* enc_tile, int row, const float x[3], const Bands3& bw, bool valid) {
+__device__ __forceinline__ void write_enc_row(uint8_t* enc_tile, uint8_t* save_img, int row, const float x[3],
+                                              const Bands3& bw, bool valid) {
     float e[ENC3_PAD];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -180,11 +139,13 @@ __device__ __forceinline__ void write_enc_row(uint8_t* enc_tile, int row, const 
         uint4 v = make_uint4(ptx::pack_bf16(e[ch * 8], e[ch * 8 + 1]), ptx::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]),
                              ptx::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]), ptx::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
         *reinterpret_cast<uint4*>(enc_tile + ch * KROW + row * 16) = v;
+        if (save_img) *reinterpret_cast<uint4*>(save_img + ch * KROW + row * 16) = v;
     }
 }
 
 // write the 32-wide encoded view direction (27 + zero pad) of one row into chunks 0..3 of an enc tile
-__device__ __forceinline__ void write_venc_row(uint8_t* enc_tile, int row, const float v3[3], const BandsV& bw, bool valid) {
+__device__ __forceinline__ void write_venc_row(uint8_t* enc_tile, uint8_t* save_img, int row, const float v3[3],
+                                               const BandsV& bw, bool valid) {
     float e[ENCV_PAD];
     float inv = 1.f / fmaxf(sqrtf(v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2]), 1e-12f);
 #pragma unroll
@@ -206,6 +167,7 @@ __device__ __forceinline__ void write_venc_row(uint8_t* enc_tile, int row, const
         uint4 v = make_uint4(ptx::pack_bf16(e[ch * 8], e[ch * 8 + 1]), ptx::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]),
                              ptx::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]), ptx::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
         *reinterpret_cast<uint4*>(enc_tile + ch * KROW + row * 16) = v;
+        if (save_img) *reinterpret_cast<uint4*>(save_img + ch * KROW + row * 16) = v;
     }
 }
 
@@ -309,6 +271,8 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
             const int64_t tile = pair * 2 + slot;
             const int64_t g = tile * TILE + row;
             const bool valid = tile < ntiles && g < S;
+            uint8_t* save_tile = (save && tile < ntiles) ? save + tile * SAVE_TILE_BYTES : nullptr;
+            uint32_t* mask_tile = save_tile ? reinterpret_cast<uint32_t*>(save_tile + SV_MASK) : nullptr;
             float v3[3] = {0.f, 0.f, 1.f};
             {
                 float x[3] = {0.f, 0.f, 0.f};
@@ -321,11 +285,10 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         x[c] = __fadd_rn(center[r * 3 + c], __fmul_rn(v3[c], d));
                     }
                 }
-                write_enc_row(enc, row, x, bw3, valid);
+                write_enc_row(enc, save_tile ? save_tile + SV_ENC : nullptr, row, x, bw3, valid);
             }
             ptx::fence_proxy_async();
             ptx::mbar_arrive(&a_ready[slot]);
-            uint8_t* save_tile = save ? save + tile * SAVE_TILE_BYTES : nullptr;
             for (int l = 0; l < NLAYER; ++l, ++full_uses) {
                 ptx::mbar_wait(&acc_full[slot], full_uses & 1);
                 ptx::tc_fence_after();
@@ -338,11 +301,14 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         ptx::tmem_ld32(tacc + cc * 32, v);
                         ptx::tmem_ld_wait();
                         uint32_t pk[16];
+                        uint32_t bits = 0;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float a = fmaxf(__uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j], 0.f);
                             float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1], 0.f);
                             pk[j] = ptx::pack_bf16(a, b);
+                            bits |= (a > 0.f ? 1u : 0u) << (2 * j);
+                            bits |= (b > 0.f ? 1u : 0u) << (2 * j + 1);
                             if (l == 6) {   // density head: row 0 of layer 7 applied to h6 (nerf.py:427)
                                 __nv_bfloat162 q = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
                                 sig_acc += cst[C_W7R0 + cc * 32 + 2 * j] * __low2float(q) +
@@ -353,16 +319,18 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         for (int q = 0; q < 4; ++q) {
                             uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
                             *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
-                            if (save_tile && tile < ntiles)
-                                *reinterpret_cast<uint4*>(save_tile + (int64_t)l * ACT_BYTES + (cc * 4 + q) * KROW + row * 16) = o;
+                            if (save_tile)
+                                *reinterpret_cast<uint4*>(save_tile + SV_H + (int64_t)l * ACT_BYTES + (cc * 4 + q) * KROW + row * 16) = o;
                         }
+                        if (mask_tile) mask_tile[(l * MASK_WORDS + cc) * TILE + row] = bits;
                     }
                     if (l == 6 && valid) {
                         float pre = sig_acc + cst[C_MISC];
                         sigma_out[g] = softplus_f(pre);
                         if (sig_pre) sig_pre[g] = pre;
                     }
-                    if (l == 7) write_venc_row(enc, row, v3, bwv, valid);   // A columns 256..287 of rgb0
+                    if (l == 7)   // A columns 256..287 of rgb0
+                        write_venc_row(enc, save_tile ? save_tile + SV_VENC : nullptr, row, v3, bwv, valid);
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
                     ptx::mbar_arrive(&a_ready[slot]);
@@ -375,11 +343,14 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         ptx::tmem_ld32(tacc + cc * 32, v);
                         ptx::tmem_ld_wait();
                         uint32_t pk[16];
+                        uint32_t bits = 0;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float a = fmaxf(__uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j], 0.f);
                             float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1], 0.f);
                             pk[j] = ptx::pack_bf16(a, b);
+                            bits |= (a > 0.f ? 1u : 0u) << (2 * j);
+                            bits |= (b > 0.f ? 1u : 0u) << (2 * j + 1);
                             __nv_bfloat162 q = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
                             float ra = __low2float(q), rb = __high2float(q);
                             const int col = cc * 32 + 2 * j;
@@ -387,11 +358,12 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                             o1 += cst[C_WRGB1 + RGBW + col] * ra + cst[C_WRGB1 + RGBW + col + 1] * rb;
                             o2 += cst[C_WRGB1 + 2 * RGBW + col] * ra + cst[C_WRGB1 + 2 * RGBW + col + 1] * rb;
                         }
-                        if (save_tile && tile < ntiles) {
+                        if (save_tile) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                *reinterpret_cast<uint4*>(save_tile + 8 * (int64_t)ACT_BYTES + (cc * 4 + q) * KROW + row * 16) =
+                                *reinterpret_cast<uint4*>(save_tile + SV_HR + (cc * 4 + q) * KROW + row * 16) =
                                     make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                            mask_tile[(8 * MASK_WORDS + cc) * TILE + row] = bits;
                         }
                     }
                     if (valid) {
@@ -425,6 +397,8 @@ int tc_fwd(const float* P, const float* center, const float* ray, const float* d
     if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
     const int64_t groups = STREAM_BYTES / 16;
     niw::note_launch(), pack_weights_kernel<<<niw_blocks(groups, 256), 256, 0, st>>>(P, w.wstream, w.consts);
+    if (training)
+        niw::note_launch(), pack_weights_bwd_kernel<<<niw_blocks(BSTREAM_BYTES / 16, 256), 256, 0, st>>>(P, w.bstream);
     NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     const int64_t npairs = ((S + TILE - 1) / TILE + 1) / 2;
     int grid = niw_num_sms();
@@ -434,11 +408,6 @@ int tc_fwd(const float* P, const float* center, const float* ray, const float* d
                                              training ? w.save : nullptr);
     NIW_LAUNCH_CHECK();
     return 0;
-}
-
-int tc_bwd(const float*, const float*, const float*, const float*, int64_t, int, const Bands3&, const BandsV&, void*,
-           size_t, const float*, const float*, float*, float*, float*, cudaStream_t) {
-    return NIW_E_UNSUPP;
 }
 
 }  // namespace niw

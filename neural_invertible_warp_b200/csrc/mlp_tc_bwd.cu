@@ -1,0 +1,529 @@
+// Backward of the fused positional-encoding + NeRF MLP on tcgen05 (sm_100a).
+// SURVEY.md section 8 rows a6+a7+a8 (autograd of reference model/nerf.py:416-456).
+//
+// Two kernels:
+//
+//  tc_dx_kernel   activation-gradient chain, one pass over the tiles, same warp roles and
+//                 shared-memory operand images as the forward kernel: the TRANSPOSED weights are
+//                 streamed (bulk async copies) through a ring, G_l = dL/dz_l of a 128-sample tile
+//                 is the K-major A operand, the product lands in TMEM, and the epilogue threads
+//                 (one per sample row) apply the saved ReLU bit masks, re-pack to BF16 as the next
+//                 A operand and store the G image for the weight-gradient pass.  The first step
+//                 (sigmoid/softplus derivatives and the 3->128 rgb layer) and the last one (the
+//                 derivative of the positional encoding and the reduction of d_center / d_ray over
+//                 a ray's samples) run on the CUDA cores in the same threads.
+//
+//  tc_dw_kernel   weight gradients dW_l = G_l^T . X_l as tensor-core GEMMs with K = samples: the
+//                 saved X_l (forward) and G_l (dX pass) tile images are read as MN-major operands
+//                 exactly as they lie in HBM (no transposition), each CTA owns one
+//                 (layer, 128-output-row half, sample slice) and keeps its 128 x 256 fp32
+//                 accumulator in TMEM across all its tiles; bias gradients and the two CUDA-core
+//                 head layers ride along as N = 16 products against a small image holding
+//                 [g_rgb_pre(3), g_sigma_pre, 1].  Slices are summed by tc_dw_reduce_kernel.
+#include "tc_layout.cuh"
+
+namespace niw {
+namespace tc {
+
+// ==========================================================================================
+// dX pass
+// ==========================================================================================
+
+constexpr int BX_NSTAGE = 4;
+constexpr int BX_ACT = 0;                                   // 2 x 64 KB G tiles
+constexpr int BX_RING = BX_ACT + 2 * ACT_BYTES;
+constexpr int BX_CONST = BX_RING + BX_NSTAGE * STAGE_BYTES;  // W7 row 0 [256] + Wrgb1 [3][128]
+constexpr int BX_CONST_FLOATS = WIDTH + 3 * RGBW;
+constexpr int BX_BAR = BX_CONST + BX_CONST_FLOATS * 4;
+constexpr int BX_TOTAL = BX_BAR + 128;
+static_assert(BX_TOTAL <= 227 * 1024, "shared memory budget (dX pass)");
+
+// reduce v over the 32 rows of a warp when they all belong to ray r (uniform), else per-thread atomics
+__device__ __forceinline__ void ray_atomic_add3(float* dst, int64_t r, const float v[3], bool valid, bool uniform) {
+    if (uniform) {
+        float a = warp_sum(valid ? v[0] : 0.f), b = warp_sum(valid ? v[1] : 0.f), c = warp_sum(valid ? v[2] : 0.f);
+        if ((threadIdx.x & 31) == 0 && r >= 0) { atomicAdd(dst + r * 3, a); atomicAdd(dst + r * 3 + 1, b); atomicAdd(dst + r * 3 + 2, c); }
+    } else if (valid) {
+        atomicAdd(dst + r * 3, v[0]); atomicAdd(dst + r * 3 + 1, v[1]); atomicAdd(dst + r * 3 + 2, v[2]);
+    }
+}
+
+__global__ void __launch_bounds__(384, 1)
+tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ consts_g, const float* __restrict__ center,
+             const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N, Bands3 bw3, BandsV bwv,
+             const float* __restrict__ d_rgb, const float* __restrict__ d_sigma, const float* __restrict__ sig_pre,
+             const float* __restrict__ rgb_keep, uint8_t* __restrict__ save, float* __restrict__ scratch,
+             float* __restrict__ dP, float* __restrict__ d_center, float* __restrict__ d_ray) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BX_BAR);
+    uint64_t* w_full = bars;                    // [BX_NSTAGE]
+    uint64_t* w_empty = bars + BX_NSTAGE;       // [BX_NSTAGE]
+    uint64_t* a_ready = bars + 2 * BX_NSTAGE;   // [2]
+    uint64_t* acc_full = a_ready + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    float* cst = reinterpret_cast<float*>(smem + BX_CONST);   // [0,256): W7 row 0; [256, 640): Wrgb1
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (S + TILE - 1) / TILE;
+    const int64_t npairs = (ntiles + 1) / 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BX_NSTAGE; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], TILE); ptx::mbar_init(&acc_full[i], 1); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+    if (warp == 3) for (int i = lane; i < BX_CONST_FLOATS; i += 32) cst[i] = consts_g[C_W7R0 + i];
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= transposed-weight producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+                const uint8_t* src = bstream;
+                for (int s = 0; s < NSTEP; ++s) {
+                    const uint32_t bytes = (uint32_t)step_n(s) * CHUNK_K * 2;
+                    for (int c = 0; c < step_chunks(s); ++c, ++it) {
+                        const uint32_t st = it % BX_NSTAGE, ph = (it / BX_NSTAGE) & 1;
+                        ptx::mbar_wait(&w_empty[st], ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&w_full[st], bytes);
+                        ptx::bulk_g2s(smem + BX_RING + st * STAGE_BYTES, src, bytes, &w_full[st]);
+                        src += bytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, ready_uses = 0;
+            const uint32_t act0 = ptx::smem_addr(smem + BX_ACT), ring0 = ptx::smem_addr(smem + BX_RING);
+            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+                for (int s = 0; s < NSTEP; ++s, ++ready_uses) {
+                    const int rows = step_n(s), nch = step_chunks(s);
+                    const uint32_t idesc = ptx::idesc_bf16(TILE, rows, 0, 0);
+                    for (int c = 0; c < nch; ++c, ++it) {
+                        const uint32_t st = it % BX_NSTAGE, ph = (it / BX_NSTAGE) & 1;
+                        ptx::mbar_wait(&w_full[st], ph);
+                        ptx::tc_fence_after();
+#pragma unroll
+                        for (int sl = 0; sl < 2; ++sl) {
+                            if (c == 0) { ptx::mbar_wait(&a_ready[sl], ready_uses & 1); ptx::tc_fence_after(); }
+                            const uint32_t a_base = act0 + sl * ACT_BYTES + c * (CHUNK_K / 8) * KROW;
+                            const uint32_t b_base = ring0 + st * STAGE_BYTES;
+#pragma unroll
+                            for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
+                                uint64_t ad = ptx::smem_desc(a_base + ks * 2 * KROW, KROW, 128);
+                                uint64_t bd = ptx::smem_desc(b_base + ks * 2 * rows * 16, rows * 16, 128);
+                                ptx::mma_bf16(tmem_base + sl * WIDTH, ad, bd, idesc, (c | ks) != 0);
+                            }
+                            if (c == nch - 1) ptx::mma_commit(&acc_full[sl]);
+                        }
+                        ptx::mma_commit(&w_empty[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue warpgroups (one thread per sample row) =================
+        const int slot = (warp - 4) >> 2;
+        const int row = ((warp & 3) << 5) | lane;
+        uint8_t* act = smem + BX_ACT + slot * ACT_BYTES;
+        const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * WIDTH;
+        float* scr = scratch + ((size_t)blockIdx.x * 2 + slot) * ENC3_PAD * TILE;
+        const bool uniform = (N % 32) == 0;       // the 32 rows of a warp then share one ray
+        uint32_t full_uses = 0;
+        for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+            const int64_t tile = pair * 2 + slot;
+            const int64_t g = tile * TILE + row;
+            const bool valid = tile < ntiles && g < S;
+            const int64_t r = valid ? g / N : -1;
+            uint8_t* rec = tile < ntiles ? save + tile * SAVE_TILE_BYTES : nullptr;
+            const uint32_t* mask = rec ? reinterpret_cast<const uint32_t*>(rec + SV_MASK) : nullptr;
+            // ---- step "-1": derivatives of sigmoid / softplus, the 128->3 layer, G8 -> A tile ----
+            float g3[3] = {0.f, 0.f, 0.f}, gs = 0.f;
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { float y = rgb_keep[g * 3 + c]; g3[c] = d_rgb[g * 3 + c] * y * (1.f - y); }
+                gs = d_sigma[g] * sigmoid_f(sig_pre[g]);             // softplus'(x) = sigmoid(x)
+            }
+            {
+                // bias gradients of the two CUDA-core heads
+                float b0 = warp_sum(g3[0]), b1 = warp_sum(g3[1]), b2 = warp_sum(g3[2]), b3 = warp_sum(gs);
+                if (lane == 0) {
+                    atomicAdd(dP + RGB1_B, b0); atomicAdd(dP + RGB1_B + 1, b1); atomicAdd(dP + RGB1_B + 2, b2);
+                    atomicAdd(dP + feat_b_off(7), b3);
+                }
+            }
+#pragma unroll 1
+            for (int cc = 0; cc < RGBW / 32; ++cc) {
+                const uint32_t bits = mask ? mask[(8 * MASK_WORDS + cc) * TILE + row] : 0u;
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c0 = cc * 32 + 2 * j;
+                    float a = g3[0] * cst[WIDTH + c0] + g3[1] * cst[WIDTH + RGBW + c0] + g3[2] * cst[WIDTH + 2 * RGBW + c0];
+                    float b = g3[0] * cst[WIDTH + c0 + 1] + g3[1] * cst[WIDTH + RGBW + c0 + 1] + g3[2] * cst[WIDTH + 2 * RGBW + c0 + 1];
+                    a = (bits >> (2 * j)) & 1u ? a : 0.f;
+                    b = (bits >> (2 * j + 1)) & 1u ? b : 0.f;
+                    pk[j] = ptx::pack_bf16(a, b);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                    *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
+                    if (rec) *reinterpret_cast<uint4*>(rec + SV_G8 + (cc * 4 + q) * KROW + row * 16) = o;
+                }
+            }
+            if (rec) {
+                // small image: columns [g_rgb_pre(3), g_sigma_pre, 1, 0, 0, 0 | 0 x 8]
+                uint4 o = make_uint4(ptx::pack_bf16(g3[0], g3[1]), ptx::pack_bf16(g3[2], gs),
+                                     ptx::pack_bf16(valid ? 1.f : 0.f, 0.f), 0u);
+                *reinterpret_cast<uint4*>(rec + SV_SMALL + row * 16) = o;
+                *reinterpret_cast<uint4*>(rec + SV_SMALL + KROW + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&a_ready[slot]);
+
+            for (int s = 0; s < NSTEP; ++s, ++full_uses) {
+                ptx::mbar_wait(&acc_full[slot], full_uses & 1);
+                ptx::tc_fence_after();
+                const int lo = step_out_layer(s);
+                if (lo >= 0) {
+                    // ---- hidden layers: (+ density rank-1 term) -> ReLU mask -> BF16 -> next A tile + G image ----
+#pragma unroll 1
+                    for (int cc = 0; cc < WIDTH / 32; ++cc) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(tacc + cc * 32, v);
+                        const uint32_t bits = mask ? mask[(lo * MASK_WORDS + cc) * TILE + row] : 0u;
+                        ptx::tmem_ld_wait();
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+                            if (s == 2) {   // dL/dh6 += g_sigma_pre * W7[0, :]   (density head, nerf.py:427)
+                                a += gs * cst[cc * 32 + 2 * j];
+                                b += gs * cst[cc * 32 + 2 * j + 1];
+                            }
+                            a = (bits >> (2 * j)) & 1u ? a : 0.f;
+                            b = (bits >> (2 * j + 1)) & 1u ? b : 0.f;
+                            pk[j] = ptx::pack_bf16(a, b);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                            *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
+                            if (rec) *reinterpret_cast<uint4*>(rec + SV_G + (int64_t)lo * ACT_BYTES + (cc * 4 + q) * KROW + row * 16) = o;
+                        }
+                    }
+                    ptx::tc_fence_before();
+                    ptx::fence_proxy_async();
+                    ptx::mbar_arrive(&a_ready[slot]);
+                } else if (s == 0) {
+                    // ---- view branch: d(encoded view) -> d(unit view) -> d ray through normalize ----
+                    uint32_t v[32];
+                    ptx::tmem_ld32(tacc, v);
+                    ptx::tmem_ld_wait();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&a_ready[slot]);            // accumulator drained; A tile unchanged
+                    float dr[3] = {0.f, 0.f, 0.f};
+                    if (valid) {
+                        float v3[3] = {ray[r * 3], ray[r * 3 + 1], ray[r * 3 + 2]};
+                        float inv = 1.f / fmaxf(sqrtf(v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2]), 1e-12f);
+                        float u[3] = {v3[0] * inv, v3[1] * inv, v3[2] * inv}, du[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float acc = __uint_as_float(v[c]);
+#pragma unroll
+                            for (int k = 0; k < LV; ++k) {
+                                float f = (float)(1 << k) * PI_F, sn, cs;
+                                sincos_reduced(u[c] * f, sn, cs);
+                                acc += bwv.w[k] * f * (cs * __uint_as_float(v[3 + c * 2 * LV + k]) -
+                                                       sn * __uint_as_float(v[3 + c * 2 * LV + LV + k]));
+                            }
+                            du[c] = acc;
+                        }
+                        float dot = u[0] * du[0] + u[1] * du[1] + u[2] * du[2];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) dr[c] = (du[c] - u[c] * dot) * inv;
+                    }
+                    ray_atomic_add3(d_ray, r, dr, valid, uniform);
+                } else if (s == 5) {
+                    // ---- skip connection: park G4 . W4[:, 256:319] (fp32) until step 10 ----
+#pragma unroll
+                    for (int cc = 0; cc < ENC3_PAD / 32; ++cc) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(tacc + cc * 32, v);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) scr[(cc * 32 + j) * TILE + row] = __uint_as_float(v[j]);
+                    }
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&a_ready[slot]);
+                } else {
+                    // ---- s == 10: d(encoded position) -> d x -> d center, d ray ----
+                    float ge[ENC3_PAD];
+#pragma unroll
+                    for (int cc = 0; cc < ENC3_PAD / 32; ++cc) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(tacc + cc * 32, v);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) ge[cc * 32 + j] = __uint_as_float(v[j]) + scr[(cc * 32 + j) * TILE + row];
+                    }
+                    ptx::tc_fence_before();   // TMEM reads done before the next pair overwrites the accumulator
+                    float dc[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float d = depth[g];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float x = __fadd_rn(center[r * 3 + c], __fmul_rn(ray[r * 3 + c], d));
+                            float acc = ge[c];
+#pragma unroll
+                            for (int k = 0; k < L3; ++k) {
+                                float f = (float)(1 << k) * PI_F, sn, cs;
+                                sincos_reduced(x * f, sn, cs);
+                                acc += bw3.w[k] * f * (cs * ge[3 + c * 2 * L3 + k] - sn * ge[3 + c * 2 * L3 + L3 + k]);
+                            }
+                            dc[c] = acc; dv[c] = acc * d;
+                        }
+                    }
+                    ray_atomic_add3(d_center, r, dc, valid, uniform);
+                    ray_atomic_add3(d_ray, r, dv, valid, uniform);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ==========================================================================================
+// dW pass
+// ==========================================================================================
+
+constexpr int BW_NSTAGE = 2;
+constexpr int BW_A = 0;                                  // 32 KB: 128 features x 128 samples
+constexpr int BW_B = BW_A + HR_BYTES;                    // 64 KB: up to 256 features x 128 samples
+constexpr int BW_S = BW_B + ACT_BYTES;                   // 4 KB small image
+constexpr int BW_STAGE = BW_S + SMALL_BYTES;             // 102400
+constexpr int BW_BAR = BW_NSTAGE * BW_STAGE;
+constexpr int BW_TOTAL = BW_BAR + 64;
+static_assert(BW_TOTAL <= 227 * 1024, "shared memory budget (dW pass)");
+constexpr int BW_SMALL_COL = 256;                        // TMEM columns [256, 272): products with the small image
+
+__global__ void __launch_bounds__(256, 1)
+tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, float* __restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + BW_BAR);   // [BW_NSTAGE]
+    uint64_t* empty = full + BW_NSTAGE;                            // [BW_NSTAGE]
+    uint64_t* done = empty + BW_NSTAGE;                            // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // which unit / slice is this CTA?
+    int ui = 0;
+    for (int i = 0; i < plan.n_units; ++i) if ((int)blockIdx.x >= plan.u[i].first_cta) ui = i;
+    const DwUnit& U = plan.u[ui];
+    const int slice = (int)blockIdx.x - U.first_cta;
+    const int64_t t0 = ntiles * slice / U.n_slices, t1 = ntiles * (slice + 1) / U.n_slices;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BW_NSTAGE; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        ptx::mbar_init(done, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t t = t0; t < t1; ++t, ++it) {
+                const uint32_t st = it % BW_NSTAGE, ph = (it / BW_NSTAGE) & 1;
+                const uint8_t* rec = save + t * SAVE_TILE_BYTES;
+                uint8_t* dst = smem + st * BW_STAGE;
+                ptx::mbar_wait(&empty[st], ph ^ 1);
+                ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)(U.a_bytes + U.b_bytes + SMALL_BYTES));
+                ptx::bulk_g2s(dst + BW_A, rec + U.a_off, (uint32_t)U.a_bytes, &full[st]);
+                if (U.b_bytes) ptx::bulk_g2s(dst + BW_B, rec + U.b_off, (uint32_t)U.b_bytes, &full[st]);
+                ptx::bulk_g2s(dst + BW_S, rec + SV_SMALL, SMALL_BYTES, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_main = ptx::idesc_bf16(TILE, U.n_main > 0 ? U.n_main : 16, 1, 1);
+            const uint32_t idesc_small = ptx::idesc_bf16(TILE, 16, 1, 1);
+            uint32_t it = 0;
+            for (int64_t t = t0; t < t1; ++t, ++it) {
+                const uint32_t st = it % BW_NSTAGE, ph = (it / BW_NSTAGE) & 1;
+                ptx::mbar_wait(&full[st], ph);
+                ptx::tc_fence_after();
+                const uint32_t base = ptx::smem_addr(smem + st * BW_STAGE);
+#pragma unroll
+                for (int ks = 0; ks < TILE / 16; ++ks) {
+                    // MN-major operands, K = samples: 16 samples = 256 B along a row group
+                    const uint64_t ad = ptx::smem_desc(base + BW_A + ks * 256, 128, KROW);
+                    const bool acc = (it | ks) != 0;
+                    if (U.n_main > 0) {
+                        const uint64_t bd = ptx::smem_desc(base + BW_B + ks * 256, 128, KROW);
+                        ptx::mma_bf16(tmem_base, ad, bd, idesc_main, acc);
+                    }
+                    const uint64_t sd = ptx::smem_desc(base + BW_S + ks * 256, 128, KROW);
+                    ptx::mma_bf16(tmem_base + BW_SMALL_COL, ad, sd, idesc_small, acc);
+                }
+                ptx::mma_commit(&empty[st]);
+            }
+            ptx::mma_commit(done);
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: TMEM -> (per-warp transpose in shared memory) -> coalesced partial-sum rows ----
+        ptx::mbar_wait(done, 0);
+        ptx::tc_fence_after();
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;                      // output feature (TMEM lane) of this thread
+        float* out = partial + (size_t)slice * NPARAMS;
+        float* tr = reinterpret_cast<float*>(smem) + wq * (32 * 33);   // stage buffers are idle now
+        const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16);
+        if (t1 > t0) {
+            if (U.kind == 0) {
+                for (int c0 = 0; c0 < U.n_main; c0 += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld32(tacc + c0, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+                    __syncwarp();
+                    const int col = c0 + lane;
+                    if (col < U.ncols) {
+                        for (int rr = 0; rr < 32; ++rr)
+                            out[U.w_base + (int64_t)(wq * 32 + rr) * U.ld + U.col0 + col] = tr[rr * 33 + lane];
+                    }
+                    __syncwarp();
+                }
+            }
+            uint32_t sv[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(sv[0]), "=r"(sv[1]), "=r"(sv[2]), "=r"(sv[3]), "=r"(sv[4]), "=r"(sv[5]), "=r"(sv[6]),
+                           "=r"(sv[7]), "=r"(sv[8]), "=r"(sv[9]), "=r"(sv[10]), "=r"(sv[11]), "=r"(sv[12]), "=r"(sv[13]),
+                           "=r"(sv[14]), "=r"(sv[15])
+                         : "r"(tacc + BW_SMALL_COL) : "memory");
+            ptx::tmem_ld_wait();
+            if (U.kind == 0) {
+                if (U.b_base >= 0) out[U.b_base + row] = __uint_as_float(sv[4]);          // sum_s G[s, row] * 1
+            } else if (U.kind == 1) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) out[RGB1_W + c * RGBW + row] = __uint_as_float(sv[c]);   // hr^T . g_rgb_pre
+            } else {
+                out[U.w_base + row] = __uint_as_float(sv[3]);                              // h6^T . g_sigma_pre
+            }
+        }
+        ptx::tc_fence_before();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// dP[i] += sum over slices of partial[s][i]
+__global__ void tc_dw_reduce_kernel(const float* __restrict__ partial, int n_slices, float* __restrict__ dP) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NPARAMS) return;
+    float acc = 0.f;
+    for (int s = 0; s < n_slices; ++s) acc += partial[(size_t)s * NPARAMS + i];
+    dP[i] += acc;
+}
+
+// ---- host: work plan of the dW pass ----
+static DwPlan make_plan(int64_t ntiles, int n_sms) {
+    DwPlan p;
+    int n = 0;
+    auto add = [&](int a_off, int b_off, int b_bytes, int n_main, int kind, int ld, int col0, int ncols, int64_t w_base,
+                   int64_t b_base) {
+        DwUnit& u = p.u[n++];
+        u.a_off = a_off; u.a_bytes = HR_BYTES; u.b_off = b_off; u.b_bytes = b_bytes; u.n_main = n_main; u.kind = kind;
+        u.ld = ld; u.col0 = col0; u.ncols = ncols; u.pad_ = 0; u.w_base = w_base; u.b_base = b_base;
+        u.first_cta = 0; u.n_slices = 1;
+    };
+    for (int l = 0; l < NFEAT; ++l) {
+        const int ro = layer_rowoff(l);
+        for (int h = 0; h < 2; ++h) {
+            const int a_off = (int)(SV_G + (int64_t)l * ACT_BYTES + h * HR_BYTES);
+            const int64_t w_base = feat_w_off(l) + (int64_t)(ro + h * 128) * feat_in(l);
+            const int64_t b_base = feat_b_off(l) + ro + h * 128;
+            if (l == 0) {
+                add(a_off, (int)SV_ENC, ENC_BYTES, ENC3_PAD, 0, feat_in(l), 0, ENC3, w_base, b_base);
+            } else {
+                add(a_off, (int)(SV_H + (int64_t)(l - 1) * ACT_BYTES), ACT_BYTES, WIDTH, 0, feat_in(l), 0, WIDTH, w_base, b_base);
+                if (l == SKIP) add(a_off, (int)SV_ENC, ENC_BYTES, ENC3_PAD, 0, feat_in(l), WIDTH, ENC3, w_base, -1);
+            }
+        }
+    }
+    add((int)SV_G8, (int)(SV_H + 7 * (int64_t)ACT_BYTES), ACT_BYTES, WIDTH, 0, WIDTH + ENCV, 0, WIDTH, RGB0_W, RGB0_B);
+    add((int)SV_G8, (int)SV_VENC, VENC_BYTES, ENCV_PAD, 0, WIDTH + ENCV, WIDTH, ENCV, RGB0_W, -1);
+    add((int)SV_HR, 0, 0, 0, 1, 0, 0, 0, RGB1_W, -1);                                        // rgb1 weights
+    for (int h = 0; h < 2; ++h)                                                               // density row of layer 7
+        add((int)(SV_H + 6 * (int64_t)ACT_BYTES + h * HR_BYTES), 0, 0, 0, 2, 0, 0, 0, feat_w_off(7) + h * 128, -1);
+    p.n_units = n;
+    // slices proportional to bytes streamed per tile, capped by the tile count and PARTIAL_SLICES
+    double total = 0;
+    for (int i = 0; i < n; ++i) total += p.u[i].a_bytes + p.u[i].b_bytes + SMALL_BYTES;
+    int budget = n_sms > n ? n_sms : n;
+    int used = 0;
+    for (int i = 0; i < n; ++i) {
+        double share = (p.u[i].a_bytes + p.u[i].b_bytes + SMALL_BYTES) / total * budget;
+        int s = (int)share;
+        if (s < 1) s = 1;
+        if (s > PARTIAL_SLICES) s = PARTIAL_SLICES;
+        if (s > ntiles) s = (int)ntiles;
+        p.u[i].n_slices = s; used += s;
+    }
+    for (int pass = 0; pass < 4 && used < budget; ++pass)      // hand out the remainder to the big units
+        for (int i = 0; i < n && used < budget; ++i)
+            if (p.u[i].b_bytes == ACT_BYTES && p.u[i].n_slices < PARTIAL_SLICES && p.u[i].n_slices < ntiles) { ++p.u[i].n_slices; ++used; }
+    int cta = 0, mx = 1;
+    for (int i = 0; i < n; ++i) { p.u[i].first_cta = cta; cta += p.u[i].n_slices; if (p.u[i].n_slices > mx) mx = p.u[i].n_slices; }
+    p.n_ctas = cta; p.max_slices = mx;
+    return p;
+}
+
+}  // namespace tc
+
+int tc_bwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N, const Bands3& b3,
+           const BandsV& bv, void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma, float* dP,
+           float* d_center, float* d_ray, cudaStream_t st) {
+    using namespace tc;
+    (void)P;
+    const int64_t S = R * (int64_t)N;
+    Workspace w = carve(ws, S, true);
+    if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
+    const int64_t ntiles = (S + TILE - 1) / TILE;
+    NIW_CUDA(cudaMemsetAsync(d_center, 0, sizeof(float) * R * 3, st));
+    NIW_CUDA(cudaMemsetAsync(d_ray, 0, sizeof(float) * R * 3, st));
+    NIW_CUDA(cudaFuncSetAttribute(tc_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_TOTAL));
+    const int64_t npairs = (ntiles + 1) / 2;
+    int grid = niw_num_sms();
+    if (grid > npairs) grid = (int)npairs;
+    niw::note_launch(), tc_dx_kernel<<<grid, 384, BX_TOTAL, st>>>(w.bstream, w.consts, center, ray, depth, S, N, b3, bv, d_rgb, d_sigma,
+                                                                 w.sig_pre, w.rgb_keep, w.save, w.scratch, dP, d_center, d_ray);
+    NIW_LAUNCH_CHECK();
+    DwPlan plan = make_plan(ntiles, niw_num_sms());
+    NIW_CUDA(cudaMemsetAsync(w.partial, 0, sizeof(float) * (size_t)plan.max_slices * NPARAMS, st));
+    NIW_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_TOTAL));
+    niw::note_launch(), tc_dw_kernel<<<plan.n_ctas, 256, BW_TOTAL, st>>>(w.save, ntiles, plan, w.partial);
+    NIW_LAUNCH_CHECK();
+    niw::note_launch(), tc_dw_reduce_kernel<<<niw_blocks(NPARAMS, 256), 256, 0, st>>>(w.partial, plan.max_slices, dP);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace niw
