@@ -71,6 +71,21 @@ int niw_raygen_unwarped(const float* intr, const float* pose_init, const int64_t
 #define NIW_NVP_FREQS 6
 #define NIW_NVP_BLOCKS 3
 #define NIW_NVP_BLOCK_FLOATS (128 * 26 + 128 + 1 + 128 * 13 + 3 * 128 + 3)
+/* Parameter packing of the NVP network (the B-sized part of DeformNetwork.forward): resolves the
+ * weight-norm re-parametrisation w = g v/||v||_row (torch.nn.utils.weight_norm, nvp_ndr.py:291-292,335-336),
+ * the code projector code_b = lin{b}_c(code) + code (nvp_ndr.py:382) and folds the latent columns of the
+ * first layers into per-image biases.  `params` / `grads` are HOST arrays of NIW_NVP_PARAM_PTRS device
+ * pointers, 12 per block b in the order
+ *     lin{b}_a_0.weight_v [128,154], .weight_g [128], .bias [128], lin{b}_a_1.weight [1,128], .bias [1],
+ *     lin{b}_b_0.weight_v [128,141], .weight_g [128], .bias [128], lin{b}_b_1.weight [3,128], .bias [3],
+ *     lin{b}_c.weight [128,128], .bias [128]
+ * code [B,128] -> wpack [3*NIW_NVP_BLOCK_FLOATS], code_bias [3,2,B,128], cb [3,B,128] (code_b, kept for backward).
+ * Backward ADDS into the `grads` buffers (the parameters' .grad tensors) and overwrites d_code [B,128]. */
+#define NIW_NVP_PARAM_PTRS 36
+int niw_nvp_pack_fwd(const float* const* params, const float* code, int B, float* wpack, float* code_bias,
+                     float* cb, void* stream);
+int niw_nvp_pack_bwd(const float* const* params, float* const* grads, const float* code, const float* cb,
+                     const float* d_wpack, const float* d_code_bias, int B, float* d_code, void* stream);
 int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                      int B, int Pt, float* out, void* stream);
 int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
@@ -110,18 +125,20 @@ int niw_composite_bwd(const float* ray, const float* rgb_s, const float* sigma, 
  * `params` is the flat fp32 parameter vector in reference state_dict order
  *     mlp_feat.0.weight [256,63], .bias, ..., mlp_feat.7.weight [257,256], .bias,
  *     mlp_rgb.0.weight [128,283], .bias, mlp_rgb.1.weight [3,128], .bias      (NIW_NERF_PARAMS floats; the BARF `progress` scalar is not part of it)
- * band_w3 [10] / band_wv [4] are the coarse-to-fine band weights (all ones without barf_c2f); these two
- * are HOST pointers (the only ones in this ABI): 14 floats the host derives from `progress`.
+ * `progress` is the DEVICE scalar of the BARF coarse-to-fine schedule (model/barf.py:254) and
+ * [c2f_start, c2f_end] is opt.barf_c2f: band k of an L-band encoding is weighted by
+ * (1 - cos(pi clamp((progress-start)/(end-start) L - k, 0, 1)))/2, evaluated on the device (no host read).
+ * progress == NULL: no annealing (plain NeRF, or barf_c2f unset).
  * center/ray [R,3], depth [R,N] -> rgb [R,N,3], sigma [R,N].  `workspace` keeps what backward
  * needs (niw_nerf_workspace_bytes; `training`=0 allows a smaller, forward-only workspace).
  * Backward ADDS into d_params (caller zeroes it once per step) and overwrites d_center, d_ray. */
 #define NIW_NERF_PARAMS 530052
 size_t niw_nerf_workspace_bytes(int64_t R, int N, int precision, int training);
 int niw_nerf_fwd(const float* params, const float* center, const float* ray, const float* depth,
-                 int64_t R, int N, const float* band_w3, const float* band_wv, int precision, int training,
+                 int64_t R, int N, const float* progress, float c2f_start, float c2f_end, int precision, int training,
                  void* workspace, size_t workspace_bytes, float* rgb, float* sigma, void* stream);
 int niw_nerf_bwd(const float* params, const float* center, const float* ray, const float* depth,
-                 int64_t R, int N, const float* band_w3, const float* band_wv, int precision,
+                 int64_t R, int N, int precision,
                  void* workspace, size_t workspace_bytes, const float* d_rgb, const float* d_sigma,
                  float* d_params, float* d_center, float* d_ray, void* stream);
 

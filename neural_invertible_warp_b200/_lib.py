@@ -26,6 +26,8 @@ SIGNATURES = {
     "niw_raygen_pose_fwd": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
     "niw_raygen_pose_bwd": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     "niw_raygen_unwarped": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
+    "niw_nvp_pack_fwd": (_c.c_int, [_P, _P, _c.c_int, _P, _P, _P, _P]),
+    "niw_nvp_pack_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int, _P, _P]),
     "niw_nvp_warp_fwd": (_c.c_int, [_P, _P, _P, _c.c_float, _c.c_int, _c.c_int, _P, _P]),
     "niw_nvp_warp_bwd": (_c.c_int, [_P, _P, _P, _c.c_float, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     "niw_sample_stratified": (_c.c_int, [_P, _c.c_int64, _c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P]),
@@ -33,8 +35,9 @@ SIGNATURES = {
     "niw_composite_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P, _P]),
     "niw_composite_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P, _P, _P]),
     "niw_nerf_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
-    "niw_nerf_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _P, _P, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _P, _P]),
-    "niw_nerf_bwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _P, _P, _c.c_int, _P, _c.c_size_t, _P, _P, _P, _P, _P, _P]),
+    "niw_nerf_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _P, _c.c_float, _c.c_float, _c.c_int, _c.c_int, _P,
+                                _c.c_size_t, _P, _P, _P]),
+    "niw_nerf_bwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _P, _P, _P, _P, _P]),
     "niw_mse_gather": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),
     "niw_tc_selftest": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
 }

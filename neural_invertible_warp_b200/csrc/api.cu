@@ -26,36 +26,34 @@ extern "C" size_t niw_nerf_workspace_bytes(int64_t R, int N, int precision, int 
     return precision == NIW_PREC_BF16 ? tc_workspace_bytes(R, N, training) : fp32_workspace_bytes(R, N, training);
 }
 
-// NOTE band_w3 / band_wv are HOST pointers (10 + 4 floats computed by the host from `progress`,
-// model/barf.py:260-264); they are passed to the kernels by value.
+// `progress` is the DEVICE scalar of the BARF schedule (model/barf.py:254); the band weights of
+// model/barf.py:260-264 are evaluated on the device and kept in the workspace for the backward pass.
 extern "C" int niw_nerf_fwd(const float* params, const float* center, const float* ray, const float* depth, int64_t R,
-                            int N, const float* band_w3, const float* band_wv, int precision, int training,
+                            int N, const float* progress, float c2f_start, float c2f_end, int precision, int training,
                             void* workspace, size_t workspace_bytes, float* rgb, float* sigma, void* stream) {
-    NIW_CHECK_ARG(params && center && ray && depth && band_w3 && band_wv && workspace && rgb && sigma && R > 0 && N > 0);
-    Bands3 b3; BandsV bv;
-    memcpy(b3.w, band_w3, sizeof(b3.w)); memcpy(bv.w, band_wv, sizeof(bv.w));
+    NIW_CHECK_ARG(params && center && ray && depth && workspace && rgb && sigma && R > 0 && N > 0);
+    if (progress && !(c2f_end != c2f_start)) return NIW_E_BADARG;
+    C2F c2f{progress, c2f_start, c2f_end};
     if (precision == NIW_PREC_FP32)
-        return fp32_fwd(params, center, ray, depth, R, N, b3, bv, training, workspace, workspace_bytes, rgb, sigma,
+        return fp32_fwd(params, center, ray, depth, R, N, c2f, training, workspace, workspace_bytes, rgb, sigma,
                         niw_stream(stream));
     if (precision == NIW_PREC_BF16)
-        return tc_fwd(params, center, ray, depth, R, N, b3, bv, training, workspace, workspace_bytes, rgb, sigma,
+        return tc_fwd(params, center, ray, depth, R, N, c2f, training, workspace, workspace_bytes, rgb, sigma,
                       niw_stream(stream));
     return NIW_E_UNSUPP;
 }
 
 extern "C" int niw_nerf_bwd(const float* params, const float* center, const float* ray, const float* depth, int64_t R,
-                            int N, const float* band_w3, const float* band_wv, int precision, void* workspace,
+                            int N, int precision, void* workspace,
                             size_t workspace_bytes, const float* d_rgb, const float* d_sigma, float* d_params,
                             float* d_center, float* d_ray, void* stream) {
-    NIW_CHECK_ARG(params && center && ray && depth && band_w3 && band_wv && workspace && d_rgb && d_sigma && d_params &&
+    NIW_CHECK_ARG(params && center && ray && depth && workspace && d_rgb && d_sigma && d_params &&
                   d_center && d_ray && R > 0 && N > 0);
-    Bands3 b3; BandsV bv;
-    memcpy(b3.w, band_w3, sizeof(b3.w)); memcpy(bv.w, band_wv, sizeof(bv.w));
     if (precision == NIW_PREC_FP32)
-        return fp32_bwd(params, center, ray, depth, R, N, b3, bv, workspace, workspace_bytes, d_rgb, d_sigma, d_params,
+        return fp32_bwd(params, center, ray, depth, R, N, workspace, workspace_bytes, d_rgb, d_sigma, d_params,
                         d_center, d_ray, niw_stream(stream));
     if (precision == NIW_PREC_BF16)
-        return tc_bwd(params, center, ray, depth, R, N, b3, bv, workspace, workspace_bytes, d_rgb, d_sigma, d_params,
+        return tc_bwd(params, center, ray, depth, R, N, workspace, workspace_bytes, d_rgb, d_sigma, d_params,
                       d_center, d_ray, niw_stream(stream));
     return NIW_E_UNSUPP;
 }

@@ -16,10 +16,12 @@ namespace niw {
 
 // one thread per sample: x = c + d*v, enc = [x, per coord: w_k sin(2^k pi x) (k<10), w_k cos(...)]
 __global__ void encode_points_kernel(const float* __restrict__ center, const float* __restrict__ ray,
-                                     const float* __restrict__ depth, int64_t S, int N, Bands3 bw,
+                                     const float* __restrict__ depth, int64_t S, int N, const float* __restrict__ bands,
                                      float* __restrict__ enc) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
+    Bands3 bw; BandsV bwv_unused;
+    load_bands(bands, bw, bwv_unused);
     int64_t r = s / N;
     float d = depth[s];
     float* e = enc + s * ENC3_PAD;
@@ -39,9 +41,16 @@ __global__ void encode_points_kernel(const float* __restrict__ center, const flo
 }
 
 // one thread per ray: view = normalize(ray) (torch F.normalize, eps 1e-12), encoded with L=4
-__global__ void encode_view_kernel(const float* __restrict__ ray, int64_t R, BandsV bw, float* __restrict__ venc) {
+__global__ void bands_kernel(C2F c2f, float* __restrict__ bands) {
+    if (threadIdx.x < NBANDS) store_bands(c2f, threadIdx.x, bands);
+}
+
+__global__ void encode_view_kernel(const float* __restrict__ ray, int64_t R, const float* __restrict__ bands,
+                                   float* __restrict__ venc) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
+    Bands3 bw3_unused; BandsV bw;
+    load_bands(bands, bw3_unused, bw);
     float v[3] = {ray[r * 3], ray[r * 3 + 1], ray[r * 3 + 2]};
     float inv = 1.f / fmaxf(sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-12f);
     float* e = venc + r * ENCV_PAD;
@@ -65,10 +74,12 @@ __global__ void encode_view_kernel(const float* __restrict__ ray, int64_t R, Ban
 // d_venc_s [S,32] (gradient wrt the per-sample copy of the view encoding) and produces
 // d_center [R,3], d_ray [R,3] (the position route x = c + d v and the view route normalize(v)).
 __global__ void encode_bwd_kernel(const float* __restrict__ center, const float* __restrict__ ray,
-                                  const float* __restrict__ depth, int64_t R, int N, Bands3 bw3, BandsV bwv,
+                                  const float* __restrict__ depth, int64_t R, int N, const float* __restrict__ bands,
                                   const float* __restrict__ d_enc, int ld_enc, const float* __restrict__ d_venc_s,
                                   int ld_venc, float* __restrict__ d_center, float* __restrict__ d_ray) {
     const int lane = threadIdx.x & 31;
+    Bands3 bw3; BandsV bwv;
+    load_bands(bands, bw3, bwv);
     int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= R) return;
     float c3[3] = {center[r * 3], center[r * 3 + 1], center[r * 3 + 2]};
@@ -354,13 +365,14 @@ __global__ void softplus_bwd_kernel(const float* __restrict__ d_sigma, const flo
 namespace {
 
 struct Fp32Workspace {
-    float *enc, *venc, *h[NFEAT], *hr, *sig_pre, *rgb_keep, *gA, *gB, *g_enc, *g_venc, *g_hr, *g3, *gs;
+    float *bands, *enc, *venc, *h[NFEAT], *hr, *sig_pre, *rgb_keep, *gA, *gB, *g_enc, *g_venc, *g_hr, *g3, *gs;
 };
 
 size_t carve(Fp32Workspace* w, float* base, int64_t S, int64_t R, bool training) {
     size_t off = 0;
     auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) & ~size_t(63); return p; };
     Fp32Workspace t;
+    t.bands = take(NBANDS);
     t.enc = take(S * ENC3_PAD);
     t.venc = take(R * ENCV_PAD);
     for (int l = 0; l < NFEAT; ++l) t.h[l] = nullptr;
@@ -413,13 +425,14 @@ size_t fp32_workspace_bytes(int64_t R, int N, int training) {
 }
 
 static int fp32_fwd_chunk(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
-                          const Bands3& b3, const BandsV& bv, bool training, float* wsbase, float* rgb, float* sigma,
+                          const C2F& c2f, bool training, float* wsbase, float* rgb, float* sigma,
                           cudaStream_t st) {
     const int64_t S = R * N;
     Fp32Workspace w;
     carve(&w, wsbase, S, R, training);
-    niw::note_launch(), encode_points_kernel<<<niw_blocks(S, 128), 128, 0, st>>>(center, ray, depth, S, N, b3, w.enc);
-    niw::note_launch(), encode_view_kernel<<<niw_blocks(R, 128), 128, 0, st>>>(ray, R, bv, w.venc);
+    niw::note_launch(), bands_kernel<<<1, 32, 0, st>>>(c2f, w.bands);
+    niw::note_launch(), encode_points_kernel<<<niw_blocks(S, 128), 128, 0, st>>>(center, ray, depth, S, N, w.bands, w.enc);
+    niw::note_launch(), encode_view_kernel<<<niw_blocks(R, 128), 128, 0, st>>>(ray, R, w.bands, w.venc);
     for (int l = 0; l < NFEAT; ++l) {
         const float* Wl = P + feat_w_off(l);
         const float* bl = P + feat_b_off(l);
@@ -446,14 +459,14 @@ static int fp32_fwd_chunk(const float* P, const float* center, const float* ray,
 }
 
 int fp32_fwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
-             const Bands3& b3, const BandsV& bv, int training, void* ws, size_t ws_bytes, float* rgb, float* sigma,
+             const C2F& c2f, int training, void* ws, size_t ws_bytes, float* rgb, float* sigma,
              cudaStream_t st) {
     if (ws_bytes < fp32_workspace_bytes(R, N, training)) return NIW_E_WORKSPACE;
-    if (training) return fp32_fwd_chunk(P, center, ray, depth, R, N, b3, bv, true, (float*)ws, rgb, sigma, st);
+    if (training) return fp32_fwd_chunk(P, center, ray, depth, R, N, c2f, true, (float*)ws, rgb, sigma, st);
     const int64_t chunk = fp32_eval_chunk_rays(N);
     for (int64_t r0 = 0; r0 < R; r0 += chunk) {
         int64_t rc = R - r0 < chunk ? R - r0 : chunk;
-        int e = fp32_fwd_chunk(P, center + r0 * 3, ray + r0 * 3, depth + r0 * N, rc, N, b3, bv, false, (float*)ws,
+        int e = fp32_fwd_chunk(P, center + r0 * 3, ray + r0 * 3, depth + r0 * N, rc, N, c2f, false, (float*)ws,
                                rgb + r0 * N * 3, sigma + r0 * N, st);
         if (e) return e;
     }
@@ -461,7 +474,7 @@ int fp32_fwd(const float* P, const float* center, const float* ray, const float*
 }
 
 int fp32_bwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
-             const Bands3& b3, const BandsV& bv, void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma,
+             void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma,
              float* dP, float* d_center, float* d_ray, cudaStream_t st) {
     if (ws_bytes < fp32_workspace_bytes(R, N, 1)) return NIW_E_WORKSPACE;
     const int64_t S = R * N;
@@ -515,7 +528,7 @@ int fp32_bwd(const float* P, const float* center, const float* ray, const float*
         }
         float* t = g; g = gn; gn = t;
     }
-    niw::note_launch(), encode_bwd_kernel<<<niw_blocks(R * 32, 128), 128, 0, st>>>(center, ray, depth, R, N, b3, bv, w.g_enc, ENC3_PAD,
+    niw::note_launch(), encode_bwd_kernel<<<niw_blocks(R * 32, 128), 128, 0, st>>>(center, ray, depth, R, N, w.bands, w.g_enc, ENC3_PAD,
                                                               w.g_venc, ENCV_PAD, d_center, d_ray);
     return (int)cudaPeekAtLastError();
 }

@@ -40,7 +40,8 @@ static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 // ------------------------------------------------------------------------------------------
 // weight packing: fp32 parameters -> BF16 chunk stream in MMA consumption order + fp32 constants
 // ------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ stream, float* __restrict__ consts) {
+__global__ void pack_weights_kernel(const float* __restrict__ P, C2F c2f, uint8_t* __restrict__ stream,
+                                    float* __restrict__ consts) {
     // one thread per 16-byte group (8 consecutive k of one row)
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ngroups = STREAM_BYTES / 16;
@@ -69,6 +70,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ P, uint8_t* __rest
     if (gid < C_FLOATS) {
         int i = (int)gid;
         float v;
+        if (i >= C_BANDS) {
+            store_bands(c2f, i - C_BANDS, consts + C_BANDS);
+            return;
+        }
         if (i < C_W7R0) {
             int l = i / WIDTH, n = i % WIDTH;
             v = n < layer_rows(l) ? P[layer_boff(l) + n + layer_rowoff(l)] : 0.f;
@@ -178,7 +183,7 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(384, 1)
 tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ consts_g, const float* __restrict__ center,
-              const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N, Bands3 bw3, BandsV bwv,
+              const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N,
               float* __restrict__ rgb_out, float* __restrict__ sigma_out, float* __restrict__ sig_pre,
               float* __restrict__ rgb_keep, uint8_t* __restrict__ save) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -205,6 +210,8 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    Bands3 bw3; BandsV bwv;
+    load_bands(cst + C_BANDS, bw3, bwv);
 
     if (warp == 0) {
         // ================= weight producer =================
@@ -389,21 +396,21 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
 
 size_t tc_workspace_bytes(int64_t R, int N, int training) { return tc::carve(nullptr, R * (int64_t)N, training != 0).bytes; }
 
-int tc_fwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N, const Bands3& b3,
-           const BandsV& bv, int training, void* ws, size_t ws_bytes, float* rgb, float* sigma, cudaStream_t st) {
+int tc_fwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N, const C2F& c2f,
+           int training, void* ws, size_t ws_bytes, float* rgb, float* sigma, cudaStream_t st) {
     using namespace tc;
     const int64_t S = R * (int64_t)N;
     Workspace w = carve(ws, S, training != 0);
     if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
     const int64_t groups = STREAM_BYTES / 16;
-    niw::note_launch(), pack_weights_kernel<<<niw_blocks(groups, 256), 256, 0, st>>>(P, w.wstream, w.consts);
+    niw::note_launch(), pack_weights_kernel<<<niw_blocks(groups, 256), 256, 0, st>>>(P, c2f, w.wstream, w.consts);
     if (training)
         niw::note_launch(), pack_weights_bwd_kernel<<<niw_blocks(BSTREAM_BYTES / 16, 256), 256, 0, st>>>(P, w.bstream);
     NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     const int64_t npairs = ((S + TILE - 1) / TILE + 1) / 2;
     int grid = niw_num_sms();
     if (grid > npairs) grid = (int)npairs;
-    niw::note_launch(), tc_fwd_kernel<<<grid, 384, SM_TOTAL, st>>>(w.wstream, w.consts, center, ray, depth, S, N, b3, bv, rgb, sigma,
+    niw::note_launch(), tc_fwd_kernel<<<grid, 384, SM_TOTAL, st>>>(w.wstream, w.consts, center, ray, depth, S, N, rgb, sigma,
                                              training ? w.sig_pre : nullptr, training ? w.rgb_keep : nullptr,
                                              training ? w.save : nullptr);
     NIW_LAUNCH_CHECK();

@@ -33,7 +33,7 @@ constexpr int BX_NSTAGE = 4;
 constexpr int BX_ACT = 0;                                   // 2 x 64 KB G tiles
 constexpr int BX_RING = BX_ACT + 2 * ACT_BYTES;
 constexpr int BX_CONST = BX_RING + BX_NSTAGE * STAGE_BYTES;  // W7 row 0 [256] + Wrgb1 [3][128]
-constexpr int BX_CONST_FLOATS = WIDTH + 3 * RGBW;
+constexpr int BX_CONST_FLOATS = WIDTH + 3 * RGBW + NBANDS;   // ... + band weights
 constexpr int BX_BAR = BX_CONST + BX_CONST_FLOATS * 4;
 constexpr int BX_TOTAL = BX_BAR + 128;
 static_assert(BX_TOTAL <= 227 * 1024, "shared memory budget (dX pass)");
@@ -50,7 +50,7 @@ __device__ __forceinline__ void ray_atomic_add3(float* dst, int64_t r, const flo
 
 __global__ void __launch_bounds__(384, 1)
 tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ consts_g, const float* __restrict__ center,
-             const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N, Bands3 bw3, BandsV bwv,
+             const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N,
              const float* __restrict__ d_rgb, const float* __restrict__ d_sigma, const float* __restrict__ sig_pre,
              const float* __restrict__ rgb_keep, uint8_t* __restrict__ save, float* __restrict__ scratch,
              float* __restrict__ dP, float* __restrict__ d_center, float* __restrict__ d_ray) {
@@ -73,11 +73,16 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
-    if (warp == 3) for (int i = lane; i < BX_CONST_FLOATS; i += 32) cst[i] = consts_g[C_W7R0 + i];
+    if (warp == 3) {
+        for (int i = lane; i < WIDTH + 3 * RGBW; i += 32) cst[i] = consts_g[C_W7R0 + i];
+        if (lane < NBANDS) cst[WIDTH + 3 * RGBW + lane] = consts_g[C_BANDS + lane];
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    Bands3 bw3; BandsV bwv;
+    load_bands(cst + WIDTH + 3 * RGBW, bw3, bwv);
 
     if (warp == 0) {
         // ================= transposed-weight producer =================
@@ -498,8 +503,8 @@ static DwPlan make_plan(int64_t ntiles, int n_sms) {
 
 }  // namespace tc
 
-int tc_bwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N, const Bands3& b3,
-           const BandsV& bv, void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma, float* dP,
+int tc_bwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
+           void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma, float* dP,
            float* d_center, float* d_ray, cudaStream_t st) {
     using namespace tc;
     (void)P;
@@ -513,7 +518,7 @@ int tc_bwd(const float* P, const float* center, const float* ray, const float* d
     const int64_t npairs = (ntiles + 1) / 2;
     int grid = niw_num_sms();
     if (grid > npairs) grid = (int)npairs;
-    niw::note_launch(), tc_dx_kernel<<<grid, 384, BX_TOTAL, st>>>(w.bstream, w.consts, center, ray, depth, S, N, b3, bv, d_rgb, d_sigma,
+    niw::note_launch(), tc_dx_kernel<<<grid, 384, BX_TOTAL, st>>>(w.bstream, w.consts, center, ray, depth, S, N, d_rgb, d_sigma,
                                                                  w.sig_pre, w.rgb_keep, w.save, w.scratch, dP, d_center, d_ray);
     NIW_LAUNCH_CHECK();
     DwPlan plan = make_plan(ntiles, niw_num_sms());

@@ -2,12 +2,20 @@
 //   DeformNetwork.forward    reference model/nvp/nvp_ndr.py:365-468
 //   Embedder.embed (anneal)  reference model/nvp/embedder.py:41-50   (point-index quirk kept)
 //   euler2rot_2dinv          reference model/nvp/nvp_ndr.py:166-174
-// The reference runs ~900 tiny ATen launches per call.  Here one kernel evaluates all three
-// coupling blocks for one point per thread; the per-image latent contribution to each first
-// layer (W[:,emb:] . code_b + bias) is folded into `code_bias` by the host (B x 128, PyTorch),
-// so the kernel only sees the 26- / 13-wide embedded coordinates.  Backward recomputes the
-// forward per block, and reduces weight gradients over the block's 128 points in shared memory
-// (thread j owns hidden unit j) before one atomicAdd per weight per CTA.
+//   weight_norm first layers reference model/nvp/nvp_ndr.py:291-292,335-336
+// The reference issues ~900 tiny ATen launches per call (plus as many again in backward).  Here:
+//
+//   nvp_pack_fwd_kernel   (3 CTAs)  weight-norm resolution w = g v/||v||, code projection
+//                                   code_b = W_c code + b_c + code, and the per-image first-layer
+//                                   biases b_0 + w[:, emb:] code_b  ->  wpack, code_bias
+//   nvp_fwd_kernel        one WARP per point, lanes = hidden units (4 each): all three coupling
+//                         blocks, weights of all blocks resident in shared memory
+//   nvp_bwd_kernel        one warp per point, forward recomputed; weight gradients are
+//                         accumulated in registers over the warp's points (block-outer order),
+//                         reduced across the CTA in shared memory and flushed with one atomic
+//                         per weight per CTA
+//   nvp_pack_bwd_kernel   (3 CTAs)  back through the biases, the code projector and weight-norm,
+//                                   accumulating straight into the parameters' .grad buffers
 #include "common.cuh"
 #include <math.h>
 
@@ -15,8 +23,10 @@ namespace {
 
 constexpr int HID = NIW_NVP_HIDDEN;        // 128
 constexpr int NF = NIW_NVP_FREQS;          // 6
+constexpr int NB = NIW_NVP_BLOCKS;         // 3
 constexpr int EA = 2 * (1 + 2 * NF);       // 26 embedded inputs of part a
 constexpr int EB = 1 * (1 + 2 * NF);       // 13 embedded inputs of part b
+constexpr int DF = 128;                    // latent code width
 constexpr int OFF_W1A = 0;
 constexpr int OFF_W2A = OFF_W1A + HID * EA;
 constexpr int OFF_B2A = OFF_W2A + HID;
@@ -25,8 +35,20 @@ constexpr int OFF_W2B = OFF_W1B + HID * EB;
 constexpr int OFF_B2B = OFF_W2B + 3 * HID;
 constexpr int BLOCK_FLOATS = OFF_B2B + 3;
 static_assert(BLOCK_FLOATS == NIW_NVP_BLOCK_FLOATS, "wpack layout");
-constexpr int PTS = 128;                   // points (= threads) per CTA
 constexpr float BETA = 100.f;
+constexpr float PI_F = 3.14159274101257324f;   // fp32(pi), as the reference's fp32 freq tensor
+constexpr int U = HID / 32;                // hidden units per lane
+
+// shared-memory image of one block's weights with odd row strides (bank-conflict free for
+// lane-strided rows): W1a [128][27], W2a [128], b2a, W1b [128][13], W2b [3][128], b2b [3]
+constexpr int SA = EA + 1;                 // 27
+constexpr int S_W1A = 0;
+constexpr int S_W2A = S_W1A + HID * SA;
+constexpr int S_B2A = S_W2A + HID;
+constexpr int S_W1B = S_B2A + 1;
+constexpr int S_W2B = S_W1B + HID * EB;
+constexpr int S_B2B = S_W2B + 3 * HID;
+constexpr int S_BLOCK = ((S_B2B + 3 + 3) / 4) * 4;   // 5640 floats
 
 struct Bands { float w[NF]; };
 
@@ -46,40 +68,6 @@ __device__ __forceinline__ float quirk_scale(const Bands& bw, int n) {
     return 1.f;
 }
 
-template <int D>
-__device__ __forceinline__ void embed(const float* x, float scale, float* e) {
-#pragma unroll
-    for (int c = 0; c < D; ++c) e[c] = scale * x[c];
-#pragma unroll
-    for (int k = 0; k < NF; ++k) {
-        const float f = (float)(1 << k) * 3.14159274101257324f;  // fp32(pi) * 2^k, as the reference's fp32 freq tensor
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            float s, co;
-            sincosf(x[c] * f, &s, &co);
-            e[D + k * 2 * D + c] = scale * s;
-            e[D + k * 2 * D + D + c] = scale * co;
-        }
-    }
-}
-
-// d(embedding)/dx contracted with de
-template <int D>
-__device__ __forceinline__ void embed_bwd(const float* x, float scale, const float* de, float* dx) {
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-        float acc = de[c];
-#pragma unroll
-        for (int k = 0; k < NF; ++k) {
-            const float f = (float)(1 << k) * 3.14159274101257324f;
-            float s, co;
-            sincosf(x[c] * f, &s, &co);
-            acc += f * (co * de[D + k * 2 * D + c] - s * de[D + k * 2 * D + D + c]);
-        }
-        dx[c] += scale * acc;
-    }
-}
-
 __device__ __forceinline__ void axes(int blk, int& foc, int& o0, int& o1) {
     // form 0 (blocks 0..2): focus z, y, x; the other two in ascending order (nvp_ndr.py:389-399)
     int m = blk % 3;
@@ -88,218 +76,318 @@ __device__ __forceinline__ void axes(int blk, int& foc, int& o0, int& o1) {
     o1 = m == 0 ? 1 : 2;
 }
 
-template <int NIN>
-__device__ __forceinline__ float hidden_pre(const float* __restrict__ W1, const float* __restrict__ bias, int j,
-                                            const float* e) {
-    float pre = bias[j];
+// register-array access with a runtime index, compiled to selects (no local-memory spill)
+__device__ __forceinline__ float sel3(const float x[3], int i) { return i == 0 ? x[0] : (i == 1 ? x[1] : x[2]); }
+__device__ __forceinline__ void put3(float x[3], int i, float v) { if (i == 0) x[0] = v; else if (i == 1) x[1] = v; else x[2] = v; }
+
+__device__ __forceinline__ void load_weights_smem(float* sw, const float* __restrict__ wpack, int nblocks) {
+    for (int b = 0; b < nblocks; ++b) {
+        const float* w = wpack + (size_t)b * BLOCK_FLOATS;
+        float* s = sw + (size_t)b * S_BLOCK;
+        for (int i = threadIdx.x; i < HID * EA; i += blockDim.x) s[S_W1A + (i / EA) * SA + (i % EA)] = w[OFF_W1A + i];
+        for (int i = threadIdx.x; i < HID; i += blockDim.x) s[S_W2A + i] = w[OFF_W2A + i];
+        for (int i = threadIdx.x; i < HID * EB; i += blockDim.x) s[S_W1B + i] = w[OFF_W1B + i];
+        for (int i = threadIdx.x; i < 3 * HID; i += blockDim.x) s[S_W2B + i] = w[OFF_W2B + i];
+        if (threadIdx.x == 0) { s[S_B2A] = w[OFF_B2A]; s[S_B2B] = w[OFF_B2B]; s[S_B2B + 1] = w[OFF_B2B + 1]; s[S_B2B + 2] = w[OFF_B2B + 2]; }
+    }
+}
+
+// embedding of D coordinates into e[D*(1+2NF)], computed cooperatively: lane i < D*NF evaluates
+// one (frequency, coordinate) sin/cos pair; every lane then reads the whole vector from shared memory
+template <int D>
+__device__ __forceinline__ void embed_coop(const float* x, float scale, float* e, int lane) {
+    if (lane < D) e[lane] = scale * ((D == 1 || lane == 0) ? x[0] : x[D - 1]);
+    if (lane < D * NF) {
+        const int k = lane / D, c = lane % D;
+        const float xc = (D == 1 || c == 0) ? x[0] : x[D - 1];
+        float s, co;
+        sincosf(xc * ((float)(1 << k) * PI_F), &s, &co);
+        e[D + k * 2 * D + c] = scale * s;
+        e[D + k * 2 * D + D + c] = scale * co;
+    }
+    __syncwarp();
+}
+
+// d(embedding)/dx contracted with de (every lane holds the full, already reduced de)
+template <int D>
+__device__ __forceinline__ void embed_bwd(const float* x, float scale, const float* de, float* dx) {
 #pragma unroll
-    for (int i = 0; i < NIN; ++i) pre += W1[j * NIN + i] * e[i];
-    return pre;
+    for (int c = 0; c < D; ++c) {
+        float acc = de[c];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) {
+            const float f = (float)(1 << k) * PI_F;
+            float s, co;
+            sincosf(x[c] * f, &s, &co);
+            acc += f * (co * de[D + k * 2 * D + c] - s * de[D + k * 2 * D + D + c]);
+        }
+        dx[c] += scale * acc;
+    }
 }
 
-__device__ __forceinline__ void load_block_weights(float* sw, const float* __restrict__ wpack, int blk) {
-    for (int i = threadIdx.x; i < BLOCK_FLOATS; i += blockDim.x) sw[i] = wpack[blk * BLOCK_FLOATS + i];
-}
+struct BlockFwd { float xo[2]; float xf; float y[2]; float c, s; };
 
-// forward of one coupling block for one point; returns intermediate values needed by backward
-struct BlockFwd { float xo[2]; float xf_in; float xf; float y[2]; float c, s; };
-
-__device__ __forceinline__ BlockFwd block_forward(const float* sw, const float* biasA, const float* biasB,
-                                                  float sa, float sb, float x[3], int blk) {
+// forward of one coupling block for the warp's point; x is replicated in every lane.
+// es: per-warp scratch in shared memory (EA floats)
+__device__ __forceinline__ BlockFwd block_forward(const float* sw, const float* __restrict__ biasA,
+                                                  const float* __restrict__ biasB, float sa, float sb, float x[3], int blk,
+                                                  float* es, int lane) {
     int foc, o0, o1;
     axes(blk, foc, o0, o1);
     BlockFwd r;
-    r.xo[0] = x[o0]; r.xo[1] = x[o1]; r.xf_in = x[foc];
-    float e[EA];
-    embed<2>(r.xo, sa, e);
-    float delta = sw[OFF_B2A];
-    for (int j = 0; j < HID; ++j)
-        delta += sw[OFF_W2A + j] * softplus100(hidden_pre<EA>(sw + OFF_W1A, biasA, j, e));
-    r.xf = r.xf_in - delta;
-    float e2[EB];
-    embed<1>(&r.xf, sb, e2);
-    float o[3] = {sw[OFF_B2B], sw[OFF_B2B + 1], sw[OFF_B2B + 2]};
-    for (int j = 0; j < HID; ++j) {
-        float h = softplus100(hidden_pre<EB>(sw + OFF_W1B, biasB, j, e2));
-        o[0] += sw[OFF_W2B + j] * h; o[1] += sw[OFF_W2B + HID + j] * h; o[2] += sw[OFF_W2B + 2 * HID + j] * h;
+    r.xo[0] = sel3(x, o0); r.xo[1] = sel3(x, o1);
+    __syncwarp();
+    embed_coop<2>(r.xo, sa, es, lane);
+    float part = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int j = lane + 32 * u;
+        float pre = biasA[j];
+        const float* w = sw + S_W1A + j * SA;
+#pragma unroll
+        for (int i = 0; i < EA; ++i) pre += w[i] * es[i];
+        part += sw[S_W2A + j] * softplus100(pre);
     }
-    sincosf(o[0], &r.s, &r.c);
-    r.y[0] = r.xo[0] - o[1]; r.y[1] = r.xo[1] - o[2];
-    x[foc] = r.xf;
-    x[o0] = r.c * r.y[0] + r.s * r.y[1];      // [[c, s], [-s, c]] (euler2rot_2dinv as assembled)
-    x[o1] = -r.s * r.y[0] + r.c * r.y[1];
+    const float delta = sw[S_B2A] + warp_sum(part);
+    r.xf = sel3(x, foc) - delta;
+    __syncwarp();
+    embed_coop<1>(&r.xf, sb, es, lane);
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int j = lane + 32 * u;
+        float pre = biasB[j];
+        const float* w = sw + S_W1B + j * EB;
+#pragma unroll
+        for (int i = 0; i < EB; ++i) pre += w[i] * es[i];
+        const float h = softplus100(pre);
+        p0 += sw[S_W2B + j] * h; p1 += sw[S_W2B + HID + j] * h; p2 += sw[S_W2B + 2 * HID + j] * h;
+    }
+    const float o0v = sw[S_B2B] + warp_sum(p0), o1v = sw[S_B2B + 1] + warp_sum(p1), o2v = sw[S_B2B + 2] + warp_sum(p2);
+    sincosf(o0v, &r.s, &r.c);
+    r.y[0] = r.xo[0] - o1v; r.y[1] = r.xo[1] - o2v;
+    put3(x, foc, r.xf);
+    put3(x, o0, r.c * r.y[0] + r.s * r.y[1]);      // [[c, s], [-s, c]] (euler2rot_2dinv as assembled)
+    put3(x, o1, -r.s * r.y[0] + r.c * r.y[1]);
     return r;
 }
 
-__global__ void __launch_bounds__(PTS)
+constexpr int FWD_WARPS = 8;
+constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)NB * S_BLOCK + FWD_WARPS * 32);
+
+__global__ void __launch_bounds__(FWD_WARPS * 32)
 nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
                Bands bw, int B, int Pt, float* __restrict__ out) {
-    __shared__ float sw[BLOCK_FLOATS];
-    int64_t t = (int64_t)blockIdx.x * PTS + threadIdx.x;
-    bool valid = t < (int64_t)B * Pt;
-    int b = valid ? (int)(t / Pt) : 0, n = valid ? (int)(t % Pt) : 0;
-    float x[3] = {0.f, 0.f, 0.f};
-    if (valid) { x[0] = pts[t * 3]; x[1] = pts[t * 3 + 1]; x[2] = pts[t * 3 + 2]; }
-    float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
-    for (int blk = 0; blk < NIW_NVP_BLOCKS; ++blk) {
-        __syncthreads();
-        load_block_weights(sw, wpack, blk);
-        __syncthreads();
-        const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
-        const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
-        block_forward(sw, biasA, biasB, sa, sb, x, blk);
-    }
-    if (valid) { out[t * 3] = x[0]; out[t * 3 + 1] = x[1]; out[t * 3 + 2] = x[2]; }
-}
-
-// sum_p A[p][j] * V[p][i] for i < ncols, thread j; results atomically added to dst[j*ldj + i*ldi]
-__device__ __forceinline__ void reduce_outer(const float* A, const float* V, int vstride, int ncols, float* dst,
-                                             int ldj, int ldi) {
-    int j = threadIdx.x;
-    for (int i = 0; i < ncols; ++i) {
-        float acc = 0.f;
-        for (int p = 0; p < PTS; ++p) acc += A[p * (HID + 1) + j] * V[p * vstride + i];
-        atomicAdd(dst + (size_t)j * ldj + (size_t)i * ldi, acc);
-    }
-}
-
-// per-image column sums of A (bias gradient): thread j walks the CTA's points in order
-__device__ __forceinline__ void reduce_bias(const float* A, int64_t t0, int Pt, int64_t total, float* dbias_part,
-                                            int B) {
-    int j = threadIdx.x;
-    float acc = 0.f;
-    int cur = -1;
-    for (int p = 0; p < PTS; ++p) {
-        int64_t t = t0 + p;
-        if (t >= total) break;
-        int b = (int)(t / Pt);
-        if (b != cur) {
-            if (cur >= 0) atomicAdd(dbias_part + (size_t)cur * HID + j, acc);
-            cur = b; acc = 0.f;
-        }
-        acc += A[p * (HID + 1) + j];
-    }
-    if (cur >= 0) atomicAdd(dbias_part + (size_t)cur * HID + j, acc);
-}
-
-__global__ void __launch_bounds__(PTS)
-nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
-               Bands bw, int B, int Pt, const float* __restrict__ d_out, float* __restrict__ d_wpack,
-               float* __restrict__ d_code_bias) {
     extern __shared__ float smem[];
-    float* sw = smem;                               // BLOCK_FLOATS (padded to 5512)
-    float* A = smem + 5512;                         // [PTS][HID+1]
-    float* V = A + PTS * (HID + 1);                 // [PTS][EA]  (embedding / dout staging)
+    float* sw = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* es = smem + (size_t)NB * S_BLOCK + warp * 32;
+    load_weights_smem(sw, wpack, NB);
+    __syncthreads();
     const int64_t total = (int64_t)B * Pt;
-    const int64_t t0 = (int64_t)blockIdx.x * PTS;
-    const int64_t t = t0 + threadIdx.x;
-    const bool valid = t < total;
-    const int b = valid ? (int)(t / Pt) : 0, n = valid ? (int)(t % Pt) : 0;
-    const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
-    float xin[NIW_NVP_BLOCKS][3];
-    float x[3] = {0.f, 0.f, 0.f};
-    if (valid) { x[0] = pts[t * 3]; x[1] = pts[t * 3 + 1]; x[2] = pts[t * 3 + 2]; }
-    // pass 0: forward, remembering each block's input
-    for (int blk = 0; blk < NIW_NVP_BLOCKS; ++blk) {
-        __syncthreads();
-        load_block_weights(sw, wpack, blk);
-        __syncthreads();
-        xin[blk][0] = x[0]; xin[blk][1] = x[1]; xin[blk][2] = x[2];
-        if (blk + 1 < NIW_NVP_BLOCKS) {
+    for (int64_t t = (int64_t)blockIdx.x * FWD_WARPS + warp; t < total; t += (int64_t)gridDim.x * FWD_WARPS) {
+        const int b = (int)(t / Pt), n = (int)(t % Pt);
+        float x[3] = {pts[t * 3], pts[t * 3 + 1], pts[t * 3 + 2]};
+        const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
+#pragma unroll 1
+        for (int blk = 0; blk < NB; ++blk) {
             const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
             const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
-            block_forward(sw, biasA, biasB, sa, sb, x, blk);
+            block_forward(sw + (size_t)blk * S_BLOCK, biasA, biasB, sa, sb, x, blk, es, lane);
+        }
+        if (lane < 3) out[t * 3 + lane] = sel3(x, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: block-outer order so that one block's weight-gradient accumulators live in registers
+// ------------------------------------------------------------------------------------------
+constexpr int BWD_WARPS = 8;
+constexpr int MAX_PTS_PER_WARP = 128;     // per-point state kept in shared memory: xin[3][3] + dx[3]
+constexpr int PT_STATE = 12;
+constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)S_BLOCK + BLOCK_FLOATS + BWD_WARPS * 32 +
+                                             (size_t)BWD_WARPS * MAX_PTS_PER_WARP * PT_STATE);
+
+__global__ void __launch_bounds__(BWD_WARPS * 32, 1)
+nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
+               Bands bw, int B, int Pt, int pts_per_warp, const float* __restrict__ d_out, float* __restrict__ d_wpack,
+               float* __restrict__ d_code_bias) {
+    extern __shared__ float smem[];
+    float* sw = smem;                                   // one block's weights (padded image)
+    float* sacc = sw + S_BLOCK;                         // CTA-level gradient accumulators (wpack layout)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* es = sacc + BLOCK_FLOATS + warp * 32;
+    float* state = sacc + BLOCK_FLOATS + BWD_WARPS * 32 + (size_t)warp * MAX_PTS_PER_WARP * PT_STATE;
+    const int64_t total = (int64_t)B * Pt;
+    const int64_t gw = (int64_t)blockIdx.x * BWD_WARPS + warp;
+    const int64_t p0 = gw * pts_per_warp;
+    int np = (int)(total - p0 < pts_per_warp ? total - p0 : pts_per_warp);
+    if (np < 0) np = 0;
+
+    // per-point state in shared memory: stt[3*blk .. 3*blk+2] = input of block blk, stt[9..11] = running gradient
+    // ---- pass 0: forward through blocks 0 .. NB-2 remembering each block's input; dx <- d_out ----
+    for (int blk = 0; blk + 1 < NB; ++blk) {
+        __syncthreads();
+        load_weights_smem(sw, wpack + (size_t)blk * BLOCK_FLOATS, 1);
+        __syncthreads();
+        for (int i = 0; i < np; ++i) {
+            const int64_t t = p0 + i;
+            const int b = (int)(t / Pt), n = (int)(t % Pt);
+            float* stt = state + i * PT_STATE;
+            float x[3];
+            if (blk == 0) {
+                x[0] = pts[t * 3]; x[1] = pts[t * 3 + 1]; x[2] = pts[t * 3 + 2];
+                if (lane < 3) { stt[lane] = sel3(x, lane); stt[9 + lane] = d_out[t * 3 + lane]; }
+            } else {
+                x[0] = stt[blk * 3]; x[1] = stt[blk * 3 + 1]; x[2] = stt[blk * 3 + 2];
+            }
+            const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
+            const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
+            const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
+            block_forward(sw, biasA, biasB, sa, sb, x, blk, es, lane);
+            if (lane < 3) stt[(blk + 1) * 3 + lane] = sel3(x, lane);
+            __syncwarp();
         }
     }
-    float dx[3] = {0.f, 0.f, 0.f};
-    if (valid) { dx[0] = d_out[t * 3]; dx[1] = d_out[t * 3 + 1]; dx[2] = d_out[t * 3 + 2]; }
-    for (int blk = NIW_NVP_BLOCKS - 1; blk >= 0; --blk) {
-        if (blk != NIW_NVP_BLOCKS - 1) {
-            __syncthreads();
-            load_block_weights(sw, wpack, blk);
-            __syncthreads();
-        }
-        const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
-        const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
-        float* dW = d_wpack + (size_t)blk * BLOCK_FLOATS;
-        float* dbA = d_code_bias + (size_t)(blk * 2 + 0) * B * HID;
-        float* dbB = d_code_bias + (size_t)(blk * 2 + 1) * B * HID;
+
+    // ---- passes 2,1,0: backward of one block for all points of the warp ----
+    for (int blk = NB - 1; blk >= 0; --blk) {
+        __syncthreads();
+        load_weights_smem(sw, wpack + (size_t)blk * BLOCK_FLOATS, 1);
+        for (int i = threadIdx.x; i < BLOCK_FLOATS; i += blockDim.x) sacc[i] = 0.f;
+        __syncthreads();
         int foc, o0, o1;
         axes(blk, foc, o0, o1);
-        float xx[3] = {xin[blk][0], xin[blk][1], xin[blk][2]};
-        BlockFwd f = block_forward(sw, biasA, biasB, sa, sb, xx, blk);
-        // ---------------- part b backward ----------------
-        float g0 = dx[o0], g1 = dx[o1];
-        float dy0 = f.c * g0 - f.s * g1, dy1 = f.s * g0 + f.c * g1;
-        float dth = g0 * (-f.s * f.y[0] + f.c * f.y[1]) + g1 * (-f.c * f.y[0] - f.s * f.y[1]);
-        float dout[3] = {dth, -dy0, -dy1};
-        if (!valid) { dout[0] = dout[1] = dout[2] = 0.f; }
-        float dxo[2] = {dy0, dy1};
-        float dxf = dx[foc];
-        float e2[EB];
-        embed<1>(&f.xf, sb, e2);
-        for (int j = 0; j < HID; ++j)
-            A[threadIdx.x * (HID + 1) + j] = valid ? softplus100(hidden_pre<EB>(sw + OFF_W1B, biasB, j, e2)) : 0.f;
-        V[threadIdx.x * EA + 0] = dout[0]; V[threadIdx.x * EA + 1] = dout[1]; V[threadIdx.x * EA + 2] = dout[2];
-        __syncthreads();
-        reduce_outer(A, V, EA, 3, dW + OFF_W2B, 1, HID);               // dW2b[m][j]
-        if (threadIdx.x < 3) {
-            float acc = 0.f;
-            for (int p = 0; p < PTS; ++p) acc += V[p * EA + threadIdx.x];
-            atomicAdd(dW + OFF_B2B + threadIdx.x, acc);
+        float aW1a[U][EA], aW1b[U][EB], aW2a[U], aW2b[U][3], ab2a = 0.f, ab2b[3] = {0.f, 0.f, 0.f};
+        float abA[U], abB[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            aW2a[u] = 0.f; abA[u] = 0.f; abB[u] = 0.f;
+#pragma unroll
+            for (int i = 0; i < EA; ++i) aW1a[u][i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < EB; ++i) aW1b[u][i] = 0.f;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) aW2b[u][m] = 0.f;
+        }
+        int cur_img = -1;
+        float* dbA = d_code_bias + (size_t)(blk * 2 + 0) * B * HID;
+        float* dbB = d_code_bias + (size_t)(blk * 2 + 1) * B * HID;
+        for (int i = 0; i < np; ++i) {
+            const int64_t t = p0 + i;
+            const int b = (int)(t / Pt), n = (int)(t % Pt);
+            if (b != cur_img) {
+                if (cur_img >= 0) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        atomicAdd(dbA + (size_t)cur_img * HID + lane + 32 * u, abA[u]);
+                        atomicAdd(dbB + (size_t)cur_img * HID + lane + 32 * u, abB[u]);
+                        abA[u] = 0.f; abB[u] = 0.f;
+                    }
+                }
+                cur_img = b;
+            }
+            float* stt = state + i * PT_STATE;
+            __syncwarp();
+            float x[3] = {stt[blk * 3], stt[blk * 3 + 1], stt[blk * 3 + 2]};
+            float dx[3] = {stt[9], stt[10], stt[11]};
+            const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
+            const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
+            const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
+            float xx[3] = {x[0], x[1], x[2]};
+            const BlockFwd f = block_forward(sw, biasA, biasB, sa, sb, xx, blk, es, lane);
+            // ---------------- part b backward ----------------
+            const float g0 = sel3(dx, o0), g1 = sel3(dx, o1);
+            const float dy0 = f.c * g0 - f.s * g1, dy1 = f.s * g0 + f.c * g1;
+            const float dth = g0 * (-f.s * f.y[0] + f.c * f.y[1]) + g1 * (-f.c * f.y[0] - f.s * f.y[1]);
+            const float dout[3] = {dth, -dy0, -dy1};
+            float dxo[2] = {dy0, dy1};
+            float dxf = sel3(dx, foc);
+            // es currently holds embed<1>(xf) (left there by block_forward)
+            float de2[EB];
+#pragma unroll
+            for (int q = 0; q < EB; ++q) de2[q] = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = lane + 32 * u;
+                float pre = biasB[j];
+                const float* w = sw + S_W1B + j * EB;
+#pragma unroll
+                for (int q = 0; q < EB; ++q) pre += w[q] * es[q];
+                const float h = softplus100(pre);
+                const float dh = sw[S_W2B + j] * dout[0] + sw[S_W2B + HID + j] * dout[1] + sw[S_W2B + 2 * HID + j] * dout[2];
+                const float dpre = dh * softplus100_grad(pre);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) aW2b[u][m] += dout[m] * h;
+                abB[u] += dpre;
+#pragma unroll
+                for (int q = 0; q < EB; ++q) { aW1b[u][q] += dpre * es[q]; de2[q] += w[q] * dpre; }
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m) ab2b[m] += dout[m];
+#pragma unroll
+            for (int q = 0; q < EB; ++q) de2[q] = warp_sum(de2[q]);
+            embed_bwd<1>(&f.xf, sb, de2, &dxf);
+            // ---------------- part a backward ----------------
+            const float ddelta = -dxf;
+            __syncwarp();
+            embed_coop<2>(f.xo, sa, es, lane);
+            float de[EA];
+#pragma unroll
+            for (int q = 0; q < EA; ++q) de[q] = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = lane + 32 * u;
+                float pre = biasA[j];
+                const float* w = sw + S_W1A + j * SA;
+#pragma unroll
+                for (int q = 0; q < EA; ++q) pre += w[q] * es[q];
+                const float h = softplus100(pre);
+                const float dpre = sw[S_W2A + j] * ddelta * softplus100_grad(pre);
+                aW2a[u] += ddelta * h;
+                abA[u] += dpre;
+#pragma unroll
+                for (int q = 0; q < EA; ++q) { aW1a[u][q] += dpre * es[q]; de[q] += w[q] * dpre; }
+            }
+            ab2a += ddelta;
+#pragma unroll
+            for (int q = 0; q < EA; ++q) de[q] = warp_sum(de[q]);
+            embed_bwd<2>(f.xo, sa, de, dxo);
+            __syncwarp();
+            if (lane == 0) { stt[9 + foc] = dxf; stt[9 + o0] = dxo[0]; stt[9 + o1] = dxo[1]; }
+        }
+        if (cur_img >= 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                atomicAdd(dbA + (size_t)cur_img * HID + lane + 32 * u, abA[u]);
+                atomicAdd(dbB + (size_t)cur_img * HID + lane + 32 * u, abB[u]);
+            }
+        }
+        // ---- CTA-level reduction in shared memory, then one global atomic per weight ----
+        if (np > 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = lane + 32 * u;
+#pragma unroll
+                for (int q = 0; q < EA; ++q) atomicAdd(sacc + OFF_W1A + j * EA + q, aW1a[u][q]);
+#pragma unroll
+                for (int q = 0; q < EB; ++q) atomicAdd(sacc + OFF_W1B + j * EB + q, aW1b[u][q]);
+                atomicAdd(sacc + OFF_W2A + j, aW2a[u]);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) atomicAdd(sacc + OFF_W2B + m * HID + j, aW2b[u][m]);
+            }
+            if (lane == 0) {
+                atomicAdd(sacc + OFF_B2A, ab2a);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) atomicAdd(sacc + OFF_B2B + m, ab2b[m]);
+            }
         }
         __syncthreads();
-        float de2[EB];
-#pragma unroll
-        for (int i = 0; i < EB; ++i) de2[i] = 0.f;
-        for (int j = 0; j < HID; ++j) {
-            float pre = hidden_pre<EB>(sw + OFF_W1B, biasB, j, e2);
-            float dh = sw[OFF_W2B + j] * dout[0] + sw[OFF_W2B + HID + j] * dout[1] + sw[OFF_W2B + 2 * HID + j] * dout[2];
-            float dpre = dh * softplus100_grad(pre);
-            A[threadIdx.x * (HID + 1) + j] = dpre;
-#pragma unroll
-            for (int i = 0; i < EB; ++i) de2[i] += sw[OFF_W1B + j * EB + i] * dpre;
+        float* dW = d_wpack + (size_t)blk * BLOCK_FLOATS;
+        for (int i = threadIdx.x; i < BLOCK_FLOATS; i += blockDim.x) {
+            const float v = sacc[i];
+            if (v != 0.f) atomicAdd(dW + i, v);
         }
-#pragma unroll
-        for (int i = 0; i < EB; ++i) V[threadIdx.x * EA + i] = valid ? e2[i] : 0.f;
-        __syncthreads();
-        reduce_outer(A, V, EA, EB, dW + OFF_W1B, EB, 1);               // dW1b[j][i]
-        reduce_bias(A, t0, Pt, total, dbB, B);
-        __syncthreads();
-        embed_bwd<1>(&f.xf, sb, de2, &dxf);
-        // ---------------- part a backward ----------------
-        float ddelta = valid ? -dxf : 0.f;
-        float e[EA];
-        embed<2>(f.xo, sa, e);
-        for (int j = 0; j < HID; ++j)
-            A[threadIdx.x * (HID + 1) + j] = valid ? softplus100(hidden_pre<EA>(sw + OFF_W1A, biasA, j, e)) : 0.f;
-        V[threadIdx.x * EA + 0] = ddelta;
-        __syncthreads();
-        reduce_outer(A, V, EA, 1, dW + OFF_W2A, 1, HID);                // dW2a[j]
-        if (threadIdx.x == 0) {
-            float acc = 0.f;
-            for (int p = 0; p < PTS; ++p) acc += V[p * EA];
-            atomicAdd(dW + OFF_B2A, acc);
-        }
-        __syncthreads();
-        float de[EA];
-#pragma unroll
-        for (int i = 0; i < EA; ++i) de[i] = 0.f;
-        for (int j = 0; j < HID; ++j) {
-            float pre = hidden_pre<EA>(sw + OFF_W1A, biasA, j, e);
-            float dpre = sw[OFF_W2A + j] * ddelta * softplus100_grad(pre);
-            A[threadIdx.x * (HID + 1) + j] = dpre;
-#pragma unroll
-            for (int i = 0; i < EA; ++i) de[i] += sw[OFF_W1A + j * EA + i] * dpre;
-        }
-#pragma unroll
-        for (int i = 0; i < EA; ++i) V[threadIdx.x * EA + i] = valid ? e[i] : 0.f;
-        __syncthreads();
-        reduce_outer(A, V, EA, EA, dW + OFF_W1A, EA, 1);               // dW1a[j][i]
-        reduce_bias(A, t0, Pt, total, dbA, B);
-        __syncthreads();
-        embed_bwd<2>(f.xo, sa, de, dxo);
-        dx[foc] = dxf; dx[o0] = dxo[0]; dx[o1] = dxo[1];
     }
 }
 
@@ -313,16 +401,189 @@ Bands make_bands(float alpha_ratio) {
     return bw;
 }
 
-constexpr size_t BWD_SMEM = sizeof(float) * (5512 + PTS * (HID + 1) + PTS * EA);
+// ------------------------------------------------------------------------------------------
+// pack: parameters -> effective weights + per-image biases, and its backward
+// ------------------------------------------------------------------------------------------
+// pointer table, per block b (12 entries): v_a, g_a, b0_a, W1_a, b1_a, v_b, g_b, b0_b, W1_b, b1_b, W_c, b_c
+struct PtrTable { const float* p[NIW_NVP_PARAM_PTRS]; };
+struct GradTable { float* p[NIW_NVP_PARAM_PTRS]; };
+constexpr int MAX_IMG = 96;                // images per call (dynamic shared memory: ~2 KB per image)
+constexpr int LDC = DF + 1;
+
+__global__ void __launch_bounds__(256)
+nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, float* __restrict__ wpack,
+                    float* __restrict__ code_bias, float* __restrict__ cb_out) {
+    extern __shared__ float s_cb[];            // [B][LDC]
+    const int blk = blockIdx.x, tid = threadIdx.x;
+    const float* const* P = T.p + blk * 12;
+    const float *Wc = P[10], *bc = P[11];
+    float* wp = wpack + (size_t)blk * BLOCK_FLOATS;
+    // code_b[img][k] = code + b_c + W_c code      (nvp_ndr.py:382)
+    for (int idx = tid; idx < B * DF; idx += blockDim.x) {
+        const int img = idx / DF, k = idx % DF;
+        const float* c = code + (size_t)img * DF;
+        float acc = c[k] + bc[k];
+        for (int m = 0; m < DF; ++m) acc += Wc[(size_t)k * DF + m] * c[m];
+        s_cb[img * LDC + k] = acc;
+        cb_out[((size_t)blk * B + img) * DF + k] = acc;
+    }
+    // effective first-layer weights (embedded-coordinate columns) and the output layers
+    const int part = tid >> 7, j = tid & 127;                  // thread = (part, hidden unit)
+    const int emb = part == 0 ? EA : EB, ld = emb + DF;
+    const float* v = P[part * 5 + 0] + (size_t)j * ld;
+    float nrm2 = 0.f;
+    for (int c = 0; c < ld; ++c) nrm2 += v[c] * v[c];
+    const float scale = P[part * 5 + 1][j] / sqrtf(nrm2);
+    for (int c = 0; c < emb; ++c) wp[(part == 0 ? OFF_W1A : OFF_W1B) + j * emb + c] = v[c] * scale;
+    if (part == 0) {
+        wp[OFF_W2A + j] = P[3][j];
+        if (j == 0) wp[OFF_B2A] = P[4][0];
+    } else {
+        for (int m = 0; m < 3; ++m) wp[OFF_W2B + m * HID + j] = P[8][m * HID + j];
+        if (j < 3) wp[OFF_B2B + j] = P[9][j];
+    }
+    __syncthreads();
+    const float b0 = P[part * 5 + 2][j];
+    for (int img = 0; img < B; ++img) {
+        float acc = 0.f;
+        for (int k = 0; k < DF; ++k) acc += v[emb + k] * s_cb[img * LDC + k];
+        code_bias[((size_t)(blk * 2 + part) * B + img) * HID + j] = b0 + scale * acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, const float* __restrict__ cb, int B,
+                    const float* __restrict__ d_wpack, const float* __restrict__ d_code_bias, float* __restrict__ d_code) {
+    extern __shared__ float sm[];
+    float* s_cb = sm;                          // [B][LDC]      code_b
+    float* s_dcb = s_cb + (size_t)B * LDC;     // [2][B][LDC]   d(code_bias) of both parts
+    float* s_dc = s_dcb + 2 * (size_t)B * LDC; // [B][LDC]      d(code_b)
+    float* s_scale = s_dc + (size_t)B * LDC;   // [2][HID]
+    const int blk = blockIdx.x, tid = threadIdx.x;
+    const float* const* P = T.p + blk * 12;
+    float* const* Gp = G.p + blk * 12;
+    const float* dwp = d_wpack + (size_t)blk * BLOCK_FLOATS;
+    const int part = tid >> 7, j = tid & 127;
+    const int emb = part == 0 ? EA : EB, ld = emb + DF;
+    const float* v = P[part * 5 + 0] + (size_t)j * ld;
+    const float g = P[part * 5 + 1][j];
+    float nrm2 = 0.f;
+    for (int c = 0; c < ld; ++c) nrm2 += v[c] * v[c];
+    const float nrm = sqrtf(nrm2), scale = g / nrm;
+    s_scale[part * HID + j] = scale;
+    for (int idx = tid; idx < B * DF; idx += blockDim.x) s_cb[(idx / DF) * LDC + idx % DF] = cb[(size_t)blk * B * DF + idx];
+    for (int idx = tid; idx < 2 * B * HID; idx += blockDim.x) {
+        const int p = idx / (B * HID), r = idx % (B * HID);
+        s_dcb[((size_t)p * B + r / HID) * LDC + r % HID] = d_code_bias[((size_t)(blk * 2 + p) * B) * HID + r];
+    }
+    // output layers: the gradient is the kernel's own (every element has exactly one writer here)
+    if (part == 0) {
+        Gp[3][j] += dwp[OFF_W2A + j];
+        if (j == 0) Gp[4][0] += dwp[OFF_B2A];
+    } else {
+        for (int m = 0; m < 3; ++m) Gp[8][m * HID + j] += dwp[OFF_W2B + m * HID + j];
+        if (j < 3) Gp[9][j] += dwp[OFF_B2B + j];
+    }
+    __syncthreads();
+    // d b0[j] = sum_img dcb ; d w0[j][emb+k] = sum_img dcb[img][j] cb[img][k]
+    const float* my_dcb = s_dcb + (size_t)part * B * LDC + j;
+    float db0 = 0.f;
+    for (int img = 0; img < B; ++img) db0 += my_dcb[img * LDC];
+    Gp[part * 5 + 2][j] += db0;
+    const float* dW1 = dwp + (part == 0 ? OFF_W1A : OFF_W1B) + j * emb;
+    float dot = 0.f;
+    for (int c = 0; c < emb; ++c) dot += dW1[c] * v[c];
+    for (int k = 0; k < DF; ++k) {
+        float dw = 0.f;
+        for (int img = 0; img < B; ++img) dw += my_dcb[img * LDC] * s_cb[img * LDC + k];
+        dot += dw * v[emb + k];
+    }
+    // weight-norm backward: w = g v/||v||
+    Gp[part * 5 + 1][j] += dot / nrm;
+    float* dv = Gp[part * 5 + 0] + (size_t)j * ld;
+    const float coef = dot / nrm2;
+    for (int c = 0; c < emb; ++c) dv[c] += scale * (dW1[c] - v[c] * coef);
+    for (int k = 0; k < DF; ++k) {
+        float dw = 0.f;
+        for (int img = 0; img < B; ++img) dw += my_dcb[img * LDC] * s_cb[img * LDC + k];
+        dv[emb + k] += scale * (dw - v[emb + k] * coef);
+    }
+    // d code_b[img][k] = sum_part sum_j dcb[part][img][j] w0[j][emb+k]
+    for (int idx = tid; idx < B * DF; idx += blockDim.x) {
+        const int img = idx / DF, k = idx % DF;
+        float acc = 0.f;
+        for (int p = 0; p < 2; ++p) {
+            const int e2 = p == 0 ? EA : EB, l2 = e2 + DF;
+            const float* vp = P[p * 5 + 0] + e2 + k;
+            const float* d = s_dcb + ((size_t)p * B + img) * LDC;
+            for (int jj = 0; jj < HID; ++jj) acc += d[jj] * vp[(size_t)jj * l2] * s_scale[p * HID + jj];
+        }
+        s_dc[img * LDC + k] = acc;
+    }
+    __syncthreads();
+    // code projector: code_b = W_c code + b_c + code
+    const float* Wc = P[10];
+    for (int idx = tid; idx < DF * DF; idx += blockDim.x) {
+        const int k = idx / DF, m = idx % DF;
+        float acc = 0.f;
+        for (int img = 0; img < B; ++img) acc += s_dc[img * LDC + k] * code[(size_t)img * DF + m];
+        Gp[10][idx] += acc;
+    }
+    for (int k = tid; k < DF; k += blockDim.x) {
+        float acc = 0.f;
+        for (int img = 0; img < B; ++img) acc += s_dc[img * LDC + k];
+        Gp[11][k] += acc;
+    }
+    for (int idx = tid; idx < B * DF; idx += blockDim.x) {
+        const int img = idx / DF, m = idx % DF;
+        float acc = s_dc[img * LDC + m];
+        for (int k = 0; k < DF; ++k) acc += s_dc[img * LDC + k] * Wc[(size_t)k * DF + m];
+        atomicAdd(d_code + idx, acc);        // three blocks (CTAs) contribute
+    }
+}
 
 }  // namespace
+
+extern "C" int niw_nvp_pack_fwd(const float* const* params, const float* code, int B, float* wpack, float* code_bias,
+                                float* cb, void* stream) {
+    NIW_CHECK_ARG(params && code && wpack && code_bias && cb && B > 0);
+    PtrTable T;
+    for (int i = 0; i < NIW_NVP_PARAM_PTRS; ++i) { NIW_CHECK_ARG(params[i]); T.p[i] = params[i]; }
+    if (B > MAX_IMG) return NIW_E_UNSUPP;
+    const size_t smem = sizeof(float) * (size_t)B * LDC;
+    if (smem > 48 * 1024)
+        NIW_CUDA(cudaFuncSetAttribute(nvp_pack_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    niw::note_launch(), nvp_pack_fwd_kernel<<<NB, 256, smem, niw_stream(stream)>>>(T, code, B, wpack, code_bias, cb);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int niw_nvp_pack_bwd(const float* const* params, float* const* grads, const float* code, const float* cb,
+                                const float* d_wpack, const float* d_code_bias, int B, float* d_code, void* stream) {
+    NIW_CHECK_ARG(params && grads && code && cb && d_wpack && d_code_bias && d_code && B > 0);
+    if (B > MAX_IMG) return NIW_E_UNSUPP;
+    PtrTable T; GradTable G;
+    for (int i = 0; i < NIW_NVP_PARAM_PTRS; ++i) { NIW_CHECK_ARG(params[i] && grads[i]); T.p[i] = params[i]; G.p[i] = grads[i]; }
+    cudaStream_t st = niw_stream(stream);
+    NIW_CUDA(cudaMemsetAsync(d_code, 0, sizeof(float) * (size_t)B * DF, st));
+    const size_t smem = sizeof(float) * (4 * (size_t)B * LDC + 2 * HID);
+    if (smem > 48 * 1024)
+        NIW_CUDA(cudaFuncSetAttribute(nvp_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    niw::note_launch(), nvp_pack_bwd_kernel<<<NB, 256, smem, st>>>(T, G, code, cb, B, d_wpack, d_code_bias, d_code);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                                 int B, int Pt, float* out, void* stream) {
     NIW_CHECK_ARG(wpack && code_bias && pts && out && B > 0 && Pt > 0);
-    int64_t total = (int64_t)B * Pt;
-    niw::note_launch(), nvp_fwd_kernel<<<niw_blocks(total, PTS), PTS, 0, niw_stream(stream)>>>(wpack, code_bias, pts,
-                                                                          make_bands(alpha_ratio), B, Pt, out);
+    const int64_t total = (int64_t)B * Pt;
+    NIW_CUDA(cudaFuncSetAttribute(nvp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
+    int64_t blocks = (total + FWD_WARPS - 1) / FWD_WARPS;
+    const int64_t cap = (int64_t)niw_num_sms() * 2;
+    if (blocks > cap) blocks = cap;
+    niw::note_launch(), nvp_fwd_kernel<<<(unsigned)blocks, FWD_WARPS * 32, FWD_SMEM, niw_stream(stream)>>>(
+        wpack, code_bias, pts, make_bands(alpha_ratio), B, Pt, out);
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -331,12 +592,19 @@ extern "C" int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, cons
                                 int B, int Pt, const float* d_out, float* d_wpack, float* d_code_bias, void* stream) {
     NIW_CHECK_ARG(wpack && code_bias && pts && d_out && d_wpack && d_code_bias && B > 0 && Pt > 0);
     cudaStream_t st = niw_stream(stream);
-    NIW_CUDA(cudaMemsetAsync(d_wpack, 0, sizeof(float) * NIW_NVP_BLOCKS * BLOCK_FLOATS, st));
-    NIW_CUDA(cudaMemsetAsync(d_code_bias, 0, sizeof(float) * NIW_NVP_BLOCKS * 2 * (size_t)B * HID, st));
+    NIW_CUDA(cudaMemsetAsync(d_wpack, 0, sizeof(float) * NB * BLOCK_FLOATS, st));
+    NIW_CUDA(cudaMemsetAsync(d_code_bias, 0, sizeof(float) * NB * 2 * (size_t)B * HID, st));
     NIW_CUDA(cudaFuncSetAttribute(nvp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-    int64_t total = (int64_t)B * Pt;
-    niw::note_launch(), nvp_bwd_kernel<<<niw_blocks(total, PTS), PTS, BWD_SMEM, st>>>(wpack, code_bias, pts, make_bands(alpha_ratio), B, Pt,
-                                                                 d_out, d_wpack, d_code_bias);
+    const int64_t total = (int64_t)B * Pt;
+    // points per warp: enough to amortise the per-CTA gradient flush, few enough to fill the GPU
+    const int64_t warps_max = (int64_t)niw_num_sms() * BWD_WARPS;
+    int64_t ppw = (total + warps_max - 1) / warps_max;
+    if (ppw < 8) ppw = 8;
+    if (ppw > MAX_PTS_PER_WARP) ppw = MAX_PTS_PER_WARP;
+    const int64_t warps = (total + ppw - 1) / ppw;
+    const int64_t blocks = (warps + BWD_WARPS - 1) / BWD_WARPS;
+    niw::note_launch(), nvp_bwd_kernel<<<(unsigned)blocks, BWD_WARPS * 32, BWD_SMEM, st>>>(
+        wpack, code_bias, pts, make_bands(alpha_ratio), B, Pt, (int)ppw, d_out, d_wpack, d_code_bias);
     NIW_LAUNCH_CHECK();
     return 0;
 }

@@ -32,7 +32,8 @@ constexpr int C_BIAS = 0;                         // [9][256]
 constexpr int C_W7R0 = C_BIAS + NLAYER * WIDTH;   // [256]  density row of layer 7
 constexpr int C_WRGB1 = C_W7R0 + WIDTH;           // [3][128]
 constexpr int C_MISC = C_WRGB1 + 3 * RGBW;        // b7[0], brgb1[0..2]
-constexpr int C_FLOATS = C_MISC + 4;
+constexpr int C_BANDS = C_MISC + 4;               // [NBANDS] coarse-to-fine band weights (evaluated on the device)
+constexpr int C_FLOATS = C_BANDS + NBANDS;
 
 // ---- per-tile record saved by the forward pass (training) and extended by the dX pass ---------
 constexpr int64_t SV_H = 0;                                  // h0..h7 images

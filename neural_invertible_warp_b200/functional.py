@@ -300,13 +300,19 @@ def band_weights(progress, c2f, L):
 
 
 class _NerfSamples(torch.autograd.Function):
+    """``flat`` is the 530 052-float parameter vector the kernels read.  Two ways to receive its
+    gradient: (a) ``flat`` itself requires grad (functional use, tests) -> returned through autograd;
+    (b) ``module`` is a NeRFCore whose ``nn.Linear`` parameters (passed as ``*params`` so autograd knows
+    the output depends on them) own a flat gradient buffer -> the kernels accumulate straight into it
+    and None is returned for the parameters (no per-parameter accumulate launches)."""
+
     @staticmethod
-    def forward(ctx, params, center, ray, depth, bw3, bwv, precision, training):
+    def forward(ctx, flat, center, ray, depth, progress, c2f, precision, training, module, *params):
         lib = _lib.load()
-        params, center, ray, depth = _f32(params, "params"), _f32(center, "center"), _f32(ray, "ray"), _f32(depth, "depth")
-        if params.numel() != NIW_NERF_PARAMS:
+        flat, center, ray, depth = _f32(flat, "params"), _f32(center, "center"), _f32(ray, "ray"), _f32(depth, "depth")
+        if flat.numel() != NIW_NERF_PARAMS:
             raise RuntimeError("niw_b200: the MLP kernels implement the 8x256/skip-4/128-RGB architecture "
-                               "(%d parameters); got %d" % (NIW_NERF_PARAMS, params.numel()))
+                               "(%d parameters); got %d" % (NIW_NERF_PARAMS, flat.numel()))
         R, N = depth.shape
         nbytes = lib.niw_nerf_workspace_bytes(R, N, precision, int(training))
         if nbytes == 0:
@@ -314,45 +320,68 @@ class _NerfSamples(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=depth.device)
         rgb = torch.empty(R, N, 3, device=depth.device)
         sigma = torch.empty(R, N, device=depth.device)
-        b3 = (_c.c_float * 10)(*bw3)
-        bv = (_c.c_float * 4)(*bwv)
+        c0, c1 = (float(c2f[0]), float(c2f[1])) if progress is not None else (0.0, 1.0)
         with _timed("nerf_fwd"):
-            _lib.check(lib.niw_nerf_fwd(_p(params), _p(center), _p(ray), _p(depth), R, N, b3, bv, precision,
+            _lib.check(lib.niw_nerf_fwd(_p(flat), _p(center), _p(ray), _p(depth), R, N, _p(progress), c0, c1, precision,
                                         int(training), _p(ws), nbytes, _p(rgb), _p(sigma), _stream()))
         if training:
-            ctx.save_for_backward(params, center, ray, depth, ws)
-            ctx.cfg = (tuple(bw3), tuple(bwv), precision, nbytes)
+            ctx.save_for_backward(flat, center, ray, depth, ws)
+            ctx.cfg = (precision, nbytes, module, len(params))
         return rgb, sigma
 
     @staticmethod
     def backward(ctx, d_rgb, d_sigma):
-        params, center, ray, depth, ws = ctx.saved_tensors
-        bw3, bwv, precision, nbytes = ctx.cfg
+        flat, center, ray, depth, ws = ctx.saved_tensors
+        precision, nbytes, module, n_params = ctx.cfg
         R, N = depth.shape
-        d_params = torch.zeros_like(params)
+        target = module.flat_grad_pointer() if (module is not None and n_params) else None
+        if target is None:
+            d_params = torch.zeros_like(flat)
+            dp = _p(d_params)
+        else:
+            d_params = None
+            dp = _c.c_void_p(target)
         d_center = torch.empty_like(center)
         d_ray = torch.empty_like(ray)
         if d_rgb is None:
             d_rgb = torch.zeros(R, N, 3, device=depth.device)
         if d_sigma is None:
             d_sigma = torch.zeros(R, N, device=depth.device)
-        b3 = (_c.c_float * 10)(*bw3)
-        bv = (_c.c_float * 4)(*bwv)
         d_rgb, d_sigma = d_rgb.contiguous(), d_sigma.contiguous()
         with _timed("nerf_bwd"):
-            _lib.check(_lib.load().niw_nerf_bwd(_p(params), _p(center), _p(ray), _p(depth), R, N, b3, bv, precision,
-                                                _p(ws), nbytes, _p(d_rgb), _p(d_sigma), _p(d_params), _p(d_center),
+            _lib.check(_lib.load().niw_nerf_bwd(_p(flat), _p(center), _p(ray), _p(depth), R, N, precision,
+                                                _p(ws), nbytes, _p(d_rgb), _p(d_sigma), dp, _p(d_center),
                                                 _p(d_ray), _stream()))
-        return d_params, d_center, d_ray, None, None, None, None, None
+        if n_params and d_params is not None:
+            # slow path: the module's gradients are not one flat buffer -> hand slices back to autograd
+            pg = tuple(g.view_as(p) for g, p in zip(torch.split(d_params, [p.numel() for p in module.mlp_parameters()]),
+                                                     module.mlp_parameters()))
+            return (None, d_center, d_ray, None, None, None, None, None, None) + pg
+        return (d_params if not n_params else None, d_center, d_ray, None, None, None, None, None, None) + (None,) * n_params
 
 
-def nerf_forward_samples(params, center, ray, depth, bw3, bwv, precision=NIW_PREC_FP32, training=None):
+def nerf_forward_samples(params, center, ray, depth, progress=None, c2f=None, precision=NIW_PREC_FP32, training=None,
+                         module=None):
     """NeRF.forward_samples (model/nerf.py:449-456 -> :416-447, with camera.py:517-521 and the BARF
     encoding model/barf.py:256-268).  params: flat [530052] fp32; center/ray [R,3]; depth [R,N]
-    -> rgb [R,N,3], sigma [R,N]."""
+    -> rgb [R,N,3], sigma [R,N].  ``progress`` (device scalar tensor, or a float) and ``c2f`` = (start, end)
+    select the coarse-to-fine band weights, evaluated on the device; None = no annealing.  With
+    ``module`` (a NeRFCore) the parameter gradients are accumulated into the module's flat gradient
+    buffer by the kernels (see _NerfSamples)."""
+    if c2f is None:
+        progress = None
+    elif progress is None:
+        raise RuntimeError("niw_b200: barf_c2f needs the progress scalar")
+    elif not torch.is_tensor(progress):
+        progress = torch.tensor(float(progress), dtype=torch.float32, device=depth.device)
+    else:
+        progress = _f32(progress.detach(), "progress")
+    mparams = tuple(module.mlp_parameters()) if module is not None else ()
     if training is None:
-        training = torch.is_grad_enabled() and (params.requires_grad or center.requires_grad or ray.requires_grad)
-    return _NerfSamples.apply(params, center, ray, depth, list(bw3), list(bwv), precision_code(precision), bool(training))
+        training = torch.is_grad_enabled() and (params.requires_grad or center.requires_grad or ray.requires_grad
+                                                or any(p.requires_grad for p in mparams))
+    return _NerfSamples.apply(params, center, ray, depth, progress, c2f, precision_code(precision), bool(training),
+                              module, *mparams)
 
 
 # --------------------------------------------------------------------------------------------

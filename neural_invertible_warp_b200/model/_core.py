@@ -98,20 +98,70 @@ class NeRFCore(nn.Module):
             nn.init.zeros_(linear.bias)
 
     # -- helpers ----------------------------------------------------------------------------
-    def flat_parameters(self):
-        """The 530 052 MLP parameters as one fp32 vector in state_dict order (autograd splits the
-        gradient back onto the ``nn.Linear`` parameters)."""
+    def mlp_parameters(self):
+        """The 20 MLP parameter tensors in state_dict order (weights then bias per layer)."""
         ps = []
         for lin in list(self.mlp_feat) + list(self.mlp_rgb):
-            ps += [lin.weight.reshape(-1), lin.bias]
-        return torch.cat(ps)
+            ps += [lin.weight, lin.bias]
+        return ps
 
-    def band_weights(self, opt):
-        """Coarse-to-fine weights of the L_3D / L_view bands (model/barf.py:256-268): all ones
-        for plain NeRF or when ``barf_c2f`` is unset."""
-        c2f = opt.barf_c2f if (self.has_progress and opt.get("barf_c2f") is not None) else None
-        prog = float(self.progress.data) if self.has_progress else 0.0
-        return (F.band_weights(prog, c2f, opt.arch.posenc.L_3D), F.band_weights(prog, c2f, opt.arch.posenc.L_view))
+    def _is_flat(self, tensors, base):
+        """True if ``tensors`` are consecutive contiguous slices starting at data pointer ``base``."""
+        off = 0
+        for t in tensors:
+            if t is None or not t.is_contiguous() or t.data_ptr() != base + 4 * off:
+                return False
+            off += t.numel()
+        return True
+
+    def flat_parameters(self):
+        """The 530 052 MLP parameters as ONE fp32 vector in state_dict order, without a copy: the
+        ``nn.Linear`` parameters are kept as views into a flat buffer owned by this module (re-made
+        whenever they stop being views, e.g. after ``.to(device)``; ``load_state_dict`` and the
+        optimisers update in place and keep them).  state_dict keys and shapes are untouched."""
+        ps = self.mlp_parameters()
+        flat = getattr(self, "_flat_values", None)
+        if flat is None or flat.device != ps[0].device or not self._is_flat([p.data for p in ps], flat.data_ptr()):
+            with torch.no_grad():
+                flat = torch.cat([p.data.reshape(-1) for p in ps])
+                off = 0
+                for p in ps:
+                    p.data = flat[off:off + p.numel()].view_as(p)
+                    off += p.numel()
+            self._flat_values = flat
+        return flat
+
+    def flat_grad_pointer(self):
+        """Device pointer of a flat fp32 gradient buffer whose consecutive slices are the ``.grad`` of the
+        20 MLP parameters, or None when their gradients are laid out otherwise (then autograd accumulates
+        them).  If no parameter has a gradient yet, this module's own zeroed flat buffer is attached."""
+        ps = self.mlp_parameters()
+        if any(not p.requires_grad for p in ps):
+            return None
+        grads = [p.grad for p in ps]
+        if all(g is None for g in grads):
+            fg = getattr(self, "_flat_grads", None)
+            if fg is None or fg.device != ps[0].device:
+                fg = torch.zeros(sum(p.numel() for p in ps), device=ps[0].device)
+                self._flat_grads = fg
+            else:
+                fg.zero_()
+            off = 0
+            for p in ps:
+                p.grad = fg[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            return fg.data_ptr()
+        if grads[0] is not None and self._is_flat(grads, grads[0].data_ptr()):
+            return grads[0].data_ptr()
+        return None
+
+    def c2f_schedule(self, opt):
+        """(progress device scalar, (start, end)) of the BARF coarse-to-fine encoding (model/barf.py:256-268),
+        or (None, None) for plain NeRF / unset ``barf_c2f``.  The band weights are evaluated on the
+        device from the ``progress`` Parameter: no host read per step."""
+        if self.has_progress and opt.get("barf_c2f") is not None:
+            return self.progress.data, tuple(opt.barf_c2f)
+        return None, None
 
     @staticmethod
     def precision(opt):
@@ -132,8 +182,9 @@ class NeRFCore(nn.Module):
         pts = points_3D.reshape(-1, 3)
         view = ray_unit.expand_as(points_3D).reshape(-1, 3)
         depth = torch.zeros(pts.shape[0], 1, device=pts.device)
-        bw3, bwv = self.band_weights(opt)
-        rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), pts, view, depth, bw3, bwv, self.precision(opt))
+        progress, c2f = self.c2f_schedule(opt)
+        rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), pts, view, depth, progress, c2f, self.precision(opt),
+                                            module=self)
         return rgb.view(*shape, 3), sigma.view(*shape)
 
     def forward_samples(self, opt, center, ray, depth_samples, mode=None):
@@ -141,9 +192,10 @@ class NeRFCore(nn.Module):
         rgb_samples [B,P,N,3], density_samples [B,P,N]."""
         self._check_mode(opt, mode)
         B, P, N = depth_samples.shape[:3]
-        bw3, bwv = self.band_weights(opt)
+        progress, c2f = self.c2f_schedule(opt)
         rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), center.reshape(B * P, 3), ray.reshape(B * P, 3),
-                                            depth_samples.reshape(B * P, N), bw3, bwv, self.precision(opt))
+                                            depth_samples.reshape(B * P, N), progress, c2f, self.precision(opt),
+                                            module=self)
         return rgb.view(B, P, N, 3), sigma.view(B, P, N)
 
     def composite(self, opt, ray, rgb_samples, density_samples, depth_samples):
@@ -162,7 +214,10 @@ class NeRFCore(nn.Module):
         spectrum = input[..., None] * freq
         enc = torch.stack([spectrum.sin(), spectrum.cos()], dim=-2).reshape(*input.shape[:-1], -1)
         if self.has_progress and opt.get("barf_c2f") is not None:
-            w = torch.tensor(F.band_weights(float(self.progress.data), opt.barf_c2f, L), device=input.device)
+            start, end = opt.barf_c2f
+            alpha = (self.progress.data - start) / (end - start) * L
+            k = torch.arange(L, dtype=torch.float32, device=input.device)
+            w = (1 - ((alpha - k).clamp(min=0, max=1) * math.pi).cos()) / 2
             enc = (enc.reshape(-1, L) * w).reshape(enc.shape)
         return enc
 

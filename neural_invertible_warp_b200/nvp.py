@@ -7,11 +7,14 @@ re-parametrisation and folds the per-image latent code into per-image first-laye
 few B-sized PyTorch ops (autograd handles their backward), then evaluates all points in one CUDA
 kernel (csrc/nvp.cu).
 """
+import ctypes
 import math
+import warnings
 
 import torch
 from torch import nn
 
+from . import _lib
 from . import functional as F
 
 N_FREQ = 6
@@ -41,6 +44,55 @@ def pack_effective(p, code, n_blocks=3, n_freq=N_FREQ, prefix=""):
     return torch.cat(chunks), torch.stack(biases).view(n_blocks, 2, B, -1)
 
 
+class _NvpNetwork(torch.autograd.Function):
+    """DeformNetwork.forward as four kernels: pack (weight-norm + code projection + per-image biases),
+    warp; warp backward, pack backward.  The parameter gradients are accumulated by the pack-backward
+    kernel straight into the parameters' ``.grad`` buffers (allocated zero-filled when absent) instead
+    of being returned through autograd: that saves ~30 tiny accumulate launches per step.  The latent
+    code's gradient is returned normally."""
+
+    @staticmethod
+    def forward(ctx, code, pts, alpha_ratio, module, *params):
+        lib = _lib.load()
+        code = F._f32(code, "deformation_code")
+        pts = F._f32(pts, "input_pts")
+        B, Pt = pts.shape[0], pts.shape[1]
+        if code.shape != (B, HID):
+            raise RuntimeError("niw_b200 DeformNetwork: latent code must be [B=%d, %d], got %s" % (B, HID, tuple(code.shape)))
+        dev = pts.device
+        wpack = torch.empty(3 * F.NIW_NVP_BLOCK_FLOATS, device=dev)
+        code_bias = torch.empty(3, 2, B, HID, device=dev)
+        cb = torch.empty(3, B, HID, device=dev)
+        ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        _lib.check(lib.niw_nvp_pack_fwd(ptrs, F._p(code), B, F._p(wpack), F._p(code_bias), F._p(cb), F._stream()))
+        out = torch.empty_like(pts)
+        _lib.check(lib.niw_nvp_warp_fwd(F._p(wpack), F._p(code_bias), F._p(pts), float(alpha_ratio), B, Pt, F._p(out),
+                                        F._stream()))
+        ctx.save_for_backward(code, pts, wpack, code_bias, cb)
+        ctx.module, ctx.alpha = module, float(alpha_ratio)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        code, pts, wpack, code_bias, cb = ctx.saved_tensors
+        B, Pt = pts.shape[0], pts.shape[1]
+        d_w = torch.empty_like(wpack)
+        d_cb = torch.empty_like(code_bias)
+        d_out = d_out.contiguous()
+        _lib.check(lib.niw_nvp_warp_bwd(F._p(wpack), F._p(code_bias), F._p(pts), ctx.alpha, B, Pt, F._p(d_out), F._p(d_w),
+                                        F._p(d_cb), F._stream()))
+        params = ctx.module.ordered_parameters()
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        gptrs = (ctypes.c_void_p * len(params))(*[p.grad.data_ptr() for p in params])
+        d_code = torch.empty_like(code)
+        _lib.check(lib.niw_nvp_pack_bwd(ptrs, gptrs, F._p(code), F._p(cb), F._p(d_w), F._p(d_cb), B, F._p(d_code), F._stream()))
+        return (d_code, None, None, None) + (None,) * len(params)
+
+
 class DeformNetwork(nn.Module):
     """Drop-in for ``model.nvp.nvp_ndr.DeformNetwork`` restricted to what the target models
     instantiate (barf_inn_llff.py:54-55, pose_models/inn.py:23-27): d_in=3, n_blocks=3,
@@ -50,10 +102,11 @@ class DeformNetwork(nn.Module):
                  multires=0, weight_norm=True, actfn="softplus"):
         super().__init__()
         ok = (d_in == 3 and d_out_1 == 1 and d_out_2 == 3 and n_blocks == 3 and d_hidden == HID and n_layers == 1
-              and len(tuple(skip_in)) == 0 and multires == N_FREQ and weight_norm and actfn == "softplus")
+              and len(tuple(skip_in)) == 0 and multires == N_FREQ and weight_norm and actfn == "softplus"
+              and d_feature == HID)
         if not ok:
             raise RuntimeError("niw_b200 DeformNetwork: only the configuration used by barf_inn_llff / barf_inn_dtu "
-                               "is implemented in CUDA (3 blocks, hidden 128, 6 bands, weight-norm, softplus)")
+                               "is implemented in CUDA (3 blocks, hidden 128, latent 128, 6 bands, weight-norm, softplus)")
         self.n_blocks, self.d_feature = n_blocks, d_feature
         for b in range(n_blocks):
             for part, ori in (("a", 2), ("b", 1)):
@@ -63,7 +116,9 @@ class DeformNetwork(nn.Module):
                 nn.init.constant_(lin0.bias, 0.0)
                 nn.init.normal_(lin0.weight[:, :ori], 0.0, math.sqrt(2) / math.sqrt(d_hidden))
                 nn.init.constant_(lin0.weight[:, ori:], 0.0)
-                lin0 = nn.utils.weight_norm(lin0)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")      # legacy weight_norm: the reference's parametrisation / key names
+                    lin0 = nn.utils.weight_norm(lin0)
                 lin1 = nn.Linear(d_hidden, n_out)
                 nn.init.constant_(lin1.bias, 0.0)
                 nn.init.constant_(lin1.weight, 0.0)
@@ -74,6 +129,23 @@ class DeformNetwork(nn.Module):
             nn.init.constant_(lin.bias, 0.0)
             nn.init.constant_(lin.weight, 0.0)
             setattr(self, f"lin{b}_c", lin)
+        # weight_norm recomputes ``weight`` from (g, v) in a forward pre-hook; the CUDA path reads g and
+        # v directly, so the hooks (4 launches each) are dropped -- the parameters stay weight_g / weight_v
+        for m in self.modules():
+            for k, hook in list(m._forward_pre_hooks.items()):
+                if type(hook).__name__ == "WeightNorm":
+                    del m._forward_pre_hooks[k]
+
+    def ordered_parameters(self):
+        """The 36 tensors in the order of the C ABI's pointer table (include/niw_b200.h)."""
+        out = []
+        for b in range(self.n_blocks):
+            for part in ("a", "b"):
+                l0, l1 = getattr(self, f"lin{b}_{part}_0"), getattr(self, f"lin{b}_{part}_1")
+                out += [l0.weight_v, l0.weight_g, l0.bias, l1.weight, l1.bias]
+            lc = getattr(self, f"lin{b}_c")
+            out += [lc.weight, lc.bias]
+        return out
 
     def _params(self):
         p = {}
@@ -91,6 +163,9 @@ class DeformNetwork(nn.Module):
         """deformation_code [B,D], input_pts [B,P,1,3] -> [B,P,1,3]  (nvp_ndr.py:365)."""
         squeeze = input_pts.dim() == 4
         pts = input_pts[:, :, 0] if squeeze else input_pts
-        wpack, code_bias = pack_effective(self._params(), deformation_code, self.n_blocks)
-        out = F.nvp_warp(wpack, code_bias, pts.detach(), alpha_ratio)
+        params = self.ordered_parameters()
+        for p in params:
+            if not p.is_contiguous():
+                raise RuntimeError("niw_b200 DeformNetwork: parameters must be contiguous")
+        out = _NvpNetwork.apply(deformation_code, pts.detach(), alpha_ratio, self, *params)
         return out[:, :, None] if squeeze else out

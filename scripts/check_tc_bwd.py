@@ -19,7 +19,7 @@ center0 = (torch.randn(R, 3, generator=gen) * 0.1).to(DEV)
 ray0 = (torch.randn(R, 3, generator=gen) * 0.3 + torch.tensor([0., 0., 1.])).to(DEV)
 u = torch.rand(1, R, N, 1, generator=gen)
 depth = ora.stratified_depth(u, N, [1.2, 5.2], "metric")[0, ..., 0].to(DEV)
-bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
+prog, c2f = 0.3, [0.1, 0.5]
 target = torch.rand(R, 3, generator=gen).to(DEV)
 mode = sys.argv[3] if len(sys.argv) > 3 else "mse"
 w_rgb = (torch.rand(R, N, 3, generator=gen) - 0.5).to(DEV)
@@ -29,7 +29,7 @@ for prec in ("fp32", "bf16"):
     flat = flat0.clone().requires_grad_(True)
     c = center0.clone().requires_grad_(True)
     r = ray0.clone().requires_grad_(True)
-    rgb_s, sig_s = F.nerf_forward_samples(flat, c, r, depth, bw3, bwv, prec, training=True)
+    rgb_s, sig_s = F.nerf_forward_samples(flat, c, r, depth, prog, c2f, prec, training=True)
     if mode == "mse":
         rgb, dep, op, _ = F.composite(r, rgb_s, sig_s, depth)
         ((rgb - target) ** 2).mean().backward()

@@ -12,7 +12,7 @@ for i in range(2):
     keys += [f"mlp_rgb.{i}.weight", f"mlp_rgb.{i}.bias"]
 p = syn.nerf_params(1)
 flat = torch.cat([p[k].reshape(-1) for k in keys]).to(dev)
-bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
+prog, c2f = 0.3, [0.1, 0.5]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 modes = sys.argv[1:] or ["bf16"]
 for prec in modes:
@@ -33,7 +33,7 @@ for prec in modes:
                 flush.zero_()
                 a, b, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 a.record()
-                rgb, sig = F.nerf_forward_samples(fl, c, r, depth, bw3, bwv, prec, training=training)
+                rgb, sig = F.nerf_forward_samples(fl, c, r, depth, prog, c2f, prec, training=training)
                 b.record()
                 if training:
                     try:

@@ -209,8 +209,8 @@ def test_nerf_mlp_fp32_golden(F, golden, progress):
     pts = g["points"].reshape(-1, 3).to(DEV).requires_grad_(True)
     unit = g["ray_unit"].reshape(-1, 3).to(DEV).requires_grad_(True)
     depth = torch.zeros(pts.shape[0], 1, device=DEV)
-    bw3, bwv = F.band_weights(progress, g["c2f"], 10), F.band_weights(progress, g["c2f"], 4)
-    rgb, sigma = F.nerf_forward_samples(flat, pts, unit, depth, bw3, bwv, "fp32", training=True)
+    prog, c2f = progress, g["c2f"]
+    rgb, sigma = F.nerf_forward_samples(flat, pts, unit, depth, prog, c2f, "fp32", training=True)
     shp = g["points"].shape[:-1]
     torch.testing.assert_close(rgb.cpu().view(*shp, 3), case["rgb"], rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(sigma.cpu().view(*shp), case["density"], rtol=1e-4, atol=1e-5)
@@ -246,8 +246,8 @@ def test_nerf_fp32_vs_oracle_with_ray_grads(F, R, N):
     flat = flat_params(p_cpu).to(DEV).requires_grad_(True)
     c, r = center[0].to(DEV).requires_grad_(True), ray[0].to(DEV).requires_grad_(True)
     d = depth[0, ..., 0].to(DEV)
-    bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
-    rgb_s, sig_s = F.nerf_forward_samples(flat, c, r, d, bw3, bwv, "fp32")
+    prog, c2f = 0.3, [0.1, 0.5]
+    rgb_s, sig_s = F.nerf_forward_samples(flat, c, r, d, prog, c2f, "fp32")
     torch.testing.assert_close(rgb_s.cpu(), rgb_ref.detach()[0], rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(sig_s.cpu(), sig_ref.detach()[0], rtol=1e-4, atol=2e-5)
     rgb, dep, op, _ = F.composite(r, rgb_s, sig_s, d)

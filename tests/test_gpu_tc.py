@@ -53,9 +53,9 @@ def test_tc_forward_vs_fp32(F, R, N):
     ray = (torch.randn(R, 3, generator=gen) * 0.3 + torch.tensor([0., 0., 1.])).to(DEV)
     u = torch.rand(1, R, N, 1, generator=gen)
     depth = ora.stratified_depth(u, N, [1.2, 5.2], "metric")[0, ..., 0].to(DEV)
-    bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
-    rgb32, sig32 = F.nerf_forward_samples(flat, center, ray, depth, bw3, bwv, "fp32", training=False)
-    rgb16, sig16 = F.nerf_forward_samples(flat, center, ray, depth, bw3, bwv, "bf16", training=False)
+    prog, c2f = 0.3, [0.1, 0.5]
+    rgb32, sig32 = F.nerf_forward_samples(flat, center, ray, depth, prog, c2f, "fp32", training=False)
+    rgb16, sig16 = F.nerf_forward_samples(flat, center, ray, depth, prog, c2f, "bf16", training=False)
     torch.cuda.synchronize()
     e_rgb = (rgb16 - rgb32).abs().max().item()
     e_sig = ((sig16 - sig32).abs() / (1 + sig32.abs())).max().item()
@@ -79,9 +79,9 @@ def test_tc_forward_inverse_depth_far_samples(F):
     ray = (torch.randn(R, 3, generator=gen) * 0.2 + torch.tensor([0., 0., 1.])).to(DEV)
     u = torch.rand(1, R, N, 1, generator=gen)
     depth = ora.stratified_depth(u, N, [1, 0], "inverse")[0, ..., 0].to(DEV)
-    bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
-    o32 = F.composite(ray, *F.nerf_forward_samples(flat, center, ray, depth, bw3, bwv, "fp32", training=False), depth)
-    o16 = F.composite(ray, *F.nerf_forward_samples(flat, center, ray, depth, bw3, bwv, "bf16", training=False), depth)
+    prog, c2f = 0.3, [0.1, 0.5]
+    o32 = F.composite(ray, *F.nerf_forward_samples(flat, center, ray, depth, prog, c2f, "fp32", training=False), depth)
+    o16 = F.composite(ray, *F.nerf_forward_samples(flat, center, ray, depth, prog, c2f, "bf16", training=False), depth)
     assert (o16[0] - o32[0]).abs().max() < 1e-2
     assert (o16[2] - o32[2]).abs().max() < 1e-2
 
@@ -123,14 +123,14 @@ def test_tc_backward_vs_fp32(F, R, N, param, tol):
     u = torch.rand(1, R, N, 1, generator=gen)
     rng = [1.2, 5.2] if param == "metric" else [1, 0]
     depth = ora.stratified_depth(u, N, rng, param)[0, ..., 0].to(DEV)
-    bw3, bwv = F.band_weights(0.3, [0.1, 0.5], 10), F.band_weights(0.3, [0.1, 0.5], 4)
+    prog, c2f = 0.3, [0.1, 0.5]
     target = torch.rand(R, 3, generator=gen).to(DEV)
     grads = {}
     for prec in ("fp32", "bf16"):
         flat = flat0.clone().requires_grad_(True)
         c = center0.clone().requires_grad_(True)
         r = ray0.clone().requires_grad_(True)
-        rgb_s, sig_s = F.nerf_forward_samples(flat, c, r, depth, bw3, bwv, prec, training=True)
+        rgb_s, sig_s = F.nerf_forward_samples(flat, c, r, depth, prog, c2f, prec, training=True)
         rgb, dep, op, _ = F.composite(r, rgb_s, sig_s, depth)
         ((rgb - target) ** 2).mean().backward()
         torch.cuda.synchronize()
