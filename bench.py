@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step (C2: 1024; C5: 8192)")
     ap.add_argument("--precision", default=None, help="MLP operand precision: bf16 (tcgen05) or fp32 (CUDA cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -184,7 +185,8 @@ def workload_config(args, precision):
                          % (args.rays, N_SAMPLES, IMAGES, H, W),
                 rays_per_gpu=args.rays, samples_per_ray=N_SAMPLES, images=IMAGES, mlp_precision=precision,
                 parallelism="dp%d (rays sharded, one gradient all-reduce)" % args.gpus,
-                l2="256 MiB memset between steps, outside the per-step CUDA-event pairs")
+                l2="256 MiB memset between steps, outside the per-step CUDA-event pairs",
+                launch="one CUDA-graph replay per step (value); eager launches (e2e)" if not args.no_graph else "eager")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -224,9 +226,9 @@ def run_ours(args):
     graph.nerf.progress.data.fill_(0.3)
     var_dev = engine.synthetic_var(opt, IMAGES, seed=3)
     bucket = engine.GradBucket(graph)
-    optim = torch.optim.Adam([dict(params=graph.nerf.parameters(), lr=1e-3)], fused=True)
+    optim = torch.optim.Adam([dict(params=graph.nerf.parameters(), lr=1e-3)], fused=True, capturable=True)
     optim_pose = torch.optim.Adam([dict(params=list(graph.warp_mlp.parameters()) + list(graph.warp_latent.parameters()),
-                                        lr=5e-4)], fused=True)
+                                        lr=5e-4)], fused=True, capturable=True)
     it = 5000
     P_local = (rays_global // IMAGES + world - 1) // world
     rays_local = P_local * IMAGES
@@ -300,17 +302,34 @@ def run_ours(args):
         step_device()
     step_e2e()
     barrier()
+    step_value, graphed = step_device, False
+    if not args.no_graph:
+        try:
+            step_value = engine.CapturedStep(step_device, warmup=1)
+            graphed = True
+            for _ in range(2):
+                step_value()
+        except Exception as e:   # capture refused (e.g. a collective that cannot be captured): stay eager
+            if rank == 0:
+                print("bench.py: CUDA-graph capture unavailable (%s); timing eager launches" % str(e).splitlines()[0],
+                      file=sys.stderr)
+            step_value, graphed = step_device, False
+            torch.cuda.synchronize()
+    barrier()
 
     # ---- value: device-resident ----
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    ms_total, _ = timed(step_value, args.steps)
+    ms_total = max_over_ranks(ms_total)
+    # per-kernel CUDA-event timing (roofline leg) and the launch count: the same K steps launched eagerly
+    # (event records cannot live inside a captured graph)
     n0 = _lib.launch_count()
     with F.KernelTimer() as kt:
-        ms_total, _ = timed(step_device, args.steps)
+        ms_eager, _ = timed(step_device, args.steps)
         kernel_ms = kt.totals()
     launches = _lib.launch_count() - n0
-    ms_total = max_over_ranks(ms_total)
     # ---- e2e: host buffers in, loss out (wall clock around synchronised steps) ----
     barrier()
     t0 = time.perf_counter()
@@ -337,6 +356,8 @@ def run_ours(args):
                 frac=achieved / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
                 flop_per_launch_pair=flop_per_step, mlp_ms_per_step=mlp_ms / max(mlp_calls, 1),
                 mlp_share_of_step=mlp_ms / ms_total if ms_total > 0 else None,
+                timed="CUDA events around niw_nerf_fwd / niw_nerf_bwd on the launching stream, eager pass of the same "
+                      "%d steps (%.3f ms/step eager)" % (args.steps, ms_eager / args.steps),
                 composite_ms_per_step=comp_ms / max(mlp_calls, 1))
 
     if rank != 0:

@@ -200,24 +200,65 @@ nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
 }
 
 // ------------------------------------------------------------------------------------------
-// backward: block-outer order so that one block's weight-gradient accumulators live in registers
+// backward: block-outer order; each warp owns a private gradient accumulator in shared memory
+// (plain read-modify-write, no atomics, odd row strides), reduced across the CTA at the end of a
+// block pass and flushed with one global atomic per weight per CTA
 // ------------------------------------------------------------------------------------------
 constexpr int BWD_WARPS = 8;
-constexpr int MAX_PTS_PER_WARP = 128;     // per-point state kept in shared memory: xin[3][3] + dx[3]
+constexpr int MAX_PTS_PER_WARP = 32;      // per-point state kept in shared memory: xin[3][3] + dx[3]
 constexpr int PT_STATE = 12;
-constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)S_BLOCK + BLOCK_FLOATS + BWD_WARPS * 32 +
+constexpr int ES_FLOATS = 2 * (EA + EB) + 2;   // scaled + raw embeddings of both parts
+constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)S_BLOCK + (size_t)BWD_WARPS * S_BLOCK + BWD_WARPS * ES_FLOATS +
                                              (size_t)BWD_WARPS * MAX_PTS_PER_WARP * PT_STATE);
+static_assert(BWD_SMEM <= 227 * 1024, "shared memory budget (NVP backward)");
+
+// scaled embedding e (what the MLP sees) and the raw sin/cos (needed by the derivative)
+template <int D>
+__device__ __forceinline__ void embed_coop2(const float* x, float scale, float* e, float* raw, int lane) {
+    if (lane < D) { const float xv = (D == 1 || lane == 0) ? x[0] : x[D - 1]; e[lane] = scale * xv; raw[lane] = xv; }
+    if (lane < D * NF) {
+        const int k = lane / D, c = lane % D;
+        const float xc = (D == 1 || c == 0) ? x[0] : x[D - 1];
+        float s, co;
+        sincosf(xc * ((float)(1 << k) * PI_F), &s, &co);
+        e[D + k * 2 * D + c] = scale * s; raw[D + k * 2 * D + c] = s;
+        e[D + k * 2 * D + D + c] = scale * co; raw[D + k * 2 * D + D + c] = co;
+    }
+    __syncwarp();
+}
+template <int D>
+__device__ __forceinline__ void embed_bwd_raw(const float* raw, float scale, const float* de, float* dx) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        float acc = de[c];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) {
+            const float f = (float)(1 << k) * PI_F;
+            acc += f * (raw[D + k * 2 * D + D + c] * de[D + k * 2 * D + c] - raw[D + k * 2 * D + c] * de[D + k * 2 * D + D + c]);
+        }
+        dx[c] += scale * acc;
+    }
+}
+// softplus(beta=100) value and derivative from one exponential
+__device__ __forceinline__ void softplus100_both(float x, float& h, float& g) {
+    const float bx = BETA * x;
+    if (bx > 20.f) { h = x; g = 1.f; return; }
+    const float e = expf(bx);
+    h = log1pf(e) / BETA;
+    g = e / (1.f + e);
+}
 
 __global__ void __launch_bounds__(BWD_WARPS * 32, 1)
 nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
                Bands bw, int B, int Pt, int pts_per_warp, const float* __restrict__ d_out, float* __restrict__ d_wpack,
                float* __restrict__ d_code_bias) {
     extern __shared__ float smem[];
-    float* sw = smem;                                   // one block's weights (padded image)
-    float* sacc = sw + S_BLOCK;                         // CTA-level gradient accumulators (wpack layout)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* es = sacc + BLOCK_FLOATS + warp * 32;
-    float* state = sacc + BLOCK_FLOATS + BWD_WARPS * 32 + (size_t)warp * MAX_PTS_PER_WARP * PT_STATE;
+    float* sw = smem;                                            // one block's weights (padded image)
+    float* acc = smem + S_BLOCK + (size_t)warp * S_BLOCK;        // this warp's gradient accumulator (same padded layout)
+    float* es = smem + S_BLOCK + (size_t)BWD_WARPS * S_BLOCK + warp * ES_FLOATS;
+    float* eA = es, *rawA = es + EA, *eB = es + 2 * EA, *rawB = es + 2 * EA + EB;
+    float* state = smem + S_BLOCK + (size_t)BWD_WARPS * S_BLOCK + BWD_WARPS * ES_FLOATS + (size_t)warp * MAX_PTS_PER_WARP * PT_STATE;
     const int64_t total = (int64_t)B * Pt;
     const int64_t gw = (int64_t)blockIdx.x * BWD_WARPS + warp;
     const int64_t p0 = gw * pts_per_warp;
@@ -244,32 +285,23 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
             const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
             const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
             const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
-            block_forward(sw, biasA, biasB, sa, sb, x, blk, es, lane);
+            block_forward(sw, biasA, biasB, sa, sb, x, blk, eA, lane);
             if (lane < 3) stt[(blk + 1) * 3 + lane] = sel3(x, lane);
             __syncwarp();
         }
     }
 
-    // ---- passes 2,1,0: backward of one block for all points of the warp ----
+    // ---- passes NB-1 .. 0: backward of one block for all points of the warp ----
     for (int blk = NB - 1; blk >= 0; --blk) {
         __syncthreads();
         load_weights_smem(sw, wpack + (size_t)blk * BLOCK_FLOATS, 1);
-        for (int i = threadIdx.x; i < BLOCK_FLOATS; i += blockDim.x) sacc[i] = 0.f;
+        for (int i = lane; i < S_BLOCK; i += 32) acc[i] = 0.f;
         __syncthreads();
         int foc, o0, o1;
         axes(blk, foc, o0, o1);
-        float aW1a[U][EA], aW1b[U][EB], aW2a[U], aW2b[U][3], ab2a = 0.f, ab2b[3] = {0.f, 0.f, 0.f};
         float abA[U], abB[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            aW2a[u] = 0.f; abA[u] = 0.f; abB[u] = 0.f;
-#pragma unroll
-            for (int i = 0; i < EA; ++i) aW1a[u][i] = 0.f;
-#pragma unroll
-            for (int i = 0; i < EB; ++i) aW1b[u][i] = 0.f;
-#pragma unroll
-            for (int m = 0; m < 3; ++m) aW2b[u][m] = 0.f;
-        }
+        for (int u = 0; u < U; ++u) { abA[u] = 0.f; abB[u] = 0.f; }
         int cur_img = -1;
         float* dbA = d_code_bias + (size_t)(blk * 2 + 0) * B * HID;
         float* dbB = d_code_bias + (size_t)(blk * 2 + 1) * B * HID;
@@ -289,70 +321,89 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
             }
             float* stt = state + i * PT_STATE;
             __syncwarp();
-            float x[3] = {stt[blk * 3], stt[blk * 3 + 1], stt[blk * 3 + 2]};
-            float dx[3] = {stt[9], stt[10], stt[11]};
+            const float x[3] = {stt[blk * 3], stt[blk * 3 + 1], stt[blk * 3 + 2]};
+            const float dx[3] = {stt[9], stt[10], stt[11]};
             const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
             const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
             const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
-            float xx[3] = {x[0], x[1], x[2]};
-            const BlockFwd f = block_forward(sw, biasA, biasB, sa, sb, xx, blk, es, lane);
-            // ---------------- part b backward ----------------
-            const float g0 = sel3(dx, o0), g1 = sel3(dx, o1);
-            const float dy0 = f.c * g0 - f.s * g1, dy1 = f.s * g0 + f.c * g1;
-            const float dth = g0 * (-f.s * f.y[0] + f.c * f.y[1]) + g1 * (-f.c * f.y[0] - f.s * f.y[1]);
-            const float dout[3] = {dth, -dy0, -dy1};
-            float dxo[2] = {dy0, dy1};
-            float dxf = sel3(dx, foc);
-            // es currently holds embed<1>(xf) (left there by block_forward)
-            float de2[EB];
-#pragma unroll
-            for (int q = 0; q < EB; ++q) de2[q] = 0.f;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = lane + 32 * u;
-                float pre = biasB[j];
-                const float* w = sw + S_W1B + j * EB;
-#pragma unroll
-                for (int q = 0; q < EB; ++q) pre += w[q] * es[q];
-                const float h = softplus100(pre);
-                const float dh = sw[S_W2B + j] * dout[0] + sw[S_W2B + HID + j] * dout[1] + sw[S_W2B + 2 * HID + j] * dout[2];
-                const float dpre = dh * softplus100_grad(pre);
-#pragma unroll
-                for (int m = 0; m < 3; ++m) aW2b[u][m] += dout[m] * h;
-                abB[u] += dpre;
-#pragma unroll
-                for (int q = 0; q < EB; ++q) { aW1b[u][q] += dpre * es[q]; de2[q] += w[q] * dpre; }
-            }
-#pragma unroll
-            for (int m = 0; m < 3; ++m) ab2b[m] += dout[m];
-#pragma unroll
-            for (int q = 0; q < EB; ++q) de2[q] = warp_sum(de2[q]);
-            embed_bwd<1>(&f.xf, sb, de2, &dxf);
-            // ---------------- part a backward ----------------
-            const float ddelta = -dxf;
-            __syncwarp();
-            embed_coop<2>(f.xo, sa, es, lane);
-            float de[EA];
-#pragma unroll
-            for (int q = 0; q < EA; ++q) de[q] = 0.f;
+            // ---------------- forward, keeping activations ----------------
+            const float xo[2] = {sel3(x, o0), sel3(x, o1)};
+            embed_coop2<2>(xo, sa, eA, rawA, lane);
+            float hA[U], gA[U], part = 0.f;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int j = lane + 32 * u;
                 float pre = biasA[j];
                 const float* w = sw + S_W1A + j * SA;
 #pragma unroll
-                for (int q = 0; q < EA; ++q) pre += w[q] * es[q];
-                const float h = softplus100(pre);
-                const float dpre = sw[S_W2A + j] * ddelta * softplus100_grad(pre);
-                aW2a[u] += ddelta * h;
-                abA[u] += dpre;
-#pragma unroll
-                for (int q = 0; q < EA; ++q) { aW1a[u][q] += dpre * es[q]; de[q] += w[q] * dpre; }
+                for (int q = 0; q < EA; ++q) pre += w[q] * eA[q];
+                softplus100_both(pre, hA[u], gA[u]);
+                part += sw[S_W2A + j] * hA[u];
             }
-            ab2a += ddelta;
+            const float xf = sel3(x, foc) - (sw[S_B2A] + warp_sum(part));
+            embed_coop2<1>(&xf, sb, eB, rawB, lane);
+            float hB[U], gB[U], q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = lane + 32 * u;
+                float pre = biasB[j];
+                const float* w = sw + S_W1B + j * EB;
+#pragma unroll
+                for (int q = 0; q < EB; ++q) pre += w[q] * eB[q];
+                softplus100_both(pre, hB[u], gB[u]);
+                q0 += sw[S_W2B + j] * hB[u]; q1 += sw[S_W2B + HID + j] * hB[u]; q2 += sw[S_W2B + 2 * HID + j] * hB[u];
+            }
+            const float th = sw[S_B2B] + warp_sum(q0), t1 = sw[S_B2B + 1] + warp_sum(q1), t2 = sw[S_B2B + 2] + warp_sum(q2);
+            float sn, cs;
+            sincosf(th, &sn, &cs);
+            const float y0 = xo[0] - t1, y1 = xo[1] - t2;
+            // ---------------- part b backward ----------------
+            const float g0 = sel3(dx, o0), g1 = sel3(dx, o1);
+            const float dy0 = cs * g0 - sn * g1, dy1 = sn * g0 + cs * g1;
+            const float dth = g0 * (-sn * y0 + cs * y1) + g1 * (-cs * y0 - sn * y1);
+            const float dout[3] = {dth, -dy0, -dy1};
+            float dxo[2] = {dy0, dy1};
+            float dxf = sel3(dx, foc);
+            float de2[EB];
+#pragma unroll
+            for (int q = 0; q < EB; ++q) de2[q] = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = lane + 32 * u;
+                const float* w = sw + S_W1B + j * EB;
+                const float dh = sw[S_W2B + j] * dout[0] + sw[S_W2B + HID + j] * dout[1] + sw[S_W2B + 2 * HID + j] * dout[2];
+                const float dpre = dh * gB[u];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) acc[S_W2B + m * HID + j] += dout[m] * hB[u];
+                abB[u] += dpre;
+                float* a1 = acc + S_W1B + j * EB;
+#pragma unroll
+                for (int q = 0; q < EB; ++q) { a1[q] += dpre * eB[q]; de2[q] += w[q] * dpre; }
+            }
+            if (lane < 3) acc[S_B2B + lane] += sel3(dout, lane);
+#pragma unroll
+            for (int q = 0; q < EB; ++q) de2[q] = warp_sum(de2[q]);
+            embed_bwd_raw<1>(rawB, sb, de2, &dxf);
+            // ---------------- part a backward ----------------
+            const float ddelta = -dxf;
+            float de[EA];
+#pragma unroll
+            for (int q = 0; q < EA; ++q) de[q] = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = lane + 32 * u;
+                const float* w = sw + S_W1A + j * SA;
+                const float dpre = sw[S_W2A + j] * ddelta * gA[u];
+                acc[S_W2A + j] += ddelta * hA[u];
+                abA[u] += dpre;
+                float* a1 = acc + S_W1A + j * SA;
+#pragma unroll
+                for (int q = 0; q < EA; ++q) { a1[q] += dpre * eA[q]; de[q] += w[q] * dpre; }
+            }
+            if (lane == 0) acc[S_B2A] += ddelta;
 #pragma unroll
             for (int q = 0; q < EA; ++q) de[q] = warp_sum(de[q]);
-            embed_bwd<2>(f.xo, sa, de, dxo);
+            embed_bwd_raw<2>(rawA, sa, de, dxo);
             __syncwarp();
             if (lane == 0) { stt[9 + foc] = dxf; stt[9 + o0] = dxo[0]; stt[9 + o1] = dxo[1]; }
         }
@@ -363,29 +414,22 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
                 atomicAdd(dbB + (size_t)cur_img * HID + lane + 32 * u, abB[u]);
             }
         }
-        // ---- CTA-level reduction in shared memory, then one global atomic per weight ----
-        if (np > 0) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = lane + 32 * u;
-#pragma unroll
-                for (int q = 0; q < EA; ++q) atomicAdd(sacc + OFF_W1A + j * EA + q, aW1a[u][q]);
-#pragma unroll
-                for (int q = 0; q < EB; ++q) atomicAdd(sacc + OFF_W1B + j * EB + q, aW1b[u][q]);
-                atomicAdd(sacc + OFF_W2A + j, aW2a[u]);
-#pragma unroll
-                for (int m = 0; m < 3; ++m) atomicAdd(sacc + OFF_W2B + m * HID + j, aW2b[u][m]);
-            }
-            if (lane == 0) {
-                atomicAdd(sacc + OFF_B2A, ab2a);
-#pragma unroll
-                for (int m = 0; m < 3; ++m) atomicAdd(sacc + OFF_B2B + m, ab2b[m]);
-            }
-        }
+        // ---- CTA-level reduction of the warps' accumulators, then one global atomic per weight ----
         __syncthreads();
         float* dW = d_wpack + (size_t)blk * BLOCK_FLOATS;
+        const float* accs = smem + S_BLOCK;
         for (int i = threadIdx.x; i < BLOCK_FLOATS; i += blockDim.x) {
-            const float v = sacc[i];
+            // wpack index -> padded shared-memory index
+            int si;
+            if (i < OFF_W2A) si = S_W1A + (i / EA) * SA + (i % EA);
+            else if (i < OFF_B2A) si = S_W2A + (i - OFF_W2A);
+            else if (i < OFF_W1B) si = S_B2A;
+            else if (i < OFF_W2B) si = S_W1B + (i - OFF_W1B);
+            else if (i < OFF_B2B) si = S_W2B + (i - OFF_W2B);
+            else si = S_B2B + (i - OFF_B2B);
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < BWD_WARPS; ++w) v += accs[(size_t)w * S_BLOCK + si];
             if (v != 0.f) atomicAdd(dW + i, v);
         }
     }
@@ -409,49 +453,77 @@ struct PtrTable { const float* p[NIW_NVP_PARAM_PTRS]; };
 struct GradTable { float* p[NIW_NVP_PARAM_PTRS]; };
 constexpr int MAX_IMG = 96;                // images per call (dynamic shared memory: ~2 KB per image)
 constexpr int LDC = DF + 1;
+constexpr int PACK_THREADS = 1024;
 
-__global__ void __launch_bounds__(256)
+// squared row norm of v[j][0..ld) by one warp (coalesced)
+__device__ __forceinline__ float row_norm2(const float* __restrict__ row, int ld, int lane) {
+    float a = 0.f;
+    for (int c = lane; c < ld; c += 32) { float t = row[c]; a += t * t; }
+    return warp_sum(a);
+}
+
+// One CTA per coupling block, 32 warps.  Every reduction is done by a warp with the lanes along the
+// contiguous (reduction) axis, so all global reads are coalesced.
+__global__ void __launch_bounds__(PACK_THREADS)
 nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, float* __restrict__ wpack,
                     float* __restrict__ code_bias, float* __restrict__ cb_out) {
-    extern __shared__ float s_cb[];            // [B][LDC]
-    const int blk = blockIdx.x, tid = threadIdx.x;
+    extern __shared__ float sm[];
+    float* s_cb = sm;                          // [B][LDC]
+    float* s_scale = s_cb + (size_t)B * LDC;   // [2][HID]
+    const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = PACK_THREADS / 32;
     const float* const* P = T.p + blk * 12;
     const float *Wc = P[10], *bc = P[11];
     float* wp = wpack + (size_t)blk * BLOCK_FLOATS;
-    // code_b[img][k] = code + b_c + W_c code      (nvp_ndr.py:382)
-    for (int idx = tid; idx < B * DF; idx += blockDim.x) {
-        const int img = idx / DF, k = idx % DF;
-        const float* c = code + (size_t)img * DF;
-        float acc = c[k] + bc[k];
-        for (int m = 0; m < DF; ++m) acc += Wc[(size_t)k * DF + m] * c[m];
-        s_cb[img * LDC + k] = acc;
-        cb_out[((size_t)blk * B + img) * DF + k] = acc;
+    // (1) row scales g/||v|| and the effective embedded-coordinate columns
+    for (int r = warp; r < 2 * HID; r += nwarp) {
+        const int part = r >> 7, j = r & 127;
+        const int emb = part == 0 ? EA : EB, ld = emb + DF;
+        const float* v = P[part * 5 + 0] + (size_t)j * ld;
+        const float scale = P[part * 5 + 1][j] / sqrtf(row_norm2(v, ld, lane));
+        if (lane == 0) s_scale[r] = scale;
+        if (lane < emb) wp[(part == 0 ? OFF_W1A : OFF_W1B) + j * emb + lane] = v[lane] * scale;
     }
-    // effective first-layer weights (embedded-coordinate columns) and the output layers
-    const int part = tid >> 7, j = tid & 127;                  // thread = (part, hidden unit)
-    const int emb = part == 0 ? EA : EB, ld = emb + DF;
-    const float* v = P[part * 5 + 0] + (size_t)j * ld;
-    float nrm2 = 0.f;
-    for (int c = 0; c < ld; ++c) nrm2 += v[c] * v[c];
-    const float scale = P[part * 5 + 1][j] / sqrtf(nrm2);
-    for (int c = 0; c < emb; ++c) wp[(part == 0 ? OFF_W1A : OFF_W1B) + j * emb + c] = v[c] * scale;
-    if (part == 0) {
-        wp[OFF_W2A + j] = P[3][j];
-        if (j == 0) wp[OFF_B2A] = P[4][0];
-    } else {
-        for (int m = 0; m < 3; ++m) wp[OFF_W2B + m * HID + j] = P[8][m * HID + j];
-        if (j < 3) wp[OFF_B2B + j] = P[9][j];
+    // output layers: copies
+    for (int i = tid; i < HID; i += PACK_THREADS) wp[OFF_W2A + i] = P[3][i];
+    for (int i = tid; i < 3 * HID; i += PACK_THREADS) wp[OFF_W2B + i] = P[8][i];
+    if (tid == 0) wp[OFF_B2A] = P[4][0];
+    if (tid < 3) wp[OFF_B2B + tid] = P[9][tid];
+    // (2) code_b[img][k] = code + b_c + W_c code      (nvp_ndr.py:382): warp per output, lanes over m
+    for (int o = warp; o < B * DF; o += nwarp) {
+        const int img = o / DF, k = o % DF;
+        const float* c = code + (size_t)img * DF;
+        const float* w = Wc + (size_t)k * DF;
+        float a = 0.f;
+#pragma unroll
+        for (int m = lane; m < DF; m += 32) a += w[m] * c[m];
+        a = warp_sum(a);
+        if (lane == 0) {
+            a += c[k] + bc[k];
+            s_cb[img * LDC + k] = a;
+            cb_out[((size_t)blk * B + img) * DF + k] = a;
+        }
     }
     __syncthreads();
-    const float b0 = P[part * 5 + 2][j];
-    for (int img = 0; img < B; ++img) {
-        float acc = 0.f;
-        for (int k = 0; k < DF; ++k) acc += v[emb + k] * s_cb[img * LDC + k];
-        code_bias[((size_t)(blk * 2 + part) * B + img) * HID + j] = b0 + scale * acc;
+    // (3) per-image first-layer biases: warp per (part, j), lanes over the latent axis, loop over images
+    for (int r = warp; r < 2 * HID; r += nwarp) {
+        const int part = r >> 7, j = r & 127;
+        const int emb = part == 0 ? EA : EB, ld = emb + DF;
+        const float* v = P[part * 5 + 0] + (size_t)j * ld + emb;
+        float vl[DF / 32];
+#pragma unroll
+        for (int q = 0; q < DF / 32; ++q) vl[q] = v[lane + 32 * q];
+        const float b0 = P[part * 5 + 2][j], scale = s_scale[r];
+        for (int img = 0; img < B; ++img) {
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < DF / 32; ++q) a += vl[q] * s_cb[img * LDC + lane + 32 * q];
+            a = warp_sum(a);
+            if (lane == 0) code_bias[((size_t)(blk * 2 + part) * B + img) * HID + j] = b0 + scale * a;
+        }
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PACK_THREADS)
 nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, const float* __restrict__ cb, int B,
                     const float* __restrict__ d_wpack, const float* __restrict__ d_code_bias, float* __restrict__ d_code) {
     extern __shared__ float sm[];
@@ -459,63 +531,72 @@ nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, con
     float* s_dcb = s_cb + (size_t)B * LDC;     // [2][B][LDC]   d(code_bias) of both parts
     float* s_dc = s_dcb + 2 * (size_t)B * LDC; // [B][LDC]      d(code_b)
     float* s_scale = s_dc + (size_t)B * LDC;   // [2][HID]
-    const int blk = blockIdx.x, tid = threadIdx.x;
+    const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = PACK_THREADS / 32;
     const float* const* P = T.p + blk * 12;
     float* const* Gp = G.p + blk * 12;
     const float* dwp = d_wpack + (size_t)blk * BLOCK_FLOATS;
-    const int part = tid >> 7, j = tid & 127;
-    const int emb = part == 0 ? EA : EB, ld = emb + DF;
-    const float* v = P[part * 5 + 0] + (size_t)j * ld;
-    const float g = P[part * 5 + 1][j];
-    float nrm2 = 0.f;
-    for (int c = 0; c < ld; ++c) nrm2 += v[c] * v[c];
-    const float nrm = sqrtf(nrm2), scale = g / nrm;
-    s_scale[part * HID + j] = scale;
-    for (int idx = tid; idx < B * DF; idx += blockDim.x) s_cb[(idx / DF) * LDC + idx % DF] = cb[(size_t)blk * B * DF + idx];
-    for (int idx = tid; idx < 2 * B * HID; idx += blockDim.x) {
+    for (int idx = tid; idx < B * DF; idx += PACK_THREADS) s_cb[(idx / DF) * LDC + idx % DF] = cb[(size_t)blk * B * DF + idx];
+    for (int idx = tid; idx < 2 * B * HID; idx += PACK_THREADS) {
         const int p = idx / (B * HID), r = idx % (B * HID);
         s_dcb[((size_t)p * B + r / HID) * LDC + r % HID] = d_code_bias[((size_t)(blk * 2 + p) * B) * HID + r];
     }
-    // output layers: the gradient is the kernel's own (every element has exactly one writer here)
-    if (part == 0) {
-        Gp[3][j] += dwp[OFF_W2A + j];
-        if (j == 0) Gp[4][0] += dwp[OFF_B2A];
-    } else {
-        for (int m = 0; m < 3; ++m) Gp[8][m * HID + j] += dwp[OFF_W2B + m * HID + j];
-        if (j < 3) Gp[9][j] += dwp[OFF_B2B + j];
+    // output layers: the gradient is the warp kernel's own (every element has exactly one writer here)
+    for (int i = tid; i < HID; i += PACK_THREADS) Gp[3][i] += dwp[OFF_W2A + i];
+    for (int i = tid; i < 3 * HID; i += PACK_THREADS) Gp[8][i] += dwp[OFF_W2B + i];
+    if (tid == 0) Gp[4][0] += dwp[OFF_B2A];
+    if (tid < 3) Gp[9][tid] += dwp[OFF_B2B + tid];
+    __syncthreads();
+    // first layers: warp per (part, j); lanes along the columns of row j
+    for (int r = warp; r < 2 * HID; r += nwarp) {
+        const int part = r >> 7, j = r & 127;
+        const int emb = part == 0 ? EA : EB, ld = emb + DF;
+        const float* v = P[part * 5 + 0] + (size_t)j * ld;
+        const float g = P[part * 5 + 1][j];
+        const float nrm2 = row_norm2(v, ld, lane), nrm = sqrtf(nrm2), scale = g / nrm;
+        if (lane == 0) s_scale[r] = scale;
+        const float* my_dcb = s_dcb + (size_t)part * B * LDC + j;
+        // d b0[j] = sum_img dcb
+        float db0 = 0.f;
+        for (int img = lane; img < B; img += 32) db0 += my_dcb[img * LDC];
+        db0 = warp_sum(db0);
+        if (lane == 0) Gp[part * 5 + 2][j] += db0;
+        // gradient of the effective row: embedded columns from the warp kernel, latent columns
+        // d w0[j][emb+k] = sum_img dcb[img][j] cb[img][k]
+        const float* dW1 = dwp + (part == 0 ? OFF_W1A : OFF_W1B) + j * emb;
+        float dwe = lane < emb ? dW1[lane] : 0.f;
+        float dwl[DF / 32];
+#pragma unroll
+        for (int q = 0; q < DF / 32; ++q) dwl[q] = 0.f;
+        for (int img = 0; img < B; ++img) {
+            const float d = my_dcb[img * LDC];
+#pragma unroll
+            for (int q = 0; q < DF / 32; ++q) dwl[q] += d * s_cb[img * LDC + lane + 32 * q];
+        }
+        float dot = lane < emb ? dwe * v[lane] : 0.f;
+#pragma unroll
+        for (int q = 0; q < DF / 32; ++q) dot += dwl[q] * v[emb + lane + 32 * q];
+        dot = warp_sum(dot);
+        // weight-norm backward: w = g v/||v||
+        if (lane == 0) Gp[part * 5 + 1][j] += dot / nrm;
+        float* dv = Gp[part * 5 + 0] + (size_t)j * ld;
+        const float coef = dot / nrm2;
+        if (lane < emb) dv[lane] += scale * (dwe - v[lane] * coef);
+#pragma unroll
+        for (int q = 0; q < DF / 32; ++q) {
+            const int c = emb + lane + 32 * q;
+            dv[c] += scale * (dwl[q] - v[c] * coef);
+        }
     }
     __syncthreads();
-    // d b0[j] = sum_img dcb ; d w0[j][emb+k] = sum_img dcb[img][j] cb[img][k]
-    const float* my_dcb = s_dcb + (size_t)part * B * LDC + j;
-    float db0 = 0.f;
-    for (int img = 0; img < B; ++img) db0 += my_dcb[img * LDC];
-    Gp[part * 5 + 2][j] += db0;
-    const float* dW1 = dwp + (part == 0 ? OFF_W1A : OFF_W1B) + j * emb;
-    float dot = 0.f;
-    for (int c = 0; c < emb; ++c) dot += dW1[c] * v[c];
-    for (int k = 0; k < DF; ++k) {
-        float dw = 0.f;
-        for (int img = 0; img < B; ++img) dw += my_dcb[img * LDC] * s_cb[img * LDC + k];
-        dot += dw * v[emb + k];
-    }
-    // weight-norm backward: w = g v/||v||
-    Gp[part * 5 + 1][j] += dot / nrm;
-    float* dv = Gp[part * 5 + 0] + (size_t)j * ld;
-    const float coef = dot / nrm2;
-    for (int c = 0; c < emb; ++c) dv[c] += scale * (dW1[c] - v[c] * coef);
-    for (int k = 0; k < DF; ++k) {
-        float dw = 0.f;
-        for (int img = 0; img < B; ++img) dw += my_dcb[img * LDC] * s_cb[img * LDC + k];
-        dv[emb + k] += scale * (dw - v[emb + k] * coef);
-    }
-    // d code_b[img][k] = sum_part sum_j dcb[part][img][j] w0[j][emb+k]
-    for (int idx = tid; idx < B * DF; idx += blockDim.x) {
+    // d code_b[img][k] = sum_part sum_j dcb[part][img][j] w0[j][emb+k]: thread per (img, k), k fastest (coalesced rows)
+    for (int idx = tid; idx < B * DF; idx += PACK_THREADS) {
         const int img = idx / DF, k = idx % DF;
         float acc = 0.f;
         for (int p = 0; p < 2; ++p) {
             const int e2 = p == 0 ? EA : EB, l2 = e2 + DF;
             const float* vp = P[p * 5 + 0] + e2 + k;
             const float* d = s_dcb + ((size_t)p * B + img) * LDC;
+#pragma unroll 4
             for (int jj = 0; jj < HID; ++jj) acc += d[jj] * vp[(size_t)jj * l2] * s_scale[p * HID + jj];
         }
         s_dc[img * LDC + k] = acc;
@@ -523,20 +604,21 @@ nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, con
     __syncthreads();
     // code projector: code_b = W_c code + b_c + code
     const float* Wc = P[10];
-    for (int idx = tid; idx < DF * DF; idx += blockDim.x) {
+    for (int idx = tid; idx < DF * DF; idx += PACK_THREADS) {
         const int k = idx / DF, m = idx % DF;
         float acc = 0.f;
         for (int img = 0; img < B; ++img) acc += s_dc[img * LDC + k] * code[(size_t)img * DF + m];
         Gp[10][idx] += acc;
     }
-    for (int k = tid; k < DF; k += blockDim.x) {
+    for (int k = tid; k < DF; k += PACK_THREADS) {
         float acc = 0.f;
         for (int img = 0; img < B; ++img) acc += s_dc[img * LDC + k];
         Gp[11][k] += acc;
     }
-    for (int idx = tid; idx < B * DF; idx += blockDim.x) {
+    for (int idx = tid; idx < B * DF; idx += PACK_THREADS) {
         const int img = idx / DF, m = idx % DF;
         float acc = s_dc[img * LDC + m];
+#pragma unroll 4
         for (int k = 0; k < DF; ++k) acc += s_dc[img * LDC + k] * Wc[(size_t)k * DF + m];
         atomicAdd(d_code + idx, acc);        // three blocks (CTAs) contribute
     }
@@ -550,10 +632,10 @@ extern "C" int niw_nvp_pack_fwd(const float* const* params, const float* code, i
     PtrTable T;
     for (int i = 0; i < NIW_NVP_PARAM_PTRS; ++i) { NIW_CHECK_ARG(params[i]); T.p[i] = params[i]; }
     if (B > MAX_IMG) return NIW_E_UNSUPP;
-    const size_t smem = sizeof(float) * (size_t)B * LDC;
+    const size_t smem = sizeof(float) * ((size_t)B * LDC + 2 * HID);
     if (smem > 48 * 1024)
         NIW_CUDA(cudaFuncSetAttribute(nvp_pack_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    niw::note_launch(), nvp_pack_fwd_kernel<<<NB, 256, smem, niw_stream(stream)>>>(T, code, B, wpack, code_bias, cb);
+    niw::note_launch(), nvp_pack_fwd_kernel<<<NB, PACK_THREADS, smem, niw_stream(stream)>>>(T, code, B, wpack, code_bias, cb);
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -569,7 +651,7 @@ extern "C" int niw_nvp_pack_bwd(const float* const* params, float* const* grads,
     const size_t smem = sizeof(float) * (4 * (size_t)B * LDC + 2 * HID);
     if (smem > 48 * 1024)
         NIW_CUDA(cudaFuncSetAttribute(nvp_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    niw::note_launch(), nvp_pack_bwd_kernel<<<NB, 256, smem, st>>>(T, G, code, cb, B, d_wpack, d_code_bias, d_code);
+    niw::note_launch(), nvp_pack_bwd_kernel<<<NB, PACK_THREADS, smem, st>>>(T, G, code, cb, B, d_wpack, d_code_bias, d_code);
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -599,7 +681,7 @@ extern "C" int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, cons
     // points per warp: enough to amortise the per-CTA gradient flush, few enough to fill the GPU
     const int64_t warps_max = (int64_t)niw_num_sms() * BWD_WARPS;
     int64_t ppw = (total + warps_max - 1) / warps_max;
-    if (ppw < 8) ppw = 8;
+    if (ppw < 2) ppw = 2;
     if (ppw > MAX_PTS_PER_WARP) ppw = MAX_PTS_PER_WARP;
     const int64_t warps = (total + ppw - 1) / ppw;
     const int64_t blocks = (warps + BWD_WARPS - 1) / BWD_WARPS;

@@ -189,6 +189,31 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1):
     return loss
 
 
+class CapturedStep:
+    """A whole training step (forward, loss, backward, all-reduce, optimiser) captured once in a CUDA
+    graph and replayed: the ~45 kernel launches of a C2 step cost one graph launch instead of ~1 ms of
+    Python / launch overhead.  ``fn`` must be capture-safe: static input tensors, device RNG
+    (``torch.rand`` / ``torch.randperm`` advance the graph-registered Philox state on replay), no host
+    reads, optimisers built with ``capturable=True``.  Its return value (e.g. the loss dict) refers
+    to static tensors that every replay overwrites."""
+
+    def __init__(self, fn, warmup=3):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
+
+
 def synthetic_var(opt, B, seed=0, dtu=False):
     """A ``var`` batch shaped like ``train_data.all`` (data/llff.py:79-92, data/dtu.py:369-380) from
     the deterministic generators in ``synthetic``."""
