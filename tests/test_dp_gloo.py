@@ -1,0 +1,119 @@
+"""Data-parallel host logic on CPU: two ``gloo`` ranks shard one global ray batch the way
+``engine.train_step`` does (engine._ShardedRandperm -> contiguous 1/k slices of the shared pixel
+draw, local mean losses scaled by n_local/n_global, ONE flat-bucket all-reduce) and must end up with
+the gradient of the single-process step on the whole batch.  The per-rank compute
+is the CPU oracle (the product kernels need a GPU); what is under test is the sharding, the loss
+scaling and the GradBucket plumbing -- the same objects bench.py drives on NCCL."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, P_GLOBAL, N, H, W = 2, 12, 8, 24, 32
+ALPHA = 1.0
+CFG = dict(N=N, Nf=None, range=[1, 0], param="inverse", L_3D=10, L_view=4, skip=(4,), c2f=[0.1, 0.5])
+
+
+class _Holder(nn.Module):
+    """Parameters under the reference's names, so engine.trainable_parameters / GradBucket see what
+    they see on a real Graph (nerf.*, warp_mlp.*, warp_latent.weight; progress is skipped)."""
+
+    def __init__(self):
+        super().__init__()
+        from neural_invertible_warp_b200 import synthetic as syn
+        self.nerf = nn.ParameterDict({k.replace(".", "__"): nn.Parameter(v) for k, v in syn.nerf_params(1).items()})
+        self.warp_mlp = nn.ParameterDict({k.replace(".", "__"): nn.Parameter(v) for k, v in syn.nvp_params(2).items()})
+        self.warp_latent = nn.Embedding(B, 128, _weight=syn.latent_codes(3, B))
+        self.progress = nn.Parameter(torch.tensor(0.3))
+
+    def dicts(self):
+        return ({k.replace("__", "."): v for k, v in self.nerf.items()},
+                {k.replace("__", "."): v for k, v in self.warp_mlp.items()})
+
+
+def _local_step(holder, ray_idx, u, image, intr, scale):
+    from oracle import reference_port as ora
+    p, q = holder.dicts()
+    ray, center, *_ = ora.warped_rays(q, holder.warp_latent.weight, H, W, intr, ray_idx, ALPHA)
+    out = ora.render_rays(p, center, ray, u, CFG, progress=0.3)
+    loss = ora.mse(out["rgb"], ora.gather_pixels(image, ray_idx))
+    (loss * scale).backward()
+    return loss.detach()
+
+
+def _inputs():
+    from neural_invertible_warp_b200 import synthetic as syn
+    gen = torch.Generator().manual_seed(11)
+    u = torch.rand(B, P_GLOBAL, N, 1, generator=gen)
+    return u, syn.images(4, B, H, W), syn.intrinsics(B, H, W, 0.81)
+
+
+def _worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from neural_invertible_warp_b200 import engine
+    holder = _Holder()
+    bucket = engine.GradBucket(holder)
+    bucket.zero()
+    u, image, intr = _inputs()
+    torch.manual_seed(5)                      # every rank draws the same permutation ...
+    with engine._ShardedRandperm(rank, world, P_GLOBAL):
+        ray_idx = torch.randperm(H * W)       # ... and keeps its contiguous 1/k of the first P_GLOBAL
+    per = (P_GLOBAL + world - 1) // world
+    u_loc = u[:, rank * per:(rank + 1) * per]
+    _local_step(holder, ray_idx, u_loc, image, intr, scale=len(ray_idx) / float(P_GLOBAL))
+    bucket.allreduce()
+    if rank == 0:
+        torch.save(dict(flat=bucket.flat.clone(), n_local=len(ray_idx)), out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_step_equals_single_process_step(tmp_path):
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got["n_local"] == P_GLOBAL // 2
+
+    from neural_invertible_warp_b200 import engine
+    holder = _Holder()
+    bucket = engine.GradBucket(holder)
+    u, image, intr = _inputs()
+    torch.manual_seed(5)
+    ray_idx = torch.randperm(H * W)[:P_GLOBAL]
+    _local_step(holder, ray_idx, u, image, intr, scale=1.0)
+    ref = bucket.flat
+    assert ref.abs().max() > 0
+    rel = ((got["flat"] - ref).norm() / ref.norm()).item()
+    assert rel < 1e-5, rel
+    # progress / Kabsch outputs are never part of the bucket
+    names = [n for n, _ in engine.trainable_parameters(holder)]
+    assert "progress" not in names and len(names) == len(list(holder.parameters())) - 1
+
+
+def test_shard_ray_idx_partitions_the_global_list():
+    from neural_invertible_warp_b200 import engine
+    idx = torch.arange(100, 110)
+    for world in (1, 2, 3, 4, 8):
+        parts = [engine.shard_ray_idx(idx, r, world) for r in range(world)]
+        assert torch.equal(torch.cat(parts), idx)
+        assert max(len(p) for p in parts) == (10 + world - 1) // world
