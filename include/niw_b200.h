@@ -149,6 +149,16 @@ int niw_nerf_bwd(const float* params, const float* center, const float* ray, con
 int niw_mse_gather(const float* image, const float* rgb, const int64_t* ray_idx, int64_t idx_start,
                    int B, int P, int H, int W, float scale, float* loss, float* d_rgb, void* stream);
 
+/* ---- optimiser step (row f2): torch.optim.Adam + ExponentialLR over ONE flat fp32 segment
+ *      model/nerf.py:33-46,87,92 (optim / sched), model/barf_inn_llff.py:84-120 (optim_pose)
+ * params/grads/exp_avg/exp_avg_sq [n] (16-byte aligned).  `state` is a DEVICE array of 2 floats owned by the
+ * caller and zero-initialised: state[0] = number of steps taken so far (advanced by the kernel, so the call can be
+ * replayed from a CUDA graph), state[1] = scratch.  Update (torch's Adam, amsgrad off, maximize off):
+ *   t = state[0]+1; lr_t = lr * lr_gamma^(t-1); g += weight_decay*p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *   p -= lr_t/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) */
+int niw_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float lr_gamma, float beta1, float beta2, float eps, float weight_decay, float* state, void* stream);
+
 /* ---- tcgen05 self-test: D[128,N] = A[128,K] . B[N,K]^T with BF16 operands staged exactly as the
  * MLP kernel stages them.  variant selects the operand form under test (see csrc/mlp_tc.cu). */
 int niw_tc_selftest(const float* A, const float* Bm, int N, int K, int variant, float* D, void* stream);

@@ -99,6 +99,100 @@ class GradBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
 
+class FlatAdam:
+    """The reference's optimisers (``optim`` on ``graph.nerf``: Adam + ExponentialLR, model/nerf.py:33-46;
+    ``optim_pose`` on ``warp_mlp`` + ``warp_latent`` / ``se3_refine``: model/barf_inn_llff.py:84-104,
+    model/barf.py:46-60) as ONE kernel launch per parameter group (csrc/adam.cu, ``niw_adam_step``).
+
+    ``groups`` = [dict(params=[...], lr=, gamma=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0), ...].
+    Every group becomes a contiguous fp32 segment of one flat parameter buffer and of one flat gradient buffer
+    (the parameters / their ``.grad`` are re-pointed at views, names and shapes untouched), so this object is
+    also the data-parallel gradient bucket: ``zero`` / ``allreduce`` have GradBucket's meaning.  The step
+    count lives on the device, so ``step`` can be captured in a CUDA graph; ``gamma`` is the per-step
+    ExponentialLR factor (lr_t = lr * gamma**(t-1))."""
+
+    def __init__(self, groups):
+        from . import _lib
+        self._lib = _lib.load()
+        self.groups = []
+        dev = groups[0]["params"][0].device
+        sizes = []
+        for g in groups:
+            n = sum(p.numel() for p in g["params"])
+            sizes.append((n + 3) // 4 * 4)                      # 16-byte aligned segments
+        total = sum(sizes)
+        self.flat_params = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)    # gradients (GradBucket interface)
+        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.state = torch.zeros(len(groups), 2, device=dev, dtype=torch.float32)
+        base = 0
+        for gi, (g, size) in enumerate(zip(groups, sizes)):
+            off = base
+            for p in g["params"]:
+                if p.dtype != torch.float32 or not p.is_cuda:
+                    raise RuntimeError("niw_b200 FlatAdam: parameters must be CUDA float32 tensors")
+                n = p.numel()
+                with torch.no_grad():
+                    self.flat_params[off:off + n].copy_(p.data.reshape(-1))
+                    p.data = self.flat_params[off:off + n].view_as(p)
+                p.grad = self.flat[off:off + n].view_as(p)
+                off += n
+            b1, b2 = g.get("betas", (0.9, 0.999))
+            self.groups.append(dict(offset=base, n=size, lr=float(g["lr"]), gamma=float(g.get("gamma", 1.0)), b1=float(b1),
+                                    b2=float(b2), eps=float(g.get("eps", 1e-8)), wd=float(g.get("weight_decay", 0.0)),
+                                    params=list(g["params"])))
+            base += size
+
+    def zero(self):
+        self.flat.zero_()
+
+    zero_grad = zero
+
+    def allreduce(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+    def step(self):
+        import ctypes
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for gi, g in enumerate(self.groups):
+            o = g["offset"] * 4
+            ptr = lambda t: ctypes.c_void_p(t.data_ptr() + o)
+            rc = self._lib.niw_adam_step(ptr(self.flat_params), ptr(self.flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                         g["n"], g["lr"], g["gamma"], g["b1"], g["b2"], g["eps"], g["wd"],
+                                         ctypes.c_void_p(self.state.data_ptr() + gi * 8), st)
+            if rc:
+                raise RuntimeError("niw_adam_step: %s" % self._lib.niw_error_string(rc).decode())
+
+
+def reference_optimizer_groups(opt, graph):
+    """The parameter groups of the reference's optimisers for the target models (model/nerf.py:33-46,
+    model/barf.py:46-60, model/barf_inn_llff.py:84-104), as FlatAdam group dicts.  ExponentialLR:
+    gamma = (lr_end / lr) ** (1 / max_iter)."""
+    def sched(o):
+        lr, lr_end = float(o.lr), float(o.get("lr_end", None) or o.lr)
+        return dict(lr=lr, gamma=(lr_end / lr) ** (1.0 / opt.max_iter) if lr_end != lr else 1.0)
+    nerf_params = list(graph.nerf.parameters())
+    nerf_params = [p for n, p in graph.nerf.named_parameters() if not n.endswith("progress")]
+    if opt.nerf.fine_sampling:
+        nerf_params += [p for n, p in graph.nerf_fine.named_parameters() if not n.endswith("progress")]
+    groups = [dict(params=nerf_params, **sched(opt.optim))]
+    pose = []
+    if hasattr(graph, "se3_refine"):
+        pose += list(graph.se3_refine.parameters())
+    if hasattr(graph, "warp_mlp"):
+        pose += list(graph.warp_mlp.parameters()) + list(graph.warp_latent.parameters())
+    if hasattr(graph, "pose_net"):
+        pose += [p for n, p in graph.pose_net.named_parameters() if "pose_global" not in n]
+    if pose:
+        o = opt.optim
+        lr = float(o.get("lr_pose", None) or o.lr)
+        lr_end = float(o.get("lr_pose_end", None) or lr)
+        groups.append(dict(params=pose, lr=lr, gamma=(lr_end / lr) ** (1.0 / opt.max_iter) if lr_end != lr else 1.0))
+    return groups
+
+
 def shard_ray_idx(ray_idx, rank, world):
     """Contiguous 1/world slice of the per-image pixel list (same list on every rank)."""
     n = ray_idx.numel()

@@ -121,6 +121,10 @@ class NeRFCore(nn.Module):
         optimisers update in place and keep them).  state_dict keys and shapes are untouched."""
         ps = self.mlp_parameters()
         flat = getattr(self, "_flat_values", None)
+        if (flat is None or flat.data_ptr() != ps[0].data_ptr()) and self._is_flat([p.data for p in ps], ps[0].data_ptr()):
+            # already consecutive inside someone else's buffer (engine.FlatAdam): view it, do not move it
+            flat = ps[0].data.as_strided((sum(p.numel() for p in ps),), (1,))
+            self._flat_values = flat
         if flat is None or flat.device != ps[0].device or not self._is_flat([p.data for p in ps], flat.data_ptr()):
             with torch.no_grad():
                 flat = torch.cat([p.data.reshape(-1) for p in ps])

@@ -191,3 +191,64 @@ def test_nerf_forward_points_api(eng, golden):
     close(sig, sig_ref, rtol=1e-4, atol=1e-5)
     enc = graph.nerf.positional_encoding(opt, pts.to(DEV), 10)
     close(enc, ora.barf_encoding(pts, 10, 0.3, [0.1, 0.5])[..., 3:], rtol=1e-4, atol=2e-4)
+
+
+def _inn_graph(eng, precision="fp32", B=4, rays=64, N=32, hw=(48, 64)):
+    opt = cfgmod.builtin_options("barf_inn_llff", barf_c2f=[0.1, 0.5], device=DEV, data=dict(image_size=list(hw)),
+                                 nerf=dict(rand_rays=rays, sample_intvs=N), arch=dict(mlp_precision=precision))
+    torch.manual_seed(0)
+    graph = eng.build_graph(opt, B)
+    load_nerf(graph.nerf, syn.nerf_params(21))
+    graph.nerf.progress.data.fill_(0.3)
+    graph.warp_latent.weight.data = syn.latent_codes(22, B).to(DEV)
+    graph.warp_mlp.load_state_dict({k: v.to(DEV) for k, v in syn.nvp_params(23).items()})
+    return opt, graph, eng.synthetic_var(opt, B, 24)
+
+
+def test_flat_adam_training_matches_torch_optimizers(eng):
+    """Three train steps of barf_inn_llff with the reference's optimiser pair (torch.optim.Adam + ExponentialLR,
+    model/nerf.py:33-46, model/barf_inn_llff.py:84-104) vs engine.FlatAdam (one kernel per group), same draws;
+    the FlatAdam run is additionally replayed from a CUDA graph."""
+    gen = torch.Generator().manual_seed(9)
+    B, P, N = 4, 16, 32
+    draws = [(torch.randperm(48 * 64, generator=gen)[:P].to(DEV), torch.rand(B, P, N, 1, generator=gen).to(DEV)) for _ in range(3)]
+
+    opt, g1, var1 = _inn_graph(eng)
+    groups = eng.reference_optimizer_groups(opt, g1)
+    o1 = torch.optim.Adam([dict(params=groups[0]["params"], lr=groups[0]["lr"])])
+    o2 = torch.optim.Adam([dict(params=groups[1]["params"], lr=groups[1]["lr"])])
+    s1 = torch.optim.lr_scheduler.ExponentialLR(o1, gamma=groups[0]["gamma"])
+    s2 = torch.optim.lr_scheduler.ExponentialLR(o2, gamma=groups[1]["gamma"])
+    losses1 = []
+    for ridx, u in draws:
+        with eng.feed_draws(ray_idx=ridx, u=u):
+            loss = eng.train_step(opt, g1, cfgmod.AttrDict(var1), 5000)
+        o1.step(); o2.step(); s1.step(); s2.step()
+        losses1.append(float(loss.all.detach()))
+
+    opt, g2, var2 = _inn_graph(eng)
+    fa = eng.FlatAdam(eng.reference_optimizer_groups(opt, g2))
+    s_ridx, s_u = torch.empty_like(draws[0][0]), torch.empty_like(draws[0][1])
+
+    def body():
+        with eng.feed_draws(ray_idx=s_ridx, u=s_u):
+            loss = eng.train_step(opt, g2, cfgmod.AttrDict(var2), 5000, bucket=fa)
+        fa.step()
+        return loss.all.detach()
+    losses2 = []
+    s_ridx.copy_(draws[0][0]); s_u.copy_(draws[0][1])
+    losses2.append(float(body()))                          # eager
+    snap = (fa.flat_params.clone(), fa.exp_avg.clone(), fa.exp_avg_sq.clone(), fa.state.clone())
+    captured = eng.CapturedStep(body, warmup=1)            # warm-up + capture advance the state: restore it
+    for dst, src in zip((fa.flat_params, fa.exp_avg, fa.exp_avg_sq, fa.state), snap):
+        dst.copy_(src)
+    for ridx, u in draws[1:]:
+        s_ridx.copy_(ridx); s_u.copy_(u)
+        losses2.append(float(captured()))
+    torch.testing.assert_close(torch.tensor(losses2), torch.tensor(losses1), rtol=1e-4, atol=1e-6)
+    p1 = dict(g1.named_parameters())
+    for n, p in g2.named_parameters():
+        # Adam normalises the update (m/sqrt(v)): last-bit differences of atomically accumulated gradients move a
+        # parameter by a fraction of lr (1e-3) per step; 3 steps move it by up to 3e-3
+        torch.testing.assert_close(p.detach(), p1[n].detach(), rtol=1e-2, atol=1e-4, msg=lambda m, n=n: n + ": " + m)
+    assert fa.state[:, 0].tolist() == [3.0, 3.0]

@@ -281,3 +281,32 @@ def test_mse_gather(F):
 def test_ops_refuse_cpu_tensors(F):
     with pytest.raises(RuntimeError):
         F.composite(torch.zeros(2, 3), torch.zeros(2, 4, 3), torch.zeros(2, 4), torch.zeros(2, 4))
+
+
+def test_flat_adam_matches_torch_adam():
+    """niw_adam_step (row f2) vs torch.optim.Adam + ExponentialLR (model/nerf.py:33-46) on two groups with odd sizes,
+    20 steps, weight decay off/on."""
+    from neural_invertible_warp_b200 import engine
+    gen = torch.Generator().manual_seed(3)
+    shapes_a, shapes_b = [(257, 63), (257,), (5, 3)], [(16, 6), (7,)]
+    for wd in (0.0, 1e-2):
+        ref_a = [torch.randn(s, generator=gen).requires_grad_(True) for s in shapes_a]
+        ref_b = [torch.randn(s, generator=gen).requires_grad_(True) for s in shapes_b]
+        ours_a = [torch.nn.Parameter(t.detach().clone().to(DEV)) for t in ref_a]
+        ours_b = [torch.nn.Parameter(t.detach().clone().to(DEV)) for t in ref_b]
+        o_a = torch.optim.Adam(ref_a, lr=1e-2, weight_decay=wd)
+        o_b = torch.optim.Adam(ref_b, lr=3e-3, weight_decay=wd)
+        s_a = torch.optim.lr_scheduler.ExponentialLR(o_a, gamma=0.9)
+        fa = engine.FlatAdam([dict(params=ours_a, lr=1e-2, gamma=0.9, weight_decay=wd),
+                              dict(params=ours_b, lr=3e-3, weight_decay=wd)])
+        for it in range(20):
+            for r, o in zip(ref_a + ref_b, ours_a + ours_b):
+                g = torch.randn(r.shape, generator=gen) * (0.1 + it)
+                r.grad = g.clone()
+                o.grad.copy_(g.to(DEV))          # gradients are views into the flat bucket
+            o_a.step(); o_b.step(); s_a.step()
+            fa.step()
+        for r, o in zip(ref_a + ref_b, ours_a + ours_b):
+            torch.testing.assert_close(o.detach().cpu(), r.detach(), rtol=2e-5, atol=2e-6)
+        assert fa.state[:, 0].tolist() == [20.0, 20.0]
+        assert ours_a[0].data_ptr() == fa.flat_params.data_ptr()
