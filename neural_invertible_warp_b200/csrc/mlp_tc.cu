@@ -32,7 +32,8 @@ constexpr int NSTAGE = 3;
 constexpr int SM_ACT = 0;
 constexpr int SM_ENC = SM_ACT + 2 * ACT_BYTES;
 constexpr int SM_RING = SM_ENC + 2 * ENC_BYTES;
-constexpr int SM_CONST = SM_RING + NSTAGE * STAGE_BYTES;
+constexpr int SM_ONES = SM_RING + NSTAGE * STAGE_BYTES;
+constexpr int SM_CONST = SM_ONES + ONES_BYTES;
 constexpr int SM_BAR = SM_CONST + ((C_FLOATS * 4 + 15) / 16) * 16;
 constexpr int SM_TOTAL = SM_BAR + 128;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -52,18 +53,31 @@ __global__ void pack_weights_kernel(const float* __restrict__ P, C2F c2f, uint8_
         for (int i = 1; i < NLAYER; ++i) if (byte >= stream_off(i)) l = i;
         const int rows = layer_rows(l);
         int64_t rel = byte - stream_off(l);
-        int chunk = (int)(rel / ((int64_t)rows * CHUNK_K * 2));
-        int64_t in_chunk = rel % ((int64_t)rows * CHUNK_K * 2);
-        int kc = (int)(in_chunk / (rows * 16));          // which 8-wide k group inside the chunk
-        int n = (int)((in_chunk % (rows * 16)) / 16);
-        int k0 = chunk * CHUNK_K + kc * 8;
-        const int in_dim = layer_in(l);
-        const float* Wl = P + layer_woff(l) + (int64_t)(n + layer_rowoff(l)) * in_dim;
-        uint32_t out[4];
+        const int64_t main_bytes = (int64_t)layer_chunks(l) * rows * CHUNK_K * 2;
+        uint32_t out[4] = {0u, 0u, 0u, 0u};
+        if (rel < main_bytes) {
+            int chunk = (int)(rel / ((int64_t)rows * CHUNK_K * 2));
+            int64_t in_chunk = rel % ((int64_t)rows * CHUNK_K * 2);
+            int kc = (int)(in_chunk / (rows * 16));          // which 8-wide k group inside the chunk
+            int n = (int)((in_chunk % (rows * 16)) / 16);
+            int k0 = chunk * CHUNK_K + kc * 8;
+            const int in_dim = layer_in(l);
+            const float* Wl = P + layer_woff(l) + (int64_t)(n + layer_rowoff(l)) * in_dim;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int ka = k0 + 2 * j, kb = ka + 1;
-            out[j] = ptx::pack_bf16(ka < in_dim ? Wl[ka] : 0.f, kb < in_dim ? Wl[kb] : 0.f);
+            for (int j = 0; j < 4; ++j) {
+                int ka = k0 + 2 * j, kb = ka + 1;
+                out[j] = ptx::pack_bf16(ka < in_dim ? Wl[ka] : 0.f, kb < in_dim ? Wl[kb] : 0.f);
+            }
+        } else {
+            // bias chunk [2 k-groups][rows][8 bf16]: k = 0 -> bf16(b), k = 1 -> bf16(b - bf16(b)), rest 0
+            rel -= main_bytes;
+            const int kg = (int)(rel / (rows * 16));
+            const int n = (int)((rel % (rows * 16)) / 16);
+            if (kg == 0) {
+                const float b = P[layer_boff(l) + n + layer_rowoff(l)];
+                const float hi = __bfloat162float(__float2bfloat16(b));
+                out[0] = ptx::pack_bf16(hi, b - hi);
+            }
         }
         *reinterpret_cast<uint4*>(stream + byte) = make_uint4(out[0], out[1], out[2], out[3]);
     }
@@ -74,10 +88,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ P, C2F c2f, uint8_
             store_bands(c2f, i - C_BANDS, consts + C_BANDS);
             return;
         }
-        if (i < C_W7R0) {
-            int l = i / WIDTH, n = i % WIDTH;
-            v = n < layer_rows(l) ? P[layer_boff(l) + n + layer_rowoff(l)] : 0.f;
-        } else if (i < C_WRGB1) {
+        if (i < C_WRGB1) {
             v = P[feat_w_off(7) + (i - C_W7R0)];
         } else if (i < C_MISC) {
             v = P[RGB1_W + (i - C_WRGB1)];
@@ -144,7 +155,7 @@ __device__ __forceinline__ void write_enc_row(uint8_t* enc_tile, uint8_t* save_i
         uint4 v = make_uint4(ptx::pack_bf16(e[ch * 8], e[ch * 8 + 1]), ptx::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]),
                              ptx::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]), ptx::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
         *reinterpret_cast<uint4*>(enc_tile + ch * KROW + row * 16) = v;
-        if (save_img) *reinterpret_cast<uint4*>(save_img + ch * KROW + row * 16) = v;
+        if (save_img) *reinterpret_cast<uint4*>(save_img + hbm_img_off(ENC3_PAD, row, ch)) = v;
     }
 }
 
@@ -172,11 +183,33 @@ __device__ __forceinline__ void write_venc_row(uint8_t* enc_tile, uint8_t* save_
         uint4 v = make_uint4(ptx::pack_bf16(e[ch * 8], e[ch * 8 + 1]), ptx::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]),
                              ptx::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]), ptx::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
         *reinterpret_cast<uint4*>(enc_tile + ch * KROW + row * 16) = v;
-        if (save_img) *reinterpret_cast<uint4*>(save_img + ch * KROW + row * 16) = v;
+        if (save_img) *reinterpret_cast<uint4*>(save_img + hbm_img_off(ENCV_PAD, row, ch)) = v;
     }
 }
 
-__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+// One 32-column chunk of a layer epilogue.  The accumulator already holds W.x + b (the bias rides on the tensor
+// cores), so a pair of columns costs one F2FP.RELU (ReLU + BF16 pack) and two logic ops for the ReLU flags.
+//   act      next layer's A image in shared memory (nullptr: not needed, rgb0)
+//   save_img this layer's image in the tile record (nullptr: inference); C = image columns
+//   flags    this layer's ReLU-flag words of the tile record (nullptr: inference)
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int cc, int row, int C, uint8_t* act,
+                                               uint8_t* save_img, uint32_t* flags, uint32_t (&pk)[16]) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        pk[j] = ptx::pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        bits |= ptx::gt0_mask_bf16x2(pk[j]) & ptx::relu_mask_const(j);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        if (act) *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
+        if (save_img) *reinterpret_cast<uint4*>(save_img + hbm_img_off(C, row, cc * 4 + q)) = o;
+    }
+    if (flags) flags[cc * TILE + row] = bits;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 
 // ------------------------------------------------------------------------------------------
 // fused forward kernel
@@ -205,7 +238,13 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
-    if (warp == 3) for (int i = lane; i < C_FLOATS; i += 32) cst[i] = consts_g[i];
+    if (warp == 3) {
+        for (int i = lane; i < C_FLOATS; i += 32) cst[i] = consts_g[i];
+        // constant A image of the bias products: columns 0 and 1 are 1.0, the other 14 are 0
+        uint4* ones = reinterpret_cast<uint4*>(smem + SM_ONES);
+        for (int i = lane; i < ONES_BYTES / 16; i += 32) ones[i] = i < TILE ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        ptx::fence_proxy_async();
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -220,8 +259,9 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
             for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
                 const uint8_t* src = wstream;
                 for (int l = 0; l < NLAYER; ++l) {
-                    const uint32_t bytes = (uint32_t)layer_rows(l) * CHUNK_K * 2;
-                    for (int c = 0; c < layer_chunks(l); ++c, ++it) {
+                    const int nch = layer_chunks(l);
+                    for (int c = 0; c <= nch; ++c, ++it) {          // chunk nch is the K = 16 bias chunk
+                        const uint32_t bytes = (uint32_t)layer_rows(l) * (c < nch ? CHUNK_K : BIAS_K) * 2;
                         const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
                         ptx::mbar_wait(&w_empty[st], ph ^ 1);
                         ptx::mbar_arrive_expect_tx(&w_full[st], bytes);
@@ -236,30 +276,40 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
         if (lane == 0) {
             uint32_t it = 0, ready_uses = 0;
             const uint32_t act0 = ptx::smem_addr(smem + SM_ACT), enc0 = ptx::smem_addr(smem + SM_ENC);
-            const uint32_t ring0 = ptx::smem_addr(smem + SM_RING);
+            const uint32_t ring0 = ptx::smem_addr(smem + SM_RING), ones0 = ptx::smem_addr(smem + SM_ONES);
             for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
                 for (int l = 0; l < NLAYER; ++l, ++ready_uses) {
                     const int rows = layer_rows(l), nch = layer_chunks(l);
                     const uint32_t idesc = ptx::idesc_bf16(TILE, rows, 0, 0);
-                    for (int c = 0; c < nch; ++c, ++it) {
+                    for (int c = 0; c <= nch; ++c, ++it) {
                         const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
                         ptx::mbar_wait(&w_full[st], ph);
                         ptx::tc_fence_after();
-                        // which A tile region does this chunk multiply?
-                        const bool from_enc = (l == 0) || (c >= 8);
-                        const int kc0 = (l == 0 ? c : (c >= 8 ? c - 8 : c)) * (CHUNK_K / 8);
+                        const uint32_t b_base = ring0 + st * STAGE_BYTES;
+                        if (c < nch) {
+                            // which A tile region does this chunk multiply?
+                            const bool from_enc = (l == 0) || (c >= 8);
+                            const int kc0 = (l == 0 ? c : (c >= 8 ? c - 8 : c)) * (CHUNK_K / 8);
 #pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            if (c == 0) { ptx::mbar_wait(&a_ready[s], ready_uses & 1); ptx::tc_fence_after(); }
-                            const uint32_t a_base = (from_enc ? enc0 + s * ENC_BYTES : act0 + s * ACT_BYTES) + kc0 * KROW;
-                            const uint32_t b_base = ring0 + st * STAGE_BYTES;
+                            for (int s = 0; s < 2; ++s) {
+                                if (c == 0) { ptx::mbar_wait(&a_ready[s], ready_uses & 1); ptx::tc_fence_after(); }
+                                const uint32_t a_base = (from_enc ? enc0 + s * ENC_BYTES : act0 + s * ACT_BYTES) + kc0 * KROW;
 #pragma unroll
-                            for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
-                                uint64_t ad = ptx::smem_desc(a_base + ks * 2 * KROW, KROW, 128);
-                                uint64_t bd = ptx::smem_desc(b_base + ks * 2 * rows * 16, rows * 16, 128);
-                                ptx::mma_bf16(tmem_base + s * WIDTH, ad, bd, idesc, (c | ks) != 0);
+                                for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
+                                    uint64_t ad = ptx::smem_desc(a_base + ks * 2 * KROW, KROW, 128);
+                                    uint64_t bd = ptx::smem_desc(b_base + ks * 2 * rows * 16, rows * 16, 128);
+                                    ptx::mma_bf16(tmem_base + s * WIDTH, ad, bd, idesc, (c | ks) != 0);
+                                }
                             }
-                            if (c == nch - 1) ptx::mma_commit(&acc_full[s]);
+                        } else {
+                            // bias: D += ones[128 x 16] . [bf16(b), b - bf16(b), 0 ...]^T
+                            const uint64_t ad = ptx::smem_desc(ones0, KROW, 128);
+                            const uint64_t bd = ptx::smem_desc(b_base, rows * 16, 128);
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) {
+                                ptx::mma_bf16(tmem_base + s * WIDTH, ad, bd, idesc, true);
+                                ptx::mma_commit(&acc_full[s]);
+                            }
                         }
                         ptx::mma_commit(&w_empty[st]);
                     }
@@ -299,86 +349,76 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
             for (int l = 0; l < NLAYER; ++l, ++full_uses) {
                 ptx::mbar_wait(&acc_full[slot], full_uses & 1);
                 ptx::tc_fence_after();
-                const float* bias = cst + C_BIAS + l * WIDTH;
+                uint32_t va[32], vb[32], pk[16];
                 if (l < 8) {
+                    uint8_t* save_img = save_tile ? save_tile + SV_H + (int64_t)l * ACT_BYTES : nullptr;
+                    uint32_t* flags = mask_tile ? mask_tile + l * MASK_WORDS * TILE : nullptr;
                     float sig_acc = 0.f;
+                    ptx::tmem_ld32(tacc, va);
 #pragma unroll 1
-                    for (int cc = 0; cc < WIDTH / 32; ++cc) {
-                        uint32_t v[32];
-                        ptx::tmem_ld32(tacc + cc * 32, v);
+                    for (int c2 = 0; c2 < WIDTH / 64; ++c2) {
+                        // TMEM loads run one chunk ahead of the arithmetic
                         ptx::tmem_ld_wait();
-                        uint32_t pk[16];
-                        uint32_t bits = 0;
+                        ptx::tmem_ld32(tacc + (2 * c2 + 1) * 32, vb);
+                        epilogue_chunk(va, 2 * c2, row, WIDTH, act, save_img, flags, pk);
+                        if (l == 6) {   // density head: row 0 of layer 7 applied to h6 (nerf.py:427)
+                            const float4* w = reinterpret_cast<const float4*>(cst + C_W7R0 + (2 * c2) * 32);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = fmaxf(__uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j], 0.f);
-                            float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1], 0.f);
-                            pk[j] = ptx::pack_bf16(a, b);
-                            bits |= (a > 0.f ? 1u : 0u) << (2 * j);
-                            bits |= (b > 0.f ? 1u : 0u) << (2 * j + 1);
-                            if (l == 6) {   // density head: row 0 of layer 7 applied to h6 (nerf.py:427)
-                                __nv_bfloat162 q = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-                                sig_acc += cst[C_W7R0 + cc * 32 + 2 * j] * __low2float(q) +
-                                           cst[C_W7R0 + cc * 32 + 2 * j + 1] * __high2float(q);
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 w4 = w[q];
+                                sig_acc += w4.x * bf16_lo(pk[2 * q]) + w4.y * bf16_hi(pk[2 * q]) +
+                                           w4.z * bf16_lo(pk[2 * q + 1]) + w4.w * bf16_hi(pk[2 * q + 1]);
                             }
                         }
+                        ptx::tmem_ld_wait();
+                        if (c2 + 1 < WIDTH / 64) ptx::tmem_ld32(tacc + (2 * c2 + 2) * 32, va);
+                        epilogue_chunk(vb, 2 * c2 + 1, row, WIDTH, act, save_img, flags, pk);
+                        if (l == 6) {
+                            const float4* w = reinterpret_cast<const float4*>(cst + C_W7R0 + (2 * c2 + 1) * 32);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-                            *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
-                            if (save_tile)
-                                *reinterpret_cast<uint4*>(save_tile + SV_H + (int64_t)l * ACT_BYTES + (cc * 4 + q) * KROW + row * 16) = o;
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 w4 = w[q];
+                                sig_acc += w4.x * bf16_lo(pk[2 * q]) + w4.y * bf16_hi(pk[2 * q]) +
+                                           w4.z * bf16_lo(pk[2 * q + 1]) + w4.w * bf16_hi(pk[2 * q + 1]);
+                            }
                         }
-                        if (mask_tile) mask_tile[(l * MASK_WORDS + cc) * TILE + row] = bits;
-                    }
-                    if (l == 6 && valid) {
-                        float pre = sig_acc + cst[C_MISC];
-                        sigma_out[g] = softplus_f(pre);
-                        if (sig_pre) sig_pre[g] = pre;
                     }
                     if (l == 7)   // A columns 256..287 of rgb0
                         write_venc_row(enc, save_tile ? save_tile + SV_VENC : nullptr, row, v3, bwv, valid);
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
                     ptx::mbar_arrive(&a_ready[slot]);
+                    if (l == 6 && valid) {
+                        float pre = sig_acc + cst[C_MISC];
+                        sigma_out[g] = softplus_f(pre);
+                        if (sig_pre) sig_pre[g] = pre;
+                    }
                 } else {
                     // rgb0 epilogue: hr = relu(.), rgb = sigmoid(W_rgb1 hr + b)   (nerf.py:442-446)
                     float o0 = cst[C_MISC + 1], o1 = cst[C_MISC + 2], o2 = cst[C_MISC + 3];
+                    uint8_t* save_img = save_tile ? save_tile + SV_HR : nullptr;
+                    uint32_t* flags = mask_tile ? mask_tile + 8 * MASK_WORDS * TILE : nullptr;
 #pragma unroll 1
                     for (int cc = 0; cc < RGBW / 32; ++cc) {
-                        uint32_t v[32];
-                        ptx::tmem_ld32(tacc + cc * 32, v);
+                        ptx::tmem_ld32(tacc + cc * 32, va);
                         ptx::tmem_ld_wait();
-                        uint32_t pk[16];
-                        uint32_t bits = 0;
+                        epilogue_chunk(va, cc, row, RGBW, nullptr, save_img, flags, pk);
+                        const float4* w0 = reinterpret_cast<const float4*>(cst + C_WRGB1 + cc * 32);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = fmaxf(__uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j], 0.f);
-                            float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1], 0.f);
-                            pk[j] = ptx::pack_bf16(a, b);
-                            bits |= (a > 0.f ? 1u : 0u) << (2 * j);
-                            bits |= (b > 0.f ? 1u : 0u) << (2 * j + 1);
-                            __nv_bfloat162 q = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-                            float ra = __low2float(q), rb = __high2float(q);
-                            const int col = cc * 32 + 2 * j;
-                            o0 += cst[C_WRGB1 + col] * ra + cst[C_WRGB1 + col + 1] * rb;
-                            o1 += cst[C_WRGB1 + RGBW + col] * ra + cst[C_WRGB1 + RGBW + col + 1] * rb;
-                            o2 += cst[C_WRGB1 + 2 * RGBW + col] * ra + cst[C_WRGB1 + 2 * RGBW + col + 1] * rb;
-                        }
-                        if (save_tile) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                *reinterpret_cast<uint4*>(save_tile + SV_HR + (cc * 4 + q) * KROW + row * 16) =
-                                    make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-                            mask_tile[(8 * MASK_WORDS + cc) * TILE + row] = bits;
+                        for (int q = 0; q < 8; ++q) {
+                            const float a = bf16_lo(pk[2 * q]), b = bf16_hi(pk[2 * q]), c = bf16_lo(pk[2 * q + 1]), d = bf16_hi(pk[2 * q + 1]);
+                            const float4 x0 = w0[q], x1 = w0[RGBW / 4 + q], x2 = w0[2 * RGBW / 4 + q];
+                            o0 += x0.x * a + x0.y * b + x0.z * c + x0.w * d;
+                            o1 += x1.x * a + x1.y * b + x1.z * c + x1.w * d;
+                            o2 += x2.x * a + x2.y * b + x2.z * c + x2.w * d;
                         }
                     }
+                    ptx::tc_fence_before();   // TMEM reads done before the next pass overwrites the accumulator
                     if (valid) {
                         float r0 = sigmoid_f(o0), r1 = sigmoid_f(o1), r2 = sigmoid_f(o2);
                         rgb_out[g * 3] = r0; rgb_out[g * 3 + 1] = r1; rgb_out[g * 3 + 2] = r2;
                         if (rgb_keep) { rgb_keep[g * 3] = r0; rgb_keep[g * 3 + 1] = r1; rgb_keep[g * 3 + 2] = r2; }
                     }
-                    ptx::tc_fence_before();   // TMEM reads done before the next pass overwrites the accumulator
                 }
             }
         }

@@ -167,62 +167,69 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
 #pragma unroll 1
             for (int cc = 0; cc < RGBW / 32; ++cc) {
                 const uint32_t bits = mask ? mask[(8 * MASK_WORDS + cc) * TILE + row] : 0u;
+                const float4* w0 = reinterpret_cast<const float4*>(cst + WIDTH + cc * 32);
                 uint32_t pk[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c0 = cc * 32 + 2 * j;
-                    float a = g3[0] * cst[WIDTH + c0] + g3[1] * cst[WIDTH + RGBW + c0] + g3[2] * cst[WIDTH + 2 * RGBW + c0];
-                    float b = g3[0] * cst[WIDTH + c0 + 1] + g3[1] * cst[WIDTH + RGBW + c0 + 1] + g3[2] * cst[WIDTH + 2 * RGBW + c0 + 1];
-                    a = (bits >> (2 * j)) & 1u ? a : 0.f;
-                    b = (bits >> (2 * j + 1)) & 1u ? b : 0.f;
-                    pk[j] = ptx::pack_bf16(a, b);
+                for (int q = 0; q < 8; ++q) {
+                    const float4 x0 = w0[q], x1 = w0[RGBW / 4 + q], x2 = w0[2 * RGBW / 4 + q];
+                    const float a = g3[0] * x0.x + g3[1] * x1.x + g3[2] * x2.x, b = g3[0] * x0.y + g3[1] * x1.y + g3[2] * x2.y;
+                    const float c = g3[0] * x0.z + g3[1] * x1.z + g3[2] * x2.z, d = g3[0] * x0.w + g3[1] * x1.w + g3[2] * x2.w;
+                    pk[2 * q] = ptx::pack_bf16(a, b) & ptx::relu_mask_expand(bits << q, 2 * q);
+                    pk[2 * q + 1] = ptx::pack_bf16(c, d) & ptx::relu_mask_expand(bits << q, 2 * q + 1);
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
                     *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
-                    if (rec) *reinterpret_cast<uint4*>(rec + SV_G8 + (cc * 4 + q) * KROW + row * 16) = o;
+                    if (rec) *reinterpret_cast<uint4*>(rec + SV_G8 + hbm_img_off(RGBW, row, cc * 4 + q)) = o;
                 }
             }
-            if (rec) {
-                // small image: columns [g_rgb_pre(3), g_sigma_pre, 1, 0, 0, 0 | 0 x 8]
-                uint4 o = make_uint4(ptx::pack_bf16(g3[0], g3[1]), ptx::pack_bf16(g3[2], gs),
-                                     ptx::pack_bf16(valid ? 1.f : 0.f, 0.f), 0u);
-                *reinterpret_cast<uint4*>(rec + SV_SMALL + row * 16) = o;
-                *reinterpret_cast<uint4*>(rec + SV_SMALL + KROW + row * 16) = make_uint4(0u, 0u, 0u, 0u);
-            }
+            if (rec)   // small image: columns [g_rgb_pre(3), g_sigma_pre, 1, 0, 0, 0]
+                *reinterpret_cast<uint4*>(rec + SV_SMALL + row * 16) =
+                    make_uint4(ptx::pack_bf16(g3[0], g3[1]), ptx::pack_bf16(g3[2], gs), ptx::pack_bf16(valid ? 1.f : 0.f, 0.f), 0u);
             ptx::fence_proxy_async();
             ptx::mbar_arrive(&a_ready[slot]);
 
             for (int s = 0; s < NSTEP; ++s, ++full_uses) {
+                const int lo = step_out_layer(s);
+                uint32_t mw[MASK_WORDS];
+                if (lo >= 0) {   // the ReLU flags do not depend on the products: fetch them while the MMAs run
+#pragma unroll
+                    for (int cc = 0; cc < MASK_WORDS; ++cc) mw[cc] = mask ? mask[(lo * MASK_WORDS + cc) * TILE + row] : 0u;
+                }
                 ptx::mbar_wait(&acc_full[slot], full_uses & 1);
                 ptx::tc_fence_after();
-                const int lo = step_out_layer(s);
                 if (lo >= 0) {
                     // ---- hidden layers: (+ density rank-1 term) -> ReLU mask -> BF16 -> next A tile + G image ----
-#pragma unroll 1
-                    for (int cc = 0; cc < WIDTH / 32; ++cc) {
-                        uint32_t v[32];
-                        ptx::tmem_ld32(tacc + cc * 32, v);
-                        const uint32_t bits = mask ? mask[(lo * MASK_WORDS + cc) * TILE + row] : 0u;
-                        ptx::tmem_ld_wait();
-                        uint32_t pk[16];
+                    uint8_t* save_img = rec ? rec + SV_G + (int64_t)lo * ACT_BYTES : nullptr;
+                    uint32_t v[2][32];
+                    ptx::tmem_ld32(tacc, v[0]);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-                            if (s == 2) {   // dL/dh6 += g_sigma_pre * W7[0, :]   (density head, nerf.py:427)
-                                a += gs * cst[cc * 32 + 2 * j];
-                                b += gs * cst[cc * 32 + 2 * j + 1];
+                    for (int cc = 0; cc < WIDTH / 32; ++cc) {
+                        // TMEM loads run one chunk ahead of the arithmetic
+                        ptx::tmem_ld_wait();
+                        if (cc + 1 < WIDTH / 32) ptx::tmem_ld32(tacc + (cc + 1) * 32, v[(cc + 1) & 1]);
+                        const uint32_t (&vc)[32] = v[cc & 1];
+                        uint32_t pk[16];
+                        if (s == 2) {   // dL/dh6 += g_sigma_pre * W7[0, :]   (density head, nerf.py:427)
+                            const float4* w = reinterpret_cast<const float4*>(cst + cc * 32);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 w4 = w[q];
+                                pk[2 * q] = ptx::pack_bf16(__uint_as_float(vc[4 * q]) + gs * w4.x, __uint_as_float(vc[4 * q + 1]) + gs * w4.y);
+                                pk[2 * q + 1] = ptx::pack_bf16(__uint_as_float(vc[4 * q + 2]) + gs * w4.z, __uint_as_float(vc[4 * q + 3]) + gs * w4.w);
                             }
-                            a = (bits >> (2 * j)) & 1u ? a : 0.f;
-                            b = (bits >> (2 * j + 1)) & 1u ? b : 0.f;
-                            pk[j] = ptx::pack_bf16(a, b);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(vc[2 * j]), __uint_as_float(vc[2 * j + 1]));
                         }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] &= ptx::relu_mask_expand(mw[cc] << (j >> 1), j);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
                             *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
-                            if (rec) *reinterpret_cast<uint4*>(rec + SV_G + (int64_t)lo * ACT_BYTES + (cc * 4 + q) * KROW + row * 16) = o;
+                            if (save_img) *reinterpret_cast<uint4*>(save_img + hbm_img_off(WIDTH, row, cc * 4 + q)) = o;
                         }
                     }
                     ptx::tc_fence_before();
@@ -311,16 +318,33 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
 // ==========================================================================================
 // dW pass
 // ==========================================================================================
+// One CTA per (unit, sample slice).  A unit is one weight block dW = G^T . X with all its output rows:
+// G (up to 256 features = two M = 128 blocks) and X (N <= 256 features) are streamed as 64-sample half
+// images (contiguous in the tile record, MN-major operands with K = samples) through a 3-stage ring, and the
+// two 128 x N fp32 accumulators fill TMEM for the whole slice, so every tile costs 128 KB of HBM reads for
+// 16.8 MFLOP.  The thin products (bias gradients = G^T . 1, density row = h6^T . g_sigma, rgb1 weights =
+// hr^T . g_rgb) have no TMEM columns left: warps 4-7 compute them from the same staged half images with
+// warp-level mma.sync (m16n8k16, A = small image^T via ldmatrix.trans), accumulating in registers.
 
-constexpr int BW_NSTAGE = 2;
-constexpr int BW_A = 0;                                  // 32 KB: 128 features x 128 samples
-constexpr int BW_B = BW_A + HR_BYTES;                    // 64 KB: up to 256 features x 128 samples
-constexpr int BW_S = BW_B + ACT_BYTES;                   // 4 KB small image
-constexpr int BW_STAGE = BW_S + SMALL_BYTES;             // 102400
+constexpr int BW_NSTAGE = 3;
+constexpr int BW_A = 0;                                  // 32 KB: 64 samples x up to 256 features (G)
+constexpr int BW_B = BW_A + ACT_BYTES / 2;               // 32 KB: 64 samples x up to 256 features (X)
+constexpr int BW_S = BW_B + ACT_BYTES / 2;               // 1 KB:  64 samples x 8 columns (small image)
+constexpr int BW_STAGE = BW_S + SMALL_BYTES / 2;         // 66560
 constexpr int BW_BAR = BW_NSTAGE * BW_STAGE;
 constexpr int BW_TOTAL = BW_BAR + 64;
 static_assert(BW_TOTAL <= 227 * 1024, "shared memory budget (dW pass)");
-constexpr int BW_SMALL_COL = 256;                        // TMEM columns [256, 272): products with the small image
+static_assert(4 * 32 * 33 * 4 <= BW_STAGE, "epilogue transpose buffers fit in stage 0");
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
+// D(16x8, only rows 0-7 used) += A(16x16, rows 8-15 zero) . B(16x8)
+__device__ __forceinline__ void mma_16816_top(float (&d)[2], float (&z)[2], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(z[0]), "+f"(z[1]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(256, 1)
 tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, float* __restrict__ partial) {
@@ -337,9 +361,10 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
     const DwUnit& U = plan.u[ui];
     const int slice = (int)blockIdx.x - U.first_cta;
     const int64_t t0 = ntiles * slice / U.n_slices, t1 = ntiles * (slice + 1) / U.n_slices;
+    const int64_t nstages = 2 * (t1 - t0);     // 64-sample halves
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < BW_NSTAGE; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < BW_NSTAGE; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 5); }
         ptx::mbar_init(done, 1);
         ptx::fence_mbar_init();
     }
@@ -351,55 +376,95 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t t = t0; t < t1; ++t, ++it) {
-                const uint32_t st = it % BW_NSTAGE, ph = (it / BW_NSTAGE) & 1;
-                const uint8_t* rec = save + t * SAVE_TILE_BYTES;
+            for (int64_t it = 0; it < nstages; ++it) {
+                const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
+                const uint8_t* rec = save + (t0 + (it >> 1)) * SAVE_TILE_BYTES;
+                const int half = (int)(it & 1);
                 uint8_t* dst = smem + st * BW_STAGE;
                 ptx::mbar_wait(&empty[st], ph ^ 1);
-                ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)(U.a_bytes + U.b_bytes + SMALL_BYTES));
-                ptx::bulk_g2s(dst + BW_A, rec + U.a_off, (uint32_t)U.a_bytes, &full[st]);
-                if (U.b_bytes) ptx::bulk_g2s(dst + BW_B, rec + U.b_off, (uint32_t)U.b_bytes, &full[st]);
-                ptx::bulk_g2s(dst + BW_S, rec + SV_SMALL, SMALL_BYTES, &full[st]);
+                ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)(U.a_half + U.b_half + SMALL_BYTES / 2));
+                ptx::bulk_g2s(dst + BW_A, rec + U.a_off + half * U.a_half, (uint32_t)U.a_half, &full[st]);
+                if (U.b_half) ptx::bulk_g2s(dst + BW_B, rec + U.b_off + half * U.b_half, (uint32_t)U.b_half, &full[st]);
+                ptx::bulk_g2s(dst + BW_S, rec + SV_SMALL + half * (SMALL_BYTES / 2), SMALL_BYTES / 2, &full[st]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc_main = ptx::idesc_bf16(TILE, U.n_main > 0 ? U.n_main : 16, 1, 1);
-            const uint32_t idesc_small = ptx::idesc_bf16(TILE, 16, 1, 1);
-            uint32_t it = 0;
-            for (int64_t t = t0; t < t1; ++t, ++it) {
-                const uint32_t st = it % BW_NSTAGE, ph = (it / BW_NSTAGE) & 1;
+            const uint32_t idesc = ptx::idesc_bf16(TILE, U.n_main > 0 ? U.n_main : 16, 1, 1);
+            for (int64_t it = 0; it < nstages; ++it) {
+                const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
                 ptx::mbar_wait(&full[st], ph);
                 ptx::tc_fence_after();
                 const uint32_t base = ptx::smem_addr(smem + st * BW_STAGE);
+                if (U.n_main > 0) {
 #pragma unroll
-                for (int ks = 0; ks < TILE / 16; ++ks) {
-                    // MN-major operands, K = samples: 16 samples = 256 B along a row group
-                    const uint64_t ad = ptx::smem_desc(base + BW_A + ks * 256, 128, KROW);
-                    const bool acc = (it | ks) != 0;
-                    if (U.n_main > 0) {
-                        const uint64_t bd = ptx::smem_desc(base + BW_B + ks * 256, 128, KROW);
-                        ptx::mma_bf16(tmem_base, ad, bd, idesc_main, acc);
+                    for (int ks = 0; ks < HALF / 16; ++ks) {
+                        // MN-major operands, K = samples: 16 samples = 256 B along a feature group
+                        const uint64_t bd = ptx::smem_desc(base + BW_B + ks * 256, 128, HROW);
+                        for (int h = 0; h < U.m_halves; ++h) {
+                            const uint64_t ad = ptx::smem_desc(base + BW_A + h * 16 * HROW + ks * 256, 128, HROW);
+                            ptx::mma_bf16(tmem_base + h * WIDTH, ad, bd, idesc, (it | ks) != 0);
+                        }
                     }
-                    const uint64_t sd = ptx::smem_desc(base + BW_S + ks * 256, 128, KROW);
-                    ptx::mma_bf16(tmem_base + BW_SMALL_COL, ad, sd, idesc_small, acc);
                 }
                 ptx::mma_commit(&empty[st]);
             }
             ptx::mma_commit(done);
         }
     } else if (warp >= 4) {
+        const int wq = warp & 3;
+        // ---- thin products on the warp-level tensor path while the tiles stream ----
+        // this warp owns feature groups [wq*ga, (wq+1)*ga) of the G image and [wq*gb, ...) of the X image
+        const int ga = U.side_a ? U.a_half / HROW / 4 : 0;      // 8 (256 features) or 4 (128)
+        const int gb = U.side_b ? U.b_half / HROW / 4 : 0;
+        float acc_a[8][2], acc_b[8][2], zz[2] = {0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc_a[i][0] = acc_a[i][1] = acc_b[i][0] = acc_b[i][1] = 0.f; }
+        for (int64_t it = 0; it < nstages; ++it) {
+            const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
+            ptx::mbar_wait(&full[st], ph);
+            if (ga | gb) {
+                const uint32_t base = ptx::smem_addr(smem + st * BW_STAGE);
+                uint32_t sa[2][4];
+                ldsm_x4_trans(sa[0], base + BW_S + lane * 16);
+                ldsm_x4_trans(sa[1], base + BW_S + 512 + lane * 16);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < ga) {
+                        const uint32_t x = base + BW_A + (wq * ga + i) * HROW + lane * 16;
+                        uint32_t xb[2][4];
+                        ldsm_x4_trans(xb[0], x);
+                        ldsm_x4_trans(xb[1], x + 512);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_16816_top(acc_a[i], zz, sa[k >> 1][(k & 1) * 2], sa[k >> 1][(k & 1) * 2 + 1], xb[k >> 1][(k & 1) * 2], xb[k >> 1][(k & 1) * 2 + 1]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < gb) {
+                        const uint32_t x = base + BW_B + (wq * gb + i) * HROW + lane * 16;
+                        uint32_t xb[2][4];
+                        ldsm_x4_trans(xb[0], x);
+                        ldsm_x4_trans(xb[1], x + 512);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_16816_top(acc_b[i], zz, sa[k >> 1][(k & 1) * 2], sa[k >> 1][(k & 1) * 2 + 1], xb[k >> 1][(k & 1) * 2], xb[k >> 1][(k & 1) * 2 + 1]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[st]);
+        }
         // ---- epilogue: TMEM -> (per-warp transpose in shared memory) -> coalesced partial-sum rows ----
         ptx::mbar_wait(done, 0);
         ptx::tc_fence_after();
-        const int wq = warp & 3;
-        const int row = wq * 32 + lane;                      // output feature (TMEM lane) of this thread
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // all four warps are done with the stage buffers
         float* out = partial + (size_t)slice * NPARAMS;
-        float* tr = reinterpret_cast<float*>(smem) + wq * (32 * 33);   // stage buffers are idle now
-        const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16);
         if (t1 > t0) {
-            if (U.kind == 0) {
+            float* tr = reinterpret_cast<float*>(smem) + wq * (32 * 33);   // stage buffers are idle now
+            for (int h = 0; h < U.m_halves && U.n_main > 0; ++h) {
+                const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + h * WIDTH;
                 for (int c0 = 0; c0 < U.n_main; c0 += 32) {
                     uint32_t v[32];
                     ptx::tmem_ld32(tacc + c0, v);
@@ -410,26 +475,24 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
                     const int col = c0 + lane;
                     if (col < U.ncols) {
                         for (int rr = 0; rr < 32; ++rr)
-                            out[U.w_base + (int64_t)(wq * 32 + rr) * U.ld + U.col0 + col] = tr[rr * 33 + lane];
+                            out[U.w_base + (int64_t)(h * 128 + wq * 32 + rr) * U.ld + U.col0 + col] = tr[rr * 33 + lane];
                     }
                     __syncwarp();
                 }
             }
-            uint32_t sv[16];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                         : "=r"(sv[0]), "=r"(sv[1]), "=r"(sv[2]), "=r"(sv[3]), "=r"(sv[4]), "=r"(sv[5]), "=r"(sv[6]),
-                           "=r"(sv[7]), "=r"(sv[8]), "=r"(sv[9]), "=r"(sv[10]), "=r"(sv[11]), "=r"(sv[12]), "=r"(sv[13]),
-                           "=r"(sv[14]), "=r"(sv[15])
-                         : "r"(tacc + BW_SMALL_COL) : "memory");
-            ptx::tmem_ld_wait();
-            if (U.kind == 0) {
-                if (U.b_base >= 0) out[U.b_base + row] = __uint_as_float(sv[4]);          // sum_s G[s, row] * 1
-            } else if (U.kind == 1) {
+            // thin products: this lane holds row m = lane / 4 of small^T . X for features 8*group + 2*(lane % 4) + {0, 1}
+            const int m = lane >> 2, n0 = (lane & 3) * 2;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) out[RGB1_W + c * RGBW + row] = __uint_as_float(sv[c]);   // hr^T . g_rgb_pre
-            } else {
-                out[U.w_base + row] = __uint_as_float(sv[3]);                              // h6^T . g_sigma_pre
+            for (int i = 0; i < 8; ++i) {
+                if (i < ga) {
+                    const int f = (wq * ga + i) * 8 + n0;
+                    if (U.side_a == 1 && m == 4) { out[U.b_base + f] = acc_a[i][0]; out[U.b_base + f + 1] = acc_a[i][1]; }       // G^T . 1
+                    if (U.side_a == 2 && m < 3) { out[RGB1_W + m * RGBW + f] = acc_a[i][0]; out[RGB1_W + m * RGBW + f + 1] = acc_a[i][1]; }   // hr^T . g_rgb_pre
+                }
+                if (i < gb) {
+                    const int f = (wq * gb + i) * 8 + n0;
+                    if (m == 3) { out[U.side_b_base + f] = acc_b[i][0]; out[U.side_b_base + f + 1] = acc_b[i][1]; }              // h6^T . g_sigma_pre
+                }
             }
         }
         ptx::tc_fence_before();
@@ -452,40 +515,38 @@ __global__ void tc_dw_reduce_kernel(const float* __restrict__ partial, int n_sli
 static DwPlan make_plan(int64_t ntiles, int n_sms) {
     DwPlan p;
     int n = 0;
-    auto add = [&](int a_off, int b_off, int b_bytes, int n_main, int kind, int ld, int col0, int ncols, int64_t w_base,
-                   int64_t b_base) {
+    auto add = [&](int64_t a_off, int a_cols, int64_t b_off, int b_cols, int ld, int col0, int ncols, int64_t w_base,
+                   int64_t b_base, int side_a, int64_t side_b_base) {
         DwUnit& u = p.u[n++];
-        u.a_off = a_off; u.a_bytes = HR_BYTES; u.b_off = b_off; u.b_bytes = b_bytes; u.n_main = n_main; u.kind = kind;
-        u.ld = ld; u.col0 = col0; u.ncols = ncols; u.pad_ = 0; u.w_base = w_base; u.b_base = b_base;
+        u.a_off = (int32_t)a_off; u.a_half = a_cols / 8 * HROW; u.m_halves = a_cols / 128;
+        u.b_off = (int32_t)b_off; u.b_half = b_cols / 8 * HROW; u.n_main = b_cols;
+        u.ld = ld; u.col0 = col0; u.ncols = ncols; u.w_base = w_base; u.b_base = b_base;
+        u.side_a = side_a; u.side_b = side_b_base >= 0 ? 1 : 0; u.side_b_base = side_b_base;
         u.first_cta = 0; u.n_slices = 1;
     };
     for (int l = 0; l < NFEAT; ++l) {
         const int ro = layer_rowoff(l);
-        for (int h = 0; h < 2; ++h) {
-            const int a_off = (int)(SV_G + (int64_t)l * ACT_BYTES + h * HR_BYTES);
-            const int64_t w_base = feat_w_off(l) + (int64_t)(ro + h * 128) * feat_in(l);
-            const int64_t b_base = feat_b_off(l) + ro + h * 128;
-            if (l == 0) {
-                add(a_off, (int)SV_ENC, ENC_BYTES, ENC3_PAD, 0, feat_in(l), 0, ENC3, w_base, b_base);
-            } else {
-                add(a_off, (int)(SV_H + (int64_t)(l - 1) * ACT_BYTES), ACT_BYTES, WIDTH, 0, feat_in(l), 0, WIDTH, w_base, b_base);
-                if (l == SKIP) add(a_off, (int)SV_ENC, ENC_BYTES, ENC3_PAD, 0, feat_in(l), WIDTH, ENC3, w_base, -1);
-            }
+        const int64_t a_off = SV_G + (int64_t)l * ACT_BYTES;
+        const int64_t w_base = feat_w_off(l) + (int64_t)ro * feat_in(l), b_base = feat_b_off(l) + ro;
+        if (l == 0) {
+            add(a_off, WIDTH, SV_ENC, ENC3_PAD, feat_in(l), 0, ENC3, w_base, b_base, 1, -1);
+        } else {
+            add(a_off, WIDTH, SV_H + (int64_t)(l - 1) * ACT_BYTES, WIDTH, feat_in(l), 0, WIDTH, w_base, b_base, 1,
+                l == NFEAT - 1 ? feat_w_off(l) : -1);                                   // layer 7: + density row from h6
+            if (l == SKIP) add(a_off, WIDTH, SV_ENC, ENC3_PAD, feat_in(l), WIDTH, ENC3, w_base, -1, 0, -1);
         }
     }
-    add((int)SV_G8, (int)(SV_H + 7 * (int64_t)ACT_BYTES), ACT_BYTES, WIDTH, 0, WIDTH + ENCV, 0, WIDTH, RGB0_W, RGB0_B);
-    add((int)SV_G8, (int)SV_VENC, VENC_BYTES, ENCV_PAD, 0, WIDTH + ENCV, WIDTH, ENCV, RGB0_W, -1);
-    add((int)SV_HR, 0, 0, 0, 1, 0, 0, 0, RGB1_W, -1);                                        // rgb1 weights
-    for (int h = 0; h < 2; ++h)                                                               // density row of layer 7
-        add((int)(SV_H + 6 * (int64_t)ACT_BYTES + h * HR_BYTES), 0, 0, 0, 2, 0, 0, 0, feat_w_off(7) + h * 128, -1);
+    add(SV_G8, RGBW, SV_H + 7 * (int64_t)ACT_BYTES, WIDTH, WIDTH + ENCV, 0, WIDTH, RGB0_W, RGB0_B, 1, -1);
+    add(SV_G8, RGBW, SV_VENC, ENCV_PAD, WIDTH + ENCV, WIDTH, ENCV, RGB0_W, -1, 0, -1);
+    add(SV_HR, RGBW, 0, 0, 0, 0, 0, RGB1_W, -1, 2, -1);                                  // rgb1 weights (thin product only)
     p.n_units = n;
     // slices proportional to bytes streamed per tile, capped by the tile count and PARTIAL_SLICES
     double total = 0;
-    for (int i = 0; i < n; ++i) total += p.u[i].a_bytes + p.u[i].b_bytes + SMALL_BYTES;
+    for (int i = 0; i < n; ++i) total += 2 * (p.u[i].a_half + p.u[i].b_half) + SMALL_BYTES;
     int budget = n_sms > n ? n_sms : n;
     int used = 0;
     for (int i = 0; i < n; ++i) {
-        double share = (p.u[i].a_bytes + p.u[i].b_bytes + SMALL_BYTES) / total * budget;
+        double share = (2 * (p.u[i].a_half + p.u[i].b_half) + SMALL_BYTES) / total * budget;
         int s = (int)share;
         if (s < 1) s = 1;
         if (s > PARTIAL_SLICES) s = PARTIAL_SLICES;
@@ -494,7 +555,7 @@ static DwPlan make_plan(int64_t ntiles, int n_sms) {
     }
     for (int pass = 0; pass < 4 && used < budget; ++pass)      // hand out the remainder to the big units
         for (int i = 0; i < n && used < budget; ++i)
-            if (p.u[i].b_bytes == ACT_BYTES && p.u[i].n_slices < PARTIAL_SLICES && p.u[i].n_slices < ntiles) { ++p.u[i].n_slices; ++used; }
+            if (p.u[i].b_half == ACT_BYTES / 2 && p.u[i].n_slices < PARTIAL_SLICES && p.u[i].n_slices < ntiles) { ++p.u[i].n_slices; ++used; }
     int cta = 0, mx = 1;
     for (int i = 0; i < n; ++i) { p.u[i].first_cta = cta; cta += p.u[i].n_slices; if (p.u[i].n_slices > mx) mx = p.u[i].n_slices; }
     p.n_ctas = cta; p.max_slices = mx;

@@ -2,11 +2,15 @@
 // tile geometry, shared-memory operand images, the per-tile record saved for the backward pass,
 // weight-stream step tables and the workspace carve-up.
 //
-// Operand image (every activation / gradient tile, in shared memory and in HBM):
+// Operand image in shared memory (forward / dX kernels, every activation / gradient tile):
 //     [C/8 groups][128 rows][8 bf16]      (C = feature columns, rows = samples of the tile)
-// i.e. element (row r, column c) lives at (c/8)*2048 + r*16 + (c%8)*2 bytes.  Read as
-//   * a K-major A operand with K = features (forward / dX GEMMs):   LBO = 2048, SBO = 128
-//   * an MN-major operand with K = samples  (weight-gradient GEMM): LBO = 128,  SBO = 2048
+// i.e. element (row r, column c) lives at (c/8)*2048 + r*16 + (c%8)*2 bytes: a K-major A operand with
+// K = features, LBO = 2048, SBO = 128.
+// The copy saved in HBM for the weight-gradient pass is split into two 64-sample halves,
+//     [2 halves][C/8 groups][64 rows][8 bf16]     (hbm_img_off below)
+// so that a half image is one contiguous block (one bulk copy) and, in shared memory, an MN-major operand
+// with K = samples: LBO = 128 (8 samples), SBO = 1024 (8 features).  A warp of epilogue threads (32 rows,
+// one 16-byte group each) writes 512 contiguous bytes in either layout.
 // (no swizzle; both conventions verified on hardware by tests/test_gpu_tc.py::test_tc_selftest_variants).
 #pragma once
 #include "common.cuh"
@@ -23,17 +27,24 @@ constexpr int ACT_BYTES = TILE * WIDTH * 2;       // 65536: 256-column image
 constexpr int HR_BYTES = TILE * RGBW * 2;         // 32768: 128-column image
 constexpr int ENC_BYTES = TILE * ENC3_PAD * 2;    // 16384: 64-column image
 constexpr int VENC_BYTES = TILE * ENCV_PAD * 2;   // 8192:  32-column image
-constexpr int SMALL_BYTES = TILE * 16 * 2;        // 4096:  16-column image (g_rgb_pre[3], g_sigma_pre, 1, 0...)
+constexpr int SMALL_BYTES = TILE * 8 * 2;         // 2048:  8-column image (g_rgb_pre[3], g_sigma_pre, 1, 0, 0, 0)
+constexpr int HALF = 64;                          // samples per half image (K extent of one dW stage)
+constexpr int HROW = HALF * 16;                   // 1024: bytes of one 8-column group of a half image
 constexpr int STAGE_BYTES = WIDTH * CHUNK_K * 2;  // 16384: one weight chunk (256 rows x 32 k)
 
-// ---- fp32 constants kept in shared memory (biases, CUDA-core head weights) --------------------
+// ---- fp32 constants kept in shared memory (CUDA-core head weights, band weights) ------------------
 constexpr int NLAYER = 9;                         // forward: 8 feature layers + rgb0
-constexpr int C_BIAS = 0;                         // [9][256]
-constexpr int C_W7R0 = C_BIAS + NLAYER * WIDTH;   // [256]  density row of layer 7
+constexpr int C_W7R0 = 0;                         // [256]  density row of layer 7
 constexpr int C_WRGB1 = C_W7R0 + WIDTH;           // [3][128]
 constexpr int C_MISC = C_WRGB1 + 3 * RGBW;        // b7[0], brgb1[0..2]
 constexpr int C_BANDS = C_MISC + 4;               // [NBANDS] coarse-to-fine band weights (evaluated on the device)
 constexpr int C_FLOATS = C_BANDS + NBANDS;
+// The biases of the 9 GEMM layers ride on the tensor cores: every layer's weight stream ends with a K = 16
+// chunk whose k = 0 / 1 columns hold bf16(b) and bf16(b - bf16(b)), multiplied by a constant A image with
+// ones in those two columns (ONES_BYTES in shared memory), so the accumulator leaves TMEM with the bias added
+// (to ~16 mantissa bits) and the epilogue needs no add.
+constexpr int BIAS_K = 16;
+constexpr int ONES_BYTES = TILE * BIAS_K * 2;     // 4096: [2 k-groups][128 rows][8 bf16]
 
 // ---- per-tile record saved by the forward pass (training) and extended by the dX pass ---------
 constexpr int64_t SV_H = 0;                                  // h0..h7 images
@@ -45,9 +56,13 @@ constexpr int64_t SV_MASK = SV_VENC + VENC_BYTES;            // [9][8 words][128
 constexpr int64_t MASK_BYTES = 9 * MASK_WORDS * TILE * 4;
 constexpr int64_t SV_G = SV_MASK + MASK_BYTES;               // G0..G7: gradient wrt the pre-activation of layer l
 constexpr int64_t SV_G8 = SV_G + 8 * (int64_t)ACT_BYTES;     // gradient wrt the pre-activation of rgb0
-constexpr int64_t SV_SMALL = SV_G8 + HR_BYTES;               // 16-column image, see SMALL_BYTES
+constexpr int64_t SV_SMALL = SV_G8 + HR_BYTES;               // 8-column image, see SMALL_BYTES
 constexpr int64_t SAVE_TILE_BYTES = SV_SMALL + SMALL_BYTES;
 static_assert(SAVE_TILE_BYTES % 256 == 0, "tile record alignment");
+// byte offset of the 16-byte group (row, column group cg) inside a saved image of C columns
+__host__ __device__ constexpr int hbm_img_off(int C, int row, int cg) {
+    return (row >> 6) * (C / 8) * HROW + cg * HROW + (row & (HALF - 1)) * 16;
+}
 
 // ---- forward weight stream ----------------------------------------------------------------------
 __host__ __device__ constexpr int layer_chunks(int l) { return l == 0 ? 2 : (l == 4 ? 10 : (l == 8 ? 9 : 8)); }
@@ -56,13 +71,16 @@ __host__ __device__ constexpr int layer_in(int l) { return l == 8 ? WIDTH + ENCV
 __host__ __device__ constexpr int64_t layer_woff(int l) { return l == 8 ? RGB0_W : feat_w_off(l); }
 __host__ __device__ constexpr int64_t layer_boff(int l) { return l == 8 ? RGB0_B : feat_b_off(l); }
 __host__ __device__ constexpr int layer_rowoff(int l) { return l == 7 ? 1 : 0; }   // layer 7: row 0 is the density head
+__host__ __device__ constexpr int64_t layer_stream_bytes(int l) {
+    return (int64_t)layer_rows(l) * (layer_chunks(l) * CHUNK_K + BIAS_K) * 2;
+}
 __host__ __device__ constexpr int64_t stream_off(int l) {
     int64_t o = 0;
-    for (int i = 0; i < l; ++i) o += (int64_t)layer_chunks(i) * layer_rows(i) * CHUNK_K * 2;
+    for (int i = 0; i < l; ++i) o += layer_stream_bytes(i);
     return o;
 }
 constexpr int64_t STREAM_BYTES = stream_off(NLAYER);
-static_assert(STREAM_BYTES == 1056768, "weight stream size");
+static_assert(STREAM_BYTES == 1126400, "weight stream size");
 
 // ---- dX-pass weight stream (transposed weights): D[samples, N = inputs] = G[samples, K = outputs] . B^T ----
 // step:        0 view   1 rgb0   2 L7    3 L6    4 L5    5 L4enc  6 L4    7 L3    8 L2    9 L1    10 L0
@@ -88,14 +106,15 @@ __host__ __device__ constexpr int step_out_layer(int s) {
 
 // ---- weight-gradient pass: work units ----------------------------------------------------------
 struct DwUnit {
-    int32_t a_off, a_bytes;      // A operand (M = 128 features): byte offset inside the tile record
-    int32_t b_off, b_bytes;      // main B operand (N = n_main features); b_bytes = 0 -> no main product
-    int32_t n_main;
-    int32_t kind;                // 0: weights (+bias from the ones column)  1: rgb1 weights  2: density row
-    int32_t ld, col0, ncols;     // output: dP[w_base + lane*ld + col0 + j], j < ncols
-    int32_t pad_;
-    int64_t w_base, b_base;      // parameter offsets (b_base < 0: no bias output)
+    int32_t a_off, a_half;       // G image: byte offset inside the tile record, bytes of one 64-sample half
+    int32_t m_halves;            // 128-feature M blocks of the G image (1 or 2)
+    int32_t b_off, b_half;       // X image; b_half = 0 -> no main product
+    int32_t n_main;              // N = columns of the X image
+    int32_t ld, col0, ncols;     // output: dP[w_base + feature*ld + col0 + j], j < ncols
+    int32_t side_a;              // thin product on the G image: 0 none, 1 bias (-> b_base), 2 rgb1 weights
+    int32_t side_b;              // thin product on the X image: 1 density row (-> side_b_base)
     int32_t first_cta, n_slices; // CTAs [first_cta, first_cta + n_slices) split the tiles of this unit
+    int64_t w_base, b_base, side_b_base;
 };
 constexpr int MAX_UNITS = 24;
 struct DwPlan { DwUnit u[MAX_UNITS]; int n_units; int n_ctas; int max_slices; };
@@ -112,7 +131,7 @@ struct Workspace {
     float* partial;       // [max_slices][NPARAMS] fp32 weight-gradient partial sums
     size_t bytes;
 };
-constexpr int PARTIAL_SLICES = 12;
+constexpr int PARTIAL_SLICES = 16;
 
 inline Workspace carve(void* base, int64_t S, bool training) {
     Workspace w;

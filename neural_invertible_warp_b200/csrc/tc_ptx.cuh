@@ -21,13 +21,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires, so a
+// waiting warp does not compete with working warps for issue slots (a bare spin loop costs ~30 % of them)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -109,6 +111,35 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+// {bf16(max(lo,0)), bf16(max(hi,0))} in one instruction (F2FP.RELU)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// 0xFFFF in each half whose bf16 value is > 0 (HSET2.BM)
+__device__ __forceinline__ uint32_t gt0_mask_bf16x2(uint32_t x) {
+    uint32_t d;
+    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(0u));
+    return d;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// ---- ReLU bit masks (one 32-bit word per row and 32-column group) -------------------------------
+// Packed word j (columns 2j, 2j+1) of the group puts its two flags on byte-sign positions of the word
+// shifted left by s = j/2:  even j -> bits 7-s (column 2j) and 23-s (column 2j+1); odd j -> bits 15-s and 31-s.
+// Writing: bits |= gt0_mask(pk_j) & relu_mask_const(j)  (one LOP3).  Reading: relu_mask_expand(bits << s, j)
+// is one PRMT with sign replication and yields 0xFFFF / 0 per half, ready to AND onto a packed gradient.
+__host__ __device__ constexpr uint32_t relu_mask_const(int j) {
+    return ((1u << (7 - (j >> 1))) | (1u << (23 - (j >> 1)))) << (8 * (j & 1));
+}
+__device__ __forceinline__ uint32_t relu_mask_expand(uint32_t shifted_bits, int j) {
+    return prmt(shifted_bits, 0u, (j & 1) ? 0xBB99u : 0xAA88u);
 }
 
 }  // namespace ptx
