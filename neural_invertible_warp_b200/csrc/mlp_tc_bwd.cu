@@ -21,6 +21,9 @@
 //                 head layers ride along as N = 16 products against a small image holding
 //                 [g_rgb_pre(3), g_sigma_pre, 1].  Slices are summed by tc_dw_reduce_kernel.
 #include "tc_layout.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace niw {
 namespace tc {
@@ -327,10 +330,11 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
 // warp-level mma.sync (m16n8k16, A = small image^T via ldmatrix.trans), accumulating in registers.
 
 constexpr int BW_NSTAGE = 3;
-constexpr int BW_A = 0;                                  // 32 KB: 64 samples x up to 256 features (G)
+constexpr int BW_A = 0;                                  // 32 KB: 64 samples x up to 256 features (G [+ hr])
 constexpr int BW_B = BW_A + ACT_BYTES / 2;               // 32 KB: 64 samples x up to 256 features (X)
-constexpr int BW_S = BW_B + ACT_BYTES / 2;               // 1 KB:  64 samples x 8 columns (small image)
-constexpr int BW_STAGE = BW_S + SMALL_BYTES / 2;         // 66560
+constexpr int BW_B2 = BW_B + ACT_BYTES / 2;              // 4 KB:  64 samples x 32 columns (encoded view)
+constexpr int BW_S = BW_B2 + VENC_BYTES / 2;             // 1 KB:  64 samples x 8 columns (small image)
+constexpr int BW_STAGE = BW_S + SMALL_BYTES / 2;         // 70656
 constexpr int BW_BAR = BW_NSTAGE * BW_STAGE;
 constexpr int BW_TOTAL = BW_BAR + 64;
 static_assert(BW_TOTAL <= 227 * 1024, "shared memory budget (dW pass)");
@@ -341,14 +345,19 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t saddr) 
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
 }
 // D(16x8, only rows 0-7 used) += A(16x16, rows 8-15 zero) . B(16x8)
-__device__ __forceinline__ void mma_16816_top(float (&d)[2], float (&z)[2], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+// (d[2], d[3] are the unused rows 8-15: they stay zero, but every accumulator needs its own pair -- shared
+// dummies would chain all MMAs through one register dependency)
+__device__ __forceinline__ void mma_16816_top(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(z[0]), "+f"(z[1]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
 
 __global__ void __launch_bounds__(256, 1)
-tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, float* __restrict__ partial) {
+tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, float* __restrict__ partial,
+             unsigned long long* __restrict__ dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    unsigned long long t_start = 0;
+    if (dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + BW_BAR);   // [BW_NSTAGE]
     uint64_t* empty = full + BW_NSTAGE;                            // [BW_NSTAGE]
     uint64_t* done = empty + BW_NSTAGE;                            // [1]
@@ -376,35 +385,42 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
 
     if (warp == 0) {
         if (lane == 0) {
+            const uint32_t stage_bytes = (uint32_t)(U.a_half + U.a2_half + U.b_half + U.b2_half + SMALL_BYTES / 2);
             for (int64_t it = 0; it < nstages; ++it) {
                 const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
                 const uint8_t* rec = save + (t0 + (it >> 1)) * SAVE_TILE_BYTES;
                 const int half = (int)(it & 1);
                 uint8_t* dst = smem + st * BW_STAGE;
                 ptx::mbar_wait(&empty[st], ph ^ 1);
-                ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)(U.a_half + U.b_half + SMALL_BYTES / 2));
+                ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
                 ptx::bulk_g2s(dst + BW_A, rec + U.a_off + half * U.a_half, (uint32_t)U.a_half, &full[st]);
+                if (U.a2_half) ptx::bulk_g2s(dst + BW_A + HR_BYTES / 2, rec + U.a2_off + half * U.a2_half, (uint32_t)U.a2_half, &full[st]);
                 if (U.b_half) ptx::bulk_g2s(dst + BW_B, rec + U.b_off + half * U.b_half, (uint32_t)U.b_half, &full[st]);
+                if (U.b2_half) ptx::bulk_g2s(dst + BW_B2, rec + U.b2_off + half * U.b2_half, (uint32_t)U.b2_half, &full[st]);
                 ptx::bulk_g2s(dst + BW_S, rec + SV_SMALL + half * (SMALL_BYTES / 2), SMALL_BYTES / 2, &full[st]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = ptx::idesc_bf16(TILE, U.n_main > 0 ? U.n_main : 16, 1, 1);
+            const uint32_t idesc2 = ptx::idesc_bf16(TILE, U.n2 > 0 ? U.n2 : 16, 1, 1);
             for (int64_t it = 0; it < nstages; ++it) {
                 const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
                 ptx::mbar_wait(&full[st], ph);
                 ptx::tc_fence_after();
                 const uint32_t base = ptx::smem_addr(smem + st * BW_STAGE);
-                if (U.n_main > 0) {
 #pragma unroll
-                    for (int ks = 0; ks < HALF / 16; ++ks) {
-                        // MN-major operands, K = samples: 16 samples = 256 B along a feature group
-                        const uint64_t bd = ptx::smem_desc(base + BW_B + ks * 256, 128, HROW);
-                        for (int h = 0; h < U.m_halves; ++h) {
-                            const uint64_t ad = ptx::smem_desc(base + BW_A + h * 16 * HROW + ks * 256, 128, HROW);
-                            ptx::mma_bf16(tmem_base + h * WIDTH, ad, bd, idesc, (it | ks) != 0);
-                        }
+                for (int ks = 0; ks < HALF / 16; ++ks) {
+                    // MN-major operands, K = samples: 16 samples = 256 B along a feature group
+                    const uint64_t bd = ptx::smem_desc(base + BW_B + ks * 256, 128, HROW);
+                    for (int h = 0; h < U.m_halves; ++h) {
+                        const uint64_t ad = ptx::smem_desc(base + BW_A + h * 16 * HROW + ks * 256, 128, HROW);
+                        ptx::mma_bf16(tmem_base + h * WIDTH, ad, bd, idesc, (it | ks) != 0);
+                    }
+                    if (U.n2 > 0) {
+                        const uint64_t ad = ptx::smem_desc(base + BW_A + ks * 256, 128, HROW);
+                        const uint64_t b2 = ptx::smem_desc(base + BW_B2 + ks * 256, 128, HROW);
+                        ptx::mma_bf16(tmem_base + WIDTH, ad, b2, idesc2, (it | ks) != 0);
                     }
                 }
                 ptx::mma_commit(&empty[st]);
@@ -414,42 +430,43 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
     } else if (warp >= 4) {
         const int wq = warp & 3;
         // ---- thin products on the warp-level tensor path while the tiles stream ----
-        // this warp owns feature groups [wq*ga, (wq+1)*ga) of the G image and [wq*gb, ...) of the X image
-        const int ga = U.side_a ? U.a_half / HROW / 4 : 0;      // 8 (256 features) or 4 (128)
-        const int gb = U.side_b ? U.b_half / HROW / 4 : 0;
-        float acc_a[8][2], acc_b[8][2], zz[2] = {0.f, 0.f};
+        // this warp owns feature groups [wq*g, (wq+1)*g) of each side image, g = groups / 4 (8 or 4)
+        const int g0 = U.side[0].kind ? U.side[0].groups / 4 : 0, g1 = U.side[1].kind ? U.side[1].groups / 4 : 0;
+        float acc0[8][4], acc1[8][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc_a[i][0] = acc_a[i][1] = acc_b[i][0] = acc_b[i][1] = 0.f; }
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc0[i][q] = 0.f; acc1[i][q] = 0.f; }
         for (int64_t it = 0; it < nstages; ++it) {
             const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
             ptx::mbar_wait(&full[st], ph);
-            if (ga | gb) {
+            if (g0 | g1) {
                 const uint32_t base = ptx::smem_addr(smem + st * BW_STAGE);
                 uint32_t sa[2][4];
                 ldsm_x4_trans(sa[0], base + BW_S + lane * 16);
                 ldsm_x4_trans(sa[1], base + BW_S + 512 + lane * 16);
+                // four feature groups at a time, k outermost: consecutive MMAs hit different accumulators
+                // (a chain of dependent mma.sync costs ~33 cycles per instruction)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i < ga) {
-                        const uint32_t x = base + BW_A + (wq * ga + i) * HROW + lane * 16;
-                        uint32_t xb[2][4];
-                        ldsm_x4_trans(xb[0], x);
-                        ldsm_x4_trans(xb[1], x + 512);
+                for (int j = 0; j < 2; ++j) {
+                    const int gq = j == 0 ? g0 : g1;
+                    const uint32_t img = base + U.side[j].smem_off + lane * 16;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_16816_top(acc_a[i], zz, sa[k >> 1][(k & 1) * 2], sa[k >> 1][(k & 1) * 2 + 1], xb[k >> 1][(k & 1) * 2], xb[k >> 1][(k & 1) * 2 + 1]);
-                    }
-                }
+                    for (int i0 = 0; i0 < 8; i0 += 4) {
+                        if (i0 < gq) {
+                            uint32_t xb[4][2][4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i < gb) {
-                        const uint32_t x = base + BW_B + (wq * gb + i) * HROW + lane * 16;
-                        uint32_t xb[2][4];
-                        ldsm_x4_trans(xb[0], x);
-                        ldsm_x4_trans(xb[1], x + 512);
+                            for (int i = 0; i < 4; ++i) {
+                                ldsm_x4_trans(xb[i][0], img + (wq * gq + i0 + i) * HROW);
+                                ldsm_x4_trans(xb[i][1], img + (wq * gq + i0 + i) * HROW + 512);
+                            }
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_16816_top(acc_b[i], zz, sa[k >> 1][(k & 1) * 2], sa[k >> 1][(k & 1) * 2 + 1], xb[k >> 1][(k & 1) * 2], xb[k >> 1][(k & 1) * 2 + 1]);
+                            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    mma_16816_top(j == 0 ? acc0[i0 + i] : acc1[i0 + i], sa[k >> 1][(k & 1) * 2], sa[k >> 1][(k & 1) * 2 + 1],
+                                                  xb[i][k >> 1][(k & 1) * 2], xb[i][k >> 1][(k & 1) * 2 + 1]);
+                        }
                     }
                 }
             }
@@ -463,9 +480,13 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
         float* out = partial + (size_t)slice * NPARAMS;
         if (t1 > t0) {
             float* tr = reinterpret_cast<float*>(smem) + wq * (32 * 33);   // stage buffers are idle now
-            for (int h = 0; h < U.m_halves && U.n_main > 0; ++h) {
+            for (int h = 0; h < U.m_halves + (U.n2 > 0 ? 1 : 0); ++h) {
+                // h < m_halves: main product of M block h;  h == m_halves (= 1): second X image of M block 0
+                const bool second = h >= U.m_halves;
+                const int n = second ? U.n2 : U.n_main, ncols = second ? U.ncols2 : U.ncols, col0 = second ? U.col0_2 : U.col0;
+                const int frow = second ? 0 : h * 128;
                 const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + h * WIDTH;
-                for (int c0 = 0; c0 < U.n_main; c0 += 32) {
+                for (int c0 = 0; c0 < n; c0 += 32) {
                     uint32_t v[32];
                     ptx::tmem_ld32(tacc + c0, v);
                     ptx::tmem_ld_wait();
@@ -473,9 +494,9 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
                     for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
                     __syncwarp();
                     const int col = c0 + lane;
-                    if (col < U.ncols) {
+                    if (col < ncols) {
                         for (int rr = 0; rr < 32; ++rr)
-                            out[U.w_base + (int64_t)(h * 128 + wq * 32 + rr) * U.ld + U.col0 + col] = tr[rr * 33 + lane];
+                            out[U.w_base + (int64_t)(frow + wq * 32 + rr) * U.ld + col0 + col] = tr[rr * 33 + lane];
                     }
                     __syncwarp();
                 }
@@ -483,15 +504,17 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
             // thin products: this lane holds row m = lane / 4 of small^T . X for features 8*group + 2*(lane % 4) + {0, 1}
             const int m = lane >> 2, n0 = (lane & 3) * 2;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < ga) {
-                    const int f = (wq * ga + i) * 8 + n0;
-                    if (U.side_a == 1 && m == 4) { out[U.b_base + f] = acc_a[i][0]; out[U.b_base + f + 1] = acc_a[i][1]; }       // G^T . 1
-                    if (U.side_a == 2 && m < 3) { out[RGB1_W + m * RGBW + f] = acc_a[i][0]; out[RGB1_W + m * RGBW + f + 1] = acc_a[i][1]; }   // hr^T . g_rgb_pre
-                }
-                if (i < gb) {
-                    const int f = (wq * gb + i) * 8 + n0;
-                    if (m == 3) { out[U.side_b_base + f] = acc_b[i][0]; out[U.side_b_base + f + 1] = acc_b[i][1]; }              // h6^T . g_sigma_pre
+            for (int j = 0; j < 2; ++j) {
+                const DwSide& sd = U.side[j];
+                const int gq = j == 0 ? g0 : g1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < gq) {
+                        const int f = (wq * gq + i) * 8 + n0;
+                        const float x0 = j == 0 ? acc0[i][0] : acc1[i][0], x1 = j == 0 ? acc0[i][1] : acc1[i][1];
+                        if ((sd.kind == 1 && m == 4) || (sd.kind == 3 && m == 3)) { out[sd.base + f] = x0; out[sd.base + f + 1] = x1; }
+                        if (sd.kind == 2 && m < 3) { out[sd.base + m * RGBW + f] = x0; out[sd.base + m * RGBW + f + 1] = x1; }
+                    }
                 }
             }
         }
@@ -500,6 +523,11 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+    if (dbg && threadIdx.x == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        dbg[blockIdx.x * 2] = t_start; dbg[blockIdx.x * 2 + 1] = t_end;
+    }
 }
 
 // dP[i] += sum over slices of partial[s][i]
@@ -515,45 +543,53 @@ __global__ void tc_dw_reduce_kernel(const float* __restrict__ partial, int n_sli
 static DwPlan make_plan(int64_t ntiles, int n_sms) {
     DwPlan p;
     int n = 0;
-    auto add = [&](int64_t a_off, int a_cols, int64_t b_off, int b_cols, int ld, int col0, int ncols, int64_t w_base,
-                   int64_t b_base, int side_a, int64_t side_b_base) {
+    auto add = [&](int64_t a_off, int a_cols, int64_t b_off, int b_cols, int ld, int col0, int ncols, int64_t w_base) -> DwUnit& {
         DwUnit& u = p.u[n++];
+        u = DwUnit{};
         u.a_off = (int32_t)a_off; u.a_half = a_cols / 8 * HROW; u.m_halves = a_cols / 128;
         u.b_off = (int32_t)b_off; u.b_half = b_cols / 8 * HROW; u.n_main = b_cols;
-        u.ld = ld; u.col0 = col0; u.ncols = ncols; u.w_base = w_base; u.b_base = b_base;
-        u.side_a = side_a; u.side_b = side_b_base >= 0 ? 1 : 0; u.side_b_base = side_b_base;
+        u.ld = ld; u.col0 = col0; u.ncols = ncols; u.w_base = w_base;
         u.first_cta = 0; u.n_slices = 1;
+        return u;
+    };
+    auto side = [](DwUnit& u, int j, int smem_off, int cols, int kind, int64_t base) {
+        u.side[j].smem_off = smem_off; u.side[j].groups = cols / 8; u.side[j].kind = kind; u.side[j].base = base;
     };
     for (int l = 0; l < NFEAT; ++l) {
         const int ro = layer_rowoff(l);
         const int64_t a_off = SV_G + (int64_t)l * ACT_BYTES;
         const int64_t w_base = feat_w_off(l) + (int64_t)ro * feat_in(l), b_base = feat_b_off(l) + ro;
         if (l == 0) {
-            add(a_off, WIDTH, SV_ENC, ENC3_PAD, feat_in(l), 0, ENC3, w_base, b_base, 1, -1);
+            side(add(a_off, WIDTH, SV_ENC, ENC3_PAD, feat_in(l), 0, ENC3, w_base), 0, BW_A, WIDTH, 1, b_base);
         } else {
-            add(a_off, WIDTH, SV_H + (int64_t)(l - 1) * ACT_BYTES, WIDTH, feat_in(l), 0, WIDTH, w_base, b_base, 1,
-                l == NFEAT - 1 ? feat_w_off(l) : -1);                                   // layer 7: + density row from h6
-            if (l == SKIP) add(a_off, WIDTH, SV_ENC, ENC3_PAD, feat_in(l), WIDTH, ENC3, w_base, -1, 0, -1);
+            DwUnit& u = add(a_off, WIDTH, SV_H + (int64_t)(l - 1) * ACT_BYTES, WIDTH, feat_in(l), 0, WIDTH, w_base);
+            side(u, 0, BW_A, WIDTH, 1, b_base);
+            if (l == NFEAT - 1) side(u, 1, BW_B, WIDTH, 3, feat_w_off(l));                       // + density row from h6
+            if (l == SKIP) add(a_off, WIDTH, SV_ENC, ENC3_PAD, feat_in(l), WIDTH, ENC3, w_base);
         }
     }
-    add(SV_G8, RGBW, SV_H + 7 * (int64_t)ACT_BYTES, WIDTH, WIDTH + ENCV, 0, WIDTH, RGB0_W, RGB0_B, 1, -1);
-    add(SV_G8, RGBW, SV_VENC, ENCV_PAD, WIDTH + ENCV, WIDTH, ENCV, RGB0_W, -1, 0, -1);
-    add(SV_HR, RGBW, 0, 0, 0, 0, 0, RGB1_W, -1, 2, -1);                                  // rgb1 weights (thin product only)
+    {   // rgb0 (h7 and encoded-view columns) + rgb1 weights from the hr image staged behind G8
+        DwUnit& u = add(SV_G8, RGBW, SV_H + 7 * (int64_t)ACT_BYTES, WIDTH, WIDTH + ENCV, 0, WIDTH, RGB0_W);
+        u.b2_off = (int32_t)SV_VENC; u.b2_half = ENCV_PAD / 8 * HROW; u.n2 = ENCV_PAD; u.col0_2 = WIDTH; u.ncols2 = ENCV;
+        u.a2_off = (int32_t)SV_HR; u.a2_half = HR_BYTES / 2;
+        side(u, 0, BW_A, RGBW, 1, RGB0_B);
+        side(u, 1, BW_A + HR_BYTES / 2, RGBW, 2, RGB1_W);
+    }
     p.n_units = n;
     // slices proportional to bytes streamed per tile, capped by the tile count and PARTIAL_SLICES
+    auto bytes = [&](int i) { return 2.0 * (p.u[i].a_half + p.u[i].a2_half + p.u[i].b_half + p.u[i].b2_half) + SMALL_BYTES; };
     double total = 0;
-    for (int i = 0; i < n; ++i) total += 2 * (p.u[i].a_half + p.u[i].b_half) + SMALL_BYTES;
+    for (int i = 0; i < n; ++i) total += bytes(i);
     int budget = n_sms > n ? n_sms : n;
     int used = 0;
     for (int i = 0; i < n; ++i) {
-        double share = (2 * (p.u[i].a_half + p.u[i].b_half) + SMALL_BYTES) / total * budget;
-        int s = (int)share;
+        int s = (int)(bytes(i) / total * budget);
         if (s < 1) s = 1;
         if (s > PARTIAL_SLICES) s = PARTIAL_SLICES;
         if (s > ntiles) s = (int)ntiles;
         p.u[i].n_slices = s; used += s;
     }
-    for (int pass = 0; pass < 4 && used < budget; ++pass)      // hand out the remainder to the big units
+    for (int pass = 0; pass < 4 && used < budget; ++pass)      // hand out the remainder, largest units first
         for (int i = 0; i < n && used < budget; ++i)
             if (p.u[i].b_half == ACT_BYTES / 2 && p.u[i].n_slices < PARTIAL_SLICES && p.u[i].n_slices < ntiles) { ++p.u[i].n_slices; ++used; }
     int cta = 0, mx = 1;
@@ -585,8 +621,26 @@ int tc_bwd(const float* P, const float* center, const float* ray, const float* d
     DwPlan plan = make_plan(ntiles, niw_num_sms());
     NIW_CUDA(cudaMemsetAsync(w.partial, 0, sizeof(float) * (size_t)plan.max_slices * NPARAMS, st));
     NIW_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_TOTAL));
-    niw::note_launch(), tc_dw_kernel<<<plan.n_ctas, 256, BW_TOTAL, st>>>(w.save, ntiles, plan, w.partial);
+    // NIW_DW_DEBUG=1: per-CTA start / end times of the dW pass on stderr (synchronises; diagnostics only)
+    static const bool dw_debug = getenv("NIW_DW_DEBUG") != nullptr;
+    unsigned long long* dbg = nullptr;
+    if (dw_debug) NIW_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 2 * plan.n_ctas));
+    niw::note_launch(), tc_dw_kernel<<<plan.n_ctas, 256, BW_TOTAL, st>>>(w.save, ntiles, plan, w.partial, dbg);
     NIW_LAUNCH_CHECK();
+    if (dbg) {
+        std::vector<unsigned long long> h(2 * plan.n_ctas);
+        NIW_CUDA(cudaStreamSynchronize(st));
+        NIW_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        unsigned long long t0 = h[0];
+        for (int i = 0; i < plan.n_ctas; ++i) if (h[2 * i] < t0) t0 = h[2 * i];
+        for (int u = 0; u < plan.n_units; ++u)
+            for (int sl = 0; sl < plan.u[u].n_slices; ++sl) {
+                const int c = plan.u[u].first_cta + sl;
+                fprintf(stderr, "dw unit %2d slice %2d/%2d start %7.1f us  dur %7.1f us\n", u, sl, plan.u[u].n_slices,
+                        (h[2 * c] - t0) * 1e-3, (h[2 * c + 1] - h[2 * c]) * 1e-3);
+            }
+    }
     niw::note_launch(), tc_dw_reduce_kernel<<<niw_blocks(NPARAMS, 256), 256, 0, st>>>(w.partial, plan.max_slices, dP);
     NIW_LAUNCH_CHECK();
     return 0;

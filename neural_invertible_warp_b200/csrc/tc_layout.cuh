@@ -105,16 +105,21 @@ __host__ __device__ constexpr int step_out_layer(int s) {
 }
 
 // ---- weight-gradient pass: work units ----------------------------------------------------------
+struct DwSide { int32_t smem_off, groups, kind, pad_; int64_t base; };   // thin product on one staged image
 struct DwUnit {
     int32_t a_off, a_half;       // G image: byte offset inside the tile record, bytes of one 64-sample half
     int32_t m_halves;            // 128-feature M blocks of the G image (1 or 2)
+    int32_t a2_off, a2_half;     // second image staged behind a 128-feature G image (thin products only), 0 = none
     int32_t b_off, b_half;       // X image; b_half = 0 -> no main product
     int32_t n_main;              // N = columns of the X image
+    int32_t b2_off, b2_half, n2; // second X image of the first M block (TMEM columns 256..), 0 = none
     int32_t ld, col0, ncols;     // output: dP[w_base + feature*ld + col0 + j], j < ncols
-    int32_t side_a;              // thin product on the G image: 0 none, 1 bias (-> b_base), 2 rgb1 weights
-    int32_t side_b;              // thin product on the X image: 1 density row (-> side_b_base)
+    int32_t col0_2, ncols2;      // same for the second X image
     int32_t first_cta, n_slices; // CTAs [first_cta, first_cta + n_slices) split the tiles of this unit
-    int64_t w_base, b_base, side_b_base;
+    int64_t w_base;
+    // thin products (kind 0 none; 1 bias: row 4 -> base[f]; 2 rgb1 weights: rows 0-2 -> base[m*128 + f];
+    // 3 density row: row 3 -> base[f]) of small^T . image, image at smem_off inside the stage
+    DwSide side[2];
 };
 constexpr int MAX_UNITS = 24;
 struct DwPlan { DwUnit u[MAX_UNITS]; int n_units; int n_ctas; int max_slices; };
