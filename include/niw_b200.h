@@ -160,7 +160,8 @@ int niw_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float lr_gamma, float beta1, float beta2, float eps, float weight_decay, float* state, void* stream);
 
 /* ---- tcgen05 self-test: D[128,N] = A[128,K] . B[N,K]^T with BF16 operands staged exactly as the
- * MLP kernel stages them.  variant selects the operand form under test (see csrc/mlp_tc.cu). */
+ * MLP kernel stages them.  variant selects the operand form under test (see csrc/tc_selftest.cu); variant 4 is the
+ * CTA-pair form (tcgen05 cta_group::2): A [256,K], D [256,N]. */
 int niw_tc_selftest(const float* A, const float* Bm, int N, int K, int variant, float* D, void* stream);
 
 #ifdef __cplusplus

@@ -462,15 +462,20 @@ __device__ __forceinline__ float row_norm2(const float* __restrict__ row, int ld
     return warp_sum(a);
 }
 
-// One CTA per coupling block, 32 warps.  Every reduction is done by a warp with the lanes along the
-// contiguous (reduction) axis, so all global reads are coalesced.
+// Grid (coupling block, split): the work of one block is latency-bound in a single CTA (about 270 k warp
+// instructions), so it is spread over `gridDim.y` CTAs.  Every reduction is done by a warp with the lanes along
+// the contiguous (reduction) axis, so all global reads are coalesced.
+//   forward:  split y owns images [y*ipc, (y+1)*ipc): their code projection and per-image biases; every CTA
+//             recomputes the 256 weight-norm row scales it needs (8 rows per warp); split 0 writes wpack
 __global__ void __launch_bounds__(PACK_THREADS)
-nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, float* __restrict__ wpack,
+nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, int ipc, float* __restrict__ wpack,
                     float* __restrict__ code_bias, float* __restrict__ cb_out) {
     extern __shared__ float sm[];
-    float* s_cb = sm;                          // [B][LDC]
-    float* s_scale = s_cb + (size_t)B * LDC;   // [2][HID]
+    float* s_cb = sm;                          // [ipc][LDC]
+    float* s_scale = s_cb + (size_t)ipc * LDC; // [2][HID]
     const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = PACK_THREADS / 32;
+    const int img0 = blockIdx.y * ipc, nimg = min(ipc, B - img0);
+    const bool writer = blockIdx.y == 0;
     const float* const* P = T.p + blk * 12;
     const float *Wc = P[10], *bc = P[11];
     float* wp = wpack + (size_t)blk * BLOCK_FLOATS;
@@ -481,17 +486,18 @@ nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, float* __
         const float* v = P[part * 5 + 0] + (size_t)j * ld;
         const float scale = P[part * 5 + 1][j] / sqrtf(row_norm2(v, ld, lane));
         if (lane == 0) s_scale[r] = scale;
-        if (lane < emb) wp[(part == 0 ? OFF_W1A : OFF_W1B) + j * emb + lane] = v[lane] * scale;
+        if (writer && lane < emb) wp[(part == 0 ? OFF_W1A : OFF_W1B) + j * emb + lane] = v[lane] * scale;
     }
-    // output layers: copies
-    for (int i = tid; i < HID; i += PACK_THREADS) wp[OFF_W2A + i] = P[3][i];
-    for (int i = tid; i < 3 * HID; i += PACK_THREADS) wp[OFF_W2B + i] = P[8][i];
-    if (tid == 0) wp[OFF_B2A] = P[4][0];
-    if (tid < 3) wp[OFF_B2B + tid] = P[9][tid];
+    if (writer) {   // output layers: copies
+        for (int i = tid; i < HID; i += PACK_THREADS) wp[OFF_W2A + i] = P[3][i];
+        for (int i = tid; i < 3 * HID; i += PACK_THREADS) wp[OFF_W2B + i] = P[8][i];
+        if (tid == 0) wp[OFF_B2A] = P[4][0];
+        if (tid < 3) wp[OFF_B2B + tid] = P[9][tid];
+    }
     // (2) code_b[img][k] = code + b_c + W_c code      (nvp_ndr.py:382): warp per output, lanes over m
-    for (int o = warp; o < B * DF; o += nwarp) {
-        const int img = o / DF, k = o % DF;
-        const float* c = code + (size_t)img * DF;
+    for (int o = warp; o < nimg * DF; o += nwarp) {
+        const int li = o / DF, k = o % DF;
+        const float* c = code + (size_t)(img0 + li) * DF;
         const float* w = Wc + (size_t)k * DF;
         float a = 0.f;
 #pragma unroll
@@ -499,8 +505,8 @@ nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, float* __
         a = warp_sum(a);
         if (lane == 0) {
             a += c[k] + bc[k];
-            s_cb[img * LDC + k] = a;
-            cb_out[((size_t)blk * B + img) * DF + k] = a;
+            s_cb[li * LDC + k] = a;
+            cb_out[((size_t)blk * B + img0 + li) * DF + k] = a;
         }
     }
     __syncthreads();
@@ -513,15 +519,24 @@ nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, float* __
 #pragma unroll
         for (int q = 0; q < DF / 32; ++q) vl[q] = v[lane + 32 * q];
         const float b0 = P[part * 5 + 2][j], scale = s_scale[r];
-        for (int img = 0; img < B; ++img) {
+        for (int li = 0; li < nimg; ++li) {
             float a = 0.f;
 #pragma unroll
-            for (int q = 0; q < DF / 32; ++q) a += vl[q] * s_cb[img * LDC + lane + 32 * q];
+            for (int q = 0; q < DF / 32; ++q) a += vl[q] * s_cb[li * LDC + lane + 32 * q];
             a = warp_sum(a);
-            if (lane == 0) code_bias[((size_t)(blk * 2 + part) * B + img) * HID + j] = b0 + scale * a;
+            if (lane == 0) code_bias[((size_t)(blk * 2 + part) * B + img0 + li) * HID + j] = b0 + scale * a;
         }
     }
 }
+
+//   backward: split y owns first-layer rows [y*rpc, (y+1)*rpc) of the 256 (part, j) rows (weight-norm backward,
+//             single writer per gradient element) and latent columns k in [y*kpc, (y+1)*kpc) of d code_b, from
+//             which it derives its rows of the code-projector gradient and its partial sum of d code
+constexpr int PACK_SPLIT = 16;
+constexpr int RPC = 2 * HID / PACK_SPLIT;      // 16 rows per split
+constexpr int KPC = DF / PACK_SPLIT;           // 8 latent columns per split
+constexpr int JQ = 8;                          // partitions of the (part, j) reduction of d code_b
+static_assert(PACK_SPLIT * RPC == 2 * HID && PACK_SPLIT * KPC == DF, "pack split");
 
 __global__ void __launch_bounds__(PACK_THREADS)
 nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, const float* __restrict__ cb, int B,
@@ -529,9 +544,10 @@ nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, con
     extern __shared__ float sm[];
     float* s_cb = sm;                          // [B][LDC]      code_b
     float* s_dcb = s_cb + (size_t)B * LDC;     // [2][B][LDC]   d(code_bias) of both parts
-    float* s_dc = s_dcb + 2 * (size_t)B * LDC; // [B][LDC]      d(code_b)
-    float* s_scale = s_dc + (size_t)B * LDC;   // [2][HID]
-    const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = PACK_THREADS / 32;
+    float* s_dc = s_dcb + 2 * (size_t)B * LDC; // [B][KPC]      d(code_b), this split's columns
+    float* s_scale = s_dc + (size_t)B * KPC;   // [2][HID]  g / ||v||
+    float* s_nrm2 = s_scale + 2 * HID;         // [2][HID]  ||v||^2
+    const int blk = blockIdx.x, y = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = PACK_THREADS / 32;
     const float* const* P = T.p + blk * 12;
     float* const* Gp = G.p + blk * 12;
     const float* dwp = d_wpack + (size_t)blk * BLOCK_FLOATS;
@@ -540,20 +556,27 @@ nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, con
         const int p = idx / (B * HID), r = idx % (B * HID);
         s_dcb[((size_t)p * B + r / HID) * LDC + r % HID] = d_code_bias[((size_t)(blk * 2 + p) * B) * HID + r];
     }
-    // output layers: the gradient is the warp kernel's own (every element has exactly one writer here)
-    for (int i = tid; i < HID; i += PACK_THREADS) Gp[3][i] += dwp[OFF_W2A + i];
-    for (int i = tid; i < 3 * HID; i += PACK_THREADS) Gp[8][i] += dwp[OFF_W2B + i];
-    if (tid == 0) Gp[4][0] += dwp[OFF_B2A];
-    if (tid < 3) Gp[9][tid] += dwp[OFF_B2B + tid];
-    __syncthreads();
-    // first layers: warp per (part, j); lanes along the columns of row j
+    for (int idx = tid; idx < B * KPC; idx += PACK_THREADS) s_dc[idx] = 0.f;
+    if (y == 0) {   // output layers: the gradient is the warp kernel's own (every element has exactly one writer here)
+        for (int i = tid; i < HID; i += PACK_THREADS) Gp[3][i] += dwp[OFF_W2A + i];
+        for (int i = tid; i < 3 * HID; i += PACK_THREADS) Gp[8][i] += dwp[OFF_W2B + i];
+        if (tid == 0) Gp[4][0] += dwp[OFF_B2A];
+        if (tid < 3) Gp[9][tid] += dwp[OFF_B2B + tid];
+    }
+    // row norms of all 256 rows (the d code_b reduction below runs over every row)
     for (int r = warp; r < 2 * HID; r += nwarp) {
         const int part = r >> 7, j = r & 127;
+        const int ld = (part == 0 ? EA : EB) + DF;
+        const float nrm2 = row_norm2(P[part * 5 + 0] + (size_t)j * ld, ld, lane);
+        if (lane == 0) { s_scale[r] = P[part * 5 + 1][j] / sqrtf(nrm2); s_nrm2[r] = nrm2; }
+    }
+    __syncthreads();
+    // first layers, this split's rows: warp per (part, j); lanes along the columns of row j
+    for (int rr = warp; rr < RPC; rr += nwarp) {
+        const int r = y * RPC + rr, part = r >> 7, j = r & 127;
         const int emb = part == 0 ? EA : EB, ld = emb + DF;
         const float* v = P[part * 5 + 0] + (size_t)j * ld;
-        const float g = P[part * 5 + 1][j];
-        const float nrm2 = row_norm2(v, ld, lane), nrm = sqrtf(nrm2), scale = g / nrm;
-        if (lane == 0) s_scale[r] = scale;
+        const float scale = s_scale[r], nrm2 = s_nrm2[r], nrm = sqrtf(nrm2);
         const float* my_dcb = s_dcb + (size_t)part * B * LDC + j;
         // d b0[j] = sum_img dcb
         float db0 = 0.f;
@@ -587,40 +610,39 @@ nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, con
             dv[c] += scale * (dwl[q] - v[c] * coef);
         }
     }
-    __syncthreads();
-    // d code_b[img][k] = sum_part sum_j dcb[part][img][j] w0[j][emb+k]: thread per (img, k), k fastest (coalesced rows)
-    for (int idx = tid; idx < B * DF; idx += PACK_THREADS) {
-        const int img = idx / DF, k = idx % DF;
+    // d code_b[img][k] = sum_part sum_j dcb[part][img][j] w0[j][emb+k] for this split's k: thread (k, img, jq) sums a
+    // 1/JQ share of the 256 (part, j) rows, shares are combined with shared-memory atomics
+    for (int idx = tid; idx < KPC * B * JQ; idx += PACK_THREADS) {
+        const int kk = idx % KPC, img = (idx / KPC) % B, jq = idx / (KPC * B);
+        const int k = y * KPC + kk;
         float acc = 0.f;
-        for (int p = 0; p < 2; ++p) {
-            const int e2 = p == 0 ? EA : EB, l2 = e2 + DF;
-            const float* vp = P[p * 5 + 0] + e2 + k;
-            const float* d = s_dcb + ((size_t)p * B + img) * LDC;
-#pragma unroll 4
-            for (int jj = 0; jj < HID; ++jj) acc += d[jj] * vp[(size_t)jj * l2] * s_scale[p * HID + jj];
+        for (int r = jq * (2 * HID / JQ); r < (jq + 1) * (2 * HID / JQ); ++r) {
+            const int p = r >> 7, jj = r & 127, e2 = p == 0 ? EA : EB;
+            acc += s_dcb[((size_t)p * B + img) * LDC + jj] * P[p * 5 + 0][(size_t)jj * (e2 + DF) + e2 + k] * s_scale[r];
         }
-        s_dc[img * LDC + k] = acc;
+        atomicAdd(&s_dc[img * KPC + kk], acc);
     }
     __syncthreads();
-    // code projector: code_b = W_c code + b_c + code
+    // code projector: code_b = W_c code + b_c + code; this split's rows k of W_c / b_c
     const float* Wc = P[10];
-    for (int idx = tid; idx < DF * DF; idx += PACK_THREADS) {
-        const int k = idx / DF, m = idx % DF;
+    for (int idx = tid; idx < KPC * DF; idx += PACK_THREADS) {
+        const int kk = idx / DF, m = idx % DF;
         float acc = 0.f;
-        for (int img = 0; img < B; ++img) acc += s_dc[img * LDC + k] * code[(size_t)img * DF + m];
-        Gp[10][idx] += acc;
+        for (int img = 0; img < B; ++img) acc += s_dc[img * KPC + kk] * code[(size_t)img * DF + m];
+        Gp[10][(size_t)(y * KPC + kk) * DF + m] += acc;
     }
-    for (int k = tid; k < DF; k += PACK_THREADS) {
+    for (int kk = tid; kk < KPC; kk += PACK_THREADS) {
         float acc = 0.f;
-        for (int img = 0; img < B; ++img) acc += s_dc[img * LDC + k];
-        Gp[11][k] += acc;
+        for (int img = 0; img < B; ++img) acc += s_dc[img * KPC + kk];
+        Gp[11][y * KPC + kk] += acc;
     }
+    // d code[img][m] += (identity term for this split's columns) + sum_{k in split} d code_b[img][k] W_c[k][m]
     for (int idx = tid; idx < B * DF; idx += PACK_THREADS) {
         const int img = idx / DF, m = idx % DF;
-        float acc = s_dc[img * LDC + m];
-#pragma unroll 4
-        for (int k = 0; k < DF; ++k) acc += s_dc[img * LDC + k] * Wc[(size_t)k * DF + m];
-        atomicAdd(d_code + idx, acc);        // three blocks (CTAs) contribute
+        float acc = (m / KPC == y) ? s_dc[img * KPC + m % KPC] : 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KPC; ++kk) acc += s_dc[img * KPC + kk] * Wc[(size_t)(y * KPC + kk) * DF + m];
+        atomicAdd(d_code + idx, acc);        // three blocks x PACK_SPLIT splits contribute
     }
 }
 
@@ -632,10 +654,10 @@ extern "C" int niw_nvp_pack_fwd(const float* const* params, const float* code, i
     PtrTable T;
     for (int i = 0; i < NIW_NVP_PARAM_PTRS; ++i) { NIW_CHECK_ARG(params[i]); T.p[i] = params[i]; }
     if (B > MAX_IMG) return NIW_E_UNSUPP;
-    const size_t smem = sizeof(float) * ((size_t)B * LDC + 2 * HID);
-    if (smem > 48 * 1024)
-        NIW_CUDA(cudaFuncSetAttribute(nvp_pack_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    niw::note_launch(), nvp_pack_fwd_kernel<<<NB, PACK_THREADS, smem, niw_stream(stream)>>>(T, code, B, wpack, code_bias, cb);
+    const int nsplit = B < 32 ? B : 32, ipc = (B + nsplit - 1) / nsplit;      // images per CTA
+    const size_t smem = sizeof(float) * ((size_t)ipc * LDC + 2 * HID);
+    niw::note_launch(), nvp_pack_fwd_kernel<<<dim3(NB, (B + ipc - 1) / ipc), PACK_THREADS, smem, niw_stream(stream)>>>(
+        T, code, B, ipc, wpack, code_bias, cb);
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -648,10 +670,10 @@ extern "C" int niw_nvp_pack_bwd(const float* const* params, float* const* grads,
     for (int i = 0; i < NIW_NVP_PARAM_PTRS; ++i) { NIW_CHECK_ARG(params[i] && grads[i]); T.p[i] = params[i]; G.p[i] = grads[i]; }
     cudaStream_t st = niw_stream(stream);
     NIW_CUDA(cudaMemsetAsync(d_code, 0, sizeof(float) * (size_t)B * DF, st));
-    const size_t smem = sizeof(float) * (4 * (size_t)B * LDC + 2 * HID);
+    const size_t smem = sizeof(float) * (3 * (size_t)B * LDC + (size_t)B * KPC + 4 * HID);
     if (smem > 48 * 1024)
         NIW_CUDA(cudaFuncSetAttribute(nvp_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    niw::note_launch(), nvp_pack_bwd_kernel<<<NB, PACK_THREADS, smem, st>>>(T, G, code, cb, B, d_wpack, d_code_bias, d_code);
+    niw::note_launch(), nvp_pack_bwd_kernel<<<dim3(NB, PACK_SPLIT), PACK_THREADS, smem, st>>>(T, G, code, cb, B, d_wpack, d_code_bias, d_code);
     NIW_LAUNCH_CHECK();
     return 0;
 }

@@ -73,13 +73,78 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bm, in
     if (warp == 0) ptx::tmem_dealloc(tmem_base, (uint32_t)(N < 32 ? 32 : N));
 }
 
+// variant 4: CTA pair (cta_group::2), K-major: D[256,N] = A[256,K] . B[N,K]^T.  Each CTA stages its 128 rows of A
+// and its N/2 rows of B; the peer tells the leader that its operands are in place with a remote mbarrier arrive;
+// the leader issues the M = 256 MMAs and commits to the `done` barrier of both CTAs.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+tc_selftest_pair_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int N, int K, float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t ready, done;
+    __shared__ uint32_t tmem_base_s;
+    __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(smem);
+    __nv_bfloat16* Bs = As + 128 * K;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int NH = N / 2;
+    for (int i = tid; i < 128 * K; i += 128) {
+        int m = i / K, k = i % K;
+        As[((size_t)(k >> 3) * 128 + m) * 8 + (k & 7)] = __float2bfloat16(A[(size_t)(rank * 128 + m) * K + k]);
+    }
+    for (int i = tid; i < NH * K; i += 128) {
+        int n = i / K, k = i % K;
+        Bs[((size_t)(k >> 3) * NH + n) * 8 + (k & 7)] = __float2bfloat16(Bm[(size_t)(rank * NH + n) * K + k]);
+    }
+    if (tid == 0) { ptx::mbar_init(&ready, 2); ptx::mbar_init(&done, 1); ptx::fence_mbar_init(); }
+    if (warp == 0) ptx::tmem_alloc2(&tmem_base_s, (uint32_t)(N < 32 ? 32 : N));
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();          // barriers of both CTAs initialised, operands of both CTAs written
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) ptx::mbar_arrive_cluster(ptx::mapa(&ready, 0));
+    if (tid == 0 && rank == 0) {
+        ptx::mbar_wait_cluster(&ready, 0);
+        ptx::tc_fence_after();
+        const uint32_t a0 = ptx::smem_addr(As), b0 = ptx::smem_addr(Bs);
+        const uint32_t idesc = ptx::idesc_bf16(256, N, 0, 0);
+        for (int ks = 0; ks < K / 16; ++ks) {
+            uint64_t ad = ptx::smem_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128);
+            uint64_t bd = ptx::smem_desc(b0 + ks * 2 * (NH * 16), NH * 16, 128);
+            ptx::mma2_bf16(tmem_base, ad, bd, idesc, ks > 0);
+        }
+        ptx::mma2_commit(&done);
+    }
+    ptx::mbar_wait(&done, 0);
+    ptx::tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) D[(size_t)(rank * 128 + row) * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();          // both CTAs are done with TMEM and with each other's shared memory
+    if (warp == 0) ptx::tmem_dealloc2(tmem_base, (uint32_t)(N < 32 ? 32 : N));
+}
+
 }  // namespace
 }  // namespace niw
 
 extern "C" int niw_tc_selftest(const float* A, const float* Bm, int N, int K, int variant, float* D, void* stream) {
     NIW_CHECK_ARG(A && Bm && D);
-    if (!(N == 32 || N == 64 || N == 128 || N == 256) || K % 16 != 0 || K <= 0 || K > 256 || variant < 0 || variant > 3)
+    if (!(N == 32 || N == 64 || N == 128 || N == 256) || K % 16 != 0 || K <= 0 || K > 256 || variant < 0 || variant > 4)
         return NIW_E_UNSUPP;
+    if (variant == 4) {   // CTA pair: A has 256 rows, D is [256, N]
+        size_t smem2 = (size_t)(128 + N / 2) * K * 2;
+        NIW_CUDA(cudaFuncSetAttribute(niw::tc_selftest_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        niw::note_launch(), niw::tc_selftest_pair_kernel<<<2, 128, smem2, niw_stream(stream)>>>(A, Bm, N, K, D);
+        NIW_LAUNCH_CHECK();
+        return 0;
+    }
     size_t smem = (size_t)(128 + N) * K * 2;
     NIW_CUDA(cudaFuncSetAttribute(niw::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     niw::note_launch(), niw::tc_selftest_kernel<<<1, 128, smem, niw_stream(stream)>>>(A, Bm, N, K, variant, D);

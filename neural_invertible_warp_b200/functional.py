@@ -416,10 +416,13 @@ def mse_gather(rgb, image, ray_idx=None, idx_start=0):
 
 
 def tc_selftest(A, Bm, variant=0):
-    """D = A . Bm^T through the tcgen05 staging used by the MLP kernel (A [128,K], Bm [N,K])."""
+    """D = A . Bm^T through the tcgen05 staging used by the MLP kernel (A [128,K], Bm [N,K]; variant 4 is the
+    CTA-pair form, cta_group::2, with A [256,K])."""
     lib = _lib.load()
     A, Bm = _f32(A, "A"), _f32(Bm, "B")
     N, K = Bm.shape
-    D = torch.zeros(128, N, device=A.device)
+    if A.shape[0] != (256 if int(variant) == 4 else 128):
+        raise ValueError("tc_selftest: A must have %d rows for variant %d" % (256 if int(variant) == 4 else 128, variant))
+    D = torch.zeros(A.shape[0], N, device=A.device)
     _lib.check(lib.niw_tc_selftest(_p(A), _p(Bm), N, K, int(variant), _p(D), _stream()))
     return D

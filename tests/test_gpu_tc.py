@@ -36,6 +36,19 @@ def test_tc_selftest_variants(F, variant, N, K):
     assert err < 1e-3, "tcgen05 descriptor convention mismatch (variant %d): %.3e" % (variant, err)
 
 
+@pytest.mark.parametrize("N,K", [(256, 256), (128, 64), (32, 16)])
+def test_tc_selftest_cta_pair(F, N, K):
+    """cta_group::2: one M = 256 MMA chain over a CTA pair (each CTA stages 128 rows of A and N/2 rows of B)."""
+    gen = torch.Generator().manual_seed(7 * N + K)
+    A = torch.randn(256, K, generator=gen)
+    Bm = torch.randn(N, K, generator=gen)
+    ref = _bf16(A).double() @ _bf16(Bm).double().t()
+    D = F.tc_selftest(A.to(DEV), Bm.to(DEV), 4).cpu().double()
+    err = (D - ref).abs().max().item()
+    print("tc_selftest pair N=%d K=%d max err %.3e" % (N, K, err))
+    assert err < 1e-3, "cta_group::2 operand split mismatch: %.3e" % err
+
+
 def _flat(p):
     keys = []
     for i in range(8):
