@@ -1,41 +1,47 @@
 // Fused positional-encoding + 8x256 NeRF MLP on the 5th-generation tensor cores (tcgen05, sm_100a).
 // SURVEY.md section 8 rows a6+a7+a8; reference model/nerf.py:416-456, model/barf.py:256-268.
 //
-// Forward (tc_fwd_kernel): persistent, one CTA per SM, 384 threads.
-//   warp 0      producer: streams the pre-packed BF16 weights (1.03 MB / pass) from L2 into a
-//               3-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP)
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256|128, K=16) with the
-//               activation tile as A (shared memory, K-major, no swizzle) and the weight chunk as B
-//   warp 2      TMEM allocator (2 x 256 fp32 columns = all 512 columns)
-//   warp 3      loads biases / head weights into shared memory
+// Forward (tc_fwd_kernel): persistent, CTA PAIRS (clusters of 2 on neighbouring SMs, tcgen05 cta_group::2),
+// 384 threads per CTA.  A pair works on four 128-sample tiles at a time: slot s of CTA r holds tile 4q + 2s + r,
+// and every MMA is an M = 256 instruction over the two tiles of one slot (rows 0-127 in the leader, 128-255 in
+// its peer), so each CTA only stages HALF of every weight chunk.  That halving pays for streaming the weights
+// once per SLOT instead of once per pair of slots, which is what lets the two slots run a layer apart: while the
+// tensor cores work on slot 1, the epilogue warps turn slot 0's accumulator into the next layer's A operand.
+//   warp 0      producer: streams this CTA's half of the pre-packed BF16 weight chunks from L2 into a
+//               7-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP)
+//   warp 1      leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 (M=256, N=256|128, K=16)
+//               with the activation tiles as A (shared memory, K-major, no swizzle) and the weight halves as B,
+//               and commits to the barriers of BOTH CTAs.  peer CTA: relays "my half of the chunk has landed"
+//               to the leader
+//   warp 2      TMEM allocator (2 x 256 fp32 columns = all 512 columns, in both CTAs)
+//   warp 3      loads head weights into shared memory, builds the constant A image of the bias products
 //   warps 4-7   epilogue of tile slot 0,  warps 8-11 epilogue of tile slot 1: one thread per
-//               sample row; TMEM -> registers -> +bias, ReLU -> BF16 -> next layer's A tile in
+//               sample row; TMEM -> registers -> ReLU -> BF16 -> next layer's A tile in
 //               shared memory (and to HBM for the backward pass).  The density head (row 0 of
 //               layer 7) and the 128->3 RGB layer are folded into the epilogues as FP32 dot
-//               products, the positional encoding is computed straight into the A tile.
-// Two 128-sample tiles share every weight chunk, so weights cross L2->SMEM once per 256 samples.
+//               products, the positional encoding is computed straight into the A tile.  The biases are added
+//               by the tensor cores (a K = 16 chunk against a constant "ones" A image).
 //
 // Shared-memory operand layout (both operands, all layers): [K/8 chunks][rows][8 bf16], i.e. the
 // canonical no-swizzle K-major UMMA layout with 128 B core matrices, SBO = 128 B (8-row groups are
 // contiguous) and LBO = rows*16 B.  Epilogue thread r writes 16 B at chunk*rows*16 + r*16: a warp
-// writes 512 contiguous bytes (bank-conflict free).  The same image, stored per tile in HBM, is
-// the MN-major operand of the weight-gradient GEMM in the backward pass (K = samples).
+// writes 512 contiguous bytes (bank-conflict free).
 #include "tc_layout.cuh"
 
 namespace niw {
 
 namespace tc {
 
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 7;
 
 // shared memory map of the forward kernel
 constexpr int SM_ACT = 0;
 constexpr int SM_ENC = SM_ACT + 2 * ACT_BYTES;
 constexpr int SM_RING = SM_ENC + 2 * ENC_BYTES;
-constexpr int SM_ONES = SM_RING + NSTAGE * STAGE_BYTES;
+constexpr int SM_ONES = SM_RING + NSTAGE * HSTAGE_BYTES;
 constexpr int SM_CONST = SM_ONES + ONES_BYTES;
 constexpr int SM_BAR = SM_CONST + ((C_FLOATS * 4 + 15) / 16) * 16;
-constexpr int SM_TOTAL = SM_BAR + 128;
+constexpr int SM_TOTAL = SM_BAR + 256;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
 // ------------------------------------------------------------------------------------------
@@ -55,11 +61,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ P, C2F c2f, uint8_
         int64_t rel = byte - stream_off(l);
         const int64_t main_bytes = (int64_t)layer_chunks(l) * rows * CHUNK_K * 2;
         uint32_t out[4] = {0u, 0u, 0u, 0u};
+        const int hrows = rows / 2;                          // rows staged by one CTA of the pair
         if (rel < main_bytes) {
+            // chunk = [2 CTA halves][4 k-groups][rows/2][8 bf16]
             int chunk = (int)(rel / ((int64_t)rows * CHUNK_K * 2));
-            int64_t in_chunk = rel % ((int64_t)rows * CHUNK_K * 2);
-            int kc = (int)(in_chunk / (rows * 16));          // which 8-wide k group inside the chunk
-            int n = (int)((in_chunk % (rows * 16)) / 16);
+            int in_chunk = (int)(rel % ((int64_t)rows * CHUNK_K * 2));
+            int half = in_chunk / (hrows * CHUNK_K * 2);
+            int in_half = in_chunk % (hrows * CHUNK_K * 2);
+            int kc = in_half / (hrows * 16);                 // which 8-wide k group inside the chunk
+            int n = half * hrows + (in_half % (hrows * 16)) / 16;
             int k0 = chunk * CHUNK_K + kc * 8;
             const int in_dim = layer_in(l);
             const float* Wl = P + layer_woff(l) + (int64_t)(n + layer_rowoff(l)) * in_dim;
@@ -69,10 +79,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ P, C2F c2f, uint8_
                 out[j] = ptx::pack_bf16(ka < in_dim ? Wl[ka] : 0.f, kb < in_dim ? Wl[kb] : 0.f);
             }
         } else {
-            // bias chunk [2 k-groups][rows][8 bf16]: k = 0 -> bf16(b), k = 1 -> bf16(b - bf16(b)), rest 0
+            // bias chunk [2 CTA halves][2 k-groups][rows/2][8 bf16]: k = 0 -> bf16(b), k = 1 -> bf16(b - bf16(b)), rest 0
             rel -= main_bytes;
-            const int kg = (int)(rel / (rows * 16));
-            const int n = (int)((rel % (rows * 16)) / 16);
+            const int half = (int)(rel / (hrows * BIAS_K * 2)), in_half = (int)(rel % (hrows * BIAS_K * 2));
+            const int kg = in_half / (hrows * 16);
+            const int n = half * hrows + (in_half % (hrows * 16)) / 16;
             if (kg == 0) {
                 const float b = P[layer_boff(l) + n + layer_rowoff(l)];
                 const float hi = __bfloat162float(__float2bfloat16(b));
@@ -214,30 +225,33 @@ __device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p 
 // ------------------------------------------------------------------------------------------
 // fused forward kernel
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ consts_g, const float* __restrict__ center,
               const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N,
               float* __restrict__ rgb_out, float* __restrict__ sigma_out, float* __restrict__ sig_pre,
               float* __restrict__ rgb_keep, uint8_t* __restrict__ save) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-    uint64_t* w_full = bars;                 // [NSTAGE]
-    uint64_t* w_empty = bars + NSTAGE;       // [NSTAGE]
-    uint64_t* a_ready = bars + 2 * NSTAGE;   // [2]
-    uint64_t* acc_full = a_ready + 2;        // [2]
+    uint64_t* w_full = bars;                 // [NSTAGE] this CTA's half of the chunk has landed (leader: and the peer's)
+    uint64_t* w_empty = bars + NSTAGE;       // [NSTAGE] the MMAs reading the stage have completed (both CTAs)
+    uint64_t* a_ready = bars + 2 * NSTAGE;   // [2]      (leader) both A tiles of the slot are written, accumulators drained
+    uint64_t* acc_full = a_ready + 2;        // [2]      the slot's layer has been accumulated (both CTAs)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
     float* cst = reinterpret_cast<float*>(smem + SM_CONST);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
     const int64_t ntiles = (S + TILE - 1) / TILE;
-    const int64_t npairs = (ntiles + 1) / 2;
+    const int64_t nquads = (ntiles + 3) / 4;
+    const int64_t quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], TILE); ptx::mbar_init(&acc_full[i], 1); }
+        // leader: a stage is full when its own copy has landed (expect_tx arrive) and the peer has reported its half
+        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&w_full[i], rank == 0 ? 2 : 1); ptx::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], 2 * TILE); ptx::mbar_init(&acc_full[i], 1); }
         ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+    if (warp == 2) ptx::tmem_alloc2(tmem_slot, 512);
     if (warp == 3) {
         for (int i = lane; i < C_FLOATS; i += 32) cst[i] = consts_g[i];
         // constant A image of the bias products: columns 0 and 1 are 1.0, the other 14 are 0
@@ -247,72 +261,101 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
     }
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync_all();            // the peer's barriers are initialised before anyone signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     Bands3 bw3; BandsV bwv;
     load_bands(cst + C_BANDS, bw3, bwv);
 
     if (warp == 0) {
-        // ================= weight producer =================
+        // ================= weight producer (this CTA's half of every chunk, once per slot) =================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-                const uint8_t* src = wstream;
+            for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+                const uint8_t* lsrc = wstream;
                 for (int l = 0; l < NLAYER; ++l) {
-                    const int nch = layer_chunks(l);
-                    for (int c = 0; c <= nch; ++c, ++it) {          // chunk nch is the K = 16 bias chunk
-                        const uint32_t bytes = (uint32_t)layer_rows(l) * (c < nch ? CHUNK_K : BIAS_K) * 2;
-                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
-                        ptx::mbar_wait(&w_empty[st], ph ^ 1);
-                        ptx::mbar_arrive_expect_tx(&w_full[st], bytes);
-                        ptx::bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src, bytes, &w_full[st]);
-                        src += bytes;
+                    const int nch = layer_chunks(l), hrows = layer_rows(l) / 2;
+                    for (int s = 0; s < 2; ++s) {
+                        const uint8_t* src = lsrc;
+                        for (int c = 0; c <= nch; ++c, ++it) {          // chunk nch is the K = 16 bias chunk
+                            const uint32_t bytes = (uint32_t)hrows * (c < nch ? CHUNK_K : BIAS_K) * 2;
+                            const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                            ptx::mbar_wait(&w_empty[st], ph ^ 1);
+                            ptx::mbar_arrive_expect_tx(&w_full[st], bytes);
+                            ptx::bulk_g2s(smem + SM_RING + st * HSTAGE_BYTES, src + rank * bytes, bytes, &w_full[st]);
+                            src += 2 * bytes;
+                        }
                     }
+                    lsrc += layer_stream_bytes(l);
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 && rank != 0) {
+        // ================= peer CTA: tell the leader when this CTA's half of a chunk has landed =================
         if (lane == 0) {
-            uint32_t it = 0, ready_uses = 0;
-            const uint32_t act0 = ptx::smem_addr(smem + SM_ACT), enc0 = ptx::smem_addr(smem + SM_ENC);
-            const uint32_t ring0 = ptx::smem_addr(smem + SM_RING), ones0 = ptx::smem_addr(smem + SM_ONES);
-            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-                for (int l = 0; l < NLAYER; ++l, ++ready_uses) {
-                    const int rows = layer_rows(l), nch = layer_chunks(l);
-                    const uint32_t idesc = ptx::idesc_bf16(TILE, rows, 0, 0);
-                    for (int c = 0; c <= nch; ++c, ++it) {
-                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+            uint32_t st = 0, ph = 0;
+            const uint32_t full0 = ptx::mapa(&w_full[0], 0);
+            for (int64_t quad = quad0; quad < nquads; quad += quad_step)
+                for (int l = 0; l < NLAYER; ++l)
+                    for (int c = 0; c < 2 * (layer_chunks(l) + 1); ++c) {
+                        ptx::mbar_wait(&w_full[st], ph);
+                        ptx::mbar_arrive_cluster(full0 + st * 8);
+                        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+                    }
+        }
+    } else if ((warp == 1 || warp == 2) && rank == 0) {
+        // ================= leader CTA: MMA issuers, one thread per slot (M = 256 over the pair) =================
+        // The chunk stream alternates [slot 0: layer l][slot 1: layer l]; each issuer walks its own segments.  One
+        // thread cannot issue fast enough for both slots (~130 dependent instructions per 2 MMAs).
+        if (lane == 0) {
+            const int s = warp - 1;
+            uint32_t st = 0, ph = 0, ready_ph = 0;
+            // the other slot's chunks are waited for as well (not consumed): an issuer that merely skipped them could
+            // get two ring cycles ahead of the loads, where the parity test of an mbarrier phase aliases
+            auto skip = [&](int n) {
+                for (int i = 0; i < n; ++i) {
+                    ptx::mbar_wait(&w_full[st], ph);
+                    if (++st == NSTAGE) { st = 0; ph ^= 1; }
+                }
+            };
+            const uint32_t act_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + SM_ACT + s * ACT_BYTES), KROW);
+            const uint32_t enc_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + SM_ENC + s * ENC_BYTES), KROW);
+            const uint32_t ones_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + SM_ONES), KROW);
+            const uint32_t ring_a = ptx::smem_addr(smem + SM_RING) >> 4;
+            const uint32_t desc_hi = ptx::smem_desc_hi(128);
+            const uint32_t tacc = tmem_base + s * WIDTH;
+            for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+                for (int l = 0; l < NLAYER; ++l) {
+                    const int hrows = layer_rows(l) / 2, nch = layer_chunks(l);
+                    const uint32_t idesc = ptx::idesc_bf16(2 * TILE, 2 * hrows, 0, 0);
+                    const uint32_t b_lbo = (uint32_t)hrows << 16;            // LBO field: hrows * 16 B >> 4
+                    const uint32_t b_kstep = (uint32_t)hrows * 2;            // one K = 16 step: 2 k-groups x hrows x 16 B >> 4
+                    if (s == 1) skip(nch + 1);
+                    ptx::mbar_wait(&a_ready[s], ready_ph);
+                    ready_ph ^= 1;
+                    ptx::tc_fence_after();
+                    for (int c = 0; c < nch; ++c) {
                         ptx::mbar_wait(&w_full[st], ph);
                         ptx::tc_fence_after();
-                        const uint32_t b_base = ring0 + st * STAGE_BYTES;
-                        if (c < nch) {
-                            // which A tile region does this chunk multiply?
-                            const bool from_enc = (l == 0) || (c >= 8);
-                            const int kc0 = (l == 0 ? c : (c >= 8 ? c - 8 : c)) * (CHUNK_K / 8);
-#pragma unroll
-                            for (int s = 0; s < 2; ++s) {
-                                if (c == 0) { ptx::mbar_wait(&a_ready[s], ready_uses & 1); ptx::tc_fence_after(); }
-                                const uint32_t a_base = (from_enc ? enc0 + s * ENC_BYTES : act0 + s * ACT_BYTES) + kc0 * KROW;
-#pragma unroll
-                                for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
-                                    uint64_t ad = ptx::smem_desc(a_base + ks * 2 * KROW, KROW, 128);
-                                    uint64_t bd = ptx::smem_desc(b_base + ks * 2 * rows * 16, rows * 16, 128);
-                                    ptx::mma_bf16(tmem_base + s * WIDTH, ad, bd, idesc, (c | ks) != 0);
-                                }
-                            }
-                        } else {
-                            // bias: D += ones[128 x 16] . [bf16(b), b - bf16(b), 0 ...]^T
-                            const uint64_t ad = ptx::smem_desc(ones0, KROW, 128);
-                            const uint64_t bd = ptx::smem_desc(b_base, rows * 16, 128);
-#pragma unroll
-                            for (int s = 0; s < 2; ++s) {
-                                ptx::mma_bf16(tmem_base + s * WIDTH, ad, bd, idesc, true);
-                                ptx::mma_commit(&acc_full[s]);
-                            }
-                        }
-                        ptx::mma_commit(&w_empty[st]);
+                        // which A tile region does this chunk multiply?
+                        const bool from_enc = (l == 0) || (c >= 8);
+                        const uint32_t a_lo = (from_enc ? enc_lo : act_lo) + (uint32_t)((l == 0 || c < 8) ? c : c - 8) * (CHUNK_K / 8) * (KROW >> 4);
+                        const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
+                        ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
+                        ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
+                        ptx::mma2_commit(&w_empty[st]);
+                        if (++st == NSTAGE) { st = 0; ph ^= 1; }
                     }
+                    {   // bias: D += ones[256 x 16] . [bf16(b), b - bf16(b), 0 ...]^T
+                        ptx::mbar_wait(&w_full[st], ph);
+                        ptx::tc_fence_after();
+                        const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
+                        ptx::mma2_bf16_w(tacc, ones_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
+                        ptx::mma2_commit(&w_empty[st]);
+                        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+                    }
+                    ptx::mma2_commit(&acc_full[s]);
+                    if (s == 0) skip(nch + 1);
                 }
             }
         }
@@ -323,9 +366,10 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
         uint8_t* act = smem + SM_ACT + slot * ACT_BYTES;
         uint8_t* enc = smem + SM_ENC + slot * ENC_BYTES;
         const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * WIDTH;
+        const uint32_t ready_bar = ptx::mapa(&a_ready[slot], 0);     // the leader's barrier
         uint32_t full_uses = 0;
-        for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-            const int64_t tile = pair * 2 + slot;
+        for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+            const int64_t tile = quad * 4 + slot * 2 + rank;
             const int64_t g = tile * TILE + row;
             const bool valid = tile < ntiles && g < S;
             uint8_t* save_tile = (save && tile < ntiles) ? save + tile * SAVE_TILE_BYTES : nullptr;
@@ -345,7 +389,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                 write_enc_row(enc, save_tile ? save_tile + SV_ENC : nullptr, row, x, bw3, valid);
             }
             ptx::fence_proxy_async();
-            ptx::mbar_arrive(&a_ready[slot]);
+            ptx::mbar_arrive_cluster(ready_bar);
             for (int l = 0; l < NLAYER; ++l, ++full_uses) {
                 ptx::mbar_wait(&acc_full[slot], full_uses & 1);
                 ptx::tc_fence_after();
@@ -387,7 +431,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         write_venc_row(enc, save_tile ? save_tile + SV_VENC : nullptr, row, v3, bwv, valid);
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive(&a_ready[slot]);
+                    ptx::mbar_arrive_cluster(ready_bar);
                     if (l == 6 && valid) {
                         float pre = sig_acc + cst[C_MISC];
                         sigma_out[g] = softplus_f(pre);
@@ -425,7 +469,8 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+    ptx::cluster_sync_all();            // neither CTA leaves while its peer may still touch its shared memory / TMEM
+    if (warp == 2) ptx::tmem_dealloc2(tmem_base, 512);
 }
 
 }  // namespace tc
@@ -447,9 +492,10 @@ int tc_fwd(const float* P, const float* center, const float* ray, const float* d
     if (training)
         niw::note_launch(), pack_weights_bwd_kernel<<<niw_blocks(BSTREAM_BYTES / 16, 256), 256, 0, st>>>(P, w.bstream);
     NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    const int64_t npairs = ((S + TILE - 1) / TILE + 1) / 2;
-    int grid = niw_num_sms();
-    if (grid > npairs) grid = (int)npairs;
+    const int64_t nquads = ((S + TILE - 1) / TILE + 3) / 4;     // four tiles per CTA pair and round
+    int64_t pairs = niw_num_sms() / 2;
+    if (pairs > nquads) pairs = nquads;
+    const int grid = (int)(2 * (pairs < 1 ? 1 : pairs));
     niw::note_launch(), tc_fwd_kernel<<<grid, 384, SM_TOTAL, st>>>(w.wstream, w.consts, center, ray, depth, S, N, rgb, sigma,
                                              training ? w.sig_pre : nullptr, training ? w.rgb_keep : nullptr,
                                              training ? w.save : nullptr);

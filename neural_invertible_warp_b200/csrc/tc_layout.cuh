@@ -31,6 +31,7 @@ constexpr int SMALL_BYTES = TILE * 8 * 2;         // 2048:  8-column image (g_rg
 constexpr int HALF = 64;                          // samples per half image (K extent of one dW stage)
 constexpr int HROW = HALF * 16;                   // 1024: bytes of one 8-column group of a half image
 constexpr int STAGE_BYTES = WIDTH * CHUNK_K * 2;  // 16384: one weight chunk (256 rows x 32 k)
+constexpr int HSTAGE_BYTES = STAGE_BYTES / 2;     // 8192:  the half of a weight chunk one CTA of a pair stages
 
 // ---- fp32 constants kept in shared memory (CUDA-core head weights, band weights) ------------------
 constexpr int NLAYER = 9;                         // forward: 8 feature layers + rgb0
