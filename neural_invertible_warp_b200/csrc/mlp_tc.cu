@@ -112,7 +112,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ P, C2F c2f, uint8_
 }
 
 // transposed stream of the dX pass: step s, chunk c holds B[n][k] = W_layer[k + rowoff][col0 + n]
-// for k in [32c, 32c+32) as [4 k-groups][N rows][8 bf16]
+// for k in [32c, 32c+32) as [2 CTA halves][4 k-groups][N/2 rows][8 bf16]
 __global__ void pack_weights_bwd_kernel(const float* __restrict__ P, uint8_t* __restrict__ stream) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= BSTREAM_BYTES / 16) return;
@@ -120,12 +120,13 @@ __global__ void pack_weights_bwd_kernel(const float* __restrict__ P, uint8_t* __
     int s = 0;
 #pragma unroll
     for (int i = 1; i < NSTEP; ++i) if (byte >= bstream_off(i)) s = i;
-    const int n_rows = step_n(s);
+    const int n_rows = step_n(s), hrows = n_rows / 2;
     const int64_t rel = byte - bstream_off(s);
     const int chunk = (int)(rel / ((int64_t)n_rows * CHUNK_K * 2));
-    const int64_t in_chunk = rel % ((int64_t)n_rows * CHUNK_K * 2);
-    const int kg = (int)(in_chunk / (n_rows * 16));
-    const int n = (int)((in_chunk % (n_rows * 16)) / 16);
+    const int in_chunk = (int)(rel % ((int64_t)n_rows * CHUNK_K * 2));
+    const int half = in_chunk / (hrows * CHUNK_K * 2), in_half = in_chunk % (hrows * CHUNK_K * 2);
+    const int kg = in_half / (hrows * 16);
+    const int n = half * hrows + (in_half % (hrows * 16)) / 16;
     const int k0 = chunk * CHUNK_K + kg * 8;
     const int l = step_layer(s);
     const int in_dim = layer_in(l);
@@ -232,9 +233,12 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
               float* __restrict__ rgb_keep, uint8_t* __restrict__ save) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-    uint64_t* w_full = bars;                 // [NSTAGE] this CTA's half of the chunk has landed (leader: and the peer's)
-    uint64_t* w_empty = bars + NSTAGE;       // [NSTAGE] the MMAs reading the stage have completed (both CTAs)
-    uint64_t* a_ready = bars + 2 * NSTAGE;   // [2]      (leader) both A tiles of the slot are written, accumulators drained
+    // w_full has TWO barriers per stage, used on alternating trips round the ring: the two issuer threads skip each
+    // other's chunks without observing their phases, and with one barrier per stage the parity test of a phase
+    // aliases as soon as a thread is a full trip away from the barrier's current phase (seen as a deadlock)
+    uint64_t* w_full = bars;                 // [2][NSTAGE] this CTA's half of the chunk has landed (leader: and the peer's)
+    uint64_t* w_empty = bars + 2 * NSTAGE;   // [NSTAGE] the MMAs reading the stage have completed (both CTAs)
+    uint64_t* a_ready = bars + 3 * NSTAGE;   // [2]      (leader) both A tiles of the slot are written, accumulators drained
     uint64_t* acc_full = a_ready + 2;        // [2]      the slot's layer has been accumulated (both CTAs)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
     float* cst = reinterpret_cast<float*>(smem + SM_CONST);
@@ -247,7 +251,8 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
 
     if (threadIdx.x == 0) {
         // leader: a stage is full when its own copy has landed (expect_tx arrive) and the peer has reported its half
-        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&w_full[i], rank == 0 ? 2 : 1); ptx::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2 * NSTAGE; ++i) ptx::mbar_init(&w_full[i], rank == 0 ? 2 : 1);
+        for (int i = 0; i < NSTAGE; ++i) ptx::mbar_init(&w_empty[i], 1);
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], 2 * TILE); ptx::mbar_init(&acc_full[i], 1); }
         ptx::fence_mbar_init();
     }
@@ -270,20 +275,21 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
     if (warp == 0) {
         // ================= weight producer (this CTA's half of every chunk, once per slot) =================
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t st = 0, cyc = 0;                  // ring stage, trips round the ring
             for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
                 const uint8_t* lsrc = wstream;
                 for (int l = 0; l < NLAYER; ++l) {
                     const int nch = layer_chunks(l), hrows = layer_rows(l) / 2;
                     for (int s = 0; s < 2; ++s) {
                         const uint8_t* src = lsrc;
-                        for (int c = 0; c <= nch; ++c, ++it) {          // chunk nch is the K = 16 bias chunk
+                        for (int c = 0; c <= nch; ++c) {                // chunk nch is the K = 16 bias chunk
                             const uint32_t bytes = (uint32_t)hrows * (c < nch ? CHUNK_K : BIAS_K) * 2;
-                            const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
-                            ptx::mbar_wait(&w_empty[st], ph ^ 1);
-                            ptx::mbar_arrive_expect_tx(&w_full[st], bytes);
-                            ptx::bulk_g2s(smem + SM_RING + st * HSTAGE_BYTES, src + rank * bytes, bytes, &w_full[st]);
+                            uint64_t* full = &w_full[(cyc & 1) * NSTAGE + st];
+                            ptx::mbar_wait(&w_empty[st], (cyc & 1) ^ 1);
+                            ptx::mbar_arrive_expect_tx(full, bytes);
+                            ptx::bulk_g2s(smem + SM_RING + st * HSTAGE_BYTES, src + rank * bytes, bytes, full);
                             src += 2 * bytes;
+                            if (++st == NSTAGE) { st = 0; ++cyc; }
                         }
                     }
                     lsrc += layer_stream_bytes(l);
@@ -293,14 +299,15 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
     } else if (warp == 1 && rank != 0) {
         // ================= peer CTA: tell the leader when this CTA's half of a chunk has landed =================
         if (lane == 0) {
-            uint32_t st = 0, ph = 0;
+            uint32_t st = 0, cyc = 0;
             const uint32_t full0 = ptx::mapa(&w_full[0], 0);
             for (int64_t quad = quad0; quad < nquads; quad += quad_step)
                 for (int l = 0; l < NLAYER; ++l)
                     for (int c = 0; c < 2 * (layer_chunks(l) + 1); ++c) {
-                        ptx::mbar_wait(&w_full[st], ph);
-                        ptx::mbar_arrive_cluster(full0 + st * 8);
-                        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+                        const uint32_t fb = (cyc & 1) * NSTAGE + st;
+                        ptx::mbar_wait(&w_full[fb], (cyc >> 1) & 1);
+                        ptx::mbar_arrive_cluster(full0 + fb * 8);
+                        if (++st == NSTAGE) { st = 0; ++cyc; }
                     }
         }
     } else if ((warp == 1 || warp == 2) && rank == 0) {
@@ -309,15 +316,12 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
         // thread cannot issue fast enough for both slots (~130 dependent instructions per 2 MMAs).
         if (lane == 0) {
             const int s = warp - 1;
-            uint32_t st = 0, ph = 0, ready_ph = 0;
-            // the other slot's chunks are waited for as well (not consumed): an issuer that merely skipped them could
-            // get two ring cycles ahead of the loads, where the parity test of an mbarrier phase aliases
-            auto skip = [&](int n) {
-                for (int i = 0; i < n; ++i) {
-                    ptx::mbar_wait(&w_full[st], ph);
-                    if (++st == NSTAGE) { st = 0; ph ^= 1; }
-                }
-            };
+            uint32_t st = 0, cyc = 0, ready_ph = 0;
+            auto skip = [&](int n) { st += n; while (st >= NSTAGE) { st -= NSTAGE; ++cyc; } };   // the other slot's chunks
+            auto wait_full = [&]() { ptx::mbar_wait(&w_full[(cyc & 1) * NSTAGE + st], (cyc >> 1) & 1); };
+            // sound as long as the previous phase of a barrier (chunk X - 2*NSTAGE) has completed when an issuer starts
+            // to wait for chunk X: its previous own chunk X' was waited for and X - X' <= longest segment + 1
+            static_assert(2 * NSTAGE >= (10 + 1) + 1, "ring too short for two skipping issuers");
             const uint32_t act_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + SM_ACT + s * ACT_BYTES), KROW);
             const uint32_t enc_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + SM_ENC + s * ENC_BYTES), KROW);
             const uint32_t ones_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + SM_ONES), KROW);
@@ -335,7 +339,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                     ready_ph ^= 1;
                     ptx::tc_fence_after();
                     for (int c = 0; c < nch; ++c) {
-                        ptx::mbar_wait(&w_full[st], ph);
+                        wait_full();
                         ptx::tc_fence_after();
                         // which A tile region does this chunk multiply?
                         const bool from_enc = (l == 0) || (c >= 8);
@@ -344,15 +348,15 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
                         ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
                         ptx::mma2_commit(&w_empty[st]);
-                        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+                        if (++st == NSTAGE) { st = 0; ++cyc; }
                     }
                     {   // bias: D += ones[256 x 16] . [bf16(b), b - bf16(b), 0 ...]^T
-                        ptx::mbar_wait(&w_full[st], ph);
+                        wait_full();
                         ptx::tc_fence_after();
                         const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
                         ptx::mma2_bf16_w(tacc, ones_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
                         ptx::mma2_commit(&w_empty[st]);
-                        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+                        if (++st == NSTAGE) { st = 0; ++cyc; }
                     }
                     ptx::mma2_commit(&acc_full[s]);
                     if (s == 0) skip(nch + 1);

@@ -32,13 +32,13 @@ namespace tc {
 // dX pass
 // ==========================================================================================
 
-constexpr int BX_NSTAGE = 4;
+constexpr int BX_NSTAGE = 10;
 constexpr int BX_ACT = 0;                                   // 2 x 64 KB G tiles
 constexpr int BX_RING = BX_ACT + 2 * ACT_BYTES;
-constexpr int BX_CONST = BX_RING + BX_NSTAGE * STAGE_BYTES;  // W7 row 0 [256] + Wrgb1 [3][128]
+constexpr int BX_CONST = BX_RING + BX_NSTAGE * HSTAGE_BYTES; // W7 row 0 [256] + Wrgb1 [3][128]
 constexpr int BX_CONST_FLOATS = WIDTH + 3 * RGBW + NBANDS;   // ... + band weights
 constexpr int BX_BAR = BX_CONST + BX_CONST_FLOATS * 4;
-constexpr int BX_TOTAL = BX_BAR + 128;
+constexpr int BX_TOTAL = BX_BAR + 512;
 static_assert(BX_TOTAL <= 227 * 1024, "shared memory budget (dX pass)");
 
 // reduce v over the 32 rows of a warp when they all belong to ray r (uniform), else per-thread atomics
@@ -51,7 +51,10 @@ __device__ __forceinline__ void ray_atomic_add3(float* dst, int64_t r, const flo
     }
 }
 
-__global__ void __launch_bounds__(384, 1)
+// CTA pairs (cta_group::2), same organisation as the forward kernel (mlp_tc.cu): slot s of CTA r holds tile
+// 4q + 2s + r, every MMA is M = 256 over the two tiles of a slot, each CTA stages half of every transposed-weight
+// chunk, the two slots run one step apart, one issuer thread per slot in the leader CTA.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ consts_g, const float* __restrict__ center,
              const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N,
              const float* __restrict__ d_rgb, const float* __restrict__ d_sigma, const float* __restrict__ sig_pre,
@@ -59,80 +62,107 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
              float* __restrict__ dP, float* __restrict__ d_center, float* __restrict__ d_ray) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BX_BAR);
-    uint64_t* w_full = bars;                    // [BX_NSTAGE]
-    uint64_t* w_empty = bars + BX_NSTAGE;       // [BX_NSTAGE]
-    uint64_t* a_ready = bars + 2 * BX_NSTAGE;   // [2]
+    uint64_t* w_full = bars;                    // [2][BX_NSTAGE] (alternating trips round the ring, see mlp_tc.cu)
+    uint64_t* w_empty = bars + 2 * BX_NSTAGE;   // [BX_NSTAGE]
+    uint64_t* a_ready = bars + 3 * BX_NSTAGE;   // [2]  (leader)
     uint64_t* acc_full = a_ready + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
     float* cst = reinterpret_cast<float*>(smem + BX_CONST);   // [0,256): W7 row 0; [256, 640): Wrgb1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
     const int64_t ntiles = (S + TILE - 1) / TILE;
-    const int64_t npairs = (ntiles + 1) / 2;
+    const int64_t nquads = (ntiles + 3) / 4;
+    const int64_t quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < BX_NSTAGE; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], TILE); ptx::mbar_init(&acc_full[i], 1); }
+        for (int i = 0; i < 2 * BX_NSTAGE; ++i) ptx::mbar_init(&w_full[i], rank == 0 ? 2 : 1);
+        for (int i = 0; i < BX_NSTAGE; ++i) ptx::mbar_init(&w_empty[i], 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], 2 * TILE); ptx::mbar_init(&acc_full[i], 1); }
         ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+    if (warp == 2) ptx::tmem_alloc2(tmem_slot, 512);
     if (warp == 3) {
         for (int i = lane; i < WIDTH + 3 * RGBW; i += 32) cst[i] = consts_g[C_W7R0 + i];
         if (lane < NBANDS) cst[WIDTH + 3 * RGBW + lane] = consts_g[C_BANDS + lane];
     }
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     Bands3 bw3; BandsV bwv;
     load_bands(cst + WIDTH + 3 * RGBW, bw3, bwv);
 
     if (warp == 0) {
-        // ================= transposed-weight producer =================
+        // ================= transposed-weight producer (this CTA's half of every chunk, once per slot) =================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-                const uint8_t* src = bstream;
+            uint32_t st = 0, cyc = 0;
+            for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+                const uint8_t* ssrc = bstream;
                 for (int s = 0; s < NSTEP; ++s) {
-                    const uint32_t bytes = (uint32_t)step_n(s) * CHUNK_K * 2;
-                    for (int c = 0; c < step_chunks(s); ++c, ++it) {
-                        const uint32_t st = it % BX_NSTAGE, ph = (it / BX_NSTAGE) & 1;
-                        ptx::mbar_wait(&w_empty[st], ph ^ 1);
-                        ptx::mbar_arrive_expect_tx(&w_full[st], bytes);
-                        ptx::bulk_g2s(smem + BX_RING + st * STAGE_BYTES, src, bytes, &w_full[st]);
-                        src += bytes;
+                    const uint32_t bytes = (uint32_t)(step_n(s) / 2) * CHUNK_K * 2;
+                    for (int sl = 0; sl < 2; ++sl) {
+                        const uint8_t* src = ssrc + rank * bytes;
+                        for (int c = 0; c < step_chunks(s); ++c) {
+                            uint64_t* full = &w_full[(cyc & 1) * BX_NSTAGE + st];
+                            ptx::mbar_wait(&w_empty[st], (cyc & 1) ^ 1);
+                            ptx::mbar_arrive_expect_tx(full, bytes);
+                            ptx::bulk_g2s(smem + BX_RING + st * HSTAGE_BYTES, src, bytes, full);
+                            src += 2 * bytes;
+                            if (++st == BX_NSTAGE) { st = 0; ++cyc; }
+                        }
                     }
+                    ssrc += (int64_t)step_chunks(s) * 2 * bytes;
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 && rank != 0) {
+        // ================= peer CTA: tell the leader when this CTA's half of a chunk has landed =================
         if (lane == 0) {
-            uint32_t it = 0, ready_uses = 0;
-            const uint32_t act0 = ptx::smem_addr(smem + BX_ACT), ring0 = ptx::smem_addr(smem + BX_RING);
-            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-                for (int s = 0; s < NSTEP; ++s, ++ready_uses) {
-                    const int rows = step_n(s), nch = step_chunks(s);
-                    const uint32_t idesc = ptx::idesc_bf16(TILE, rows, 0, 0);
-                    for (int c = 0; c < nch; ++c, ++it) {
-                        const uint32_t st = it % BX_NSTAGE, ph = (it / BX_NSTAGE) & 1;
-                        ptx::mbar_wait(&w_full[st], ph);
-                        ptx::tc_fence_after();
-#pragma unroll
-                        for (int sl = 0; sl < 2; ++sl) {
-                            if (c == 0) { ptx::mbar_wait(&a_ready[sl], ready_uses & 1); ptx::tc_fence_after(); }
-                            const uint32_t a_base = act0 + sl * ACT_BYTES + c * (CHUNK_K / 8) * KROW;
-                            const uint32_t b_base = ring0 + st * STAGE_BYTES;
-#pragma unroll
-                            for (int ks = 0; ks < CHUNK_K / 16; ++ks) {
-                                uint64_t ad = ptx::smem_desc(a_base + ks * 2 * KROW, KROW, 128);
-                                uint64_t bd = ptx::smem_desc(b_base + ks * 2 * rows * 16, rows * 16, 128);
-                                ptx::mma_bf16(tmem_base + sl * WIDTH, ad, bd, idesc, (c | ks) != 0);
-                            }
-                            if (c == nch - 1) ptx::mma_commit(&acc_full[sl]);
-                        }
-                        ptx::mma_commit(&w_empty[st]);
+            uint32_t st = 0, cyc = 0;
+            const uint32_t full0 = ptx::mapa(&w_full[0], 0);
+            for (int64_t quad = quad0; quad < nquads; quad += quad_step)
+                for (int s = 0; s < NSTEP; ++s)
+                    for (int c = 0; c < 2 * step_chunks(s); ++c) {
+                        const uint32_t fb = (cyc & 1) * BX_NSTAGE + st;
+                        ptx::mbar_wait(&w_full[fb], (cyc >> 1) & 1);
+                        ptx::mbar_arrive_cluster(full0 + fb * 8);
+                        if (++st == BX_NSTAGE) { st = 0; ++cyc; }
                     }
+        }
+    } else if ((warp == 1 || warp == 2) && rank == 0) {
+        // ================= leader CTA: MMA issuers, one thread per slot =================
+        if (lane == 0) {
+            const int sl = warp - 1;
+            uint32_t st = 0, cyc = 0, ready_ph = 0;
+            auto skip = [&](int n) { st += n; while (st >= BX_NSTAGE) { st -= BX_NSTAGE; ++cyc; } };   // the other slot's chunks
+            static_assert(2 * BX_NSTAGE >= WIDTH / CHUNK_K + 1, "ring too short for two skipping issuers (see mlp_tc.cu)");
+            const uint32_t act_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + BX_ACT + sl * ACT_BYTES), KROW);
+            const uint32_t ring_a = ptx::smem_addr(smem + BX_RING) >> 4;
+            const uint32_t desc_hi = ptx::smem_desc_hi(128);
+            const uint32_t tacc = tmem_base + sl * WIDTH;
+            for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+                for (int s = 0; s < NSTEP; ++s) {
+                    const int hrows = step_n(s) / 2, nch = step_chunks(s);
+                    const uint32_t idesc = ptx::idesc_bf16(2 * TILE, 2 * hrows, 0, 0);
+                    const uint32_t b_lbo = (uint32_t)hrows << 16, b_kstep = (uint32_t)hrows * 2;
+                    if (sl == 1) skip(nch);
+                    ptx::mbar_wait(&a_ready[sl], ready_ph);
+                    ready_ph ^= 1;
+                    ptx::tc_fence_after();
+                    for (int c = 0; c < nch; ++c) {
+                        ptx::mbar_wait(&w_full[(cyc & 1) * BX_NSTAGE + st], (cyc >> 1) & 1);
+                        ptx::tc_fence_after();
+                        const uint32_t a_lo = act_lo + (uint32_t)c * (CHUNK_K / 8) * (KROW >> 4);
+                        const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
+                        ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
+                        ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
+                        ptx::mma2_commit(&w_empty[st]);
+                        if (++st == BX_NSTAGE) { st = 0; ++cyc; }
+                    }
+                    ptx::mma2_commit(&acc_full[sl]);
+                    if (sl == 0) skip(nch);
                 }
             }
         }
@@ -144,9 +174,10 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
         const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * WIDTH;
         float* scr = scratch + ((size_t)blockIdx.x * 2 + slot) * ENC3_PAD * TILE;
         const bool uniform = (N % 32) == 0;       // the 32 rows of a warp then share one ray
+        const uint32_t ready_bar = ptx::mapa(&a_ready[slot], 0);     // the leader's barrier
         uint32_t full_uses = 0;
-        for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-            const int64_t tile = pair * 2 + slot;
+        for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+            const int64_t tile = quad * 4 + slot * 2 + rank;
             const int64_t g = tile * TILE + row;
             const bool valid = tile < ntiles && g < S;
             const int64_t r = valid ? g / N : -1;
@@ -191,7 +222,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                 *reinterpret_cast<uint4*>(rec + SV_SMALL + row * 16) =
                     make_uint4(ptx::pack_bf16(g3[0], g3[1]), ptx::pack_bf16(g3[2], gs), ptx::pack_bf16(valid ? 1.f : 0.f, 0.f), 0u);
             ptx::fence_proxy_async();
-            ptx::mbar_arrive(&a_ready[slot]);
+            ptx::mbar_arrive_cluster(ready_bar);
 
             for (int s = 0; s < NSTEP; ++s, ++full_uses) {
                 const int lo = step_out_layer(s);
@@ -237,14 +268,14 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                     }
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive(&a_ready[slot]);
+                    ptx::mbar_arrive_cluster(ready_bar);
                 } else if (s == 0) {
                     // ---- view branch: d(encoded view) -> d(unit view) -> d ray through normalize ----
                     uint32_t v[32];
                     ptx::tmem_ld32(tacc, v);
                     ptx::tmem_ld_wait();
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive(&a_ready[slot]);            // accumulator drained; A tile unchanged
+                    ptx::mbar_arrive_cluster(ready_bar);            // accumulator drained; A tile unchanged
                     float dr[3] = {0.f, 0.f, 0.f};
                     if (valid) {
                         float v3[3] = {ray[r * 3], ray[r * 3 + 1], ray[r * 3 + 2]};
@@ -278,7 +309,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                         for (int j = 0; j < 32; ++j) scr[(cc * 32 + j) * TILE + row] = __uint_as_float(v[j]);
                     }
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive(&a_ready[slot]);
+                    ptx::mbar_arrive_cluster(ready_bar);
                 } else {
                     // ---- s == 10: d(encoded position) -> d x -> d center, d ray ----
                     float ge[ENC3_PAD];
@@ -315,7 +346,8 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+    ptx::cluster_sync_all();            // neither CTA leaves while its peer may still touch its shared memory / TMEM
+    if (warp == 2) ptx::tmem_dealloc2(tmem_base, 512);
 }
 
 // ==========================================================================================
@@ -612,9 +644,10 @@ int tc_bwd(const float* P, const float* center, const float* ray, const float* d
     NIW_CUDA(cudaMemsetAsync(d_center, 0, sizeof(float) * R * 3, st));
     NIW_CUDA(cudaMemsetAsync(d_ray, 0, sizeof(float) * R * 3, st));
     NIW_CUDA(cudaFuncSetAttribute(tc_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_TOTAL));
-    const int64_t npairs = (ntiles + 1) / 2;
-    int grid = niw_num_sms();
-    if (grid > npairs) grid = (int)npairs;
+    const int64_t nquads = (ntiles + 3) / 4;      // four tiles per CTA pair and round
+    int64_t pairs = niw_num_sms() / 2;
+    if (pairs > nquads) pairs = nquads;
+    const int grid = (int)(2 * (pairs < 1 ? 1 : pairs));
     niw::note_launch(), tc_dx_kernel<<<grid, 384, BX_TOTAL, st>>>(w.bstream, w.consts, center, ray, depth, S, N, d_rgb, d_sigma,
                                                                  w.sig_pre, w.rgb_keep, w.save, w.scratch, dP, d_center, d_ray);
     NIW_LAUNCH_CHECK();
