@@ -193,6 +193,16 @@ def workload_config(args, precision):
 # ours
 # ------------------------------------------------------------------------------------------------
 
+def _leave(world):
+    """End of a multi-rank run: NCCL teardown after captured graphs that hold collectives can block for minutes
+    (ncclCommDestroy waits on the graphs' communicator references), so the ranks synchronise, flush and exit."""
+    if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_ours(args):
     import torch.distributed as dist
     from neural_invertible_warp_b200 import _lib, config as cfgmod, engine, synthetic as syn
@@ -380,8 +390,7 @@ def run_ours(args):
                 composite_ms_per_step=comp_ms / max(mlp_calls, 1))
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world)
         return
 
     cpu = None
@@ -400,8 +409,7 @@ def run_ours(args):
                          ms_per_step=e2e_s / args.steps * 1e3),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu, clocks=clk)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _leave(world)
 
 
 if __name__ == "__main__":

@@ -311,10 +311,11 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                     }
         }
     } else if ((warp == 1 || warp == 2) && rank == 0) {
-        // ================= leader CTA: MMA issuers, one thread per slot (M = 256 over the pair) =================
+        // ================= leader CTA: MMA issuers, one warp per slot (M = 256 over the pair) =================
         // The chunk stream alternates [slot 0: layer l][slot 1: layer l]; each issuer walks its own segments.  One
-        // thread cannot issue fast enough for both slots (~130 dependent instructions per 2 MMAs).
-        if (lane == 0) {
+        // thread cannot issue fast enough for both slots.  The warp stays converged (uniform loop state), one elected
+        // lane issues the tcgen05 instructions.
+        {
             const int s = warp - 1;
             uint32_t st = 0, cyc = 0, ready_ph = 0;
             auto skip = [&](int n) { st += n; while (st >= NSTAGE) { st -= NSTAGE; ++cyc; } };   // the other slot's chunks
@@ -335,7 +336,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                     const uint32_t b_lbo = (uint32_t)hrows << 16;            // LBO field: hrows * 16 B >> 4
                     const uint32_t b_kstep = (uint32_t)hrows * 2;            // one K = 16 step: 2 k-groups x hrows x 16 B >> 4
                     if (s == 1) skip(nch + 1);
-                    ptx::mbar_wait(&a_ready[s], ready_ph);
+                    ptx::mbar_wait_fast(&a_ready[s], ready_ph);
                     ready_ph ^= 1;
                     ptx::tc_fence_after();
                     for (int c = 0; c < nch; ++c) {
@@ -345,20 +346,26 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         const bool from_enc = (l == 0) || (c >= 8);
                         const uint32_t a_lo = (from_enc ? enc_lo : act_lo) + (uint32_t)((l == 0 || c < 8) ? c : c - 8) * (CHUNK_K / 8) * (KROW >> 4);
                         const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
-                        ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
-                        ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
-                        ptx::mma2_commit(&w_empty[st]);
+                        if (ptx::elect_one()) {
+                            ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
+                            ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
+                            ptx::mma2_commit(&w_empty[st]);
+                        }
+                        __syncwarp();
                         if (++st == NSTAGE) { st = 0; ++cyc; }
                     }
                     {   // bias: D += ones[256 x 16] . [bf16(b), b - bf16(b), 0 ...]^T
                         wait_full();
                         ptx::tc_fence_after();
                         const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
-                        ptx::mma2_bf16_w(tacc, ones_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
-                        ptx::mma2_commit(&w_empty[st]);
+                        if (ptx::elect_one()) {
+                            ptx::mma2_bf16_w(tacc, ones_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
+                            ptx::mma2_commit(&w_empty[st]);
+                            ptx::mma2_commit(&acc_full[s]);
+                        }
+                        __syncwarp();
                         if (++st == NSTAGE) { st = 0; ++cyc; }
                     }
-                    ptx::mma2_commit(&acc_full[s]);
                     if (s == 0) skip(nch + 1);
                 }
             }
@@ -395,7 +402,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
             ptx::fence_proxy_async();
             ptx::mbar_arrive_cluster(ready_bar);
             for (int l = 0; l < NLAYER; ++l, ++full_uses) {
-                ptx::mbar_wait(&acc_full[slot], full_uses & 1);
+                ptx::mbar_wait_fast(&acc_full[slot], full_uses & 1);
                 ptx::tc_fence_after();
                 uint32_t va[32], vb[32], pk[16];
                 if (l < 8) {

@@ -132,8 +132,8 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                     }
         }
     } else if ((warp == 1 || warp == 2) && rank == 0) {
-        // ================= leader CTA: MMA issuers, one thread per slot =================
-        if (lane == 0) {
+        // ================= leader CTA: MMA issuers, one warp per slot (converged, one elected lane issues) =================
+        {
             const int sl = warp - 1;
             uint32_t st = 0, cyc = 0, ready_ph = 0;
             auto skip = [&](int n) { st += n; while (st >= BX_NSTAGE) { st -= BX_NSTAGE; ++cyc; } };   // the other slot's chunks
@@ -148,7 +148,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                     const uint32_t idesc = ptx::idesc_bf16(2 * TILE, 2 * hrows, 0, 0);
                     const uint32_t b_lbo = (uint32_t)hrows << 16, b_kstep = (uint32_t)hrows * 2;
                     if (sl == 1) skip(nch);
-                    ptx::mbar_wait(&a_ready[sl], ready_ph);
+                    ptx::mbar_wait_fast(&a_ready[sl], ready_ph);
                     ready_ph ^= 1;
                     ptx::tc_fence_after();
                     for (int c = 0; c < nch; ++c) {
@@ -156,12 +156,15 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                         ptx::tc_fence_after();
                         const uint32_t a_lo = act_lo + (uint32_t)c * (CHUNK_K / 8) * (KROW >> 4);
                         const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
-                        ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
-                        ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
-                        ptx::mma2_commit(&w_empty[st]);
+                        if (ptx::elect_one()) {
+                            ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
+                            ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
+                            ptx::mma2_commit(&w_empty[st]);
+                            if (c == nch - 1) ptx::mma2_commit(&acc_full[sl]);
+                        }
+                        __syncwarp();
                         if (++st == BX_NSTAGE) { st = 0; ++cyc; }
                     }
-                    ptx::mma2_commit(&acc_full[sl]);
                     if (sl == 0) skip(nch);
                 }
             }
@@ -231,7 +234,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
 #pragma unroll
                     for (int cc = 0; cc < MASK_WORDS; ++cc) mw[cc] = mask ? mask[(lo * MASK_WORDS + cc) * TILE + row] : 0u;
                 }
-                ptx::mbar_wait(&acc_full[slot], full_uses & 1);
+                ptx::mbar_wait_fast(&acc_full[slot], full_uses & 1);
                 ptx::tc_fence_after();
                 if (lo >= 0) {
                     // ---- hidden layers: (+ density rank-1 term) -> ReLU mask -> BF16 -> next A tile + G image ----

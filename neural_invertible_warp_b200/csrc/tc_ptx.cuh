@@ -4,6 +4,9 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#ifndef NIW_FAST_WAIT_NS
+#define NIW_FAST_WAIT_NS 20000u
+#endif
 
 namespace niw {
 namespace ptx {
@@ -34,6 +37,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
+}
+// latency-critical waits (accumulator ready / operand ready): short suspend hint
+__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity), "r"(NIW_FAST_WAIT_NS) : "memory");
+    } while (!ok);
+}
+
+// one lane of a fully converged warp (always the same one).  Keeping the issuing warp converged and electing only
+// around the tcgen05 instructions lets the compiler keep loop state and descriptors in uniform registers; a
+// `if (lane == 0)` region makes them per-thread values that need an ELECT + R2UR sequence per operand.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "selp.b32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- 1-D bulk async copy global -> shared (completes on an mbarrier) ------------------------
