@@ -62,15 +62,16 @@ int niw_raygen_unwarped(const float* intr, const float* pose_init, const int64_t
  * 3 coupling blocks, hidden 128, 6 frequency bands, Softplus(beta=100), including the reference's
  * point-index annealing quirk.  `wpack` holds the EFFECTIVE (weight-norm resolved) weights,
  * NIW_NVP_BLOCK_FLOATS floats per block in the order
- *     W1a[128][26], W2a[128], b2a[1], W1b[128][13], W2b[3][128], b2b[3]
- * (W1* = the columns of lin{b}_{a,b}_0 that multiply the embedded coordinates).  `code_bias`
+ *     W1a[128][27] (26 used, row stride 27), W2a[128], b2a[1], W1b[128][13], W2b[3][128], b2b[3], pad to a multiple of 4
+ * (W1* = the columns of lin{b}_{a,b}_0 that multiply the embedded coordinates) -- the shared-memory image the warp
+ * kernels use (odd row strides: bank-conflict free), so staging a block is one straight 16-byte-vector copy.  `code_bias`
  * [3][2][B][128] holds, per block / part / image, lin_0.bias + W_0[:, emb:] . code_b where
  * code_b = lin{b}_c(code)+code -- a B-sized product done by the host in PyTorch.
  * pts/out are [B,Pt,3].  Backward overwrites d_wpack (same layout) and d_code_bias. */
 #define NIW_NVP_HIDDEN 128
 #define NIW_NVP_FREQS 6
 #define NIW_NVP_BLOCKS 3
-#define NIW_NVP_BLOCK_FLOATS (128 * 26 + 128 + 1 + 128 * 13 + 3 * 128 + 3)
+#define NIW_NVP_BLOCK_FLOATS 5636   /* ((128*27 + 128 + 1 + 128*13 + 3*128 + 3) + 3) / 4 * 4 */
 /* Parameter packing of the NVP network (the B-sized part of DeformNetwork.forward): resolves the
  * weight-norm re-parametrisation w = g v/||v||_row (torch.nn.utils.weight_norm, nvp_ndr.py:291-292,335-336),
  * the code projector code_b = lin{b}_c(code) + code (nvp_ndr.py:382) and folds the latent columns of the

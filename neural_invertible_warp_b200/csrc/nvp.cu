@@ -27,20 +27,9 @@ constexpr int NB = NIW_NVP_BLOCKS;         // 3
 constexpr int EA = 2 * (1 + 2 * NF);       // 26 embedded inputs of part a
 constexpr int EB = 1 * (1 + 2 * NF);       // 13 embedded inputs of part b
 constexpr int DF = 128;                    // latent code width
-constexpr int OFF_W1A = 0;
-constexpr int OFF_W2A = OFF_W1A + HID * EA;
-constexpr int OFF_B2A = OFF_W2A + HID;
-constexpr int OFF_W1B = OFF_B2A + 1;
-constexpr int OFF_W2B = OFF_W1B + HID * EB;
-constexpr int OFF_B2B = OFF_W2B + 3 * HID;
-constexpr int BLOCK_FLOATS = OFF_B2B + 3;
-static_assert(BLOCK_FLOATS == NIW_NVP_BLOCK_FLOATS, "wpack layout");
-constexpr float BETA = 100.f;
-constexpr float PI_F = 3.14159274101257324f;   // fp32(pi), as the reference's fp32 freq tensor
-constexpr int U = HID / 32;                // hidden units per lane
-
-// shared-memory image of one block's weights with odd row strides (bank-conflict free for
-// lane-strided rows): W1a [128][27], W2a [128], b2a, W1b [128][13], W2b [3][128], b2b [3]
+// One block of the packed weights (wpack, d_wpack; include/niw_b200.h) IS the shared-memory image the warp kernels
+// work on, with odd row strides (bank-conflict free for lane-strided rows):
+//     W1a [128][27] (26 used), W2a [128], b2a, W1b [128][13], W2b [3][128], b2b [3], pad
 constexpr int SA = EA + 1;                 // 27
 constexpr int S_W1A = 0;
 constexpr int S_W2A = S_W1A + HID * SA;
@@ -48,7 +37,13 @@ constexpr int S_B2A = S_W2A + HID;
 constexpr int S_W1B = S_B2A + 1;
 constexpr int S_W2B = S_W1B + HID * EB;
 constexpr int S_B2B = S_W2B + 3 * HID;
-constexpr int S_BLOCK = ((S_B2B + 3 + 3) / 4) * 4;   // 5640 floats
+constexpr int S_BLOCK = ((S_B2B + 3 + 3) / 4) * 4;   // 5636 floats
+constexpr int BLOCK_FLOATS = S_BLOCK;
+static_assert(BLOCK_FLOATS == NIW_NVP_BLOCK_FLOATS, "wpack layout");
+constexpr int OFF_W1A = S_W1A, OFF_W2A = S_W2A, OFF_B2A = S_B2A, OFF_W1B = S_W1B, OFF_W2B = S_W2B, OFF_B2B = S_B2B;
+constexpr float BETA = 100.f;
+constexpr float PI_F = 3.14159274101257324f;   // fp32(pi), as the reference's fp32 freq tensor
+constexpr int U = HID / 32;                // hidden units per lane
 
 struct Bands { float w[NF]; };
 
@@ -81,15 +76,9 @@ __device__ __forceinline__ float sel3(const float x[3], int i) { return i == 0 ?
 __device__ __forceinline__ void put3(float x[3], int i, float v) { if (i == 0) x[0] = v; else if (i == 1) x[1] = v; else x[2] = v; }
 
 __device__ __forceinline__ void load_weights_smem(float* sw, const float* __restrict__ wpack, int nblocks) {
-    for (int b = 0; b < nblocks; ++b) {
-        const float* w = wpack + (size_t)b * BLOCK_FLOATS;
-        float* s = sw + (size_t)b * S_BLOCK;
-        for (int i = threadIdx.x; i < HID * EA; i += blockDim.x) s[S_W1A + (i / EA) * SA + (i % EA)] = w[OFF_W1A + i];
-        for (int i = threadIdx.x; i < HID; i += blockDim.x) s[S_W2A + i] = w[OFF_W2A + i];
-        for (int i = threadIdx.x; i < HID * EB; i += blockDim.x) s[S_W1B + i] = w[OFF_W1B + i];
-        for (int i = threadIdx.x; i < 3 * HID; i += blockDim.x) s[S_W2B + i] = w[OFF_W2B + i];
-        if (threadIdx.x == 0) { s[S_B2A] = w[OFF_B2A]; s[S_B2B] = w[OFF_B2B]; s[S_B2B + 1] = w[OFF_B2B + 1]; s[S_B2B + 2] = w[OFF_B2B + 2]; }
-    }
+    const uint4* src = reinterpret_cast<const uint4*>(wpack);
+    uint4* dst = reinterpret_cast<uint4*>(sw);
+    for (int i = threadIdx.x; i < nblocks * (S_BLOCK / 4); i += blockDim.x) dst[i] = src[i];
 }
 
 // embedding of D coordinates into e[D*(1+2NF)], computed cooperatively: lane i < D*NF evaluates
@@ -295,7 +284,7 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
     for (int blk = NB - 1; blk >= 0; --blk) {
         __syncthreads();
         load_weights_smem(sw, wpack + (size_t)blk * BLOCK_FLOATS, 1);
-        for (int i = lane; i < S_BLOCK; i += 32) acc[i] = 0.f;
+        for (int i = lane; i < S_BLOCK / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
         int foc, o0, o1;
         axes(blk, foc, o0, o1);
@@ -419,17 +408,9 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
         float* dW = d_wpack + (size_t)blk * BLOCK_FLOATS;
         const float* accs = smem + S_BLOCK;
         for (int i = threadIdx.x; i < BLOCK_FLOATS; i += blockDim.x) {
-            // wpack index -> padded shared-memory index
-            int si;
-            if (i < OFF_W2A) si = S_W1A + (i / EA) * SA + (i % EA);
-            else if (i < OFF_B2A) si = S_W2A + (i - OFF_W2A);
-            else if (i < OFF_W1B) si = S_B2A;
-            else if (i < OFF_W2B) si = S_W1B + (i - OFF_W1B);
-            else if (i < OFF_B2B) si = S_W2B + (i - OFF_W2B);
-            else si = S_B2B + (i - OFF_B2B);
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < BWD_WARPS; ++w) v += accs[(size_t)w * S_BLOCK + si];
+            for (int w = 0; w < BWD_WARPS; ++w) v += accs[(size_t)w * S_BLOCK + i];
             if (v != 0.f) atomicAdd(dW + i, v);
         }
     }
@@ -486,7 +467,7 @@ nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, int ipc, 
         const float* v = P[part * 5 + 0] + (size_t)j * ld;
         const float scale = P[part * 5 + 1][j] / sqrtf(row_norm2(v, ld, lane));
         if (lane == 0) s_scale[r] = scale;
-        if (writer && lane < emb) wp[(part == 0 ? OFF_W1A : OFF_W1B) + j * emb + lane] = v[lane] * scale;
+        if (writer && lane < emb) wp[(part == 0 ? OFF_W1A + j * SA : OFF_W1B + j * EB) + lane] = v[lane] * scale;
     }
     if (writer) {   // output layers: copies
         for (int i = tid; i < HID; i += PACK_THREADS) wp[OFF_W2A + i] = P[3][i];
@@ -585,7 +566,7 @@ nvp_pack_bwd_kernel(PtrTable T, GradTable G, const float* __restrict__ code, con
         if (lane == 0) Gp[part * 5 + 2][j] += db0;
         // gradient of the effective row: embedded columns from the warp kernel, latent columns
         // d w0[j][emb+k] = sum_img dcb[img][j] cb[img][k]
-        const float* dW1 = dwp + (part == 0 ? OFF_W1A : OFF_W1B) + j * emb;
+        const float* dW1 = dwp + (part == 0 ? OFF_W1A + j * SA : OFF_W1B + j * EB);
         float dwe = lane < emb ? dW1[lane] : 0.f;
         float dwl[DF / 32];
 #pragma unroll

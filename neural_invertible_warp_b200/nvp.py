@@ -22,7 +22,7 @@ HID = 128
 
 
 def pack_effective(p, code, n_blocks=3, n_freq=N_FREQ, prefix=""):
-    """(state-dict-style params, code [B,D]) -> (wpack [3*5508], code_bias [3,2,B,128]).
+    """(state-dict-style params, code [B,D]) -> (wpack [3*5636], code_bias [3,2,B,128]).
 
     w = g * v / ||v||_row is torch's legacy ``nn.utils.weight_norm`` (dim=0) used at
     model/nvp/nvp_ndr.py:291-292,335-336; code_b = lin_c(code) + code is :382.
@@ -37,9 +37,14 @@ def pack_effective(p, code, n_blocks=3, n_freq=N_FREQ, prefix=""):
                 w0 = v * (g / v.norm(dim=1, keepdim=True))
             else:
                 w0 = p[name + ".weight"]
-            chunks += [w0[:, :emb].reshape(-1), p[f"{prefix}lin{b}_{part}_1.weight"].reshape(-1),
+            w1 = w0[:, :emb]
+            if part == "a":      # the packed image keeps W1a with an odd row stride (27), include/niw_b200.h
+                w1 = torch.nn.functional.pad(w1, (0, 1))
+            chunks += [w1.reshape(-1), p[f"{prefix}lin{b}_{part}_1.weight"].reshape(-1),
                        p[f"{prefix}lin{b}_{part}_1.bias"].reshape(-1)]
             biases.append(torch.addmm(p[name + ".bias"], cb, w0[:, emb:].t()))
+        used = sum(c.numel() for c in chunks) - b * F.NIW_NVP_BLOCK_FLOATS
+        chunks.append(code.new_zeros(F.NIW_NVP_BLOCK_FLOATS - used))     # pad the block to a multiple of 4 floats
     B = code.shape[0]
     return torch.cat(chunks), torch.stack(biases).view(n_blocks, 2, B, -1)
 
