@@ -24,10 +24,23 @@ def test_library_is_blackwell_native():
     """SASS of the fused MLP kernel holds tcgen05 MMAs (UTC*MMA), TMEM loads (LDTM) and bulk async
     copies (UBLKCP) -- not a recompiled mma.sync path."""
     sass = subprocess.run(["cuobjdump", "-sass", build.LIB], capture_output=True, text=True).stdout
-    assert "UTCHMMA" in sass or "UTCMMA" in sass
     assert "LDTM" in sass
     assert "UBLKCP" in sass
-    assert "HMMA." not in sass.replace("UTCHMMA", "")
+    funcs = {}
+    for chunk in sass.split("Function : ")[1:]:
+        funcs[chunk.split("\n", 1)[0].strip()] = chunk
+    def kernel(name):
+        hits = [v for k, v in funcs.items() if name in k]
+        assert len(hits) == 1, (name, [k for k in funcs if name in k])
+        return hits[0]
+    # forward and dX chain: CTA-pair tcgen05 MMAs (cta_group::2) and nothing from the warp-level mma.sync path
+    for name in ("tc_fwd_kernel", "tc_dx_kernel"):
+        k = kernel(name)
+        assert "UTCHMMA.2CTA" in k, name
+        assert "HMMA." not in k.replace("UTCHMMA", ""), name
+    # weight-gradient pass: tcgen05 for the GEMMs; the thin bias / head products are warp-level m16n8k16 by design
+    k = kernel("tc_dw_kernel")
+    assert "UTCHMMA" in k and "HMMA.16816" in k
 
 
 def test_ops_fail_loudly_without_cuda():
