@@ -242,9 +242,12 @@ def run_ours(args):
     P_local = (rays_global // IMAGES + world - 1) // world
     rays_local = P_local * IMAGES
 
+    ray_draws = engine.device_ray_draws(dev, seed=20)      # same seed on every rank: one global draw, sliced per rank
+
     def step_device():
         v = cfgmod.AttrDict(var_dev)
-        loss = engine.train_step(opt, graph, v, it, bucket=adam, rank=rank, world=world)
+        with ray_draws:
+            loss = engine.train_step(opt, graph, v, it, bucket=adam, rank=rank, world=world)
         adam.step()
         return loss
 
@@ -269,7 +272,7 @@ def run_ours(args):
         with engine.feed_draws(ray_idx=static["ray_idx"], u=static["u"]):
             v = graph.forward(opt, v, mode="train", iter=it)
         loss = engine.summarize_loss(opt, graph.compute_loss(opt, v, mode="train"))
-        (loss.all * (1.0 / world)).backward()
+        (loss.all if world == 1 else loss.all * (1.0 / world)).backward()
         if world > 1:
             adam.allreduce()
         adam.step()

@@ -92,6 +92,12 @@ int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pt
 int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                      int B, int Pt, const float* d_out, float* d_wpack, float* d_code_bias, void* stream);
 
+/* ---- random pixel subset   model/nerf.py:268 (`torch.randperm(H*W)[:rand_rays//B]`)
+ * out[i] = pi(i), i < k, for a keyed random bijection pi of [0,n): the first k entries of a random permutation
+ * without sorting n keys.  `counter` (device, caller-zeroed) is advanced by the kernel, so replays of a captured
+ * graph draw fresh subsets.  Own random stream (not torch's generator): parity tests feed the reference's draws. */
+int niw_sample_pixels(int64_t n, int k, uint64_t seed, uint64_t* counter, int64_t* out, void* stream);
+
 /* ---- (a4) Graph.sample_depth   model/nerf.py:334-344
  * depth[r,k] = ((u+k)/N)*scale + dmin, optionally 1/(.+1e-8); evaluated with the reference's
  * rounding sequence (no FMA contraction).  u [n_rays*N] or NULL (=0.5, un-stratified). */

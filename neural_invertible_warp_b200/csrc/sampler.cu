@@ -105,6 +105,43 @@ __global__ void pdf_merge_kernel(const float* __restrict__ pdf, const float* __r
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Random pixel subset: the first k entries of a random permutation of [0, n) -- what the reference draws with
+// torch.randperm(H*W)[:rand_rays//B] (model/nerf.py:268), which sorts H*W random keys (5 radix-sort passes,
+// ~70 us at 480x640) to keep 64 of them.  Here entry i is pi(i) for a keyed bijection pi of [0, 2^b) (4-round
+// Feistel network, b = bit length of n-1 rounded up to even) with cycle walking back into [0, n): a prefix of a
+// permutation by construction, O(k) work, no global state besides a call counter (so CUDA-graph replays draw new
+// subsets).  Different random stream than torch's generator: used where the draw itself is the only requirement.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {      // lowbias32
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__global__ void sample_pixels_kernel(int64_t n, int k, uint64_t seed, unsigned long long* __restrict__ counter,
+                                     int64_t* __restrict__ out) {
+    const unsigned long long call = *counter;
+    int bits = 2;
+    while ((1ull << bits) < (unsigned long long)n) bits += 2;
+    const int hb = bits / 2;
+    const uint32_t hmask = (1u << hb) - 1u;
+    uint32_t key[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) key[r] = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x9E3779B9u * (uint32_t)(4 * call + r + 1)) ^ (uint32_t)(call >> 32));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+        uint64_t x = (uint64_t)i;
+        do {                                             // cycle walking: expected < 4 trips (2^b < 4n)
+            uint32_t L = (uint32_t)(x >> hb) & hmask, R = (uint32_t)x & hmask;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { const uint32_t t = L ^ (mix32(R ^ key[r]) & hmask); L = R; R = t; }
+            x = ((uint64_t)L << hb) | R;
+        } while (x >= (uint64_t)n);
+        out[i] = (int64_t)x;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = call + 1;      // single block (k <= a few thousand)
+}
+
 }  // namespace
 
 extern "C" int niw_sample_stratified(const float* u, int64_t n_rays, int N, float scale, float dmin, int inverse,
@@ -134,6 +171,14 @@ extern "C" int niw_sample_pdf_merge(const float* pdf, const float* depth_coarse,
     if (blocks > cap) blocks = cap;
     niw::note_launch(), pdf_merge_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, smem, niw_stream(stream)>>>(
         pdf, depth_coarse, unif, bins, R, N, Nf, npow2, fine, idx, merged);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int niw_sample_pixels(int64_t n, int k, uint64_t seed, uint64_t* counter, int64_t* out, void* stream) {
+    NIW_CHECK_ARG(counter && out && n > 0 && k > 0 && k <= n && n <= (int64_t(1) << 40));
+    // one block: the counter is read by every thread before the last one advances it
+    niw::note_launch(), sample_pixels_kernel<<<1, 1024, 0, niw_stream(stream)>>>(n, k, seed, reinterpret_cast<unsigned long long*>(counter), out);
     NIW_LAUNCH_CHECK();
     return 0;
 }

@@ -64,13 +64,15 @@ def trainable_parameters(graph):
 
 def summarize_loss(opt, loss):
     """model/base.py:130-142: loss.all = sum_k 10**w_k loss_k."""
-    total = 0.
+    total = None
     for key in list(loss.keys()):
         if key == "all":
             continue
         if opt.loss_weight[key] is not None:
-            total = total + 10 ** float(opt.loss_weight[key]) * loss[key]
-    loss.update(all=total)
+            w = 10 ** float(opt.loss_weight[key])
+            term = loss[key] if w == 1.0 else w * loss[key]     # no launch for the common weight 10**0
+            total = term if total is None else total + term
+    loss.update(all=0. if total is None else total)
     return loss
 
 
@@ -222,6 +224,44 @@ class _ShardedRandperm:
         torch.randperm = self._orig
 
 
+class device_ray_draws:
+    """Makes ``torch.randperm(n, device=cuda)[:k]`` inside ``Graph.forward`` an O(k) kernel: the reference sorts
+    H*W random keys to keep ``rand_rays // B`` of them (model/nerf.py:268; five radix-sort passes per step).
+    ``torch.randperm`` is replaced by a lazy stand-in whose ``[:k]`` slice launches ``F.sample_pixels`` -- the
+    first k entries of a random permutation, drawn from the library's own counter-based stream (capturable:
+    replays advance the device counter).  Under data parallelism every rank passes the same seed and counter
+    value, so all ranks see the same global draw and ``_ShardedRandperm`` still slices it consistently."""
+
+    class _Lazy:
+        def __init__(self, n, counter, seed):
+            self.n, self.counter, self.seed = n, counter, seed
+
+        def __getitem__(self, sl):
+            if not (isinstance(sl, slice) and sl.start in (None, 0) and sl.step in (None, 1) and sl.stop is not None):
+                raise TypeError("device_ray_draws: only randperm(n)[:k] is supported")
+            from . import functional as F
+            return F.sample_pixels(self.n, min(int(sl.stop), self.n), self.counter, self.seed)
+
+    def __init__(self, device, seed=0):
+        self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+        self.seed = seed
+
+    def __enter__(self):
+        self._perm = torch.randperm
+        me = self
+
+        def randperm(n, **k):
+            dev = k.get("device", None)
+            if dev is None or torch.device(dev).type != "cuda":
+                return me._perm(n, **k)
+            return device_ray_draws._Lazy(int(n), me.counter, me.seed)
+        torch.randperm = randperm
+        return self
+
+    def __exit__(self, *exc):
+        torch.randperm = self._perm
+
+
 class feed_draws:
     """Feed host-made random draws to ``Graph.forward``: the next ``torch.randperm`` returns
     ``ray_idx`` and the next ``torch.rand`` returns ``u`` (both already on the device).  This is
@@ -277,7 +317,7 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1):
     scale = 1.0
     if world > 1:
         scale = len(var.ray_idx) / float(n_global)
-    (loss.all * scale).backward()
+    (loss.all if scale == 1.0 else loss.all * scale).backward()
     if bucket is not None and world > 1:
         bucket.allreduce()
     return loss

@@ -415,6 +415,44 @@ def mse_gather(rgb, image, ray_idx=None, idx_start=0):
     return _MseGather.apply(rgb, image, _idx(ray_idx, rgb.device), int(idx_start))
 
 
+def sample_pixels(n, k, counter, seed=0):
+    """First k entries of a random permutation of range(n) (the reference's ``torch.randperm(n)[:k]``,
+    model/nerf.py:268) in O(k): int64 [k] on ``counter``'s device.  ``counter`` is a zero-initialised int64 [1]
+    device tensor owned by the caller; the kernel advances it (fresh draw per call / per graph replay)."""
+    if not counter.is_cuda:
+        raise RuntimeError("niw_b200: counter must be a CUDA tensor (no CPU fallback)")
+    if counter.dtype != torch.int64 or counter.numel() != 1:
+        raise ValueError("sample_pixels: counter must be an int64 tensor with one element")
+    out = torch.empty(int(k), dtype=torch.int64, device=counter.device)
+    _lib.check(_lib.load().niw_sample_pixels(int(n), int(k), int(seed) & (2 ** 64 - 1), _p(counter), _p(out), _stream()))
+    return out
+
+
+class _RaysFromWarp(torch.autograd.Function):
+    """warped [B,2P,3] = [grid rows ; centre rows] -> (ray = grid - centre, centre), both contiguous [B,P,3]
+    (model/barf_inn_llff.py:352-356).  One autograd node instead of the slice / sub / reshape chain: backward is
+    d_warped = [d_ray ; d_centre - d_ray] in two launches (the eager chain costs ~10 tiny ones per step)."""
+
+    @staticmethod
+    def forward(ctx, warped, P):
+        ctx.P = P
+        grid, center = warped[:, :P], warped[:, P:]
+        return torch.sub(grid, center), center.contiguous()
+
+    @staticmethod
+    def backward(ctx, d_ray, d_center):
+        if d_ray is None and d_center is None:
+            return None, None
+        if d_ray is None:
+            return torch.cat([torch.zeros_like(d_center), d_center], dim=1), None
+        lower = -d_ray if d_center is None else d_center - d_ray
+        return torch.cat([d_ray, lower], dim=1), None
+
+
+def rays_from_warp(warped, P):
+    return _RaysFromWarp.apply(warped, int(P))
+
+
 def tc_selftest(A, Bm, variant=0):
     """D = A . Bm^T through the tcgen05 staging used by the MLP kernel (A [128,K], Bm [N,K]; variant 4 is the
     CTA-pair form, cta_group::2, with A [256,K])."""

@@ -5,6 +5,7 @@ import math
 import torch
 
 from .. import camera
+from .. import functional as F
 from . import barf, nerf_inn_llff
 from ._core import NeRFCore
 
@@ -63,8 +64,8 @@ class Graph(nerf_inn_llff.Graph):
             else:
                 alpha_ratio = 1
             warped = self.warp_mlp.forward(self._latent(opt), pts.unsqueeze(2), alpha_ratio=alpha_ratio)[:, :, 0]
-            grid_3D, center_3D = warped[:, :P], warped[:, P:]
-            return grid_3D - center_3D, center_3D, grid_3D, alpha_ratio
+            ray, center_3D = F.rays_from_warp(warped, P)
+            return ray, center_3D, warped[:, :P], alpha_ratio
         if mode == "render_train":
             # the reference's branch calls warp_mlp.forward with a wrong arity (:378, SURVEY.md A.6 iii)
             # and has no live caller; implemented with the evident intent (image ``ind``, alpha 1).

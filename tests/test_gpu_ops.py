@@ -278,6 +278,26 @@ def test_mse_gather(F):
     torch.testing.assert_close(x.grad.cpu(), rgb.grad * 3, rtol=1e-5, atol=1e-8)
 
 
+def test_sample_pixels_is_a_permutation_prefix(F):
+    """niw_sample_pixels: k distinct indices in range, the full draw (k = n) is a permutation, successive calls
+    differ (device counter), marginals are uniform to sampling error."""
+    n = 48 * 64
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    full = F.sample_pixels(n, n, counter, seed=3).cpu()
+    assert torch.equal(full.sort().values, torch.arange(n))
+    a = F.sample_pixels(n, 64, counter, seed=3).cpu()
+    b = F.sample_pixels(n, 64, counter, seed=3).cpu()
+    assert int(counter) == 3 and a.unique().numel() == 64 and not torch.equal(a, b)
+    assert int(a.min()) >= 0 and int(a.max()) < n
+    hits = torch.zeros(8)
+    for _ in range(400):
+        d = F.sample_pixels(307200, 64, counter, seed=7).cpu()
+        assert d.unique().numel() == 64 and int(d.max()) < 307200
+        hits += torch.bincount(d * 8 // 307200, minlength=8).float()
+    frac = hits / hits.sum()
+    assert (frac - 0.125).abs().max() < 0.01, frac      # 25 600 draws: sigma of a bin share ~ 0.002
+
+
 def test_ops_refuse_cpu_tensors(F):
     with pytest.raises(RuntimeError):
         F.composite(torch.zeros(2, 3), torch.zeros(2, 4, 3), torch.zeros(2, 4), torch.zeros(2, 4))
