@@ -32,11 +32,54 @@ static inline unsigned niw_blocks(int64_t work, int per_block) {
     return (unsigned)(b < 1 ? 1 : b);
 }
 
+// grid of a grid-stride kernel: every SM filled to the kernel's occupancy exactly once (no partial second wave)
+template <typename K>
+static inline unsigned niw_resident_grid(K kernel, int threads, size_t smem, int64_t max_blocks) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int64_t g = (int64_t)niw_num_sms() * per_sm;
+    if (g > max_blocks) g = max_blocks;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// C consecutive floats of one lane as 128-bit (C % 4 == 0) or 64-bit (C even) accesses; the address must be
+// aligned accordingly (launchers check the base pointers, the per-lane offsets are multiples of C floats)
+template <int C>
+__device__ __forceinline__ void vload(const float* __restrict__ p, float (&v)[C]) {
+    static_assert(C % 2 == 0, "even chunk");
+    if constexpr (C % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < C / 2; ++q) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(p) + q);
+            v[2 * q] = t.x; v[2 * q + 1] = t.y;
+        }
+    }
+}
+template <int C>
+__device__ __forceinline__ void vstore(float* __restrict__ p, const float (&v)[C]) {
+    static_assert(C % 2 == 0, "even chunk");
+    if constexpr (C % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q)
+            *(reinterpret_cast<float4*>(p) + q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < C / 2; ++q) *(reinterpret_cast<float2*>(p) + q) = make_float2(v[2 * q], v[2 * q + 1]);
+    }
+}
+static inline bool niw_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // pixel index -> camera-frame grid point K^-1 (x+.5, y+.5, 1)   (camera.py:430-436)
 struct Mat3 { float m[9]; };
@@ -55,7 +98,8 @@ __device__ __forceinline__ Mat3 inverse3x3(const float* __restrict__ K) {
 }
 
 __device__ __forceinline__ void pixel_to_cam(const Mat3& Ki, int64_t pix, int W, float g[3]) {
-    float x = (float)(pix % W) + 0.5f, y = (float)(pix / W) + 0.5f;
+    const uint32_t px = (uint32_t)pix, yy = px / (uint32_t)W;     // pixel indices of one image fit 32 bits
+    float x = (float)(px - yy * (uint32_t)W) + 0.5f, y = (float)yy + 0.5f;
     g[0] = Ki.m[0] * x + Ki.m[1] * y + Ki.m[2];
     g[1] = Ki.m[3] * x + Ki.m[4] * y + Ki.m[5];
     g[2] = Ki.m[6] * x + Ki.m[7] * y + Ki.m[8];

@@ -1,8 +1,11 @@
 // Volume compositing.  reference model/nerf.py:458-474.
-// One warp per ray; samples are visited 32 at a time (coalesced), with a warp-shuffle inclusive
-// scan of sigma*delta per chunk and a running carry, so transmittance never leaves registers.
-// The backward pass walks the chunks in reverse with a suffix scan and reuses the saved
-// transmittance and weights (no exp in backward).  HBM-bound: 24 B/sample fwd, 40 B/sample bwd.
+// One warp per ray.  Fast kernels (N = 32*CH, CH in {2,4,6,8}): every lane owns CH CONSECUTIVE samples, moved
+// as 128/64-bit vectors (all of a ray's sigma / depth / rgb loads are issued before any arithmetic: ~3 KB in
+// flight per warp), a per-lane serial prefix plus one warp-shuffle scan of the lane totals gives the optical
+// depth, so transmittance never leaves registers.  The backward pass is the mirrored suffix scan and reuses
+// the forward's saved transmittance (weights are recomputed as T (1 - exp(-sigma delta)) when the caller did
+// not keep them).  Generic kernels (any N): samples visited 32 at a time with a running carry.
+// HBM-bound: 24 B/sample forward (one of prob / trans written), 40 B/sample backward.
 #include "common.cuh"
 
 namespace {
@@ -96,8 +99,8 @@ composite_bwd_kernel(const float* __restrict__ ray, const float* __restrict__ rg
             float d = ok ? dp[i] : 0.f;
             float dn = (i + 1 < N) ? dp[i + 1] : 0.f;
             float intv = (i + 1 < N) ? (dn - d) : 1e10f;
-            float w = ok ? prob[r * N + i] : 0.f;
             float T = ok ? trans[r * N + i] : 0.f;
+            float w = !ok ? 0.f : (prob ? prob[r * N + i] : T * (1.f - expf(-(sg[i] * (intv * len)))));
             float c0 = ok ? cs[i * 3] : 0.f, c1 = ok ? cs[i * 3 + 1] : 0.f, c2 = ok ? cs[i * 3 + 2] : 0.f;
             float v = gr * c0 + gg * c1 + gb * c2 + gd * d + go;
             float wv = w * v;
@@ -124,10 +127,114 @@ composite_bwd_kernel(const float* __restrict__ ray, const float* __restrict__ rg
     }
 }
 
+// ---- fast kernels: N = 32 * CH ---------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(WARPS * 32)
+composite_fwd_vec_kernel(const float* __restrict__ ray, const float* __restrict__ rgb_s, const float* __restrict__ sigma,
+                         const float* __restrict__ depth_s, int64_t R, float bg, float* __restrict__ rgb,
+                         float* __restrict__ depth, float* __restrict__ opacity, float* __restrict__ prob,
+                         float* __restrict__ trans) {
+    constexpr int N = 32 * CH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
+        float sg[CH], d[CH], c[3 * CH];
+        vload<CH>(sigma + r * N + lane * CH, sg);
+        vload<CH>(depth_s + r * N + lane * CH, d);
+        vload<3 * CH>(rgb_s + (r * N + lane * CH) * 3, c);
+        const float rx = ray[r * 3], ry = ray[r * 3 + 1], rz = ray[r * 3 + 2];
+        const float len = sqrtf(rx * rx + ry * ry + rz * rz);
+        const float dnext = __shfl_down_sync(0xffffffffu, d[0], 1);
+        float sd[CH], ps[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const float intv = k + 1 < CH ? d[k + 1] - d[k] : (lane < 31 ? dnext - d[k] : 1e10f);   // last = 1e10 (nerf.py:461)
+            sd[k] = sg[k] * (intv * len);
+            ps[k] = k ? ps[k - 1] + sd[k] : sd[k];
+        }
+        float incl = warp_incl_scan(ps[CH - 1], lane);
+        float before = __shfl_up_sync(0xffffffffu, incl, 1);      // optical depth in front of this lane's first sample
+        if (lane == 0) before = 0.f;
+        float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_o = 0.f, w[CH], T[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            T[k] = expf(-(k ? before + ps[k - 1] : before));
+            w[k] = T[k] * (1.f - expf(-sd[k]));
+            a_r += w[k] * c[3 * k]; a_g += w[k] * c[3 * k + 1]; a_b += w[k] * c[3 * k + 2];
+            a_d += w[k] * d[k]; a_o += w[k];
+        }
+        if (prob) vstore<CH>(prob + r * N + lane * CH, w);
+        if (trans) vstore<CH>(trans + r * N + lane * CH, T);
+        a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b); a_d = warp_sum(a_d); a_o = warp_sum(a_o);
+        if (lane == 0) {
+            if (bg >= 0.f) { float k = bg * (1.f - a_o); a_r += k; a_g += k; a_b += k; }
+            rgb[r * 3] = a_r; rgb[r * 3 + 1] = a_g; rgb[r * 3 + 2] = a_b;
+            depth[r] = a_d; opacity[r] = a_o;
+        }
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(WARPS * 32)
+composite_bwd_vec_kernel(const float* __restrict__ ray, const float* __restrict__ rgb_s, const float* __restrict__ sigma,
+                         const float* __restrict__ depth_s, const float* __restrict__ prob,
+                         const float* __restrict__ trans, int64_t R, float bg, const float* __restrict__ d_rgb,
+                         const float* __restrict__ d_depth, const float* __restrict__ d_opacity,
+                         float* __restrict__ d_rgb_s, float* __restrict__ d_sigma, float* __restrict__ d_ray) {
+    constexpr int N = 32 * CH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
+        float sg[CH], d[CH], c[3 * CH], T[CH], w[CH];
+        vload<CH>(sigma + r * N + lane * CH, sg);
+        vload<CH>(depth_s + r * N + lane * CH, d);
+        vload<3 * CH>(rgb_s + (r * N + lane * CH) * 3, c);
+        vload<CH>(trans + r * N + lane * CH, T);
+        if (prob) vload<CH>(prob + r * N + lane * CH, w);
+        const float rx = ray[r * 3], ry = ray[r * 3 + 1], rz = ray[r * 3 + 2];
+        const float len = sqrtf(rx * rx + ry * ry + rz * rz);
+        const float gr = d_rgb ? d_rgb[r * 3] : 0.f, gg = d_rgb ? d_rgb[r * 3 + 1] : 0.f, gb = d_rgb ? d_rgb[r * 3 + 2] : 0.f;
+        const float gd = d_depth ? d_depth[r] : 0.f;
+        float go = d_opacity ? d_opacity[r] : 0.f;
+        if (bg >= 0.f) go -= bg * (gr + gg + gb);
+        const float dnext = __shfl_down_sync(0xffffffffu, d[0], 1);
+        float intv[CH], v[CH], sfx[CH];                           // sfx[k] = sum_{j >= k, same lane} w_j v_j
+#pragma unroll
+        for (int k = CH - 1; k >= 0; --k) {
+            intv[k] = k + 1 < CH ? d[k + 1] - d[k] : (lane < 31 ? dnext - d[k] : 1e10f);
+            if (!prob) w[k] = T[k] * (1.f - expf(-(sg[k] * (intv[k] * len))));
+            v[k] = gr * c[3 * k] + gg * c[3 * k + 1] + gb * c[3 * k + 2] + gd * d[k] + go;
+            sfx[k] = k + 1 < CH ? sfx[k + 1] + w[k] * v[k] : w[k] * v[k];
+        }
+        const float incl = warp_suffix_incl_scan(sfx[0], lane);
+        float later = __shfl_down_sync(0xffffffffu, incl, 1);     // sum over the lanes behind this one
+        if (lane == 31) later = 0.f;
+        float ds[CH], dc[3 * CH], dlen = 0.f;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const float after = (k + 1 < CH ? sfx[k + 1] : 0.f) + later;
+            const float dsd = (T[k] - w[k]) * v[k] - after;
+            ds[k] = dsd * (intv[k] * len);
+            dlen += dsd * sg[k] * intv[k];
+            dc[3 * k] = w[k] * gr; dc[3 * k + 1] = w[k] * gg; dc[3 * k + 2] = w[k] * gb;
+        }
+        vstore<CH>(d_sigma + r * N + lane * CH, ds);
+        vstore<3 * CH>(d_rgb_s + (r * N + lane * CH) * 3, dc);
+        dlen = warp_sum(dlen);
+        if (lane == 0 && d_ray) {
+            const float k = len > 0.f ? dlen / len : 0.f;         // d||ray||/dray = ray/||ray||
+            d_ray[r * 3] = k * rx; d_ray[r * 3 + 1] = k * ry; d_ray[r * 3 + 2] = k * rz;
+        }
+    }
+}
+
 inline unsigned grid_for(int64_t R) {
     int64_t blocks = (R + WARPS - 1) / WARPS;
     int64_t cap = (int64_t)niw_num_sms() * 8;   // 8 x 256 threads = 64 warps / SM resident
     return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+template <typename K>
+inline unsigned grid_vec(K kernel, int64_t R) {
+    return niw_resident_grid(kernel, WARPS * 32, 0, (R + WARPS - 1) / WARPS);
 }
 
 }  // namespace
@@ -136,8 +243,16 @@ extern "C" int niw_composite_fwd(const float* ray, const float* rgb_s, const flo
                                  int64_t R, int N, float bg, float* rgb, float* depth, float* opacity, float* prob,
                                  float* trans, void* stream) {
     NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && rgb && depth && opacity && R > 0 && N > 0);
-    niw::note_launch(), composite_fwd_kernel<<<grid_for(R), WARPS * 32, 0, niw_stream(stream)>>>(ray, rgb_s, sigma, depth_s, R, N, bg, rgb,
-                                                                            depth, opacity, prob, trans);
+    cudaStream_t st = niw_stream(stream);
+    const bool al = niw_aligned16(rgb_s) && niw_aligned16(sigma) && niw_aligned16(depth_s) && niw_aligned16(prob) && niw_aligned16(trans);
+    niw::note_launch();
+#define NIW_FWD(CH) composite_fwd_vec_kernel<CH><<<grid_vec(composite_fwd_vec_kernel<CH>, R), WARPS * 32, 0, st>>>(ray, rgb_s, sigma, depth_s, R, bg, rgb, depth, opacity, prob, trans)
+    if (al && N == 64) NIW_FWD(2);
+    else if (al && N == 128) NIW_FWD(4);
+    else if (al && N == 192) NIW_FWD(6);
+    else if (al && N == 256) NIW_FWD(8);
+    else composite_fwd_kernel<<<grid_for(R), WARPS * 32, 0, st>>>(ray, rgb_s, sigma, depth_s, R, N, bg, rgb, depth, opacity, prob, trans);
+#undef NIW_FWD
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -146,9 +261,18 @@ extern "C" int niw_composite_bwd(const float* ray, const float* rgb_s, const flo
                                  const float* prob, const float* trans, int64_t R, int N, float bg,
                                  const float* d_rgb, const float* d_depth, const float* d_opacity, float* d_rgb_s,
                                  float* d_sigma, float* d_ray, void* stream) {
-    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && prob && trans && d_rgb_s && d_sigma && R > 0 && N > 0);
-    niw::note_launch(), composite_bwd_kernel<<<grid_for(R), WARPS * 32, 0, niw_stream(stream)>>>(
-        ray, rgb_s, sigma, depth_s, prob, trans, R, N, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma, d_ray);
+    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && trans && d_rgb_s && d_sigma && R > 0 && N > 0);   // prob may be NULL
+    cudaStream_t st = niw_stream(stream);
+    const bool al = niw_aligned16(rgb_s) && niw_aligned16(sigma) && niw_aligned16(depth_s) && niw_aligned16(prob) &&
+                    niw_aligned16(trans) && niw_aligned16(d_rgb_s) && niw_aligned16(d_sigma);
+    niw::note_launch();
+#define NIW_BWD(CH) composite_bwd_vec_kernel<CH><<<grid_vec(composite_bwd_vec_kernel<CH>, R), WARPS * 32, 0, st>>>(ray, rgb_s, sigma, depth_s, prob, trans, R, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma, d_ray)
+    if (al && N == 64) NIW_BWD(2);
+    else if (al && N == 128) NIW_BWD(4);
+    else if (al && N == 192) NIW_BWD(6);
+    else if (al && N == 256) NIW_BWD(8);
+    else composite_bwd_kernel<<<grid_for(R), WARPS * 32, 0, st>>>(ray, rgb_s, sigma, depth_s, prob, trans, R, N, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma, d_ray);
+#undef NIW_BWD
     NIW_LAUNCH_CHECK();
     return 0;
 }

@@ -31,22 +31,43 @@ __device__ __forceinline__ void cam_to_world(const PoseInv& q, const float g[3],
         out[j] = q.R[0 * 3 + j] * g[0] + q.R[1 * 3 + j] * g[1] + q.R[2 * 3 + j] * g[2] + q.tinv[j];
 }
 
-__global__ void raygen_pose_fwd_kernel(const float* __restrict__ pose, const float* __restrict__ intr,
-                                       const int64_t* __restrict__ ray_idx, int64_t idx_start, int B, int P, int W,
-                                       float* __restrict__ center, float* __restrict__ ray) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)B * P) return;
-    int b = (int)(t / P), p = (int)(t % P);
-    int64_t pix = ray_idx ? ray_idx[p] : idx_start + p;
-    Mat3 Ki = inverse3x3(intr + b * 9);
-    PoseInv q = load_pose(pose + b * 12);
-    float g[3], gw[3];
-    pixel_to_cam(Ki, pix, W, g);
-    cam_to_world(q, g, gw);
+// grid (chunks of 4 * blockDim pixels, B): the image's K^-1 and inverted pose are computed once per block, every
+// thread emits 4 consecutive rays as three 128-bit stores per output (24 B/ray written, nothing read but ray_idx)
+__global__ void __launch_bounds__(256)
+raygen_pose_fwd_kernel(const float* __restrict__ pose, const float* __restrict__ intr,
+                       const int64_t* __restrict__ ray_idx, int64_t idx_start, int P, int W, int vec,
+                       float* __restrict__ center, float* __restrict__ ray) {
+    __shared__ Mat3 s_Ki;
+    __shared__ PoseInv s_q;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) { s_Ki = inverse3x3(intr + b * 9); s_q = load_pose(pose + b * 12); }
+    __syncthreads();
+    const Mat3 Ki = s_Ki;
+    const PoseInv q = s_q;
+    for (int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; p0 < P; p0 += gridDim.x * blockDim.x * 4) {
+        float oc[12], orr[12];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        center[t * 3 + j] = q.tinv[j];
-        ray[t * 3 + j] = gw[j] - q.tinv[j];  // grid_3D - center_3D  (camera.py:442)
+        for (int j = 0; j < 4; ++j) {
+            const int p = p0 + j < P ? p0 + j : P - 1;
+            const int64_t pix = ray_idx ? ray_idx[p] : idx_start + p;
+            float g[3], gw[3];
+            pixel_to_cam(Ki, pix, W, g);
+            cam_to_world(q, g, gw);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                oc[j * 3 + c] = q.tinv[c];
+                orr[j * 3 + c] = gw[c] - q.tinv[c];   // grid_3D - center_3D  (camera.py:442)
+            }
+        }
+        const int64_t t0 = (int64_t)b * P + p0;
+        if (vec && p0 + 3 < P) {
+            vstore<12>(center + t0 * 3, oc);
+            vstore<12>(ray + t0 * 3, orr);
+        } else {
+            for (int j = 0; j < 4 && p0 + j < P; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { center[(t0 + j) * 3 + c] = oc[j * 3 + c]; ray[(t0 + j) * 3 + c] = orr[j * 3 + c]; }
+        }
     }
 }
 
@@ -129,9 +150,14 @@ __global__ void raygen_unwarped_kernel(const float* __restrict__ intr, const flo
 extern "C" int niw_raygen_pose_fwd(const float* pose, const float* intr, const int64_t* ray_idx, int64_t idx_start,
                                    int B, int P, int H, int W, float* center, float* ray, void* stream) {
     NIW_CHECK_ARG(pose && intr && center && ray && B > 0 && P > 0 && H > 0 && W > 0);
-    int64_t n = (int64_t)B * P;
-    niw::note_launch(), raygen_pose_fwd_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, B, P, W,
-                                                                              center, ray);
+    const int threads = P >= 1024 ? 256 : 64;
+    // a block amortises its K^-1 / pose prologue over many pixels: about 8 resident blocks per SM in total
+    unsigned bx = niw_blocks((P + 3) / 4, threads);
+    const unsigned want = (unsigned)((niw_num_sms() * 8 + B - 1) / B);
+    if (bx > want) bx = want;
+    dim3 grid(bx, B);
+    const int vec = (P % 4 == 0) && niw_aligned16(center) && niw_aligned16(ray);
+    niw::note_launch(), raygen_pose_fwd_kernel<<<grid, threads, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, P, W, vec, center, ray);
     NIW_LAUNCH_CHECK();
     return 0;
 }

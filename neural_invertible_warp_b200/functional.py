@@ -240,7 +240,7 @@ def sample_pdf_merge(pdf, depth_coarse, Nf, depth_range, want_idx=False, want_fi
 
 class _Composite(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ray, rgb_s, sigma, depth_s, bg):
+    def forward(ctx, ray, rgb_s, sigma, depth_s, bg, want_prob):
         lib = _lib.load()
         ray, rgb_s, sigma, depth_s = _f32(ray, "ray"), _f32(rgb_s, "rgb_samples"), _f32(sigma, "density_samples"), \
             _f32(depth_s, "depth_samples")
@@ -249,19 +249,26 @@ class _Composite(torch.autograd.Function):
         rgb = torch.empty(R, 3, device=dev)
         depth = torch.empty(R, device=dev)
         opacity = torch.empty(R, device=dev)
-        prob = torch.empty(R, N, device=dev)
-        trans = torch.empty(R, N, device=dev)
+        # one of the two per-sample outputs is normally enough (24 B/sample): the weights when the caller samples
+        # from them (fine pass), the transmittance when a backward pass will follow
+        need_grad = any(ctx.needs_input_grad[:3])
+        prob = torch.empty(R, N, device=dev) if want_prob else None
+        trans = torch.empty(R, N, device=dev) if need_grad else None
         with _timed("composite_fwd"):
             _lib.check(lib.niw_composite_fwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), R, N, float(bg), _p(rgb),
                                              _p(depth), _p(opacity), _p(prob), _p(trans), _stream()))
-        ctx.save_for_backward(ray, rgb_s, sigma, depth_s, prob, trans)
+        if need_grad:
+            ctx.save_for_backward(ray, rgb_s, sigma, depth_s, trans, *([prob] if want_prob else []))
         ctx.bg = float(bg)
+        if prob is None:
+            prob = torch.empty(0, device=dev)
         ctx.mark_non_differentiable(prob)
         return rgb, depth, opacity, prob
 
     @staticmethod
     def backward(ctx, d_rgb, d_depth, d_opacity, _d_prob):
-        ray, rgb_s, sigma, depth_s, prob, trans = ctx.saved_tensors
+        ray, rgb_s, sigma, depth_s, trans, *rest = ctx.saved_tensors
+        prob = rest[0] if rest else None
         R, N = sigma.shape
         d_rgb_s = torch.empty_like(rgb_s)
         d_sigma = torch.empty_like(sigma)
@@ -272,15 +279,16 @@ class _Composite(torch.autograd.Function):
             _lib.check(_lib.load().niw_composite_bwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), _p(prob), _p(trans), R,
                                                      N, ctx.bg, _p(d_rgb), _p(d_depth), _p(d_opacity), _p(d_rgb_s),
                                                      _p(d_sigma), _p(d_ray), _stream()))
-        return d_ray, d_rgb_s, d_sigma, None, None
+        return d_ray, d_rgb_s, d_sigma, None, None, None
 
 
-def composite(ray, rgb_samples, density_samples, depth_samples, bgcolor=None):
+def composite(ray, rgb_samples, density_samples, depth_samples, bgcolor=None, want_prob=True):
     """NeRF.composite (model/nerf.py:458-474) on flattened rays: ray [R,3], rgb_samples [R,N,3],
-    density_samples [R,N], depth_samples [R,N] -> rgb [R,3], depth [R], opacity [R], prob [R,N].
+    density_samples [R,N], depth_samples [R,N] -> rgb [R,3], depth [R], opacity [R], prob [R,N]
+    (``want_prob=False``: an empty tensor -- the render pipeline asks for the weights only when it resamples from them).
     No gradient flows to depth_samples (they come from torch.rand / no_grad in the reference)."""
     bg = -1.0 if bgcolor is None else float(bgcolor)
-    return _Composite.apply(ray, rgb_samples, density_samples, depth_samples, bg)
+    return _Composite.apply(ray, rgb_samples, density_samples, depth_samples, bg, bool(want_prob))
 
 
 # --------------------------------------------------------------------------------------------

@@ -202,13 +202,15 @@ class NeRFCore(nn.Module):
                                             module=self)
         return rgb.view(B, P, N, 3), sigma.view(B, P, N)
 
-    def composite(self, opt, ray, rgb_samples, density_samples, depth_samples):
-        """model/nerf.py:458-474 -> rgb [B,P,3], depth [B,P,1], opacity [B,P,1], prob [B,P,N,1]."""
+    def composite(self, opt, ray, rgb_samples, density_samples, depth_samples, want_prob=True):
+        """model/nerf.py:458-474 -> rgb [B,P,3], depth [B,P,1], opacity [B,P,1], prob [B,P,N,1]
+        (``want_prob=False``, used by the render pipeline when nothing samples from the weights: prob is None)."""
         B, P, N = density_samples.shape
         bg = opt.data.bgcolor if opt.nerf.setbg_opaque else None
         rgb, depth, opacity, prob = F.composite(ray.reshape(B * P, 3), rgb_samples.reshape(B * P, N, 3),
-                                                density_samples.reshape(B * P, N), depth_samples.reshape(B * P, N), bg)
-        return rgb.view(B, P, 3), depth.view(B, P, 1), opacity.view(B, P, 1), prob.view(B, P, N, 1)
+                                                density_samples.reshape(B * P, N), depth_samples.reshape(B * P, N), bg,
+                                                want_prob=want_prob)
+        return rgb.view(B, P, 3), depth.view(B, P, 1), opacity.view(B, P, 1), (prob.view(B, P, N, 1) if want_prob else None)
 
     def positional_encoding(self, opt, input, L):
         """model/nerf.py:476-483 (+ the BARF weighting of model/barf.py:256-268 in subclasses with
@@ -258,7 +260,8 @@ class RenderCore(nn.Module):
             center, ray = camera.convert_NDC(opt, center, ray, intr=intr)
         depth_samples = self.sample_depth(opt, B, num_rays=P, depth_range=depth_range)
         rgb_s, sigma_s = self.nerf.forward_samples(opt, center, ray, depth_samples, mode=mode)
-        rgb, depth, opacity, prob = self.nerf.composite(opt, ray, rgb_s, sigma_s, depth_samples)
+        rgb, depth, opacity, prob = self.nerf.composite(opt, ray, rgb_s, sigma_s, depth_samples,
+                                                        want_prob=bool(opt.nerf.fine_sampling))
         ret = edict(rgb=rgb, depth=depth, opacity=opacity)
         if opt.nerf.fine_sampling:
             N = depth_samples.shape[2]
@@ -268,7 +271,7 @@ class RenderCore(nn.Module):
                                                   opt.nerf.sample_intvs_fine, opt.nerf.depth.range, want_fine=False)
                 depth_samples = merged.view(B, P, -1, 1)
             rgb_s, sigma_s = self.nerf_fine.forward_samples(opt, center, ray, depth_samples, mode=mode)
-            rgb_f, depth_f, opacity_f, _ = self.nerf_fine.composite(opt, ray, rgb_s, sigma_s, depth_samples)
+            rgb_f, depth_f, opacity_f, _ = self.nerf_fine.composite(opt, ray, rgb_s, sigma_s, depth_samples, want_prob=False)
             ret.update(rgb_fine=rgb_f, depth_fine=depth_f, opacity_fine=opacity_f)
         return ret
 

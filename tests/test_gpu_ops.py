@@ -132,7 +132,7 @@ def test_composite_golden(F, golden):
     assert rel_l2(ins[2].grad.view(B, R, N), g["d_sigma"]) < 1e-4
 
 
-@pytest.mark.parametrize("R,N", [(300, 128), (77, 50), (5, 1), (64, 192)])
+@pytest.mark.parametrize("R,N", [(300, 128), (77, 50), (5, 1), (64, 192), (129, 64), (41, 256), (9, 96)])
 def test_composite_vs_oracle(F, R, N):
     gen = torch.Generator().manual_seed(R * N)
     ray = torch.randn(1, R, 3, generator=gen)
@@ -150,6 +150,106 @@ def test_composite_vs_oracle(F, R, N):
     sum((a.reshape(w[0].shape) * w[0].to(DEV)).sum() for a, w in zip(out[:3], gw)).backward()
     for a, b in zip(ins, ins_ref):
         assert rel_l2(a.grad, b.grad[0]) < 2e-4
+
+
+@pytest.mark.parametrize("N", [64, 128, 192, 100])
+def test_composite_without_weights_matches(F, N):
+    """want_prob=False (training without a fine pass: only the transmittance is kept, the backward recomputes the
+    weights) must give the same outputs and gradients as the weight-keeping call, and an eval call (no grad) the
+    same outputs with nothing saved."""
+    gen = torch.Generator().manual_seed(N)
+    R = 203
+    ray = torch.randn(R, 3, generator=gen).to(DEV)
+    rgb_s = torch.rand(R, N, 3, generator=gen).to(DEV)
+    sig = (torch.rand(R, N, generator=gen) * 4).to(DEV)
+    depth = ((torch.rand(R, N, generator=gen) + torch.arange(N)) / N * 4 + 1).to(DEV)
+    gw = [torch.rand(R, 3, generator=gen).to(DEV) - 0.5, torch.rand(R, generator=gen).to(DEV) - 0.5, torch.rand(R, generator=gen).to(DEV) - 0.5]
+    grads = []
+    outs = []
+    for want in (True, False):
+        ins = [t.clone().requires_grad_(True) for t in (ray, rgb_s, sig)]
+        out = F.composite(ins[0], ins[1], ins[2], depth, want_prob=want)
+        assert out[3].numel() == (R * N if want else 0)
+        sum((a * w).sum() for a, w in zip(out[:3], gw)).backward()
+        grads.append([t.grad.clone() for t in ins])
+        outs.append([t.detach().clone() for t in out[:3]])
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(grads[0], grads[1]):
+        assert torch.equal(a, b), "recomputed weights must equal the stored ones bit for bit"
+    with torch.no_grad():
+        out = F.composite(ray, rgb_s, sig, depth, want_prob=True)
+    for a, b in zip(out[:3], outs[0]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("N,Nf", [(64, 128), (128, 128), (64, 64), (128, 64)])
+def test_pdf_sampler_fast_path_hard_cases(F, N, Nf):
+    """Register-resident warp kernel (histogram search + merge path) on the cases that stress its shortcuts:
+    peaked / all-zero / tiny-valued pdfs (searchsorted ties and empty bins), opaque and transparent rays, and a
+    descending coarse list (must fall back to the sort and still be exact)."""
+    gen = torch.Generator().manual_seed(N * 1000 + Nf)
+    R = 600
+    pdf = torch.rand(1, R, N, generator=gen) ** 6
+    pdf = pdf / pdf.sum(-1, keepdim=True) * torch.rand(1, R, 1, generator=gen)
+    pdf[0, 0::9] = 0                                               # transparent rays
+    pdf[0, 1::9, :] = 0; pdf[0, 1::9, N // 2] = 1.0                # one opaque bin
+    pdf[0, 2::9, : N - 3] = 0                                      # mass at the far end
+    pdf[0, 3::9] *= 1e-30                                          # denormal-range weights
+    pdf[0, 4::9] = torch.round(pdf[0, 4::9] * 256) / 256           # CDF values that tie with the query grid
+    pdf[0, 5::9] = 1.0 / N                                         # uniform: every query lands on a bin edge
+    u = torch.rand(1, R, N, 1, generator=gen)
+    rng = [1.2, 5.2]
+    coarse = ora.stratified_depth(u, N, rng, "metric")
+    coarse[0, 7::9] = coarse[0, 7::9].flip(1)                      # descending -> not mergeable
+    fine_ref, idx_ref = ora.pdf_depth(pdf, N, Nf, rng, return_idx=True)
+    merged_ref = ora.merge_depth(coarse, fine_ref)
+    fine, idx, merged = F.sample_pdf_merge(pdf[0].to(DEV), coarse[0, ..., 0].to(DEV), Nf, rng, want_idx=True)
+    assert torch.equal(idx.cpu(), idx_ref[0])
+    assert torch.equal(fine.cpu(), fine_ref[0, ..., 0])
+    assert torch.equal(merged.cpu(), merged_ref[0, ..., 0])
+    # descending bins (inverse-depth style range): fine samples come out descending -> sort fallback
+    rng2 = [5.2, 1.2]
+    fine_ref, idx_ref = ora.pdf_depth(pdf, N, Nf, rng2, return_idx=True)
+    merged_ref = ora.merge_depth(coarse, fine_ref)
+    fine, idx, merged = F.sample_pdf_merge(pdf[0].to(DEV), coarse[0, ..., 0].to(DEV), Nf, rng2, want_idx=True)
+    assert torch.equal(idx.cpu(), idx_ref[0])
+    assert torch.equal(fine.cpu(), fine_ref[0, ..., 0])
+    assert torch.equal(merged.cpu(), merged_ref[0, ..., 0])
+
+
+def test_pdf_sampler_large_batch_properties(F):
+    """C4-sized batch (one 480x640 frame of rays is 307 200; here 200 000): bins bit-exact against the oracle on a
+    strided subset, merged rows sorted and a permutation-invariant checksum (sum of coarse + fine) preserved."""
+    gen = torch.Generator().manual_seed(5)
+    R, N, Nf = 200000, 64, 128
+    pdf = torch.rand(1, R, N, generator=gen) ** 8
+    pdf = pdf / pdf.sum(-1, keepdim=True) * torch.rand(1, R, 1, generator=gen)
+    u = torch.rand(1, R, N, 1, generator=gen)
+    rng = [1.2, 5.2]
+    coarse = ora.stratified_depth(u, N, rng, "metric")
+    fine, idx, merged = F.sample_pdf_merge(pdf[0].to(DEV), coarse[0, ..., 0].to(DEV), Nf, rng, want_idx=True)
+    sub = slice(0, R, 97)
+    fine_ref, idx_ref = ora.pdf_depth(pdf[:, sub], N, Nf, rng, return_idx=True)
+    assert torch.equal(idx.cpu()[sub], idx_ref[0])
+    assert torch.equal(fine.cpu()[sub], fine_ref[0, ..., 0])
+    assert bool((merged[:, 1:] >= merged[:, :-1]).all())
+    both = torch.cat([coarse[0, ..., 0].to(DEV), fine], 1).sort(1).values
+    assert torch.equal(both, merged)
+
+
+@pytest.mark.parametrize("B,P", [(3, 4096), (2, 1027), (5, 6)])
+def test_raygen_pose_shapes(F, B, P):
+    """vectorised (P % 4 == 0) and scalar store paths against the oracle camera model"""
+    H, W = 48, 64
+    gen = torch.Generator().manual_seed(B * P)
+    pose = syn.llff_poses(11, B)
+    intr = syn.intrinsics(B, H, W, 0.81)
+    idx = torch.randint(0, H * W, (P,), generator=gen)
+    c_ref, r_ref = ora.center_and_ray(H, W, pose, intr)
+    c, r = F.raygen_pose(pose.to(DEV), intr.to(DEV), H, W, ray_idx=idx.to(DEV))
+    torch.testing.assert_close(c.cpu(), c_ref[:, idx], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(r.cpu(), r_ref[:, idx], rtol=1e-5, atol=1e-5)
 
 
 def _nvp_pack(p, code):
