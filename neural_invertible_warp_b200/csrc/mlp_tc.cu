@@ -253,7 +253,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
         // leader: a stage is full when its own copy has landed (expect_tx arrive) and the peer has reported its half
         for (int i = 0; i < 2 * NSTAGE; ++i) ptx::mbar_init(&w_full[i], rank == 0 ? 2 : 1);
         for (int i = 0; i < NSTAGE; ++i) ptx::mbar_init(&w_empty[i], 1);
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], 2 * TILE); ptx::mbar_init(&acc_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], 2 * TILE / 32); ptx::mbar_init(&acc_full[i], 1); }
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc2(tmem_slot, 512);
@@ -400,7 +400,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                 write_enc_row(enc, save_tile ? save_tile + SV_ENC : nullptr, row, x, bw3, valid);
             }
             ptx::fence_proxy_async();
-            ptx::mbar_arrive_cluster(ready_bar);
+            ptx::warp_arrive_cluster(ready_bar);
             for (int l = 0; l < NLAYER; ++l, ++full_uses) {
                 ptx::mbar_wait_fast(&acc_full[slot], full_uses & 1);
                 ptx::tc_fence_after();
@@ -442,7 +442,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         write_venc_row(enc, save_tile ? save_tile + SV_VENC : nullptr, row, v3, bwv, valid);
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive_cluster(ready_bar);
+                    ptx::warp_arrive_cluster(ready_bar);
                     if (l == 6 && valid) {
                         float pre = sig_acc + cst[C_MISC];
                         sigma_out[g] = softplus_f(pre);

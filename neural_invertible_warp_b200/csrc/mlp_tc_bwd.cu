@@ -78,7 +78,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * BX_NSTAGE; ++i) ptx::mbar_init(&w_full[i], rank == 0 ? 2 : 1);
         for (int i = 0; i < BX_NSTAGE; ++i) ptx::mbar_init(&w_empty[i], 1);
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], 2 * TILE); ptx::mbar_init(&acc_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_ready[i], 2 * TILE / 32); ptx::mbar_init(&acc_full[i], 1); }
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc2(tmem_slot, 512);
@@ -225,7 +225,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                 *reinterpret_cast<uint4*>(rec + SV_SMALL + row * 16) =
                     make_uint4(ptx::pack_bf16(g3[0], g3[1]), ptx::pack_bf16(g3[2], gs), ptx::pack_bf16(valid ? 1.f : 0.f, 0.f), 0u);
             ptx::fence_proxy_async();
-            ptx::mbar_arrive_cluster(ready_bar);
+            ptx::warp_arrive_cluster(ready_bar);
 
             for (int s = 0; s < NSTEP; ++s, ++full_uses) {
                 const int lo = step_out_layer(s);
@@ -271,14 +271,14 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                     }
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive_cluster(ready_bar);
+                    ptx::warp_arrive_cluster(ready_bar);
                 } else if (s == 0) {
                     // ---- view branch: d(encoded view) -> d(unit view) -> d ray through normalize ----
                     uint32_t v[32];
                     ptx::tmem_ld32(tacc, v);
                     ptx::tmem_ld_wait();
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive_cluster(ready_bar);            // accumulator drained; A tile unchanged
+                    ptx::warp_arrive_cluster(ready_bar);            // accumulator drained; A tile unchanged
                     float dr[3] = {0.f, 0.f, 0.f};
                     if (valid) {
                         float v3[3] = {ray[r * 3], ray[r * 3 + 1], ray[r * 3 + 2]};
@@ -312,7 +312,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                         for (int j = 0; j < 32; ++j) scr[(cc * 32 + j) * TILE + row] = __uint_as_float(v[j]);
                     }
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive_cluster(ready_bar);
+                    ptx::warp_arrive_cluster(ready_bar);
                 } else {
                     // ---- s == 10: d(encoded position) -> d x -> d center, d ray ----
                     float ge[ENC3_PAD];

@@ -151,9 +151,9 @@ extern "C" int niw_raygen_pose_fwd(const float* pose, const float* intr, const i
                                    int B, int P, int H, int W, float* center, float* ray, void* stream) {
     NIW_CHECK_ARG(pose && intr && center && ray && B > 0 && P > 0 && H > 0 && W > 0);
     const int threads = P >= 1024 ? 256 : 64;
-    // a block amortises its K^-1 / pose prologue over many pixels: about 8 resident blocks per SM in total
+    // a block amortises its K^-1 / pose prologue over many pixels: a few waves of blocks in total
     unsigned bx = niw_blocks((P + 3) / 4, threads);
-    const unsigned want = (unsigned)((niw_num_sms() * 8 + B - 1) / B);
+    const unsigned want = (unsigned)((niw_num_sms() * 64 + B - 1) / B);
     if (bx > want) bx = want;
     dim3 grid(bx, B);
     const int vec = (P % 4 == 0) && niw_aligned16(center) && niw_aligned16(ray);

@@ -144,6 +144,13 @@ __device__ __forceinline__ uint32_t mapa(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// one arrival per WARP: every lane has ordered its own shared-memory writes / TMEM reads (fence.proxy.async,
+// tcgen05.fence::before_thread_sync) before the __syncwarp, which orders them before lane 0's arrive.  256 per-thread
+// arrivals on one barrier serialise at the barrier (half of them crossing the cluster network).
+__device__ __forceinline__ void warp_arrive_cluster(uint32_t cluster_addr) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(cluster_addr);
+}
 // wait on a barrier whose arrivals (also) come from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {   // one full warp in EACH CTA of the pair
