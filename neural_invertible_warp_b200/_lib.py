@@ -46,7 +46,8 @@ SIGNATURES = {
 
 
 def library_path():
-    return _build.LIB
+    """csrc/libniw_b200.so; NIW_B200_LIB selects another build of the same sources (kernel-tuning experiments)."""
+    return os.environ.get("NIW_B200_LIB") or _build.LIB
 
 
 def load(build_if_missing=True):
@@ -55,7 +56,7 @@ def load(build_if_missing=True):
     if _LIB is not None:
         return _LIB
     path = library_path()
-    if build_if_missing:
+    if build_if_missing and not os.environ.get("NIW_B200_LIB"):
         try:
             if _build.needs_build():
                 _build.build()

@@ -34,32 +34,34 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """``extra_flags`` / ``out``: tuning builds (e.g. -DNIW_NSTAGE=6 into another .so, loaded via NIW_B200_LIB)."""
+    if not force and not needs_build() and out is None:
         return LIB
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + list(extra_flags)
     objs = []
     procs = []
-    os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
+    bdir = os.path.join(CSRC, "build" if out is None else "build_" + os.path.basename(out).replace(".so", ""))
+    os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(CSRC, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
-        if verbose and out.strip():
-            print(out)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, log))
+        if verbose and log.strip():
+            print(log)
+    cmd = [nvcc, "-shared", "-o", out or LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

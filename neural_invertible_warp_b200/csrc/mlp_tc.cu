@@ -27,12 +27,15 @@
 // contiguous) and LBO = rows*16 B.  Epilogue thread r writes 16 B at chunk*rows*16 + r*16: a warp
 // writes 512 contiguous bytes (bank-conflict free).
 #include "tc_layout.cuh"
+#ifndef NIW_NSTAGE
+#define NIW_NSTAGE 7
+#endif
 
 namespace niw {
 
 namespace tc {
 
-constexpr int NSTAGE = 7;
+constexpr int NSTAGE = NIW_NSTAGE;
 
 // shared memory map of the forward kernel
 constexpr int SM_ACT = 0;
