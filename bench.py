@@ -34,6 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# DRAM bytes of one niw_nerf_fwd + niw_nerf_bwd pair at 1 024 rays x 128 samples, from the committed ncu --set full
+# capture profiles/r1_mlp_c2_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum of tc_fwd / tc_dx / tc_dw)
+MLP_DRAM_BYTES_C2 = int(580.98e6 + 604.24e6 + 1234.36e6)
 MLP_FLOP_FWD = 2 * 527872              # per sample (un-padded dims)
 MLP_FLOP_TRAIN = 3 * MLP_FLOP_FWD      # fwd + dX + dW
 N_SAMPLES = 128
@@ -52,6 +55,7 @@ def parse():
     ap.add_argument("--precision", default=None, help="MLP operand precision: bf16 (tcgen05) or fp32 (CUDA cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-micro", action="store_true", help="skip the standalone HBM-kernel timings (hbm_kernels)")
     return ap.parse_args()
 
 
@@ -252,43 +256,70 @@ def run_ours(args):
         return loss
 
     # ---- e2e leg: the step's host-side inputs (camera batch, pixel indices, stratified uniforms) wait in pinned
-    # memory (a pool of `steps` batches drawn before the timed region, as a prefetching loader would hold them),
-    # are copied to static device buffers every step, the step runs (one CUDA-graph replay), the loss is read back ----
+    # memory (a pool of `steps` batches drawn before the timed region, as a prefetching loader would hold them).
+    # Every step copies its batch to one of TWO static device buffer sets on a copy stream (overlapping the previous
+    # step's kernels), replays the CUDA graph captured over that set, and copies the loss to pinned memory; the host
+    # reads each step's loss one step late, so it never drains the GPU ----
     gen = torch.Generator().manual_seed(1234 + rank)
     n_pool = max(args.steps, 1)
     pool_ridx = torch.stack([torch.randperm(H * W, generator=gen)[:P_local] for _ in range(n_pool)]).pin_memory()
     pool_u = torch.rand(n_pool, IMAGES, P_local, N_SAMPLES, 1, generator=gen).pin_memory()
     pin = dict(idx=torch.arange(IMAGES).pin_memory(), intr=var_dev.intr.cpu().pin_memory(),
                pose=var_dev.pose.cpu().pin_memory())
-    static = dict(idx=torch.empty(IMAGES, dtype=torch.int64, device=dev), intr=torch.empty_like(var_dev.intr),
-                  pose=torch.empty_like(var_dev.pose), ray_idx=torch.empty(P_local, dtype=torch.int64, device=dev),
-                  u=torch.empty(IMAGES, P_local, N_SAMPLES, 1, device=dev))
-    h2d = sum(t.numel() * t.element_size() for t in static.values())
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step_static():
-        v = cfgmod.AttrDict(idx=static["idx"], intr=static["intr"], pose=static["pose"], image=var_dev.image)
-        adam.zero()
-        with engine.feed_draws(ray_idx=static["ray_idx"], u=static["u"]):
-            v = graph.forward(opt, v, mode="train", iter=it)
-        loss = engine.summarize_loss(opt, graph.compute_loss(opt, v, mode="train"))
-        (loss.all if world == 1 else loss.all * (1.0 / world)).backward()
-        if world > 1:
-            adam.allreduce()
-        adam.step()
-        return loss.all.detach()
+    def make_static():
+        return dict(idx=torch.empty(IMAGES, dtype=torch.int64, device=dev), intr=torch.empty_like(var_dev.intr),
+                    pose=torch.empty_like(var_dev.pose), ray_idx=torch.empty(P_local, dtype=torch.int64, device=dev),
+                    u=torch.empty(IMAGES, P_local, N_SAMPLES, 1, device=dev))
+    statics = [make_static(), make_static()]
+    h2d = sum(t.numel() * t.element_size() for t in statics[0].values())
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]       # the set's copies have landed
+    consumed = [torch.cuda.Event() for _ in range(2)]    # the step reading the set (and its loss copy) has finished
 
-    e2e_body = [step_static]
+    def make_step_static(static):
+        def step_static():
+            v = cfgmod.AttrDict(idx=static["idx"], intr=static["intr"], pose=static["pose"], image=var_dev.image)
+            adam.zero()
+            with engine.feed_draws(ray_idx=static["ray_idx"], u=static["u"]):
+                v = graph.forward(opt, v, mode="train", iter=it)
+            loss = engine.summarize_loss(opt, graph.compute_loss(opt, v, mode="train"))
+            (loss.all if world == 1 else loss.all * (1.0 / world)).backward()
+            if world > 1:
+                adam.allreduce()
+            adam.step()
+            return loss.all.detach()
+        return step_static
 
-    def step_e2e(i):
-        static["ray_idx"].copy_(pool_ridx[i % n_pool], non_blocking=True)
-        static["u"].copy_(pool_u[i % n_pool], non_blocking=True)
-        for k in ("idx", "intr", "pose"):
-            static[k].copy_(pin[k], non_blocking=True)
-        loss = e2e_body[0]()
-        loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the user reads the loss
-        return float(loss_host)
+    e2e_body = [make_step_static(statics[0]), make_step_static(statics[1])]
+
+    def run_e2e(steps):
+        """`steps` end-to-end steps; returns the losses the host read (all of them, each one step late)."""
+        main = torch.cuda.current_stream()
+        losses = []
+        for i in range(steps):
+            b = i & 1
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(consumed[b])          # step i-2 is done with this buffer set
+                st = statics[b]
+                st["ray_idx"].copy_(pool_ridx[i % n_pool], non_blocking=True)
+                st["u"].copy_(pool_u[i % n_pool], non_blocking=True)
+                for k in ("idx", "intr", "pose"):
+                    st[k].copy_(pin[k], non_blocking=True)
+                ready[b].record(copy_stream)
+            main.wait_event(ready[b])
+            loss = e2e_body[b]()
+            loss_host[b].copy_(loss, non_blocking=True)
+            consumed[b].record(main)
+            if i >= 1:
+                consumed[1 - b].synchronize()                    # the user reads the previous step's loss
+                losses.append(float(loss_host[1 - b]))
+        if steps:
+            consumed[(steps - 1) & 1].synchronize()
+            losses.append(float(loss_host[(steps - 1) & 1]))
+        return losses
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -323,7 +354,7 @@ def run_ours(args):
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
         step_device()
-    step_e2e(0)
+    run_e2e(2)
     barrier()
     step_value, graphed = step_device, False
     if not args.no_graph:
@@ -339,13 +370,15 @@ def run_ours(args):
             step_value, graphed = step_device, False
             torch.cuda.synchronize()
         if graphed:
+            eager_bodies = list(e2e_body)
             try:
-                e2e_body[0] = engine.CapturedStep(step_static, warmup=1)
-                step_e2e(0)
+                for b in range(2):
+                    e2e_body[b] = engine.CapturedStep(eager_bodies[b], warmup=1)
+                run_e2e(2)
             except Exception as e:
                 if rank == 0:
                     print("bench.py: e2e graph capture unavailable (%s)" % str(e).splitlines()[0], file=sys.stderr)
-                e2e_body[0] = step_static
+                e2e_body[:] = eager_bodies
                 torch.cuda.synchronize()
     barrier()
 
@@ -365,10 +398,10 @@ def run_ours(args):
     # ---- e2e: host buffers in, loss out (wall clock around synchronised steps) ----
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(i)
+    e2e_losses = run_e2e(args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert len(e2e_losses) == args.steps and all(l == l for l in e2e_losses), "e2e leg: every step's loss must be read"
     clk = clocks.stop() if rank == 0 else None
 
     ms_per_step = ms_total / args.steps
@@ -383,9 +416,16 @@ def run_ours(args):
     flop_per_step = MLP_FLOP_TRAIN * rays_local * N_SAMPLES
     achieved = flop_per_step * mlp_calls / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
     comp_ms = kernel_ms.get("composite_fwd", (0, 0.0))[1] + kernel_ms.get("composite_bwd", (0, 0.0))[1]
+    traffic = MLP_DRAM_BYTES_C2 if (rays_local == 1024 and precision == "bf16") else None
+    mlp_ms_call = mlp_ms / max(mlp_calls, 1)
     roof = dict(bound="tensor", kernel="niw_nerf_fwd + niw_nerf_bwd (fused PE + 8x256 MLP, fwd + dX + dW)",
                 achieved=achieved, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
-                frac=achieved / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
+                frac=achieved / pk["bf16_tflops_sustained"], traffic=traffic,
+                traffic_note="DRAM bytes per launch pair from profiles/r1_mlp_c2_ncu_full.md (the saved bf16 activation / "
+                             "gradient tile images; algorithmic operand bytes are 1.1 MB of weights)",
+                hbm_view=(dict(gbs=traffic / (mlp_ms_call * 1e-3) / 1e9, frac=traffic / (mlp_ms_call * 1e-3) / 1e9 / pk["hbm_gbs"],
+                               peak=pk["hbm_gbs"]) if traffic and mlp_ms_call > 0 else None),
+                peak_source=pk["source"] + " (sustained bf16)",
                 flop_per_launch_pair=flop_per_step, mlp_ms_per_step=mlp_ms / max(mlp_calls, 1),
                 mlp_share_of_step=mlp_ms / ms_total if ms_total > 0 else None,
                 timed="CUDA events around niw_nerf_fwd / niw_nerf_bwd on the launching stream, eager pass of the same "
@@ -404,13 +444,29 @@ def run_ours(args):
                    sample="3 steps (after 1 warm-up) of the same C2 step, %d rays x %d samples, oracle/reference_port.py on "
                           "torch CPU fp32, %.2f s/step" % (args.rays, N_SAMPLES, dt))
 
+    hbm = None
+    if world == 1 and not args.no_micro:
+        # sampler / compositor / raygen alone at 262 144 rays (inputs larger than L2, L2 flushed between launches):
+        # algorithmic bytes / CUDA-event time against the measured HBM copy bandwidth
+        del flush
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import micro_hbm
+        m = micro_hbm.measure(verbose=False, dev=dev)
+        hbm = dict(rays=m["rays"], peak_gbs=m["peak_gbs"], peak_source=pk["source"],
+                   kernels={k: dict(gbs=round(v["gbs"], 1), frac=round(v["frac"], 3), ms=round(v["ms"], 4), bytes=v["bytes"])
+                            for k, v in m["kernels"].items()})
+
     line = dict(metric=METRIC, value=value, unit="rays/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=("bf16" if precision == "bf16" else "fp32"), data="synthetic",
                 config=workload_config(args, precision), mlp_evals_per_s=value * N_SAMPLES,
                 e2e=dict(value=e2e_value, unit="rays/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                         ms_per_step=e2e_s / args.steps * 1e3),
-                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, clocks=clk)
+                         ms_per_step=e2e_s / args.steps * 1e3,
+                         how="public Graph API; host batch in pinned memory -> H2D on a copy stream into one of two static "
+                             "buffer sets -> CUDA-graph replay -> loss to pinned memory; the host reads every step's loss, "
+                             "one step late; wall clock over all steps"),
+                gpu_launches=launches, roofline=roof, hbm_kernels=hbm, cpu_baseline=cpu, clocks=clk)
     print(json.dumps(line))
     _leave(world)
 

@@ -31,21 +31,26 @@ __device__ __forceinline__ void cam_to_world(const PoseInv& q, const float g[3],
         out[j] = q.R[0 * 3 + j] * g[0] + q.R[1 * 3 + j] * g[1] + q.R[2 * 3 + j] * g[2] + q.tinv[j];
 }
 
-// grid (chunks of 4 * blockDim pixels, B): the image's K^-1 and inverted pose are computed once per block, every
-// thread emits 4 consecutive rays as three 128-bit stores per output (24 B/ray written, nothing read but ray_idx)
-__global__ void __launch_bounds__(256)
+// grid (chunks of pixels, B): the image's K^-1 and inverted pose are computed once per block; a warp produces 128
+// consecutive rays per iteration (4 per lane), stages the 384 floats of each output in shared memory and writes them
+// back as 128-bit stores that are contiguous across the warp (24 B/ray written, nothing read but ray_idx)
+constexpr int RG_WARPS = 8;
+__global__ void __launch_bounds__(RG_WARPS * 32)
 raygen_pose_fwd_kernel(const float* __restrict__ pose, const float* __restrict__ intr,
                        const int64_t* __restrict__ ray_idx, int64_t idx_start, int P, int W, int vec,
                        float* __restrict__ center, float* __restrict__ ray) {
     __shared__ Mat3 s_Ki;
     __shared__ PoseInv s_q;
-    const int b = blockIdx.y;
+    __shared__ __align__(16) float s_stage[RG_WARPS][384];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { s_Ki = inverse3x3(intr + b * 9); s_q = load_pose(pose + b * 12); }
     __syncthreads();
     const Mat3 Ki = s_Ki;
     const PoseInv q = s_q;
-    for (int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; p0 < P; p0 += gridDim.x * blockDim.x * 4) {
-        float oc[12], orr[12];
+    float* stage = s_stage[warp];
+    for (int w0 = (blockIdx.x * RG_WARPS + warp) * 128; w0 < P; w0 += gridDim.x * RG_WARPS * 128) {
+        const int p0 = w0 + lane * 4;
+        float orr[12];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int p = p0 + j < P ? p0 + j : P - 1;
@@ -54,19 +59,26 @@ raygen_pose_fwd_kernel(const float* __restrict__ pose, const float* __restrict__
             pixel_to_cam(Ki, pix, W, g);
             cam_to_world(q, g, gw);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                oc[j * 3 + c] = q.tinv[c];
-                orr[j * 3 + c] = gw[c] - q.tinv[c];   // grid_3D - center_3D  (camera.py:442)
-            }
+            for (int c = 0; c < 3; ++c) orr[j * 3 + c] = gw[c] - q.tinv[c];   // grid_3D - center_3D  (camera.py:442)
         }
-        const int64_t t0 = (int64_t)b * P + p0;
-        if (vec && p0 + 3 < P) {
-            vstore<12>(center + t0 * 3, oc);
-            vstore<12>(ray + t0 * 3, orr);
+        const int64_t t0 = (int64_t)b * P + w0;                  // first ray of the warp
+        if (vec && w0 + 128 <= P) {
+            __syncwarp();
+            vstore<12>(stage + lane * 12, orr);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int f = (i * 32 + lane) * 4;               // float offset inside the warp's 384-float block
+                *reinterpret_cast<float4*>(ray + t0 * 3 + f) = *reinterpret_cast<const float4*>(stage + f);
+                // the centre repeats with period 3 floats: float f holds component f % 3
+                const int m = f % 3;
+                *reinterpret_cast<float4*>(center + t0 * 3 + f) =
+                    make_float4(q.tinv[m], q.tinv[(m + 1) % 3], q.tinv[(m + 2) % 3], q.tinv[m]);
+            }
         } else {
             for (int j = 0; j < 4 && p0 + j < P; ++j)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) { center[(t0 + j) * 3 + c] = oc[j * 3 + c]; ray[(t0 + j) * 3 + c] = orr[j * 3 + c]; }
+                for (int c = 0; c < 3; ++c) { center[(t0 + lane * 4 + j) * 3 + c] = q.tinv[c]; ray[(t0 + lane * 4 + j) * 3 + c] = orr[j * 3 + c]; }
         }
     }
 }
@@ -150,13 +162,13 @@ __global__ void raygen_unwarped_kernel(const float* __restrict__ intr, const flo
 extern "C" int niw_raygen_pose_fwd(const float* pose, const float* intr, const int64_t* ray_idx, int64_t idx_start,
                                    int B, int P, int H, int W, float* center, float* ray, void* stream) {
     NIW_CHECK_ARG(pose && intr && center && ray && B > 0 && P > 0 && H > 0 && W > 0);
-    const int threads = P >= 1024 ? 256 : 64;
+    const int threads = RG_WARPS * 32;
     // a block amortises its K^-1 / pose prologue over many pixels: a few waves of blocks in total
-    unsigned bx = niw_blocks((P + 3) / 4, threads);
-    const unsigned want = (unsigned)((niw_num_sms() * 64 + B - 1) / B);
+    unsigned bx = niw_blocks(P, RG_WARPS * 128);
+    const unsigned want = (unsigned)((niw_num_sms() * 32 + B - 1) / B);
     if (bx > want) bx = want;
     dim3 grid(bx, B);
-    const int vec = (P % 4 == 0) && niw_aligned16(center) && niw_aligned16(ray);
+    const int vec = ((int64_t)P * 3 % 4 == 0) && niw_aligned16(center) && niw_aligned16(ray);
     niw::note_launch(), raygen_pose_fwd_kernel<<<grid, threads, 0, niw_stream(stream)>>>(pose, intr, ray_idx, idx_start, P, W, vec, center, ray);
     NIW_LAUNCH_CHECK();
     return 0;

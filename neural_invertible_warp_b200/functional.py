@@ -249,6 +249,7 @@ class _Composite(torch.autograd.Function):
         rgb = torch.empty(R, 3, device=dev)
         depth = torch.empty(R, device=dev)
         opacity = torch.empty(R, device=dev)
+        ctx.set_materialize_grads(False)     # unused outputs (depth / opacity under an rgb-only loss) arrive as None, not zeros
         # one of the two per-sample outputs is normally enough (24 B/sample): the weights when the caller samples
         # from them (fine pass), the transmittance when a backward pass will follow
         need_grad = any(ctx.needs_input_grad[:3])
@@ -269,6 +270,8 @@ class _Composite(torch.autograd.Function):
     def backward(ctx, d_rgb, d_depth, d_opacity, _d_prob):
         ray, rgb_s, sigma, depth_s, trans, *rest = ctx.saved_tensors
         prob = rest[0] if rest else None
+        if d_rgb is None and d_depth is None and d_opacity is None:
+            return None, None, None, None, None, None
         R, N = sigma.shape
         d_rgb_s = torch.empty_like(rgb_s)
         d_sigma = torch.empty_like(sigma)

@@ -21,7 +21,17 @@ def main():
     ap.add_argument("--rays", type=int, default=65536 * 4)
     ap.add_argument("--reps", type=int, default=10)
     a = ap.parse_args()
-    dev = "cuda:0"
+    res = measure(a.rays, a.reps, a.once, verbose=True)
+    if a.json:
+        json.dump(res, open(a.json, "w"), indent=1)
+
+
+def measure(rays=65536 * 4, reps=10, once=False, verbose=False, dev="cuda:0"):
+    """{kernel: {ms, bytes (algorithmic), gbs, frac of the measured HBM peak}} at `rays` rays."""
+    class A:
+        pass
+    a = A()
+    a.rays, a.reps, a.once = rays, reps, once
     peak = 6650.0
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -47,8 +57,9 @@ def main():
         ts.sort()
         ms = ts[len(ts) // 2]
         res[name] = dict(ms=ms, bytes=nbytes, gbs=nbytes / ms / 1e6, frac=nbytes / ms / 1e6 / peak)
-        print("%-22s %8.3f ms  %7.1f MB  %7.1f GB/s  %.3f of %.0f" % (name, ms, nbytes / 1e6, nbytes / ms / 1e6,
-                                                                     nbytes / ms / 1e6 / peak, peak))
+        if verbose:
+            print("%-22s %8.3f ms  %7.1f MB  %7.1f GB/s  %.3f of %.0f" % (name, ms, nbytes / 1e6, nbytes / ms / 1e6,
+                                                                         nbytes / ms / 1e6 / peak, peak))
 
     # stratified: 8 B/sample
     u = torch.rand(S, device=dev, generator=g)
@@ -86,8 +97,7 @@ def main():
     pose = torch.eye(3, 4, device=dev).repeat(B, 1, 1)
     intr = torch.tensor([[0.81 * W, 0, W / 2], [0, 0.81 * W, H / 2], [0, 0, 1]], device=dev).repeat(B, 1, 1)
     run("raygen_pose", lambda: F.raygen_pose(pose, intr, H, W), 24 * B * H * W)
-    if a.json:
-        json.dump(dict(rays=R, peak_gbs=peak, kernels=res), open(a.json, "w"), indent=1)
+    return dict(rays=R, samples_per_ray=N, pdf_shape=[Nc, Nf], peak_gbs=peak, kernels=res)
 
 
 if __name__ == "__main__":
