@@ -8,6 +8,7 @@ lacks (it asserts a single GPU, options.py:103).
 * ``summarize_loss``   -- model/base.py:130-142 without the NaN/Inf host syncs.
 * ``train_step``       -- ``graph.forward`` -> ``compute_loss`` -> ``backward`` (model/nerf.py:77-101 minus
                           the optimiser), optionally over a 1/k ray shard with one gradient all-reduce.
+* ``test_time_photometric_optim`` -- model/barf.py:153-169.
 * ``GradBucket``       -- flat fp32 bucket of every trainable gradient: ONE NCCL all-reduce per step
                           (SURVEY.md section 8e); rays shard, parameters replicate.
 """
@@ -321,6 +322,28 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1):
     if bucket is not None and world > 1:
         bucket.allreduce()
     return loss
+
+
+def test_time_photometric_optim(opt, graph, var, iters=None, lr=None, on_step=None):
+    """``Model.evaluate_test_time_photometric_optim`` (reference model/barf.py:153-169): absorb the remaining pose
+    error of ONE held-out view in a fresh se(3) parameter by ``opt.optim.test_iter`` Adam steps on the photometric
+    loss of ``rand_rays`` random pixels per step (``mode="test-optim"``: the pose gradient comes out of the
+    ray-generation kernel's backward).  ``on_step(it, loss, se3)`` is called after every update (tests, logging).
+    Returns ``var`` with ``se3_refine_test`` / ``pose_refine_test`` set, as the reference does."""
+    var.se3_refine_test = torch.nn.Parameter(torch.zeros(1, 6, device=opt.device))
+    optimizer = getattr(torch.optim, opt.optim.algo)
+    optim_pose = optimizer([dict(params=[var.se3_refine_test], lr=opt.optim.lr_pose if lr is None else lr)])
+    with torch.enable_grad():
+        for it in range(opt.optim.test_iter if iters is None else iters):
+            optim_pose.zero_grad()
+            var.pose_refine_test = camera.lie.se3_to_SE3(var.se3_refine_test)
+            var = graph.forward(opt, var, mode="test-optim")
+            loss = summarize_loss(opt, graph.compute_loss(opt, var, mode="test-optim"))
+            loss.all.backward()
+            optim_pose.step()
+            if on_step is not None:
+                on_step(it, loss, var.se3_refine_test)
+    return var
 
 
 class CapturedStep:

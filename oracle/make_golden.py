@@ -326,6 +326,75 @@ def golden_graph_inn_dtu():
                                grads_fine=grad_digest({k: v.grad for k, v in graph.nerf_fine.named_parameters() if v.grad is not None})))
 
 
+def golden_state_dicts():
+    """Checkpoint inventory: ``graph.state_dict()`` keys and shapes of the reference Graphs as the reference's engine
+    builds them (util.save_checkpoint stores exactly this dict, util.py:147-156)."""
+    out = {}
+    barf = ref_shim.import_reference("model.barf")
+    opt = _opt("barf_llff", "barf", parent="nerf_inn_llff", barf_c2f=[0.1, 0.5], data=dict(image_size=[24, 32]))
+    g = barf.Graph(opt)
+    g.se3_refine = torch.nn.Embedding(3, 6)                      # model/barf.py:42
+    out["barf"] = {k: list(v.shape) for k, v in g.state_dict().items()}
+    mod = ref_shim.import_reference("model.barf_inn_llff")
+    nvp = ref_shim.import_reference("model.nvp.nvp_ndr")
+    opt = _opt("barf_inn_llff", "barf_inn_llff", barf_c2f=[0.1, 0.5], data=dict(image_size=[24, 32]))
+    g = mod.Graph(opt)
+    g.warp_latent = torch.nn.Embedding(3, 128)                   # model/barf_inn_llff.py:41-55
+    g.warp_mlp = nvp.DeformNetwork(d_feature=128, d_in=3, d_out_1=1, d_out_2=3, n_blocks=3, d_hidden=128, n_layers=1,
+                                   skip_in=[], multires=6, weight_norm=True, actfn="softplus")
+    g.global_rigid = torch.nn.Embedding(3, 12)
+    out["barf_inn_llff"] = {k: list(v.shape) for k, v in g.state_dict().items()}
+    mod = ref_shim.import_reference("model.barf_inn_dtu")
+    inn = ref_shim.import_reference("model.pose_models.inn")
+    opt = _opt("barf_inn_dtu", "barf_inn_dtu", barf_c2f=[0.1, 0.5], data=dict(image_size=[18, 24]),
+               nerf=dict(fine_sampling=True))
+    var = _synthetic_var(opt, 3, 73, dtu=True)
+    g = mod.Graph(opt, inn.INNPoseParams(opt, 3, var.pose.clone(), device="cpu"))
+    out["barf_inn_dtu"] = {k: list(v.shape) for k, v in g.state_dict().items()}
+    save("state_dicts", out)
+
+
+def golden_test_optim():
+    """Test-time photometric pose optimisation (model/barf.py:153-169): the reference's loop body, executed on the
+    reference Graph for a few Adam steps on one held-out view; draws, per-step losses and the se3 trajectory recorded."""
+    barf = ref_shim.import_reference("model.barf")
+    camera = ref_shim.import_reference("camera")
+    opt = _opt("barf_llff", "barf", parent="nerf_inn_llff", barf_c2f=[0.1, 0.5],
+               data=dict(image_size=[24, 32]), nerf=dict(rand_rays=48, sample_intvs=16), optim=dict(test_photo=True))
+    graph = barf.Graph(opt)
+    load_nerf(graph.nerf, syn.nerf_params(80))
+    graph.nerf.progress.data.fill_(1.0)
+    gen = torch.Generator().manual_seed(81)
+    Rm = camera.lie.so3_to_SO3(torch.randn(3, generator=gen) * 0.1)
+    graph.sim3 = ref_shim._AttrDict(t0=torch.randn(1, 3, generator=gen) * 0.1, t1=torch.randn(1, 3, generator=gen) * 0.1,
+                                    s0=torch.tensor(1.3), s1=torch.tensor(0.8), R=Rm)      # model/barf.py:113
+    var = _synthetic_var(opt, 1, 82)
+    lr = 1.e-2
+    iters = 6
+    var.se3_refine_test = torch.nn.Parameter(torch.zeros(1, 6))
+    optim = torch.optim.Adam([dict(params=[var.se3_refine_test], lr=lr)])
+    torch.manual_seed(1000)
+    ridx, us, losses, traj, grads = [], [], [], [], []
+    for it in range(iters):
+        optim.zero_grad()
+        var.pose_refine_test = camera.lie.se3_to_SE3(var.se3_refine_test)
+        with record_rng() as log:
+            var = graph.forward(opt, var, mode="test-optim")
+            loss = graph.compute_loss(opt, var, mode="test-optim")
+        total = sum(10 ** float(opt.loss_weight[k]) * loss[k] for k in loss if opt.loss_weight.get(k) is not None)
+        total.backward()
+        grads.append(var.se3_refine_test.grad.clone())
+        optim.step()
+        ridx.append(log["randperm"][0][:opt.nerf.rand_rays])
+        us.append(log["rand"][0])
+        losses.append(total.detach().clone())
+        traj.append(var.se3_refine_test.data.clone())
+    save("test_optim", dict(H=24, W=32, N=16, rand_rays=48, nerf_seed=80, var_seed=82, progress=1.0, lr=lr, iters=iters,
+                            sim3=dict(t0=graph.sim3.t0, t1=graph.sim3.t1, s0=graph.sim3.s0, s1=graph.sim3.s1, R=graph.sim3.R),
+                            ray_idx=torch.stack(ridx), u=torch.stack(us), losses=torch.stack(losses), se3=torch.stack(traj),
+                            d_se3=torch.stack(grads)))
+
+
 def golden_options():
     """Hot-path option fields of the YAMLs the target models use (checked against config.py)."""
     out = {}
@@ -344,6 +413,6 @@ def golden_options():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["camera", "sampler", "nerf_mlp", "composite", "nvp", "graph_barf",
-                             "graph_inn_llff", "graph_inn_dtu", "options"]
+                             "graph_inn_llff", "graph_inn_dtu", "options", "state_dicts", "test_optim"]
     for w in which:
         globals()["golden_" + w]()

@@ -23,7 +23,7 @@ if has micro; then
 fi
 if has launches; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${TAG}_launches.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-micro > $O/${TAG}_launches.log 2>&1
 fi
 if has ncu_mlp; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:'tc_(fwd|dx|dw)_kernel' -s 6 -c 3 -f \
@@ -31,7 +31,7 @@ if has ncu_mlp; then
 fi
 if has ncu_hbm; then
   timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'composite_(fwd|bwd)_kernel|stratified_kernel|pdf_merge_kernel|raygen_pose' -c 8 -f \
+    -k regex:'composite_|stratified_kernel|pdf_merge|raygen_pose' -c 8 -f \
     -o $O/${TAG}_hbm python scripts/micro_hbm.py --once > $O/${TAG}_ncu_hbm.log 2>&1
 fi
 ls -la $O | tail -30
