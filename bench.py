@@ -285,9 +285,12 @@ def run_ours(args):
             with engine.feed_draws(ray_idx=static["ray_idx"], u=static["u"]):
                 v = graph.forward(opt, v, mode="train", iter=it)
             loss = engine.summarize_loss(opt, graph.compute_loss(opt, v, mode="train"))
-            (loss.all if world == 1 else loss.all * (1.0 / world)).backward()
             if world > 1:
+                with engine.overlap_allreduce(graph, adam):
+                    (loss.all * (1.0 / world)).backward()
                 adam.allreduce()
+            else:
+                loss.all.backward()
             adam.step()
             return loss.all.detach()
         return step_static
@@ -471,7 +474,17 @@ def run_ours(args):
     _leave(world)
 
 
+def _protect_stdout():
+    """The driver parses ONE JSON line from stdout: libraries that chat on fd 1 (NCCL prints its version there) are sent
+    to stderr, and only ``print`` from this script reaches the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _protect_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -102,7 +102,78 @@ class GradBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
 
-class FlatAdam:
+class SegmentedAllreduce:
+    """All-reduce of a flat gradient buffer made of per-group segments (``self.flat``, ``self.groups`` with
+    ``offset`` / ``n``).  A segment whose gradients are final before the backward pass ends can be reduced early
+    with ``allreduce_group_async`` (NCCL runs it on its own stream, concurrently with the rest of the backward);
+    ``allreduce`` then reduces whatever is left and joins the early ones.  Without early segments it is ONE
+    collective over the whole buffer."""
+
+    _pending = None
+
+    @staticmethod
+    def _active(group):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def _segment(self, gi):
+        g = self.groups[gi]
+        return self.flat[g["offset"]:g["offset"] + g["n"]]
+
+    def allreduce_group_async(self, gi, group=None):
+        if not self._active(group):
+            return
+        if self._pending is None:
+            self._pending = {}
+        if gi not in self._pending:
+            self._pending[gi] = dist.all_reduce(self._segment(gi), op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def allreduce(self, group=None):
+        if not self._active(group):
+            return
+        pending = self._pending or {}
+        if not pending:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            return
+        for gi in range(len(self.groups)):
+            if gi not in pending:
+                dist.all_reduce(self._segment(gi), op=dist.ReduceOp.SUM, group=group)
+        for work in pending.values():
+            work.wait()                       # the current stream waits for the collective; no host block
+        self._pending = {}
+
+
+class overlap_allreduce:
+    """``with overlap_allreduce(graph, bucket): loss.backward()`` -- the NeRF MLP gradients are final as soon as the
+    fused MLP backward has run, while the pose / warp part of the backward (NVP coupling layers, ~110 us at C2) is
+    still to come: their segment of the bucket is all-reduced concurrently with it.  Only when segment 0 of the
+    bucket holds exactly the parameters of ``graph.nerf`` (+ ``nerf_fine``), as ``reference_optimizer_groups`` builds it."""
+
+    def __init__(self, graph, bucket, group=None):
+        self.mods = [graph.nerf] + ([graph.nerf_fine] if hasattr(graph, "nerf_fine") else [])
+        self.bucket, self.group = bucket, group
+        self.ok = False
+        if isinstance(bucket, SegmentedAllreduce) and SegmentedAllreduce._active(group) and len(bucket.groups) > 1:
+            mine = {id(p) for m in self.mods for p in m.mlp_parameters()}
+            self.ok = {id(p) for p in bucket.groups[0]["params"]} == mine
+
+    def __enter__(self):
+        if self.ok:
+            waiting = {id(m) for m in self.mods}
+
+            def ready(m):
+                waiting.discard(id(m))
+                if not waiting:
+                    self.bucket.allreduce_group_async(0, self.group)
+            for m in self.mods:
+                m._grads_ready = ready
+        return self
+
+    def __exit__(self, *exc):
+        for m in self.mods:
+            m._grads_ready = None
+
+
+class FlatAdam(SegmentedAllreduce):
     """The reference's optimisers (``optim`` on ``graph.nerf``: Adam + ExponentialLR, model/nerf.py:33-46;
     ``optim_pose`` on ``warp_mlp`` + ``warp_latent`` / ``se3_refine``: model/barf_inn_llff.py:84-104,
     model/barf.py:46-60) as ONE kernel launch per parameter group (csrc/adam.cu, ``niw_adam_step``).
@@ -151,10 +222,6 @@ class FlatAdam:
         self.flat.zero_()
 
     zero_grad = zero
-
-    def allreduce(self, group=None):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
     def step(self):
         import ctypes
@@ -318,9 +385,12 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1):
     scale = 1.0
     if world > 1:
         scale = len(var.ray_idx) / float(n_global)
-    (loss.all if scale == 1.0 else loss.all * scale).backward()
     if bucket is not None and world > 1:
+        with overlap_allreduce(graph, bucket):
+            (loss.all * scale).backward()
         bucket.allreduce()
+    else:
+        (loss.all if scale == 1.0 else loss.all * scale).backward()
     return loss
 
 

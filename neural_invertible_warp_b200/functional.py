@@ -363,6 +363,10 @@ class _NerfSamples(torch.autograd.Function):
             _lib.check(_lib.load().niw_nerf_bwd(_p(flat), _p(center), _p(ray), _p(depth), R, N, precision,
                                                 _p(ws), nbytes, _p(d_rgb), _p(d_sigma), dp, _p(d_center),
                                                 _p(d_ray), _stream()))
+        if target is not None:
+            ready = getattr(module, "_grads_ready", None)       # engine.overlap_allreduce: this module's gradients are final
+            if ready is not None:
+                ready(module)
         if n_params and d_params is not None:
             # slow path: the module's gradients are not one flat buffer -> hand slices back to autograd
             pg = tuple(g.view_as(p) for g, p in zip(torch.split(d_params, [p.numel() for p in module.mlp_parameters()]),

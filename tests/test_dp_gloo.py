@@ -117,3 +117,47 @@ def test_shard_ray_idx_partitions_the_global_list():
         parts = [engine.shard_ray_idx(idx, r, world) for r in range(world)]
         assert torch.equal(torch.cat(parts), idx)
         assert max(len(p) for p in parts) == (10 + world - 1) // world
+
+
+class _Segments:
+    """The bucket interface of engine.FlatAdam (flat gradient buffer + per-group segments) on CPU tensors."""
+
+    def __init__(self, sizes):
+        from neural_invertible_warp_b200 import engine
+        self.__class__ = type("_SegBucket", (engine.SegmentedAllreduce,), {})
+        self.groups, off = [], 0
+        for n in sizes:
+            self.groups.append(dict(offset=off, n=n, params=[]))
+            off += n
+        self.flat = torch.zeros(off)
+
+
+def _seg_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = {}
+    for early in ((), (0,), (0, 1), (1,)):
+        b = _Segments([8, 4, 12])
+        b.flat.copy_(torch.arange(24.0) * (rank + 1))
+        for gi in early:
+            b.allreduce_group_async(gi)          # "this segment's gradients are final": reduced while backward continues
+            b.allreduce_group_async(gi)          # idempotent within a step
+        b.allreduce()                            # the rest + join
+        assert not b._pending
+        res[early] = b.flat.clone()
+    if rank == 0:
+        torch.save(res, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_early_segment_allreduce_equals_one_collective(tmp_path):
+    """engine.SegmentedAllreduce / overlap_allreduce host logic: reducing the NeRF segment early (asynchronously) and
+    the rest at the end gives exactly the single whole-buffer all-reduce, every step."""
+    out = str(tmp_path / "seg.pt")
+    mp.spawn(_seg_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    want = torch.arange(24.0) * 3
+    for early, flat in res.items():
+        assert torch.equal(flat, want), early
