@@ -156,6 +156,17 @@ int niw_nerf_bwd(const float* params, const float* center, const float* ray, con
 int niw_mse_gather(const float* image, const float* rgb, const int64_t* ray_idx, int64_t idx_start,
                    int B, int P, int H, int W, float scale, float* loss, float* d_rgb, void* stream);
 
+/* ---- evaluation metrics (row f3)   model/nerf.py:176-183, external/pohsun_ssim/pytorch_ssim/__init__.py:7-37
+ * pred_rgb [B,H*W,3] (the renderer's layout), image [B,3,H,W] -> out [B,2] = per image (sum of squared errors,
+ * sum of the SSIM map over the 3*H*W entries; 11x11 Gaussian window sigma 1.5, zero padding).  out is zeroed here.
+ * PSNR = -10 log10(out[b][0] / (3 H W)), SSIM = out[b][1] / (3 H W). */
+int niw_image_metrics(const float* pred_rgb, const float* image, int B, int H, int W, float* out, void* stream);
+
+/* ---- depth error (row f3)   core/metrics.py:64-111
+ * pred, gt [n], valid [n] bytes or NULL -> out[5] = (#valid, sum|gt-p|, sum(gt-p)^2, sum|gt-s p|, sum(gt-s p)^2), zeroed here. */
+int niw_depth_metrics(const float* pred, const float* gt, const uint8_t* valid, int64_t n, float scale, float* out,
+                      void* stream);
+
 /* ---- optimiser step (row f2): torch.optim.Adam + ExponentialLR over ONE flat fp32 segment
  *      model/nerf.py:33-46,87,92 (optim / sched), model/barf_inn_llff.py:84-120 (optim_pose)
  * params/grads/exp_avg/exp_avg_sq [n] (16-byte aligned).  `state` is a DEVICE array of 2 floats owned by the

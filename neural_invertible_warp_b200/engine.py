@@ -9,6 +9,7 @@ lacks (it asserts a single GPU, options.py:103).
 * ``train_step``       -- ``graph.forward`` -> ``compute_loss`` -> ``backward`` (model/nerf.py:77-101 minus
                           the optimiser), optionally over a 1/k ray shard with one gradient all-reduce.
 * ``test_time_photometric_optim`` -- model/barf.py:153-169.
+* ``evaluate_view``    -- model/nerf.py:162-183 per test view: eval render + PSNR / SSIM on the device (8 f3).
 * ``GradBucket``       -- flat fp32 bucket of every trainable gradient: ONE NCCL all-reduce per step
                           (SURVEY.md section 8e); rays shard, parameters replicate.
 """
@@ -414,6 +415,25 @@ def test_time_photometric_optim(opt, graph, var, iters=None, lr=None, on_step=No
             if on_step is not None:
                 on_step(it, loss, var.se3_refine_test)
     return var
+
+
+@torch.no_grad()
+def evaluate_view(opt, graph, var, test_optim=None, fine=None):
+    """One iteration of ``Model.evaluate_full`` (reference model/nerf.py:162-183) without the file dumps and LPIPS
+    (a library network): optional test-time pose refinement, full-frame ``mode="eval"`` render, PSNR and SSIM of the
+    rendered image in one kernel (csrc/metrics.cu) that reads the renderer's [B,HW,3] output directly.  Returns
+    ``AttrDict(psnr [B], ssim [B], var)`` with device tensors: nothing is read back to the host here."""
+    from . import functional as F
+    if test_optim is None:
+        test_optim = opt.model in ("barf",) and bool(opt.optim.get("test_photo", False))
+    if test_optim:
+        var = test_time_photometric_optim(opt, graph, var)
+    takes_iter = opt.model in ("barf_inn_llff", "nerf_inn_llff", "barf_inn_dtu", "nerf_inn_dtu")
+    var = graph.forward(opt, var, mode="eval", iter=None) if takes_iter else graph.forward(opt, var, mode="eval")
+    use_fine = opt.nerf.fine_sampling if fine is None else fine
+    rgb = var.rgb_fine if (use_fine and "rgb_fine" in var) else var.rgb
+    psnr, ssim = F.image_metrics(rgb, var.image.view(-1, 3, opt.H, opt.W), opt.H, opt.W)
+    return AttrDict(psnr=psnr, ssim=ssim, var=var)
 
 
 class CapturedStep:

@@ -430,6 +430,36 @@ def mse_gather(rgb, image, ray_idx=None, idx_start=0):
     return _MseGather.apply(rgb, image, _idx(ray_idx, rgb.device), int(idx_start))
 
 
+def image_metrics(rgb, image, H, W):
+    """PSNR and SSIM of rendered views (reference model/nerf.py:176-183, pytorch_ssim.ssim): rgb [B,H*W,3] as the
+    renderer returns it, image [B,3,H,W] -> (psnr [B], ssim [B]) device tensors (no host read)."""
+    lib = _lib.load()
+    rgb, image = _f32(rgb, "rgb"), _f32(image, "image")
+    B = image.shape[0]
+    if rgb.numel() != B * H * W * 3 or image.numel() != B * 3 * H * W:
+        raise RuntimeError("niw_b200: image_metrics expects rgb [B,%d,3] and image [B,3,%d,%d]" % (H * W, H, W))
+    out = torch.empty(B, 2, device=image.device, dtype=torch.float32)
+    _lib.check(lib.niw_image_metrics(_p(rgb), _p(image), B, int(H), int(W), _p(out), _stream()))
+    n = 3.0 * H * W
+    return -10.0 * torch.log10(out[:, 0] / n), out[:, 1] / n
+
+
+def depth_metrics(pred, gt, valid=None, scale=1.0):
+    """core/metrics.py:64-111: masked mean absolute depth error and RMSE of a rendered depth map; with ``scale != 1``
+    the better of the scaled / unscaled prediction, as the reference.  Returns (abs_err, rmse) device scalars."""
+    lib = _lib.load()
+    pred, gt = _f32(pred, "pred").reshape(-1), _f32(gt, "gt").reshape(-1)
+    if valid is not None:
+        valid = valid.reshape(-1).to(torch.uint8).contiguous()
+    out = torch.empty(5, device=pred.device, dtype=torch.float32)
+    _lib.check(lib.niw_depth_metrics(_p(pred), _p(gt), _p(valid), pred.numel(), float(scale), _p(out), _stream()))
+    n = out[0]
+    abs_e, rmse = out[1] / (n + 1e-6), torch.sqrt(out[2] / n)
+    if scale != 1.0:
+        abs_e, rmse = torch.minimum(abs_e, out[3] / (n + 1e-6)), torch.minimum(rmse, torch.sqrt(out[4] / n))
+    return abs_e, rmse
+
+
 def sample_pixels(n, k, counter, seed=0):
     """First k entries of a random permutation of range(n) (the reference's ``torch.randperm(n)[:k]``,
     model/nerf.py:268) in O(k): int64 [k] on ``counter``'s device.  ``counter`` is a zero-initialised int64 [1]

@@ -395,6 +395,29 @@ def golden_test_optim():
                             d_se3=torch.stack(grads)))
 
 
+def golden_metrics():
+    """PSNR / SSIM / depth error exactly as Model.evaluate_full computes them (model/nerf.py:176-183) from the
+    reference's own pytorch_ssim and core/metrics.py, on a synthetic render / ground-truth pair."""
+    pytorch_ssim = ref_shim.import_reference("external.pohsun_ssim.pytorch_ssim")
+    metrics = ref_shim.import_reference("core.metrics")
+    H, W, B = 37, 50, 2
+    gen = torch.Generator().manual_seed(90)
+    image = syn.images(91, B, H, W)
+    rgb = (image.permute(0, 2, 3, 1).reshape(B, H * W, 3) + 0.1 * torch.randn(B, H * W, 3, generator=gen)).clamp(0, 1)
+    out = dict(H=H, W=W, B=B, image_seed=91, rgb=rgb, psnr=[], ssim=[])
+    for b in range(B):
+        rgb_map = rgb[b:b + 1].view(-1, H, W, 3).permute(0, 3, 1, 2)
+        out["psnr"].append(-10 * ((rgb_map.contiguous() - image[b:b + 1]) ** 2).mean().log10().item())
+        out["ssim"].append(pytorch_ssim.ssim(rgb_map, image[b:b + 1]).item())
+    depth_gt = torch.rand(1, H, W, generator=gen) * 3 + 1
+    valid = torch.rand(1, H, W, generator=gen) > 0.3
+    pred = (depth_gt.view(1, -1, 1) * 1.1 + 0.05 * torch.randn(1, H * W, 1, generator=gen))
+    var = ref_shim._AttrDict(depth=pred, depth_gt=depth_gt, valid_depth_gt=valid)
+    out.update(depth_gt=depth_gt, valid=valid, depth=pred, depth_scale=0.9,
+               depth_err=metrics.compute_depth_error(var, 1.0), depth_err_scaled=metrics.compute_depth_error(var, 0.9))
+    save("metrics", out)
+
+
 def golden_options():
     """Hot-path option fields of the YAMLs the target models use (checked against config.py)."""
     out = {}
@@ -413,6 +436,6 @@ def golden_options():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["camera", "sampler", "nerf_mlp", "composite", "nvp", "graph_barf",
-                             "graph_inn_llff", "graph_inn_dtu", "options", "state_dicts", "test_optim"]
+                             "graph_inn_llff", "graph_inn_dtu", "options", "state_dicts", "test_optim", "metrics"]
     for w in which:
         globals()["golden_" + w]()

@@ -405,3 +405,41 @@ def gather_pixels(image, ray_idx):
     B = image.shape[0]
     flat = image.reshape(B, 3, -1).permute(0, 2, 1)
     return flat if ray_idx is None else flat[:, ray_idx]
+
+
+# --------------------------------------------------------------------------------------
+# evaluation metrics  (model/nerf.py:176-183, external/pohsun_ssim/pytorch_ssim/__init__.py:7-37, core/metrics.py:64-111)
+# --------------------------------------------------------------------------------------
+
+def psnr(rgb_map, image):
+    """-10 log10 MSE.  model/nerf.py:179 (MSE_loss = mean squared error, model/base.py:209-211)."""
+    return -10 * ((rgb_map - image) ** 2).mean().log10()
+
+
+def ssim(img1, img2, window_size=11, sigma=1.5):
+    """pytorch_ssim.ssim with size_average=True: img [B,C,H,W]."""
+    import math
+    g = torch.tensor([math.exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
+    g = (g / g.sum())[:, None]
+    C = img1.shape[1]
+    window = (g @ g.t()).float()[None, None].expand(C, 1, window_size, window_size).contiguous()
+    conv = lambda t: torch.nn.functional.conv2d(t, window, padding=window_size // 2, groups=C)
+    mu1, mu2 = conv(img1), conv(img2)
+    mu1_sq, mu2_sq, mu12 = mu1 ** 2, mu2 ** 2, mu1 * mu2
+    s1, s2, s12 = conv(img1 * img1) - mu1_sq, conv(img2 * img2) - mu2_sq, conv(img1 * img2) - mu12
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    return (((2 * mu12 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean()
+
+
+def depth_error(pred, gt, valid, scale=1.0):
+    """core/metrics.py:64-111 (full image, B = 1): (abs_e, rmse), the better of scaled / unscaled when scale != 1."""
+    gt, pred = gt.reshape(-1)[valid.reshape(-1)], pred.reshape(-1)[valid.reshape(-1)]
+
+    def metric(d):
+        a = (gt - d).abs()
+        return (a.sum() / (a.nelement() + 1e-6)).item(), torch.sqrt(((d - gt) ** 2).mean()).item()
+    a, r = metric(pred)
+    if scale != 1.0:
+        a2, r2 = metric(pred * scale)
+        a, r = min(a, a2), min(r, r2)
+    return a, r

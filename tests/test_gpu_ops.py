@@ -252,6 +252,28 @@ def test_raygen_pose_shapes(F, B, P):
     torch.testing.assert_close(r.cpu(), r_ref[:, idx], rtol=1e-5, atol=1e-5)
 
 
+def test_eval_metrics_golden_and_full_frame(F, golden):
+    """PSNR / SSIM / depth error kernels against the reference's numbers (golden) and, on a full
+    480x640 frame, against the oracle port."""
+    g = golden("metrics")
+    H, W, B = g["H"], g["W"], g["B"]
+    image = syn.images(g["image_seed"], B, H, W)
+    psnr, ssim = F.image_metrics(g["rgb"].to(DEV), image.to(DEV), H, W)
+    torch.testing.assert_close(psnr.cpu(), torch.tensor(g["psnr"]), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(ssim.cpu(), torch.tensor(g["ssim"]), rtol=1e-5, atol=2e-6)
+    for scale, key in ((1.0, "depth_err"), (g["depth_scale"], "depth_err_scaled")):
+        a, r = F.depth_metrics(g["depth"].to(DEV), g["depth_gt"].to(DEV), g["valid"].to(DEV), scale)
+        assert abs(a.item() - g[key][0]) < 1e-5 and abs(r.item() - g[key][1]) < 1e-5
+    H, W = 480, 640
+    gen = torch.Generator().manual_seed(3)
+    image = syn.images(7, 1, H, W)
+    rgb = (image.permute(0, 2, 3, 1).reshape(1, H * W, 3) + 0.05 * torch.randn(1, H * W, 3, generator=gen)).clamp(0, 1)
+    psnr, ssim = F.image_metrics(rgb.to(DEV), image.to(DEV), H, W)
+    rgb_map = rgb.view(-1, H, W, 3).permute(0, 3, 1, 2)
+    assert abs(psnr.item() - ora.psnr(rgb_map, image).item()) < 1e-3
+    assert abs(ssim.item() - ora.ssim(rgb_map, image).item()) < 1e-5
+
+
 def _nvp_pack(p, code):
     from neural_invertible_warp_b200.nvp import pack_effective
     return pack_effective(p, code)

@@ -225,3 +225,18 @@ def test_builtin_options_match_reference_yaml(golden):
         if "warp_latent" in ref:
             assert mine.warp_latent.embed_dim == ref["warp_latent"]["embed_dim"]
             assert mine.warp_latent.enc_type == ref["warp_latent"]["enc_type"]
+
+
+def test_metrics_oracle_matches_reference(golden):
+    """the oracle's PSNR / SSIM / depth error against the reference's own pytorch_ssim and core/metrics.py."""
+    g = golden("metrics")
+    H, W, B = g["H"], g["W"], g["B"]
+    image = syn.images(g["image_seed"], B, H, W)
+    for b in range(B):
+        rgb_map = g["rgb"][b:b + 1].view(-1, H, W, 3).permute(0, 3, 1, 2)
+        assert abs(ora.psnr(rgb_map, image[b:b + 1]).item() - g["psnr"][b]) < 1e-5
+        assert abs(ora.ssim(rgb_map, image[b:b + 1]).item() - g["ssim"][b]) < 1e-6
+    a, r = ora.depth_error(g["depth"], g["depth_gt"], g["valid"], 1.0)
+    assert abs(a - g["depth_err"][0]) < 1e-6 and abs(r - g["depth_err"][1]) < 1e-6
+    a, r = ora.depth_error(g["depth"], g["depth_gt"], g["valid"], g["depth_scale"])
+    assert abs(a - g["depth_err_scaled"][0]) < 1e-6 and abs(r - g["depth_err_scaled"][1]) < 1e-6
