@@ -654,7 +654,10 @@ int tc_bwd(const float* P, const float* center, const float* ray, const float* d
     niw::note_launch(), tc_dx_kernel<<<grid, 384, BX_TOTAL, st>>>(w.bstream, w.consts, center, ray, depth, S, N, d_rgb, d_sigma,
                                                                  w.sig_pre, w.rgb_keep, w.save, w.scratch, dP, d_center, d_ray);
     NIW_LAUNCH_CHECK();
-    DwPlan plan = make_plan(ntiles, niw_num_sms());
+    // CTAs of the dW pass (one per SM by default).  The pass is HBM-bound, so fewer CTAs can carry it: NIW_DW_CTAS leaves
+    // the other SMs to a concurrent kernel (tuning knob)
+    static const int dw_ctas = getenv("NIW_DW_CTAS") ? atoi(getenv("NIW_DW_CTAS")) : 0;
+    DwPlan plan = make_plan(ntiles, dw_ctas > 0 && dw_ctas < niw_num_sms() ? dw_ctas : niw_num_sms());
     NIW_CUDA(cudaMemsetAsync(w.partial, 0, sizeof(float) * (size_t)plan.max_slices * NPARAMS, st));
     NIW_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_TOTAL));
     // NIW_DW_DEBUG=1: per-CTA start / end times of the dW pass on stderr (synchronises; diagnostics only)
