@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NIW_ABI_VERSION 1
+#define NIW_ABI_VERSION 2
 
 #define NIW_E_BADARG   (-1)  /* null pointer / non-positive size */
 #define NIW_E_UNSUPP   (-2)  /* shape or option outside what the kernels implement */
@@ -87,10 +87,14 @@ int niw_nvp_pack_fwd(const float* const* params, const float* code, int B, float
                      float* cb, void* stream);
 int niw_nvp_pack_bwd(const float* const* params, float* const* grads, const float* code, const float* cb,
                      const float* d_wpack, const float* d_code_bias, int B, float* d_code, void* stream);
+/* idx_offset / idx_split / idx_jump: position of local point n of an image in the point list the reference would have
+ * built, n < idx_split ? n + idx_offset : n + idx_offset + idx_jump (the embedder's annealing quirk, embedder.py:46-49,
+ * is keyed on it).  Identity: (0, Pt, 0).  A ray shard passes its first ray's index in the global per-image list. */
 int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
-                     int B, int Pt, float* out, void* stream);
+                     int B, int Pt, int idx_offset, int idx_split, int idx_jump, float* out, void* stream);
 int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
-                     int B, int Pt, const float* d_out, float* d_wpack, float* d_code_bias, void* stream);
+                     int B, int Pt, int idx_offset, int idx_split, int idx_jump, const float* d_out, float* d_wpack,
+                     float* d_code_bias, void* stream);
 
 /* ---- random pixel subset   model/nerf.py:268 (`torch.randperm(H*W)[:rand_rays//B]`)
  * out[i] = pi(i), i < k, for a keyed random bijection pi of [0,n): the first k entries of a random permutation

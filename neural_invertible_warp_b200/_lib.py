@@ -16,7 +16,7 @@ NIW_PREC_FP32 = 0
 NIW_PREC_BF16 = 1
 NIW_NERF_PARAMS = 530052
 NIW_NVP_BLOCK_FLOATS = ((128 * 27 + 128 + 1 + 128 * 13 + 3 * 128 + 3) + 3) // 4 * 4   # 5636, include/niw_b200.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/niw_b200.h one to one
 SIGNATURES = {
@@ -28,8 +28,8 @@ SIGNATURES = {
     "niw_raygen_unwarped": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     "niw_nvp_pack_fwd": (_c.c_int, [_P, _P, _c.c_int, _P, _P, _P, _P]),
     "niw_nvp_pack_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int, _P, _P]),
-    "niw_nvp_warp_fwd": (_c.c_int, [_P, _P, _P, _c.c_float, _c.c_int, _c.c_int, _P, _P]),
-    "niw_nvp_warp_bwd": (_c.c_int, [_P, _P, _P, _c.c_float, _c.c_int, _c.c_int, _P, _P, _P, _P]),
+    "niw_nvp_warp_fwd": (_c.c_int, [_P, _P, _P, _c.c_float] + [_c.c_int] * 5 + [_P, _P]),
+    "niw_nvp_warp_bwd": (_c.c_int, [_P, _P, _P, _c.c_float] + [_c.c_int] * 5 + [_P, _P, _P, _P]),
     "niw_sample_pixels": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_uint64, _P, _P, _P]),
     "niw_sample_stratified": (_c.c_int, [_P, _c.c_int64, _c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P]),
     "niw_sample_pdf_merge": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _P, _P, _P]),

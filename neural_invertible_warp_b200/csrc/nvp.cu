@@ -46,6 +46,12 @@ constexpr float PI_F = 3.14159274101257324f;   // fp32(pi), as the reference's f
 constexpr int U = HID / 32;                // hidden units per lane
 
 struct Bands { float w[NF]; };
+// position of local point n in the per-image point list the reference would have built (the annealing quirk below is
+// keyed on it): n < split ? n + offset : n + offset + jump.  Identity = {0, Pt, 0}.  A ray shard passes the index of its
+// first ray in the global per-image list (offset) and the rows it does not hold (jump); the de-duplicated centre row
+// of [grid rows ; one centre] lands on a centre index of the full list.
+struct IndexMap { int offset, split, jump; };
+__device__ __forceinline__ int list_index(const IndexMap& m, int n) { return n < m.split ? n + m.offset : n + m.offset + m.jump; }
 
 __device__ __forceinline__ float softplus100(float x) {
     float bx = BETA * x;
@@ -166,7 +172,7 @@ constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)NB * S_BLOCK + FWD_WARPS * 
 
 __global__ void __launch_bounds__(FWD_WARPS * 32)
 nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
-               Bands bw, int B, int Pt, float* __restrict__ out) {
+               Bands bw, IndexMap im, int B, int Pt, float* __restrict__ out) {
     extern __shared__ float smem[];
     float* sw = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -175,7 +181,7 @@ nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
     __syncthreads();
     const int64_t total = (int64_t)B * Pt;
     for (int64_t t = (int64_t)blockIdx.x * FWD_WARPS + warp; t < total; t += (int64_t)gridDim.x * FWD_WARPS) {
-        const int b = (int)(t / Pt), n = (int)(t % Pt);
+        const int b = (int)(t / Pt), n = list_index(im, (int)(t % Pt));
         float x[3] = {pts[t * 3], pts[t * 3 + 1], pts[t * 3 + 2]};
         const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
 #pragma unroll 1
@@ -239,7 +245,7 @@ __device__ __forceinline__ void softplus100_both(float x, float& h, float& g) {
 
 __global__ void __launch_bounds__(BWD_WARPS * 32, 1)
 nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
-               Bands bw, int B, int Pt, int pts_per_warp, const float* __restrict__ d_out, float* __restrict__ d_wpack,
+               Bands bw, IndexMap im, int B, int Pt, int pts_per_warp, const float* __restrict__ d_out, float* __restrict__ d_wpack,
                float* __restrict__ d_code_bias) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -262,7 +268,7 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
         __syncthreads();
         for (int i = 0; i < np; ++i) {
             const int64_t t = p0 + i;
-            const int b = (int)(t / Pt), n = (int)(t % Pt);
+            const int b = (int)(t / Pt), n = list_index(im, (int)(t % Pt));
             float* stt = state + i * PT_STATE;
             float x[3];
             if (blk == 0) {
@@ -296,7 +302,7 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
         float* dbB = d_code_bias + (size_t)(blk * 2 + 1) * B * HID;
         for (int i = 0; i < np; ++i) {
             const int64_t t = p0 + i;
-            const int b = (int)(t / Pt), n = (int)(t % Pt);
+            const int b = (int)(t / Pt), n = list_index(im, (int)(t % Pt));
             if (b != cur_img) {
                 if (cur_img >= 0) {
 #pragma unroll
@@ -660,36 +666,41 @@ extern "C" int niw_nvp_pack_bwd(const float* const* params, float* const* grads,
 }
 
 extern "C" int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
-                                int B, int Pt, float* out, void* stream) {
-    NIW_CHECK_ARG(wpack && code_bias && pts && out && B > 0 && Pt > 0);
+                                int B, int Pt, int idx_offset, int idx_split, int idx_jump, float* out, void* stream) {
+    NIW_CHECK_ARG(wpack && code_bias && pts && out && B > 0 && Pt > 0 && idx_offset >= 0 && idx_split >= 0 && idx_jump >= 0);
+    const IndexMap im{idx_offset, idx_split, idx_jump};
     const int64_t total = (int64_t)B * Pt;
     NIW_CUDA(cudaFuncSetAttribute(nvp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
     int64_t blocks = (total + FWD_WARPS - 1) / FWD_WARPS;
     const int64_t cap = (int64_t)niw_num_sms() * 2;
     if (blocks > cap) blocks = cap;
     niw::note_launch(), nvp_fwd_kernel<<<(unsigned)blocks, FWD_WARPS * 32, FWD_SMEM, niw_stream(stream)>>>(
-        wpack, code_bias, pts, make_bands(alpha_ratio), B, Pt, out);
+        wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, out);
     NIW_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
-                                int B, int Pt, const float* d_out, float* d_wpack, float* d_code_bias, void* stream) {
-    NIW_CHECK_ARG(wpack && code_bias && pts && d_out && d_wpack && d_code_bias && B > 0 && Pt > 0);
+                                int B, int Pt, int idx_offset, int idx_split, int idx_jump, const float* d_out,
+                                float* d_wpack, float* d_code_bias, void* stream) {
+    NIW_CHECK_ARG(wpack && code_bias && pts && d_out && d_wpack && d_code_bias && B > 0 && Pt > 0 && idx_offset >= 0 &&
+                  idx_split >= 0 && idx_jump >= 0);
+    const IndexMap im{idx_offset, idx_split, idx_jump};
     cudaStream_t st = niw_stream(stream);
     NIW_CUDA(cudaMemsetAsync(d_wpack, 0, sizeof(float) * NB * BLOCK_FLOATS, st));
     NIW_CUDA(cudaMemsetAsync(d_code_bias, 0, sizeof(float) * NB * 2 * (size_t)B * HID, st));
     NIW_CUDA(cudaFuncSetAttribute(nvp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     const int64_t total = (int64_t)B * Pt;
-    // points per warp: enough to amortise the per-CTA gradient flush, few enough to fill the GPU
+    // points per warp: the pass is a latency chain per warp (blocks in sequence, points in sequence), so as few as one
+    // wave of CTAs allows (one CTA per SM: its gradient accumulators fill shared memory)
     const int64_t warps_max = (int64_t)niw_num_sms() * BWD_WARPS;
     int64_t ppw = (total + warps_max - 1) / warps_max;
-    if (ppw < 2) ppw = 2;
+    if (ppw < 1) ppw = 1;
     if (ppw > MAX_PTS_PER_WARP) ppw = MAX_PTS_PER_WARP;
     const int64_t warps = (total + ppw - 1) / ppw;
     const int64_t blocks = (warps + BWD_WARPS - 1) / BWD_WARPS;
     niw::note_launch(), nvp_bwd_kernel<<<(unsigned)blocks, BWD_WARPS * 32, BWD_SMEM, st>>>(
-        wpack, code_bias, pts, make_bands(alpha_ratio), B, Pt, (int)ppw, d_out, d_wpack, d_code_bias);
+        wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, (int)ppw, d_out, d_wpack, d_code_bias);
     NIW_LAUNCH_CHECK();
     return 0;
 }

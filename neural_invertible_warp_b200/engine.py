@@ -287,10 +287,16 @@ class _ShardedRandperm:
         def randperm(*a, **k):
             return shard_ray_idx(orig(*a, **k)[:n], rank, world)
         torch.randperm = randperm
+        # where this rank's rays sit in the global per-image list (the NVP warp's annealing quirk is keyed on it)
+        from . import functional as F
+        per = (n + world - 1) // world
+        F.ray_shard = (rank * per, n)
         return self
 
     def __exit__(self, *exc):
+        from . import functional as F
         torch.randperm = self._orig
+        F.ray_shard = None
 
 
 class device_ray_draws:

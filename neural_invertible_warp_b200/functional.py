@@ -151,18 +151,32 @@ def raygen_unwarped(intr, H, W, ray_idx=None, pose_init=None, idx_start=0, num=N
 # NVP warp
 # --------------------------------------------------------------------------------------------
 
+def index_map_args(index_map, Pt):
+    """(offset, split, jump) of the C ABI's point-index map; None = identity."""
+    if index_map is None:
+        return 0, int(Pt), 0
+    o, sp, j = (int(v) for v in index_map)
+    return o, sp, j
+
+
+# ray shard of the current step, set by engine._ShardedRandperm: (index of this rank's first ray in the global per-image
+# ray list, global rays per image).  The warp's annealing quirk is keyed on the position in the GLOBAL point list.
+ray_shard = None
+
+
 class _NvpWarp(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, wpack, code_bias, pts, alpha_ratio):
+    def forward(ctx, wpack, code_bias, pts, alpha_ratio, index_map):
         lib = _lib.load()
         wpack, code_bias, pts = _f32(wpack, "wpack"), _f32(code_bias, "code_bias"), _f32(pts, "pts")
         B, Pt = pts.shape[0], pts.shape[1]
-        if wpack.numel() != 3 * NIW_NVP_BLOCK_FLOATS or tuple(code_bias.shape) != (3, 2, B, 128):
+        if wpack.numel() != 3 * NIW_NVP_BLOCK_FLOATS or code_bias.numel() != 3 * 2 * B * 128:
             raise RuntimeError("niw_b200: NVP warp supports 3 blocks x hidden 128 x 6 bands only")
         out = torch.empty_like(pts)
-        _lib.check(lib.niw_nvp_warp_fwd(_p(wpack), _p(code_bias), _p(pts), float(alpha_ratio), B, Pt, _p(out), _stream()))
+        im = index_map_args(index_map, Pt)
+        _lib.check(lib.niw_nvp_warp_fwd(_p(wpack), _p(code_bias), _p(pts), float(alpha_ratio), B, Pt, *im, _p(out), _stream()))
         ctx.save_for_backward(wpack, code_bias, pts)
-        ctx.alpha = float(alpha_ratio)
+        ctx.alpha, ctx.im = float(alpha_ratio), im
         return out
 
     @staticmethod
@@ -171,15 +185,15 @@ class _NvpWarp(torch.autograd.Function):
         B, Pt = pts.shape[0], pts.shape[1]
         d_w = torch.empty_like(wpack)
         d_cb = torch.empty_like(code_bias)
-        _lib.check(_lib.load().niw_nvp_warp_bwd(_p(wpack), _p(code_bias), _p(pts), ctx.alpha, B, Pt,
+        _lib.check(_lib.load().niw_nvp_warp_bwd(_p(wpack), _p(code_bias), _p(pts), ctx.alpha, B, Pt, *ctx.im,
                                                 _p(d_out.contiguous()), _p(d_w), _p(d_cb), _stream()))
-        return d_w, d_cb, None, None
+        return d_w, d_cb, None, None, None
 
 
-def nvp_warp(wpack, code_bias, pts, alpha_ratio):
+def nvp_warp(wpack, code_bias, pts, alpha_ratio, index_map=None):
     """DeformNetwork.forward on packed effective weights (model/nvp/nvp_ndr.py:365-468).
     pts [B,Pt,3] (no gradient: the reference detaches them, barf_inn_llff.py:328-330)."""
-    return _NvpWarp.apply(wpack, code_bias, pts, alpha_ratio)
+    return _NvpWarp.apply(wpack, code_bias, pts, alpha_ratio, index_map)
 
 
 # --------------------------------------------------------------------------------------------
@@ -496,6 +510,50 @@ class _RaysFromWarp(torch.autograd.Function):
 
 def rays_from_warp(warped, P):
     return _RaysFromWarp.apply(warped, int(P))
+
+
+class _RaysFromWarpShared(torch.autograd.Function):
+    """warped [B,P+1,3] = [grid rows ; ONE centre row] -> (ray = grid - centre, centre expanded to [B,P,3]).  All
+    centre rows of an image are the same point (camera.py:359-390), so the warp evaluates it once; backward sums the
+    P per-ray centre gradients into that row: d_warped = [d_ray ; sum_p (d_centre - d_ray)]."""
+
+    @staticmethod
+    def forward(ctx, warped, P):
+        ctx.P = P
+        grid, center = warped[:, :P], warped[:, P:P + 1]
+        return torch.sub(grid, center), center.expand(-1, P, -1).contiguous()
+
+    @staticmethod
+    def backward(ctx, d_ray, d_center):
+        if d_ray is None and d_center is None:
+            return None, None
+        if d_ray is None:
+            return torch.cat([torch.zeros_like(d_center), d_center.sum(1, keepdim=True)], dim=1), None
+        lower = -d_ray if d_center is None else d_center - d_ray
+        return torch.cat([d_ray, lower.sum(1, keepdim=True)], dim=1), None
+
+
+def rays_from_warp_shared(warped, P):
+    return _RaysFromWarpShared.apply(warped, int(P))
+
+
+# rows of the per-image point list that the embedder's annealing quirk touches (embedder.py:46-49: [d, d (2 NF + 1)),
+# d = 2 or 1, NF = 6): a centre row may be shared only if every centre row of the full list lies beyond them
+NVP_QUIRK_ROWS = 2 * (2 * 6 + 1)
+
+
+def warp_point_list(pts, P, shard=None):
+    """The point list handed to the warp for pts = [grid rows (P) ; centre rows (P)] and its index map.
+    Returns (pts', index_map, shared): with ``shared`` the centre is evaluated once per image ([grid ; centre]),
+    which is exact when all centre rows are equal (always, by construction) and none of them is an annealed row
+    (global rays per image >= 26); a ray shard maps its rows to their positions in the global list."""
+    offset, P_global = shard if shard is not None else (0, P)
+    if P_global >= NVP_QUIRK_ROWS:
+        # local row n < P -> offset + n; the shared centre row (local index P) -> a centre row of the global list
+        return torch.cat([pts[:, :P], pts[:, P:P + 1]], dim=1), (offset, P, P_global - P), True
+    if shard is None:
+        return pts, None, False
+    return pts, (offset, P, P_global - P), False
 
 
 def tc_selftest(A, Bm, variant=0):

@@ -63,8 +63,12 @@ class Graph(nerf_inn_llff.Graph):
                 alpha_ratio = max(min(iter / opt.inn.real_nvp.max_pe_iter, 1), 0)
             else:
                 alpha_ratio = 1
-            warped = self.warp_mlp.forward(self._latent(opt), pts.unsqueeze(2), alpha_ratio=alpha_ratio)[:, :, 0]
-            ray, center_3D = F.rays_from_warp(warped, P)
+            # the warp sees [grid rows ; centre] with the centre evaluated once per image when that is exact, and a ray
+            # shard's rows at their positions in the global list (functional.warp_point_list)
+            wpts, index_map, shared = F.warp_point_list(pts, P, F.ray_shard)
+            warped = self.warp_mlp.forward(self._latent(opt), wpts.unsqueeze(2), alpha_ratio=alpha_ratio,
+                                           index_map=index_map)[:, :, 0]
+            ray, center_3D = F.rays_from_warp_shared(warped, P) if shared else F.rays_from_warp(warped, P)
             return ray, center_3D, warped[:, :P], alpha_ratio
         if mode == "render_train":
             # the reference's branch calls warp_mlp.forward with a wrong arity (:378, SURVEY.md A.6 iii)

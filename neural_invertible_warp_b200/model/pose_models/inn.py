@@ -37,17 +37,21 @@ class INNPoseParams(nn.Module):
         with torch.no_grad():
             pts = camera.unwarped_points(self.opt, var.intr, ray_idx=var.ray_idx, pose_init=self.initial_poses_w2c)
         self.grid_init, self.center_init = pts[:, :P], pts[:, P:]
-        out = self.forward_inn(self.center_init, self.grid_init, iter, _pts=pts)[:, :, 0]
-        grid_pred, center_pred = out[:, :P], out[:, P:]
+        from ... import functional as F
+        wpts, index_map, shared = F.warp_point_list(pts, P, F.ray_shard)
+        out = self.forward_inn(self.center_init, self.grid_init, iter, _pts=wpts, _index_map=index_map)[:, :, 0]
+        grid_pred = out[:, :P]
+        ray, center_pred = F.rays_from_warp_shared(out, P) if shared else F.rays_from_warp(out, P)
         self.solve_for_global_transformation(grid_pred, center_pred)
-        return grid_pred - center_pred, center_pred, grid_pred
+        return ray, center_pred, grid_pred
 
-    def forward_inn(self, centers, grids, iter, _pts=None):
+    def forward_inn(self, centers, grids, iter, _pts=None, _index_map=None):
         """inn.py:81-93 -> warped [B,2P,1,3] ([grid rows ; centre rows])."""
         rn = self.opt.inn.real_nvp
         alpha_ratio = max(min(iter / rn.max_pe_iter, 1), 0) if rn.c2f == True else 1   # noqa: E712
         pts = _pts if _pts is not None else torch.cat([grids, centers], dim=1)
-        return self.pose_embedding.forward(self.pose_latent.weight, pts.unsqueeze(2), alpha_ratio=alpha_ratio)
+        return self.pose_embedding.forward(self.pose_latent.weight, pts.unsqueeze(2), alpha_ratio=alpha_ratio,
+                                           index_map=_index_map)
 
     def solve_for_global_transformation(self, grid_pred, center_pred):
         """inn.py:96-102 (roma.rigid_points_registration -> batched Kabsch in ``camera``)."""

@@ -57,7 +57,7 @@ class _NvpNetwork(torch.autograd.Function):
     code's gradient is returned normally."""
 
     @staticmethod
-    def forward(ctx, code, pts, alpha_ratio, module, *params):
+    def forward(ctx, code, pts, alpha_ratio, module, index_map, *params):
         lib = _lib.load()
         code = F._f32(code, "deformation_code")
         pts = F._f32(pts, "input_pts")
@@ -71,10 +71,11 @@ class _NvpNetwork(torch.autograd.Function):
         ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
         _lib.check(lib.niw_nvp_pack_fwd(ptrs, F._p(code), B, F._p(wpack), F._p(code_bias), F._p(cb), F._stream()))
         out = torch.empty_like(pts)
-        _lib.check(lib.niw_nvp_warp_fwd(F._p(wpack), F._p(code_bias), F._p(pts), float(alpha_ratio), B, Pt, F._p(out),
+        im = F.index_map_args(index_map, Pt)
+        _lib.check(lib.niw_nvp_warp_fwd(F._p(wpack), F._p(code_bias), F._p(pts), float(alpha_ratio), B, Pt, *im, F._p(out),
                                         F._stream()))
         ctx.save_for_backward(code, pts, wpack, code_bias, cb)
-        ctx.module, ctx.alpha = module, float(alpha_ratio)
+        ctx.module, ctx.alpha, ctx.im = module, float(alpha_ratio), im
         return out
 
     @staticmethod
@@ -85,8 +86,8 @@ class _NvpNetwork(torch.autograd.Function):
         d_w = torch.empty_like(wpack)
         d_cb = torch.empty_like(code_bias)
         d_out = d_out.contiguous()
-        _lib.check(lib.niw_nvp_warp_bwd(F._p(wpack), F._p(code_bias), F._p(pts), ctx.alpha, B, Pt, F._p(d_out), F._p(d_w),
-                                        F._p(d_cb), F._stream()))
+        _lib.check(lib.niw_nvp_warp_bwd(F._p(wpack), F._p(code_bias), F._p(pts), ctx.alpha, B, Pt, *ctx.im, F._p(d_out),
+                                        F._p(d_w), F._p(d_cb), F._stream()))
         params = ctx.module.ordered_parameters()
         for p in params:
             if p.grad is None:
@@ -95,7 +96,7 @@ class _NvpNetwork(torch.autograd.Function):
         gptrs = (ctypes.c_void_p * len(params))(*[p.grad.data_ptr() for p in params])
         d_code = torch.empty_like(code)
         _lib.check(lib.niw_nvp_pack_bwd(ptrs, gptrs, F._p(code), F._p(cb), F._p(d_w), F._p(d_cb), B, F._p(d_code), F._stream()))
-        return (d_code, None, None, None) + (None,) * len(params)
+        return (d_code, None, None, None, None) + (None,) * len(params)
 
 
 class DeformNetwork(nn.Module):
@@ -164,13 +165,15 @@ class DeformNetwork(nn.Module):
             p[f"lin{b}_c.weight"], p[f"lin{b}_c.bias"] = lc.weight, lc.bias
         return p
 
-    def forward(self, deformation_code, input_pts, alpha_ratio=0):
-        """deformation_code [B,D], input_pts [B,P,1,3] -> [B,P,1,3]  (nvp_ndr.py:365)."""
+    def forward(self, deformation_code, input_pts, alpha_ratio=0, index_map=None):
+        """deformation_code [B,D], input_pts [B,P,1,3] -> [B,P,1,3]  (nvp_ndr.py:365).  ``index_map`` (offset, split,
+        jump): where the given points sit in the point list the reference would have built (include/niw_b200.h) --
+        the embedder's annealing quirk is keyed on that position; None = the list is the reference's."""
         squeeze = input_pts.dim() == 4
         pts = input_pts[:, :, 0] if squeeze else input_pts
         params = self.ordered_parameters()
         for p in params:
             if not p.is_contiguous():
                 raise RuntimeError("niw_b200 DeformNetwork: parameters must be contiguous")
-        out = _NvpNetwork.apply(deformation_code, pts.detach(), alpha_ratio, self, *params)
+        out = _NvpNetwork.apply(deformation_code, pts.detach(), alpha_ratio, self, index_map, *params)
         return out[:, :, None] if squeeze else out

@@ -321,6 +321,62 @@ def test_nvp_vs_oracle_large(F):
         assert rel_l2(p[k].grad, q[k].grad) < 3e-3, k
 
 
+@pytest.mark.parametrize("alpha", [0.05, 0.4])
+def test_nvp_ray_shards_and_shared_centre_equal_the_full_list(F, alpha):
+    """The warp of a per-image list [grid rows (P) ; centre rows (P)] must not change when (a) the rays are split
+    into contiguous shards that pass their position in the global list (the annealing quirk of embedder.py:46-49 is
+    keyed on it) and (b) the P identical centre rows are evaluated once; outputs equal the full-list oracle and the
+    summed parameter gradients equal the full-list gradients."""
+    B, P = 2, 48
+    gen = torch.Generator().manual_seed(11)
+    grid = torch.randn(B, P, 3, generator=gen) * 0.5
+    centre = (torch.randn(B, 1, 3, generator=gen) * 0.1).expand(-1, P, -1)
+    pts_cpu = torch.cat([grid, centre], 1).contiguous()
+    p_cpu, code_cpu = syn.nvp_params(5), syn.latent_codes(6, B)
+    q = {k: v.clone().requires_grad_(True) for k, v in p_cpu.items()}
+    cg = code_cpu.clone().requires_grad_(True)
+    ref = ora.nvp_warp(q, cg, pts_cpu[:, :, None], alpha)[:, :, 0]
+    w = torch.rand(ref.shape, generator=gen) - 0.5
+    (ref * w).sum().backward()
+
+    def run(parts):
+        """parts: list of (point list, index_map, weights) evaluated separately with shared parameters"""
+        p = {k: v.to(DEV).requires_grad_(True) for k, v in p_cpu.items()}
+        code = code_cpu.to(DEV).requires_grad_(True)
+        outs = []
+        for pl, im, wl in parts:
+            wpack, code_bias = _nvp_pack(p, code)
+            o = F.nvp_warp(wpack, code_bias, pl.to(DEV), alpha, index_map=im)
+            (o * wl.to(DEV)).sum().backward()
+            outs.append(o.detach().cpu())
+        return outs, p, code
+
+    # (a) two ray shards of 24 rays, each [grid shard ; centre shard]
+    half = P // 2
+    parts = []
+    for r in range(2):
+        sl = slice(r * half, (r + 1) * half)
+        pl = torch.cat([grid[:, sl], centre[:, sl]], 1).contiguous()
+        wl = torch.cat([w[:, sl], w[:, P + r * half:P + (r + 1) * half]], 1).contiguous()
+        wpts, im, shared = F.warp_point_list(pl, half, shard=(r * half, P))
+        assert shared
+        # shared centre row: its weight is the sum of the shard's centre-row weights
+        wl = torch.cat([wl[:, :half], wl[:, half:].sum(1, keepdim=True)], 1)
+        parts.append((wpts, im, wl))
+    outs, p, code = run(parts)
+    for r in range(2):
+        sl = slice(r * half, (r + 1) * half)
+        torch.testing.assert_close(outs[r][:, :half], ref.detach()[:, sl], rtol=1e-5, atol=5e-6)
+        torch.testing.assert_close(outs[r][:, half:].expand(-1, half, -1), ref.detach()[:, P + r * half:P + (r + 1) * half],
+                                   rtol=1e-5, atol=5e-6)
+    assert rel_l2(code.grad, cg.grad) < 2e-3
+    for k in q:
+        assert rel_l2(p[k].grad, q[k].grad) < 3e-3, k
+    # (b) without the index map the shards anneal the wrong rows: the outputs must differ (the map is not a no-op)
+    o_wrong = F.nvp_warp(*_nvp_pack({k: v.to(DEV) for k, v in p_cpu.items()}, code_cpu.to(DEV)), parts[1][0].to(DEV), alpha)
+    assert (o_wrong.cpu()[:, :half] - ref.detach()[:, half:P]).abs().max() > 1e-4
+
+
 @pytest.mark.parametrize("progress", [0.2, 0.3, 1.0])
 def test_nerf_mlp_fp32_golden(F, golden, progress):
     """NeRF.forward on the golden points: centre = point, zero depth, ray = view direction."""
