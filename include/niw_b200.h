@@ -53,10 +53,19 @@ int niw_raygen_pose_bwd(const float* pose, const float* intr, const int64_t* ray
                         float* d_pose, void* stream);
 
 /* ---- (a2) camera.get_unwarped_center_and_ray   camera.py:359-390
- * Writes pts [B,2P,3] = [P grid rows ; P centre rows] in the camera frame, or in the world frame
- * of pose_init [B,3,4] when it is non-NULL (the layout barf_inn_llff.py:348 concatenates). */
+ * Writes pts [B, P + n_center, 3] = [P grid rows ; n_center centre rows] in the camera frame, or in the world frame
+ * of pose_init [B,3,4] when it is non-NULL.  n_center = P is the layout barf_inn_llff.py:348 concatenates; n_center = 1
+ * writes the (identical) centre row once. */
 int niw_raygen_unwarped(const float* intr, const float* pose_init, const int64_t* ray_idx, int64_t idx_start,
-                        int B, int P, int H, int W, float* pts, void* stream);
+                        int B, int P, int n_center, int H, int W, float* pts, void* stream);
+
+/* ---- rays from the warped point list   model/barf_inn_llff.py:352-356, model/pose_models/inn.py:75-77
+ * warped [B, P + n_center, 3] -> ray = grid rows - centre rows, center (expanded), both [B,P,3].  Backward:
+ * d_warped = [d_ray ; d_center - d_ray] (n_center = P) or [d_ray ; sum over the image's rays] (n_center = 1); d_ray or
+ * d_center may be NULL. */
+int niw_rays_from_warp_fwd(const float* warped, int B, int P, int n_center, float* ray, float* center, void* stream);
+int niw_rays_from_warp_bwd(const float* d_ray, const float* d_center, int B, int P, int n_center, float* d_warped,
+                           void* stream);
 
 /* ---- (a3) DeformNetwork.forward   model/nvp/nvp_ndr.py:365-468, model/nvp/embedder.py:41-50
  * 3 coupling blocks, hidden 128, 6 frequency bands, Softplus(beta=100), including the reference's

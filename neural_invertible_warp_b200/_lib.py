@@ -25,7 +25,9 @@ SIGNATURES = {
     "niw_launch_count": (_c.c_ulonglong, []),
     "niw_raygen_pose_fwd": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
     "niw_raygen_pose_bwd": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
-    "niw_raygen_unwarped": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
+    "niw_raygen_unwarped": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
+    "niw_rays_from_warp_fwd": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
+    "niw_rays_from_warp_bwd": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     "niw_nvp_pack_fwd": (_c.c_int, [_P, _P, _c.c_int, _P, _P, _P, _P]),
     "niw_nvp_pack_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int, _P, _P]),
     "niw_nvp_warp_fwd": (_c.c_int, [_P, _P, _P, _c.c_float] + [_c.c_int] * 5 + [_P, _P]),

@@ -186,9 +186,11 @@ def get_unwarped_center_and_ray(opt, intr=None, ray_idx=None, pose_init=None, id
     return pts[:, P:], pts[:, :P]
 
 
-def unwarped_points(opt, intr, ray_idx=None, pose_init=None, idx_start=0, num=None):
-    """[grid rows ; centre rows] [B,2P,3] -- the concatenation barf_inn_llff.py:348 feeds the warp."""
-    return F.raygen_unwarped(intr, opt.H, opt.W, ray_idx=ray_idx, pose_init=pose_init, idx_start=idx_start, num=num)
+def unwarped_points(opt, intr, ray_idx=None, pose_init=None, idx_start=0, num=None, shared_center=False):
+    """[grid rows ; centre rows] [B,2P,3] -- the concatenation barf_inn_llff.py:348 feeds the warp; with
+    ``shared_center`` [B,P+1,3]: the centre row (identical for every ray of an image) once."""
+    return F.raygen_unwarped(intr, opt.H, opt.W, ray_idx=ray_idx, pose_init=pose_init, idx_start=idx_start, num=num,
+                             shared_center=shared_center)
 
 
 def get_3D_points_from_depth(opt, center, ray, depth, multi_samples=False):

@@ -404,8 +404,10 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
     for (int i = 0; i < plan.n_units; ++i) if ((int)blockIdx.x >= plan.u[i].first_cta) ui = i;
     const DwUnit& U = plan.u[ui];
     const int slice = (int)blockIdx.x - U.first_cta;
-    const int64_t t0 = ntiles * slice / U.n_slices, t1 = ntiles * (slice + 1) / U.n_slices;
-    const int64_t nstages = 2 * (t1 - t0);     // 64-sample halves
+    // slice s owns tiles s, s + n_slices, ... and walks them from the highest down: the dX pass has just written the
+    // G images in ascending tile order, so every CTA starts on the records most likely to be still in L2
+    const int64_t my_tiles = slice < ntiles ? (ntiles - slice + U.n_slices - 1) / U.n_slices : 0;
+    const int64_t nstages = 2 * my_tiles;      // 64-sample halves
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < BW_NSTAGE; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 5); }
@@ -423,7 +425,7 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
             const uint32_t stage_bytes = (uint32_t)(U.a_half + U.a2_half + U.b_half + U.b2_half + SMALL_BYTES / 2);
             for (int64_t it = 0; it < nstages; ++it) {
                 const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
-                const uint8_t* rec = save + (t0 + (it >> 1)) * SAVE_TILE_BYTES;
+                const uint8_t* rec = save + (slice + (my_tiles - 1 - (it >> 1)) * U.n_slices) * SAVE_TILE_BYTES;
                 const int half = (int)(it & 1);
                 uint8_t* dst = smem + st * BW_STAGE;
                 ptx::mbar_wait(&empty[st], ph ^ 1);
@@ -513,7 +515,7 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
         ptx::tc_fence_after();
         asm volatile("bar.sync 1, 128;" ::: "memory");   // all four warps are done with the stage buffers
         float* out = partial + (size_t)slice * NPARAMS;
-        if (t1 > t0) {
+        if (my_tiles > 0) {
             float* tr = reinterpret_cast<float*>(smem) + wq * (32 * 33);   // stage buffers are idle now
             for (int h = 0; h < U.m_halves + (U.n2 > 0 ? 1 : 0); ++h) {
                 // h < m_halves: main product of M block h;  h == m_halves (= 1): second X image of M block 0

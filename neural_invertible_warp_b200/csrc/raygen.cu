@@ -134,9 +134,11 @@ __global__ void raygen_pose_bwd_kernel(const float* __restrict__ pose, const flo
     }
 }
 
+// pts [B, P + n_center, 3] = [P grid rows ; n_center centre rows], n_center = P (the reference's list) or 1 (all centre
+// rows of an image are the same point; the warp then evaluates it once)
 __global__ void raygen_unwarped_kernel(const float* __restrict__ intr, const float* __restrict__ pose_init,
-                                       const int64_t* __restrict__ ray_idx, int64_t idx_start, int B, int P, int W,
-                                       float* __restrict__ pts) {
+                                       const int64_t* __restrict__ ray_idx, int64_t idx_start, int B, int P, int n_center,
+                                       int W, float* __restrict__ pts) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)B * P) return;
     int b = (int)(t / P), p = (int)(t % P);
@@ -151,10 +153,65 @@ __global__ void raygen_unwarped_kernel(const float* __restrict__ intr, const flo
 #pragma unroll
         for (int j = 0; j < 3; ++j) { g[j] = gw[j]; c[j] = q.tinv[j]; }
     }
-    float* grid_row = pts + ((int64_t)b * 2 * P + p) * 3;
-    float* cen_row = pts + ((int64_t)b * 2 * P + P + p) * 3;
+    const int64_t rows = (int64_t)P + n_center;
+    float* grid_row = pts + ((int64_t)b * rows + p) * 3;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { grid_row[j] = g[j]; cen_row[j] = c[j]; }
+    for (int j = 0; j < 3; ++j) grid_row[j] = g[j];
+    if (p < n_center) {
+        float* cen_row = pts + ((int64_t)b * rows + P + p) * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cen_row[j] = c[j];
+    }
+}
+
+// ---- rays from the warped point list (model/barf_inn_llff.py:352-356, pose_models/inn.py:75-77) ----------------
+// warped [B, P + n_center, 3] -> ray = grid - centre, centre (expanded to P rows), both [B,P,3]
+__global__ void rays_from_warp_fwd_kernel(const float* __restrict__ warped, int B, int P, int n_center,
+                                          float* __restrict__ ray, float* __restrict__ center) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread per output float
+    if (i >= (int64_t)B * P * 3) return;
+    const int c = (int)(i % 3);
+    const int64_t t = i / 3;
+    const int b = (int)(t / P), p = (int)(t % P);
+    const int64_t rows = (int64_t)P + n_center;
+    const float g = warped[((int64_t)b * rows + p) * 3 + c];
+    const float ce = warped[((int64_t)b * rows + P + (n_center == 1 ? 0 : p)) * 3 + c];
+    ray[i] = g - ce;
+    center[i] = ce;
+}
+
+// d_warped = [d_ray ; d_centre - d_ray] (n_center = P) or [d_ray ; sum_p (d_centre - d_ray)] (n_center = 1); one block
+// per image, either upstream gradient may be NULL
+__global__ void __launch_bounds__(256)
+rays_from_warp_bwd_kernel(const float* __restrict__ d_ray, const float* __restrict__ d_center, int P, int n_center,
+                          float* __restrict__ d_warped) {
+    const int b = blockIdx.x;
+    const int64_t rows = (int64_t)P + n_center;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int64_t i = ((int64_t)b * P + p) * 3 + c;
+            const float dr = d_ray ? d_ray[i] : 0.f, lower = (d_center ? d_center[i] : 0.f) - dr;
+            d_warped[((int64_t)b * rows + p) * 3 + c] = dr;
+            if (n_center == 1) acc[c] += lower; else d_warped[((int64_t)b * rows + P + p) * 3 + c] = lower;
+        }
+    }
+    if (n_center == 1) {
+        __shared__ float red[3][8];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = warp_sum(acc[c]);
+            if (lane == 0) red[c][warp] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            float v = 0.f;
+            for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+            d_warped[((int64_t)b * rows + P) * 3 + threadIdx.x] = v;
+        }
+    }
 }
 
 }  // namespace
@@ -189,11 +246,26 @@ extern "C" int niw_raygen_pose_bwd(const float* pose, const float* intr, const i
 }
 
 extern "C" int niw_raygen_unwarped(const float* intr, const float* pose_init, const int64_t* ray_idx,
-                                   int64_t idx_start, int B, int P, int H, int W, float* pts, void* stream) {
-    NIW_CHECK_ARG(intr && pts && B > 0 && P > 0 && H > 0 && W > 0);
+                                   int64_t idx_start, int B, int P, int n_center, int H, int W, float* pts, void* stream) {
+    NIW_CHECK_ARG(intr && pts && B > 0 && P > 0 && H > 0 && W > 0 && (n_center == P || n_center == 1));
     int64_t n = (int64_t)B * P;
     niw::note_launch(), raygen_unwarped_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(intr, pose_init, ray_idx, idx_start, B,
-                                                                              P, W, pts);
+                                                                              P, n_center, W, pts);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int niw_rays_from_warp_fwd(const float* warped, int B, int P, int n_center, float* ray, float* center, void* stream) {
+    NIW_CHECK_ARG(warped && ray && center && B > 0 && P > 0 && (n_center == P || n_center == 1));
+    niw::note_launch(), rays_from_warp_fwd_kernel<<<niw_blocks((int64_t)B * P * 3, 256), 256, 0, niw_stream(stream)>>>(warped, B, P, n_center, ray, center);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int niw_rays_from_warp_bwd(const float* d_ray, const float* d_center, int B, int P, int n_center, float* d_warped,
+                                      void* stream) {
+    NIW_CHECK_ARG((d_ray || d_center) && d_warped && B > 0 && P > 0 && (n_center == P || n_center == 1));
+    niw::note_launch(), rays_from_warp_bwd_kernel<<<B, 256, 0, niw_stream(stream)>>>(d_ray, d_center, P, n_center, d_warped);
     NIW_LAUNCH_CHECK();
     return 0;
 }

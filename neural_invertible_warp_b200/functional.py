@@ -133,16 +133,18 @@ def raygen_pose(pose, intr, H, W, ray_idx=None, idx_start=0, num=None):
     return _RaygenPose.apply(pose, intr, ray_idx, int(idx_start), P, int(H), int(W))
 
 
-def raygen_unwarped(intr, H, W, ray_idx=None, pose_init=None, idx_start=0, num=None):
-    """camera.get_unwarped_center_and_ray (camera.py:359-390) -> pts [B,2P,3] = [grid ; centre]."""
+def raygen_unwarped(intr, H, W, ray_idx=None, pose_init=None, idx_start=0, num=None, shared_center=False):
+    """camera.get_unwarped_center_and_ray (camera.py:359-390) -> pts [B,2P,3] = [grid ; centre], or with
+    ``shared_center`` [B,P+1,3] = [grid ; the one centre row all P would repeat]."""
     lib = _lib.load()
     intr = _f32(intr, "intr")
     pose_init = _f32(pose_init, "pose_init")
     ray_idx = _idx(ray_idx, intr.device)
     P = int(ray_idx.numel()) if ray_idx is not None else int(num if num is not None else H * W - idx_start)
     B = intr.shape[0]
-    pts = torch.empty(B, 2 * P, 3, device=intr.device, dtype=torch.float32)
-    _lib.check(lib.niw_raygen_unwarped(_p(intr), _p(pose_init), _p(ray_idx), int(idx_start), B, P, int(H), int(W),
+    nc = 1 if shared_center else P
+    pts = torch.empty(B, P + nc, 3, device=intr.device, dtype=torch.float32)
+    _lib.check(lib.niw_raygen_unwarped(_p(intr), _p(pose_init), _p(ray_idx), int(idx_start), B, P, nc, int(H), int(W),
                                        _p(pts), _stream()))
     return pts
 
@@ -488,53 +490,42 @@ def sample_pixels(n, k, counter, seed=0):
 
 
 class _RaysFromWarp(torch.autograd.Function):
-    """warped [B,2P,3] = [grid rows ; centre rows] -> (ray = grid - centre, centre), both contiguous [B,P,3]
-    (model/barf_inn_llff.py:352-356).  One autograd node instead of the slice / sub / reshape chain: backward is
-    d_warped = [d_ray ; d_centre - d_ray] in two launches (the eager chain costs ~10 tiny ones per step)."""
+    """warped [B,P+nc,3] = [grid rows ; centre rows] -> (ray = grid - centre, centre), both contiguous [B,P,3]
+    (model/barf_inn_llff.py:352-356); nc = P (the reference's list) or 1 (the centre evaluated once per image: backward
+    sums the P per-ray centre gradients into that row).  One launch each way (the eager slice / sub / expand / sum / cat
+    chain is ~8 tiny ones)."""
 
     @staticmethod
-    def forward(ctx, warped, P):
-        ctx.P = P
-        grid, center = warped[:, :P], warped[:, P:]
-        return torch.sub(grid, center), center.contiguous()
+    def forward(ctx, warped, P, nc):
+        warped = _f32(warped, "warped")
+        B = warped.shape[0]
+        if warped.shape[1] != P + nc:
+            raise RuntimeError("niw_b200: rays_from_warp expects [B,%d,3], got %s" % (P + nc, tuple(warped.shape)))
+        ctx.dims = (B, P, nc)
+        ctx.set_materialize_grads(False)
+        ray = torch.empty(B, P, 3, device=warped.device, dtype=torch.float32)
+        center = torch.empty_like(ray)
+        _lib.check(_lib.load().niw_rays_from_warp_fwd(_p(warped), B, P, nc, _p(ray), _p(center), _stream()))
+        return ray, center
 
     @staticmethod
     def backward(ctx, d_ray, d_center):
         if d_ray is None and d_center is None:
-            return None, None
-        if d_ray is None:
-            return torch.cat([torch.zeros_like(d_center), d_center], dim=1), None
-        lower = -d_ray if d_center is None else d_center - d_ray
-        return torch.cat([d_ray, lower], dim=1), None
+            return None, None, None
+        B, P, nc = ctx.dims
+        like = d_ray if d_ray is not None else d_center
+        d_warped = torch.empty(B, P + nc, 3, device=like.device, dtype=torch.float32)
+        c = lambda t: None if t is None else t.contiguous()
+        _lib.check(_lib.load().niw_rays_from_warp_bwd(_p(c(d_ray)), _p(c(d_center)), B, P, nc, _p(d_warped), _stream()))
+        return d_warped, None, None
 
 
 def rays_from_warp(warped, P):
-    return _RaysFromWarp.apply(warped, int(P))
-
-
-class _RaysFromWarpShared(torch.autograd.Function):
-    """warped [B,P+1,3] = [grid rows ; ONE centre row] -> (ray = grid - centre, centre expanded to [B,P,3]).  All
-    centre rows of an image are the same point (camera.py:359-390), so the warp evaluates it once; backward sums the
-    P per-ray centre gradients into that row: d_warped = [d_ray ; sum_p (d_centre - d_ray)]."""
-
-    @staticmethod
-    def forward(ctx, warped, P):
-        ctx.P = P
-        grid, center = warped[:, :P], warped[:, P:P + 1]
-        return torch.sub(grid, center), center.expand(-1, P, -1).contiguous()
-
-    @staticmethod
-    def backward(ctx, d_ray, d_center):
-        if d_ray is None and d_center is None:
-            return None, None
-        if d_ray is None:
-            return torch.cat([torch.zeros_like(d_center), d_center.sum(1, keepdim=True)], dim=1), None
-        lower = -d_ray if d_center is None else d_center - d_ray
-        return torch.cat([d_ray, lower.sum(1, keepdim=True)], dim=1), None
+    return _RaysFromWarp.apply(warped, int(P), int(P))
 
 
 def rays_from_warp_shared(warped, P):
-    return _RaysFromWarpShared.apply(warped, int(P))
+    return _RaysFromWarp.apply(warped, int(P), 1)
 
 
 # rows of the per-image point list that the embedder's annealing quirk touches (embedder.py:46-49: [d, d (2 NF + 1)),
@@ -542,15 +533,25 @@ def rays_from_warp_shared(warped, P):
 NVP_QUIRK_ROWS = 2 * (2 * 6 + 1)
 
 
+def shared_center_ok(P, shard=None):
+    """May the P identical centre rows of an image be evaluated once?  Only if none of the centre rows of the
+    (global) per-image list is one the annealing quirk touches."""
+    P_global = shard[1] if shard is not None else P
+    return P_global >= NVP_QUIRK_ROWS
+
+
 def warp_point_list(pts, P, shard=None):
-    """The point list handed to the warp for pts = [grid rows (P) ; centre rows (P)] and its index map.
-    Returns (pts', index_map, shared): with ``shared`` the centre is evaluated once per image ([grid ; centre]),
-    which is exact when all centre rows are equal (always, by construction) and none of them is an annealed row
-    (global rays per image >= 26); a ray shard maps its rows to their positions in the global list."""
+    """The point list handed to the warp and its index map, for pts = [grid rows (P) ; centre rows (P or 1)].
+    Returns (pts', index_map, shared).  ``shared``: the centre is evaluated once per image ([grid ; centre]), exact
+    because all centre rows are equal by construction and none of them is an annealed row; a ray shard maps its rows
+    to their positions in the global per-image list."""
     offset, P_global = shard if shard is not None else (0, P)
-    if P_global >= NVP_QUIRK_ROWS:
+    if shared_center_ok(P, shard):
         # local row n < P -> offset + n; the shared centre row (local index P) -> a centre row of the global list
-        return torch.cat([pts[:, :P], pts[:, P:P + 1]], dim=1), (offset, P, P_global - P), True
+        wpts = pts if pts.shape[1] == P + 1 else torch.cat([pts[:, :P], pts[:, P:P + 1]], dim=1)
+        return wpts, (offset, P, P_global - P), True
+    if pts.shape[1] != 2 * P:
+        raise RuntimeError("niw_b200: a shared centre row needs at least %d rays per image" % NVP_QUIRK_ROWS)
     if shard is None:
         return pts, None, False
     return pts, (offset, P, P_global - P), False

@@ -56,9 +56,10 @@ class Graph(nerf_inn_llff.Graph):
             _, pose_init = self._initial_pose(opt, var)
             P = len(var.ray_idx)
             # [grid ; centre] rows for the sampled pixels only, no gradient (:325-330, :348)
+            shared = F.shared_center_ok(P, F.ray_shard)
             with torch.no_grad():
-                pts = camera.unwarped_points(opt, var.intr, ray_idx=var.ray_idx, pose_init=pose_init)
-            var.grid_cam, var.center_cam = pts[:, :P], pts[:, P:]
+                pts = camera.unwarped_points(opt, var.intr, ray_idx=var.ray_idx, pose_init=pose_init, shared_center=shared)
+            var.grid_cam, var.center_cam = pts[:, :P], (pts[:, P:].expand(-1, P, -1) if shared else pts[:, P:])
             if opt.inn.real_nvp.c2f == True:   # noqa: E712  (the reference compares with == True)
                 alpha_ratio = max(min(iter / opt.inn.real_nvp.max_pe_iter, 1), 0)
             else:

@@ -34,10 +34,12 @@ class INNPoseParams(nn.Module):
         if mode != "train":
             raise AssertionError("get_warped_rays_in_world is a training-path function")
         P = len(var.ray_idx)
-        with torch.no_grad():
-            pts = camera.unwarped_points(self.opt, var.intr, ray_idx=var.ray_idx, pose_init=self.initial_poses_w2c)
-        self.grid_init, self.center_init = pts[:, :P], pts[:, P:]
         from ... import functional as F
+        shared = F.shared_center_ok(P, F.ray_shard)
+        with torch.no_grad():
+            pts = camera.unwarped_points(self.opt, var.intr, ray_idx=var.ray_idx, pose_init=self.initial_poses_w2c,
+                                         shared_center=shared)
+        self.grid_init, self.center_init = pts[:, :P], (pts[:, P:].expand(-1, P, -1) if shared else pts[:, P:])
         wpts, index_map, shared = F.warp_point_list(pts, P, F.ray_shard)
         out = self.forward_inn(self.center_init, self.grid_init, iter, _pts=wpts, _index_map=index_map)[:, :, 0]
         grid_pred = out[:, :P]
