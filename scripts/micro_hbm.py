@@ -37,6 +37,14 @@ def measure(rays=65536 * 4, reps=10, once=False, verbose=False, dev="cuda:0"):
     if os.path.exists(pk):
         peak = json.load(open(pk))["hbm_gbs"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    drain = torch.empty(256 << 20, dtype=torch.uint8, device=dev).zero_()
+
+    def flush_l2():
+        """Write a buffer larger than L2, then read another one: the second pass pushes the first one's dirty lines
+        out to HBM, so the timed kernel starts on a cold AND clean L2 (otherwise up to 126 MB of write-backs from the
+        flush itself land inside the timed kernel and are billed to it)."""
+        flush.zero_()
+        drain.view(torch.int32).sum()
     g = torch.Generator(device=dev).manual_seed(0)
     R, N, Nc, Nf = a.rays, 128, 64, 128
     S = R * N
@@ -49,7 +57,7 @@ def measure(rays=65536 * 4, reps=10, once=False, verbose=False, dev="cuda:0"):
                 fn()
         ts = []
         for _ in range(reps):
-            flush.zero_()
+            flush_l2()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()
