@@ -326,6 +326,7 @@ def run_ours(args):
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     drain = torch.empty(256 << 20, dtype=torch.uint8, device=dev).zero_()
+    sync_token = torch.zeros(1, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -343,6 +344,10 @@ def run_ours(args):
             # are written back before the step starts (cold and clean L2)
             flush.zero_()
             drain.view(torch.int32).sum()
+            if world > 1:
+                # the flush is rank-local work outside the timed region: re-align the ranks on the device before the start
+                # event, or its jitter shows up inside the step as time spent waiting in the gradient all-reduce
+                dist.all_reduce(sync_token)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); step_fn(); b.record()
             evs.append((a, b))
