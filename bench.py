@@ -441,7 +441,8 @@ def run_ours(args):
                 flop_per_launch_pair=flop_per_step, mlp_ms_per_step=mlp_ms / max(mlp_calls, 1),
                 mlp_share_of_step=mlp_ms / ms_total if ms_total > 0 else None,
                 timed="CUDA events around niw_nerf_fwd / niw_nerf_bwd on the launching stream, eager pass of the same "
-                      "%d steps (%.3f ms/step eager)" % (args.steps, ms_eager / args.steps),
+                      "%d steps (%.3f ms/step eager); the BF16 weight packing (2 kernels, ~11 us) runs earlier on a side "
+                      "stream (niw_nerf_pack) and is outside this bracket" % (args.steps, ms_eager / args.steps),
                 composite_ms_per_step=comp_ms / max(mlp_calls, 1))
 
     if rank != 0:

@@ -157,6 +157,12 @@ size_t niw_nerf_workspace_bytes(int64_t R, int N, int precision, int training);
 int niw_nerf_fwd(const float* params, const float* center, const float* ray, const float* depth,
                  int64_t R, int N, const float* progress, float c2f_start, float c2f_end, int precision, int training,
                  void* workspace, size_t workspace_bytes, float* rgb, float* sigma, void* stream);
+/* The parameter-only part of niw_nerf_fwd for NIW_PREC_BF16 (fp32 parameters -> BF16 weight streams and constants in
+ * `workspace`): it does not depend on the rays, so a caller may run it early on another stream; pass
+ * `training | NIW_NERF_PREPACKED` to the following niw_nerf_fwd on the same workspace to skip it there. */
+#define NIW_NERF_PREPACKED 2
+int niw_nerf_pack(const float* params, const float* progress, float c2f_start, float c2f_end, int precision,
+                  int training, int64_t R, int N, void* workspace, size_t workspace_bytes, void* stream);
 int niw_nerf_bwd(const float* params, const float* center, const float* ray, const float* depth,
                  int64_t R, int N, int precision,
                  void* workspace, size_t workspace_bytes, const float* d_rgb, const float* d_sigma,

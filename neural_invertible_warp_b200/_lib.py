@@ -14,6 +14,7 @@ _LIB = None
 
 NIW_PREC_FP32 = 0
 NIW_PREC_BF16 = 1
+NIW_NERF_PREPACKED = 2
 NIW_NERF_PARAMS = 530052
 NIW_NVP_BLOCK_FLOATS = ((128 * 27 + 128 + 1 + 128 * 13 + 3 * 128 + 3) + 3) // 4 * 4   # 5636, include/niw_b200.h
 ABI_VERSION = 2
@@ -40,6 +41,7 @@ SIGNATURES = {
     "niw_nerf_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
     "niw_nerf_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _P, _c.c_float, _c.c_float, _c.c_int, _c.c_int, _P,
                                 _c.c_size_t, _P, _P, _P]),
+    "niw_nerf_pack": (_c.c_int, [_P, _P, _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _P, _c.c_size_t, _P]),
     "niw_nerf_bwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _P, _P, _P, _P, _P]),
     "niw_mse_gather": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),
     "niw_image_metrics": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),

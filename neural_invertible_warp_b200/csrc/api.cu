@@ -23,6 +23,7 @@ extern "C" const char* niw_error_string(int code) {
 
 extern "C" size_t niw_nerf_workspace_bytes(int64_t R, int N, int precision, int training) {
     if (R <= 0 || N <= 0) return 0;
+    training &= 1;
     return precision == NIW_PREC_BF16 ? tc_workspace_bytes(R, N, training) : fp32_workspace_bytes(R, N, training);
 }
 
@@ -35,12 +36,21 @@ extern "C" int niw_nerf_fwd(const float* params, const float* center, const floa
     if (progress && !(c2f_end != c2f_start)) return NIW_E_BADARG;
     C2F c2f{progress, c2f_start, c2f_end};
     if (precision == NIW_PREC_FP32)
-        return fp32_fwd(params, center, ray, depth, R, N, c2f, training, workspace, workspace_bytes, rgb, sigma,
+        return fp32_fwd(params, center, ray, depth, R, N, c2f, training & 1, workspace, workspace_bytes, rgb, sigma,
                         niw_stream(stream));
     if (precision == NIW_PREC_BF16)
         return tc_fwd(params, center, ray, depth, R, N, c2f, training, workspace, workspace_bytes, rgb, sigma,
                       niw_stream(stream));
     return NIW_E_UNSUPP;
+}
+
+extern "C" int niw_nerf_pack(const float* params, const float* progress, float c2f_start, float c2f_end, int precision,
+                             int training, int64_t R, int N, void* workspace, size_t workspace_bytes, void* stream) {
+    NIW_CHECK_ARG(params && workspace && R > 0 && N > 0);
+    if (progress && !(c2f_end != c2f_start)) return NIW_E_BADARG;
+    if (precision != NIW_PREC_BF16) return NIW_E_UNSUPP;      // the FP32 path reads the parameters in place
+    C2F c2f{progress, c2f_start, c2f_end};
+    return tc_pack(params, c2f, training & 1, R, N, workspace, workspace_bytes, niw_stream(stream));
 }
 
 extern "C" int niw_nerf_bwd(const float* params, const float* center, const float* ray, const float* depth, int64_t R,

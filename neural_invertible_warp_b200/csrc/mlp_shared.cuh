@@ -43,6 +43,7 @@ int fp32_bwd(const float* P, const float* center, const float* ray, const float*
              float* dP, float* d_center, float* d_ray, cudaStream_t st);
 
 size_t tc_workspace_bytes(int64_t R, int N, int training);
+int tc_pack(const float* P, const C2F& c2f, int training, int64_t R, int N, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_fwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
            const C2F& c2f, int training, void* ws, size_t ws_bytes, float* rgb, float* sigma,
            cudaStream_t st);

@@ -495,16 +495,31 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
 
 size_t tc_workspace_bytes(int64_t R, int N, int training) { return tc::carve(nullptr, R * (int64_t)N, training != 0).bytes; }
 
+// fp32 parameters -> the BF16 weight streams + fp32 constants of the workspace.  Independent of the rays: callers may run
+// it early, on another stream, while the rays are still being produced (niw_nerf_pack).
+int tc_pack(const float* P, const C2F& c2f, int training, int64_t R, int N, void* ws, size_t ws_bytes, cudaStream_t st) {
+    using namespace tc;
+    Workspace w = carve(ws, R * (int64_t)N, training != 0);
+    if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
+    niw::note_launch(), pack_weights_kernel<<<niw_blocks(STREAM_BYTES / 16, 256), 256, 0, st>>>(P, c2f, w.wstream, w.consts);
+    if (training)
+        niw::note_launch(), pack_weights_bwd_kernel<<<niw_blocks(BSTREAM_BYTES / 16, 256), 256, 0, st>>>(P, w.bstream);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
 int tc_fwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N, const C2F& c2f,
            int training, void* ws, size_t ws_bytes, float* rgb, float* sigma, cudaStream_t st) {
     using namespace tc;
     const int64_t S = R * (int64_t)N;
+    const bool prepacked = (training & NIW_NERF_PREPACKED) != 0;     // tc_pack already ran on this workspace
+    training &= 1;
     Workspace w = carve(ws, S, training != 0);
     if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
-    const int64_t groups = STREAM_BYTES / 16;
-    niw::note_launch(), pack_weights_kernel<<<niw_blocks(groups, 256), 256, 0, st>>>(P, c2f, w.wstream, w.consts);
-    if (training)
-        niw::note_launch(), pack_weights_bwd_kernel<<<niw_blocks(BSTREAM_BYTES / 16, 256), 256, 0, st>>>(P, w.bstream);
+    if (!prepacked) {
+        int e = tc_pack(P, c2f, training, R, N, ws, ws_bytes, st);
+        if (e) return e;
+    }
     NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     const int64_t nquads = ((S + TILE - 1) / TILE + 3) / 4;     // four tiles per CTA pair and round
     int64_t pairs = niw_num_sms() / 2;

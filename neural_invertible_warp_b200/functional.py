@@ -334,7 +334,7 @@ class _NerfSamples(torch.autograd.Function):
     and None is returned for the parameters (no per-parameter accumulate launches)."""
 
     @staticmethod
-    def forward(ctx, flat, center, ray, depth, progress, c2f, precision, training, module, *params):
+    def forward(ctx, flat, center, ray, depth, progress, c2f, precision, training, module, prepacked, *params):
         lib = _lib.load()
         flat, center, ray, depth = _f32(flat, "params"), _f32(center, "center"), _f32(ray, "ray"), _f32(depth, "depth")
         if flat.numel() != NIW_NERF_PARAMS:
@@ -344,13 +344,20 @@ class _NerfSamples(torch.autograd.Function):
         nbytes = lib.niw_nerf_workspace_bytes(R, N, precision, int(training))
         if nbytes == 0:
             raise RuntimeError("niw_b200: MLP precision %d is not available in this build" % precision)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=depth.device)
+        flags = int(training)
+        if prepacked is not None:
+            # weight streams already packed into this workspace (nerf_prepack, possibly on another stream)
+            if prepacked.numel() != nbytes or precision != NIW_PREC_BF16:
+                raise RuntimeError("niw_b200: prepacked workspace does not match this call")
+            ws, flags = prepacked, flags | _lib.NIW_NERF_PREPACKED
+        else:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=depth.device)
         rgb = torch.empty(R, N, 3, device=depth.device)
         sigma = torch.empty(R, N, device=depth.device)
         c0, c1 = (float(c2f[0]), float(c2f[1])) if progress is not None else (0.0, 1.0)
         with _timed("nerf_fwd"):
             _lib.check(lib.niw_nerf_fwd(_p(flat), _p(center), _p(ray), _p(depth), R, N, _p(progress), c0, c1, precision,
-                                        int(training), _p(ws), nbytes, _p(rgb), _p(sigma), _stream()))
+                                        flags, _p(ws), nbytes, _p(rgb), _p(sigma), _stream()))
         if training:
             ctx.save_for_backward(flat, center, ray, depth, ws)
             ctx.cfg = (precision, nbytes, module, len(params))
@@ -387,32 +394,54 @@ class _NerfSamples(torch.autograd.Function):
             # slow path: the module's gradients are not one flat buffer -> hand slices back to autograd
             pg = tuple(g.view_as(p) for g, p in zip(torch.split(d_params, [p.numel() for p in module.mlp_parameters()]),
                                                      module.mlp_parameters()))
-            return (None, d_center, d_ray, None, None, None, None, None, None) + pg
-        return (d_params if not n_params else None, d_center, d_ray, None, None, None, None, None, None) + (None,) * n_params
+            return (None, d_center, d_ray, None, None, None, None, None, None, None) + pg
+        return (d_params if not n_params else None, d_center, d_ray, None, None, None, None, None, None, None) + (None,) * n_params
+
+
+def _progress_tensor(progress, c2f, device):
+    if c2f is None:
+        return None
+    if progress is None:
+        raise RuntimeError("niw_b200: barf_c2f needs the progress scalar")
+    if not torch.is_tensor(progress):
+        return torch.tensor(float(progress), dtype=torch.float32, device=device)
+    return _f32(progress.detach(), "progress")
 
 
 def nerf_forward_samples(params, center, ray, depth, progress=None, c2f=None, precision=NIW_PREC_FP32, training=None,
-                         module=None):
+                         module=None, prepacked=None):
     """NeRF.forward_samples (model/nerf.py:449-456 -> :416-447, with camera.py:517-521 and the BARF
     encoding model/barf.py:256-268).  params: flat [530052] fp32; center/ray [R,3]; depth [R,N]
     -> rgb [R,N,3], sigma [R,N].  ``progress`` (device scalar tensor, or a float) and ``c2f`` = (start, end)
     select the coarse-to-fine band weights, evaluated on the device; None = no annealing.  With
     ``module`` (a NeRFCore) the parameter gradients are accumulated into the module's flat gradient
-    buffer by the kernels (see _NerfSamples)."""
-    if c2f is None:
-        progress = None
-    elif progress is None:
-        raise RuntimeError("niw_b200: barf_c2f needs the progress scalar")
-    elif not torch.is_tensor(progress):
-        progress = torch.tensor(float(progress), dtype=torch.float32, device=depth.device)
-    else:
-        progress = _f32(progress.detach(), "progress")
+    buffer by the kernels (see _NerfSamples).  ``prepacked``: a workspace from ``nerf_prepack`` for this very call."""
+    progress = _progress_tensor(progress, c2f, depth.device)
     mparams = tuple(module.mlp_parameters()) if module is not None else ()
     if training is None:
         training = torch.is_grad_enabled() and (params.requires_grad or center.requires_grad or ray.requires_grad
                                                 or any(p.requires_grad for p in mparams))
     return _NerfSamples.apply(params, center, ray, depth, progress, c2f, precision_code(precision), bool(training),
-                              module, *mparams)
+                              module, prepacked, *mparams)
+
+
+def nerf_prepack(params, R, N, progress=None, c2f=None, precision=NIW_PREC_BF16, training=True):
+    """The ray-independent part of ``nerf_forward_samples`` (BF16 path): allocate the call's workspace and pack the
+    weight streams into it on the CURRENT stream -- which may be a side stream running while the rays are still being
+    produced.  Returns the workspace to pass as ``prepacked`` (``training`` must be what that call will use), or None
+    when there is nothing to hoist (FP32 path)."""
+    precision = precision_code(precision)
+    if precision != NIW_PREC_BF16:
+        return None
+    lib = _lib.load()
+    params = _f32(params, "params")
+    progress = _progress_tensor(progress, c2f, params.device)
+    nbytes = lib.niw_nerf_workspace_bytes(R, N, precision, int(bool(training)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=params.device)
+    c0, c1 = (float(c2f[0]), float(c2f[1])) if progress is not None else (0.0, 1.0)
+    _lib.check(lib.niw_nerf_pack(_p(params), _p(progress), c0, c1, precision, int(bool(training)), R, N, _p(ws), nbytes,
+                                 _stream()))
+    return ws
 
 
 # --------------------------------------------------------------------------------------------

@@ -191,7 +191,7 @@ class NeRFCore(nn.Module):
                                             module=self)
         return rgb.view(*shape, 3), sigma.view(*shape)
 
-    def forward_samples(self, opt, center, ray, depth_samples, mode=None):
+    def forward_samples(self, opt, center, ray, depth_samples, mode=None, prepacked=None):
         """model/nerf.py:449-456: center, ray [B,P,3], depth_samples [B,P,N,1] ->
         rgb_samples [B,P,N,3], density_samples [B,P,N]."""
         self._check_mode(opt, mode)
@@ -199,8 +199,15 @@ class NeRFCore(nn.Module):
         progress, c2f = self.c2f_schedule(opt)
         rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), center.reshape(B * P, 3), ray.reshape(B * P, 3),
                                             depth_samples.reshape(B * P, N), progress, c2f, self.precision(opt),
-                                            module=self)
+                                            module=self, prepacked=prepacked)
         return rgb.view(B, P, N, 3), sigma.view(B, P, N)
+
+    def prepack(self, opt, n_rays, n_samples):
+        """Workspace of the coming ``forward_samples`` call with the weight streams already packed (current stream);
+        None when the precision has nothing to hoist.  Training-ness is decided as that call will decide it."""
+        training = torch.is_grad_enabled() and any(p.requires_grad for p in self.mlp_parameters())
+        progress, c2f = self.c2f_schedule(opt)
+        return F.nerf_prepack(self.flat_parameters(), n_rays, n_samples, progress, c2f, self.precision(opt), training), training
 
     def composite(self, opt, ray, rgb_samples, density_samples, depth_samples, want_prob=True):
         """model/nerf.py:458-474 -> rgb [B,P,3], depth [B,P,1], opacity [B,P,1], prob [B,P,N,1]
@@ -253,13 +260,40 @@ class RenderCore(nn.Module):
         return fine.view(B, P, -1, 1)
 
     # -- rays -> pixels ---------------------------------------------------------------------
-    def _render_rays(self, opt, center, ray, intr, mode, depth_range=None):
+    def prefetch_render(self, opt, B, P, depth_range=None):
+        """The part of the render pass that does not depend on the rays -- the stratified depth samples and the coarse
+        network's packed BF16 weight streams -- launched on a side stream so that it overlaps the pose / warp kernels
+        that produce the rays (~19 us of small kernels at C2).  Returns a token for ``_render_rays(prefetched=...)``."""
+        cur = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            depth_samples = self.sample_depth(opt, B, num_rays=P, depth_range=depth_range)
+            ws, training = self.nerf.prepack(opt, B * P, depth_samples.shape[2])
+        return depth_samples, ws, training, side
+
+    def _render_rays(self, opt, center, ray, intr, mode, depth_range=None, prefetched=None):
         """Everything after ray generation in model/nerf.py:301-319."""
         B, P = ray.shape[:2]
         if opt.camera.ndc:
             center, ray = camera.convert_NDC(opt, center, ray, intr=intr)
-        depth_samples = self.sample_depth(opt, B, num_rays=P, depth_range=depth_range)
-        rgb_s, sigma_s = self.nerf.forward_samples(opt, center, ray, depth_samples, mode=mode)
+        ws = None
+        if prefetched is not None:
+            depth_samples, ws, training, side = prefetched
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(side)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in (depth_samples, ws):       # allocated on the side stream, consumed (and freed) on this one
+                    if t is not None:
+                        t.record_stream(cur)
+            if ws is not None and training != (torch.is_grad_enabled() and (center.requires_grad or ray.requires_grad or
+                                                                             any(p.requires_grad for p in self.nerf.mlp_parameters()))):
+                ws = None                            # the call will decide otherwise: let it pack for itself
+        else:
+            depth_samples = self.sample_depth(opt, B, num_rays=P, depth_range=depth_range)
+        rgb_s, sigma_s = self.nerf.forward_samples(opt, center, ray, depth_samples, mode=mode, prepacked=ws)
         rgb, depth, opacity, prob = self.nerf.composite(opt, ray, rgb_s, sigma_s, depth_samples,
                                                         want_prob=bool(opt.nerf.fine_sampling))
         ret = edict(rgb=rgb, depth=depth, opacity=opacity)
@@ -281,11 +315,11 @@ class RenderCore(nn.Module):
         center, ray = camera.get_center_and_ray(opt, pose, intr=intr, ray_idx=ray_idx, idx_start=idx_start, num=num)
         return self._render_rays(opt, center, ray, intr, mode, depth_range=depth_range)
 
-    def _render_local(self, opt, ray, center, intr=None, ray_idx=None, mode=None, depth_range=None):
+    def _render_local(self, opt, ray, center, intr=None, ray_idx=None, mode=None, depth_range=None, prefetched=None):
         """model/nerf_inn_llff.py:581-612 / nerf_inn_dtu.py:420-456: render given world-frame rays."""
         if ray_idx is not None:
             center, ray = center[:, ray_idx], ray[:, ray_idx]
-        return self._render_rays(opt, center, ray, intr, mode, depth_range=depth_range)
+        return self._render_rays(opt, center, ray, intr, mode, depth_range=depth_range, prefetched=prefetched)
 
     def _slices(self, opt, render_slice):
         """model/nerf.py:321-332: ``rand_rays`` pixels at a time, concatenated along the ray axis."""

@@ -37,8 +37,11 @@ class Graph(base.Graph):
         if opt.nerf.rand_rays and mode in ["train", "test-optim"]:
             var.ray_idx = torch.randperm(opt.H * opt.W, device=opt.device)[:opt.nerf.rand_rays // batch_size]
             if mode == "train":
+                # depth samples and packed MLP weights do not depend on the rays: a side stream prepares them while the
+                # warp kernels of get_pose run (same draws, same values; only the launch order differs)
+                pre = self.prefetch_render(opt, batch_size, len(var.ray_idx)) if not opt.camera.ndc else None
                 ray, center, grid_3D, alpha_ratio = self.get_pose(opt, var, mode=mode, iter=iter)
-                ret = self.render_local(opt, ray, center, intr=var.intr, mode=mode)
+                ret = self._render_local(opt, ray, center, intr=var.intr, mode=mode, prefetched=pre)
                 # the un-warped points were generated inside get_pose (one kernel instead of the
                 # reference's two full-frame grids, nerf_inn_llff.py:519 and barf_inn_llff.py:325)
                 ret.update(grid_3D=grid_3D, center=center, grid_cam=var.grid_cam, center_cam=var.center_cam,
