@@ -201,6 +201,11 @@ int niw_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * CTA-pair form (tcgen05 cta_group::2): A [256,K], D [256,N]. */
 int niw_tc_selftest(const float* A, const float* Bm, int N, int K, int variant, float* D, void* stream);
 
+/* ---- probe (diagnostics, scripts/probe_tmem.py): cycles of a tcgen05.mma stream (what & 1: iters x 16 MMAs of
+ * M = 128, N = 256, K = 16 into TMEM columns 0-255) and of four warps draining TMEM columns 256-511 (what & 2: iters x
+ * 128 KB), alone or concurrently, on one SM.  out[0] = MMA cycles, out[1] = slowest reader's cycles (device int64[2]). */
+int niw_tc_probe(int what, int iters, long long* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

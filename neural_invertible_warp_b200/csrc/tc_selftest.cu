@@ -131,6 +131,59 @@ tc_selftest_pair_kernel(const float* __restrict__ A, const float* __restrict__ B
     if (warp == 0) ptx::tmem_dealloc2(tmem_base, (uint32_t)(N < 32 ? 32 : N));
 }
 
+// ---- probe: do tcgen05.mma (accumulating into TMEM) and tcgen05.ld (draining TMEM) overlap on one SM? -------------
+// what & 1: one thread issues `iters` x 16 MMAs (M = 128, N = 256, K = 16: one 256-deep layer of the MLP per iteration)
+//           into TMEM columns [0, 256);
+// what & 2: warps 4-7 read TMEM columns [256, 512) `iters` times (128 lanes x 256 columns x 4 B = 128 KB per iteration:
+//           one layer's accumulator, as the MLP epilogue does).
+// out[0] = cycles of the MMA stream, out[1] = cycles of the slowest reading warp (clock64 on the SM).
+__global__ void __launch_bounds__(256)
+tc_probe_kernel(int what, int iters, long long* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (128 + 256) * 16 * 2 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
+    if (tid == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); out[0] = 0; out[1] = 0; }
+    if (warp == 0) ptx::tmem_alloc(&tmem_base_s, 512);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if ((what & 1) && tid == 32) {
+        const uint32_t a0 = ptx::smem_addr(smem), b0 = a0 + 128 * 16 * 2;
+        const uint32_t idesc = ptx::idesc_bf16(128, 256, 0, 0);
+        const uint64_t ad = ptx::smem_desc(a0, 128 * 16, 128), bd = ptx::smem_desc(b0, 256 * 16, 128);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it)
+            for (int ks = 0; ks < 16; ++ks) ptx::mma_bf16(tmem_base, ad, bd, idesc, (it | ks) != 0);
+        ptx::mma_commit(&bar);
+        ptx::mbar_wait(&bar, 0);
+        out[0] = clock64() - t0;
+    }
+    if ((what & 2) && warp >= 4) {
+        const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+        uint32_t v[32], acc = 0;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+            for (int c = 0; c < 256; c += 32) {
+                ptx::tmem_ld32(tacc + c, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc ^= v[j];
+            }
+        }
+        const long long dt = clock64() - t0;
+        if (acc == 0x12345678u) out[1] = -1;            // keep the loads alive
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)dt);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 }  // namespace niw
 
@@ -148,6 +201,13 @@ extern "C" int niw_tc_selftest(const float* A, const float* Bm, int N, int K, in
     size_t smem = (size_t)(128 + N) * K * 2;
     NIW_CUDA(cudaFuncSetAttribute(niw::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     niw::note_launch(), niw::tc_selftest_kernel<<<1, 128, smem, niw_stream(stream)>>>(A, Bm, N, K, variant, D);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int niw_tc_probe(int what, int iters, long long* out, void* stream) {
+    NIW_CHECK_ARG(out && iters > 0 && what >= 1 && what <= 3);
+    niw::note_launch(), niw::tc_probe_kernel<<<1, 256, (128 + 256) * 16 * 2, niw_stream(stream)>>>(what, iters, out);
     NIW_LAUNCH_CHECK();
     return 0;
 }
