@@ -27,7 +27,6 @@
 // contiguous) and LBO = rows*16 B.  Epilogue thread r writes 16 B at chunk*rows*16 + r*16: a warp
 // writes 512 contiguous bytes (bank-conflict free).
 #include "tc_layout.cuh"
-#include <cstdlib>
 #ifndef NIW_NSTAGE
 #define NIW_NSTAGE 7
 #endif
@@ -488,312 +487,6 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
     if (warp == 2) ptx::tmem_dealloc2(tmem_base, 512);
 }
 
-
-// ------------------------------------------------------------------------------------------
-// fused forward kernel, chain form: ONE tile pair per CTA pair, layers ping-pong between the two TMEM accumulators
-// ------------------------------------------------------------------------------------------
-// The slot form above runs two tile pairs a layer apart and pays, per layer and slot, MMA + epilogue + two hand-offs in
-// sequence.  Here a CTA pair works on one pair of tiles at a time: layer l accumulates into accumulator l & 1, its epilogue
-// (8 warps: two threads per sample row, 128 columns each) writes the next A tile K-chunk by K-chunk and signals a barrier
-// per chunk, and the issuer starts layer l+1's MMAs into the OTHER accumulator as those chunks appear -- a layer costs
-// max(epilogue, MMA) instead of their sum.  The A tile is updated in place: the MMAs of layer l have completed (that is
-// what starts epilogue l), and epilogue l+1 cannot start before the MMAs of layer l+1 have.
-//   warp 0     weight producer (this CTA's half of every chunk, 16-stage ring)
-//   warp 1     leader: MMA issuer; peer: relays "my half has landed"
-//   warp 2     TMEM allocator      warp 3   head weights / bias "ones" image
-//   warps 4-11 epilogue: warp w drains TMEM lanes 32 (w % 4).., columns 128 ((w - 4) / 4)..
-constexpr int CH_NSTAGE = 16;
-constexpr int CH_ACT = 0;
-constexpr int CH_ENC = CH_ACT + ACT_BYTES;
-constexpr int CH_RING = CH_ENC + ENC_BYTES;
-constexpr int CH_ONES = CH_RING + CH_NSTAGE * HSTAGE_BYTES;
-constexpr int CH_CONST = CH_ONES + ONES_BYTES;
-constexpr int CH_XCH = CH_CONST + ((C_FLOATS * 4 + 15) / 16) * 16;   // [128 rows][3] partial head sums of the upper column half
-constexpr int CH_BAR = CH_XCH + TILE * 3 * 4;
-constexpr int CH_TOTAL = CH_BAR + 512;
-static_assert(CH_TOTAL <= 227 * 1024, "shared memory budget (chain forward)");
-
-// columns [32 HALF, 32 HALF + 32) of the 64-wide encoded position: each of the two threads of a row evaluates only
-// the sincos it needs
-template <int HALF>
-__device__ __forceinline__ void write_enc_half(uint8_t* enc_tile, uint8_t* save_img, int row, const float x[3],
-                                               const Bands3& bw, bool valid) {
-    float e[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) e[i] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        if (HALF == 0) e[c] = valid ? x[c] : 0.f;
-#pragma unroll
-        for (int k = 0; k < L3; ++k) {
-            const int cs_ = 3 + c * 2 * L3 + k, cc_ = cs_ + L3;         // columns of sin / cos
-            const bool ws = (cs_ >> 5) == HALF, wc = (cc_ >> 5) == HALF;
-            if (ws || wc) {
-                float sn, cs;
-                sincos_reduced(x[c] * ((float)(1 << k) * PI_F), sn, cs);
-                if (ws) e[cs_ & 31] = valid ? bw.w[k] * sn : 0.f;
-                if (wc) e[cc_ & 31] = valid ? bw.w[k] * cs : 0.f;
-            }
-        }
-    }
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        uint4 v = make_uint4(ptx::pack_bf16(e[ch * 8], e[ch * 8 + 1]), ptx::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]),
-                             ptx::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]), ptx::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
-        *reinterpret_cast<uint4*>(enc_tile + (HALF * 4 + ch) * KROW + row * 16) = v;
-        if (save_img) *reinterpret_cast<uint4*>(save_img + hbm_img_off(ENC3_PAD, row, HALF * 4 + ch)) = v;
-    }
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-tc_fwd_chain_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ consts_g, const float* __restrict__ center,
-                    const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N,
-                    float* __restrict__ rgb_out, float* __restrict__ sigma_out, float* __restrict__ sig_pre,
-                    float* __restrict__ rgb_keep, uint8_t* __restrict__ save) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CH_BAR);
-    uint64_t* w_full = bars;                       // [CH_NSTAGE] this CTA's half of the chunk has landed (leader: and the peer's)
-    uint64_t* w_empty = w_full + CH_NSTAGE;        // [CH_NSTAGE] the MMAs reading the stage have completed (both CTAs)
-    uint64_t* chunk_rdy = w_empty + CH_NSTAGE;     // [8] (leader) K-chunk c of the next A tile is written in both CTAs
-    uint64_t* enc_rdy = chunk_rdy + 8;             // [2] (leader) K-chunk c of the encoded-position tile
-    uint64_t* venc_rdy = enc_rdy + 2;              // [1] (leader) encoded view direction (chunk 0 of the enc tile)
-    uint64_t* acc_full = venc_rdy + 1;             // [2] the layer in accumulator a is complete (both CTAs)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
-    static_assert((2 * CH_NSTAGE + 8 + 2 + 1 + 2) * 8 + 4 <= 512, "barrier area");
-    float* cst = reinterpret_cast<float*>(smem + CH_CONST);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();
-    const int64_t ntiles = (S + TILE - 1) / TILE;
-    const int64_t nunits = (ntiles + 1) / 2;                       // a unit = the two tiles of a CTA pair
-    const int64_t unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < CH_NSTAGE; ++i) { ptx::mbar_init(&w_full[i], rank == 0 ? 2 : 1); ptx::mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 8; ++i) ptx::mbar_init(&chunk_rdy[i], 8);          // 4 warps (lane quarters) x 2 CTAs
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&enc_rdy[i], 8); ptx::mbar_init(&acc_full[i], 1); }
-        ptx::mbar_init(venc_rdy, 4 * 2);                                       // the upper-half warps of both CTAs
-        ptx::fence_mbar_init();
-    }
-    if (warp == 2) ptx::tmem_alloc2(tmem_slot, 512);
-    if (warp == 3) {
-        for (int i = lane; i < C_FLOATS; i += 32) cst[i] = consts_g[i];
-        uint4* ones = reinterpret_cast<uint4*>(smem + CH_ONES);
-        for (int i = lane; i < ONES_BYTES / 16; i += 32) ones[i] = i < TILE ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-        ptx::fence_proxy_async();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync_all();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    Bands3 bw3; BandsV bwv;
-    load_bands(cst + C_BANDS, bw3, bwv);
-
-    if (warp == 0) {
-        // ================= weight producer =================
-        if (lane == 0) {
-            uint32_t st = 0, cyc = 0;
-            for (int64_t unit = unit0; unit < nunits; unit += unit_step) {
-                const uint8_t* src = wstream;
-                for (int l = 0; l < NLAYER; ++l) {
-                    const int nch = layer_chunks(l), hrows = layer_rows(l) / 2;
-                    for (int c = 0; c <= nch; ++c) {                    // chunk nch is the K = 16 bias chunk
-                        const uint32_t bytes = (uint32_t)hrows * (c < nch ? CHUNK_K : BIAS_K) * 2;
-                        ptx::mbar_wait(&w_empty[st], (cyc & 1) ^ 1);
-                        ptx::mbar_arrive_expect_tx(&w_full[st], bytes);
-                        ptx::bulk_g2s(smem + CH_RING + st * HSTAGE_BYTES, src + rank * bytes, bytes, &w_full[st]);
-                        src += 2 * bytes;
-                        if (++st == CH_NSTAGE) { st = 0; ++cyc; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1 && rank != 0) {
-        // ================= peer CTA: tell the leader when this CTA's half of a chunk has landed =================
-        if (lane == 0) {
-            uint32_t st = 0, cyc = 0;
-            const uint32_t full0 = ptx::mapa(&w_full[0], 0);
-            for (int64_t unit = unit0; unit < nunits; unit += unit_step)
-                for (int l = 0; l < NLAYER; ++l)
-                    for (int c = 0; c <= layer_chunks(l); ++c) {
-                        ptx::mbar_wait(&w_full[st], cyc & 1);
-                        ptx::mbar_arrive_cluster(full0 + st * 8);
-                        if (++st == CH_NSTAGE) { st = 0; ++cyc; }
-                    }
-        }
-    } else if (warp == 1) {
-        // ================= leader CTA: MMA issuer (converged warp, one elected lane issues) =================
-        uint32_t st = 0, cyc = 0, cph = 0, tph = 0;         // ring position; parity of the chunk barriers, of the per-tile barriers
-        const uint32_t act_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + CH_ACT), KROW);
-        const uint32_t enc_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + CH_ENC), KROW);
-        const uint32_t ones_lo = ptx::smem_desc_lo(ptx::smem_addr(smem + CH_ONES), KROW);
-        const uint32_t ring_a = ptx::smem_addr(smem + CH_RING) >> 4;
-        const uint32_t desc_hi = ptx::smem_desc_hi(128);
-        for (int64_t unit = unit0; unit < nunits; unit += unit_step) {
-            for (int l = 0; l < NLAYER; ++l) {
-                const int hrows = layer_rows(l) / 2, nch = layer_chunks(l);
-                const uint32_t idesc = ptx::idesc_bf16(2 * TILE, 2 * hrows, 0, 0);
-                const uint32_t b_lbo = (uint32_t)hrows << 16, b_kstep = (uint32_t)hrows * 2;
-                const uint32_t tacc = tmem_base + (uint32_t)(l & 1) * WIDTH;
-                if (l == 0) {
-                    // the whole encoded tile first: it also tells that the previous unit's last epilogue has drained accumulator 0
-                    ptx::mbar_wait_fast(&enc_rdy[0], tph);
-                    ptx::mbar_wait_fast(&enc_rdy[1], tph);
-                }
-                for (int c = 0; c < nch; ++c) {
-                    const bool from_enc = (l == 0) || (c >= 8);
-                    if (!from_enc) ptx::mbar_wait_fast(&chunk_rdy[c], cph);
-                    else if (l == 8) ptx::mbar_wait_fast(venc_rdy, tph);
-                    ptx::mbar_wait(&w_full[st], cyc & 1);
-                    ptx::tc_fence_after();
-                    const uint32_t a_lo = (from_enc ? enc_lo : act_lo) + (uint32_t)((l == 0 || c < 8) ? c : c - 8) * (CHUNK_K / 8) * (KROW >> 4);
-                    const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
-                    if (ptx::elect_one()) {
-                        ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
-                        ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
-                        ptx::mma2_commit(&w_empty[st]);
-                    }
-                    __syncwarp();
-                    if (++st == CH_NSTAGE) { st = 0; ++cyc; }
-                }
-                {   // bias: D += ones[256 x 16] . [bf16(b), b - bf16(b), 0 ...]^T
-                    ptx::mbar_wait(&w_full[st], cyc & 1);
-                    ptx::tc_fence_after();
-                    const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
-                    if (ptx::elect_one()) {
-                        ptx::mma2_bf16_w(tacc, ones_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
-                        ptx::mma2_commit(&w_empty[st]);
-                        ptx::mma2_commit(&acc_full[l & 1]);
-                    }
-                    __syncwarp();
-                    if (++st == CH_NSTAGE) { st = 0; ++cyc; }
-                }
-                if (l >= 1) cph ^= 1;          // the chunk barriers complete once per layer that reads the A tile
-            }
-            tph ^= 1;
-        }
-    } else if (warp >= 4) {
-        // ================= epilogue warps (two threads per sample row, 128 accumulator columns each) =================
-        const int e = warp - 4, half = e >> 2;
-        const int row = ((warp & 3) << 5) | lane;                    // TMEM lanes 32 (warp % 4) ..
-        uint8_t* act = smem + CH_ACT;
-        uint8_t* enc = smem + CH_ENC;
-        float* xch = reinterpret_cast<float*>(smem + CH_XCH) + row * 3;
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t chunk_bar0 = ptx::mapa(&chunk_rdy[0], 0), enc_bar0 = ptx::mapa(&enc_rdy[0], 0), venc_bar = ptx::mapa(venc_rdy, 0);
-        uint32_t use0 = 0, use1 = 0;                                  // phases consumed of the two accumulator barriers
-        for (int64_t unit = unit0; unit < nunits; unit += unit_step) {
-            const int64_t tile = unit * 2 + rank;
-            const int64_t g = tile * TILE + row;
-            const bool valid = tile < ntiles && g < S;
-            uint8_t* save_tile = (save && tile < ntiles) ? save + tile * SAVE_TILE_BYTES : nullptr;
-            uint32_t* mask_tile = save_tile ? reinterpret_cast<uint32_t*>(save_tile + SV_MASK) : nullptr;
-            float v3[3] = {0.f, 0.f, 1.f};
-            {
-                float x[3] = {0.f, 0.f, 0.f};
-                if (valid) {
-                    const int64_t r = g / N;
-                    const float d = depth[g];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        v3[c] = ray[r * 3 + c];
-                        x[c] = __fadd_rn(center[r * 3 + c], __fmul_rn(v3[c], d));
-                    }
-                }
-                if (half == 0) write_enc_half<0>(enc, save_tile ? save_tile + SV_ENC : nullptr, row, x, bw3, valid);
-                else write_enc_half<1>(enc, save_tile ? save_tile + SV_ENC : nullptr, row, x, bw3, valid);
-            }
-            ptx::tc_fence_before();
-            ptx::fence_proxy_async();
-            ptx::warp_arrive_cluster(enc_bar0 + half * 8);
-            for (int l = 0; l < NLAYER; ++l) {
-                const int a = l & 1;
-                ptx::mbar_wait_fast(&acc_full[a], (a ? use1 : use0) & 1);
-                if (a) ++use1; else ++use0;
-                ptx::tc_fence_after();
-                uint32_t va[32], vb[32], pk[16];
-                if (l < 8) {
-                    uint8_t* save_img = save_tile ? save_tile + SV_H + (int64_t)l * ACT_BYTES : nullptr;
-                    uint32_t* flags = mask_tile ? mask_tile + l * MASK_WORDS * TILE : nullptr;
-                    const uint32_t tacc = lane_base + a * WIDTH + half * (WIDTH / 2);
-                    float sig_acc = 0.f;
-                    ptx::tmem_ld32(tacc, va);
-#pragma unroll
-                    for (int c1 = 0; c1 < 4; ++c1) {
-                        const int cc = half * 4 + c1;                  // 32-column chunk = K-chunk cc of the next layer's A tile
-                        uint32_t (&cur)[32] = (c1 & 1) ? vb : va;
-                        ptx::tmem_ld_wait();
-                        if (c1 + 1 < 4) ptx::tmem_ld32(tacc + (c1 + 1) * 32, (c1 & 1) ? va : vb);
-                        epilogue_chunk(cur, cc, row, WIDTH, act, save_img, flags, pk);
-                        if (l == 6) {   // density head: row 0 of layer 7 applied to h6 (nerf.py:427)
-                            const float4* w = reinterpret_cast<const float4*>(cst + C_W7R0 + cc * 32);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 w4 = w[q];
-                                sig_acc += w4.x * bf16_lo(pk[2 * q]) + w4.y * bf16_hi(pk[2 * q]) +
-                                           w4.z * bf16_lo(pk[2 * q + 1]) + w4.w * bf16_hi(pk[2 * q + 1]);
-                            }
-                        }
-                        if (c1 == 3) ptx::tc_fence_before();          // this warp's TMEM reads of the accumulator are done
-                        ptx::fence_proxy_async();
-                        ptx::warp_arrive_cluster(chunk_bar0 + cc * 8); // the issuer may multiply K-chunk cc of the next layer
-                    }
-                    if (l == 7 && half == 1) {   // A columns 256..287 of rgb0
-                        write_venc_row(enc, save_tile ? save_tile + SV_VENC : nullptr, row, v3, bwv, valid);
-                        ptx::fence_proxy_async();
-                        ptx::warp_arrive_cluster(venc_bar);
-                    }
-                    if (l == 6) {     // the two column halves of the density dot product meet in shared memory
-                        if (half == 1) xch[0] = sig_acc;
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
-                        if (half == 0 && valid) {
-                            float pre = sig_acc + xch[0] + cst[C_MISC];
-                            sigma_out[g] = softplus_f(pre);
-                            if (sig_pre) sig_pre[g] = pre;
-                        }
-                    }
-                } else {
-                    // rgb0 epilogue: hr = relu(.), rgb = sigmoid(W_rgb1 hr + b)   (nerf.py:442-446); 64 columns per thread
-                    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-                    uint8_t* save_img = save_tile ? save_tile + SV_HR : nullptr;
-                    uint32_t* flags = mask_tile ? mask_tile + 8 * MASK_WORDS * TILE : nullptr;
-                    const uint32_t tacc8 = lane_base + a * WIDTH + half * (RGBW / 2);
-#pragma unroll 1
-                    for (int c1 = 0; c1 < RGBW / 64; ++c1) {
-                        const int cc = half * 2 + c1;
-                        ptx::tmem_ld32(tacc8 + c1 * 32, va);
-                        ptx::tmem_ld_wait();
-                        epilogue_chunk(va, cc, row, RGBW, nullptr, save_img, flags, pk);
-                        const float4* w0 = reinterpret_cast<const float4*>(cst + C_WRGB1 + cc * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float x = bf16_lo(pk[2 * q]), y = bf16_hi(pk[2 * q]), z = bf16_lo(pk[2 * q + 1]), w = bf16_hi(pk[2 * q + 1]);
-                            const float4 x0 = w0[q], x1 = w0[RGBW / 4 + q], x2 = w0[2 * RGBW / 4 + q];
-                            o0 += x0.x * x + x0.y * y + x0.z * z + x0.w * w;
-                            o1 += x1.x * x + x1.y * y + x1.z * z + x1.w * w;
-                            o2 += x2.x * x + x2.y * y + x2.z * z + x2.w * w;
-                        }
-                    }
-                    ptx::tc_fence_before();   // TMEM reads done before the next unit's layer 0 overwrites accumulator 0
-                    if (half == 1) { xch[0] = o0; xch[1] = o1; xch[2] = o2; }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (half == 0 && valid) {
-                        float r0 = sigmoid_f(o0 + xch[0] + cst[C_MISC + 1]), r1 = sigmoid_f(o1 + xch[1] + cst[C_MISC + 2]),
-                              r2 = sigmoid_f(o2 + xch[2] + cst[C_MISC + 3]);
-                        rgb_out[g * 3] = r0; rgb_out[g * 3 + 1] = r1; rgb_out[g * 3 + 2] = r2;
-                        if (rgb_keep) { rgb_keep[g * 3] = r0; rgb_keep[g * 3 + 1] = r1; rgb_keep[g * 3 + 2] = r2; }
-                    }
-                }
-            }
-        }
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync_all();            // neither CTA leaves while its peer may still touch its shared memory / TMEM
-    if (warp == 2) ptx::tmem_dealloc2(tmem_base, 512);
-}
-
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------
@@ -826,18 +519,6 @@ int tc_fwd(const float* P, const float* center, const float* ray, const float* d
     if (!prepacked) {
         int e = tc_pack(P, c2f, training, R, N, ws, ws_bytes, st);
         if (e) return e;
-    }
-    static const bool chain = getenv("NIW_FWD_CHAIN") != nullptr && atoi(getenv("NIW_FWD_CHAIN")) != 0;
-    if (chain) {
-        NIW_CUDA(cudaFuncSetAttribute(tc_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_TOTAL));
-        const int64_t nunits = ((S + TILE - 1) / TILE + 1) / 2;   // two tiles per CTA pair and round
-        int64_t prs = niw_num_sms() / 2;
-        if (prs > nunits) prs = nunits;
-        niw::note_launch(), tc_fwd_chain_kernel<<<(int)(2 * (prs < 1 ? 1 : prs)), 384, CH_TOTAL, st>>>(
-            w.wstream, w.consts, center, ray, depth, S, N, rgb, sigma, training ? w.sig_pre : nullptr,
-            training ? w.rgb_keep : nullptr, training ? w.save : nullptr);
-        NIW_LAUNCH_CHECK();
-        return 0;
     }
     NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     const int64_t nquads = ((S + TILE - 1) / TILE + 3) / 4;     // four tiles per CTA pair and round
