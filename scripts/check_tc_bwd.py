@@ -3,7 +3,6 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from neural_invertible_warp_b200 import functional as F, synthetic as syn
-from oracle import reference_port as ora
 
 DEV = "cuda:0"
 keys = []
@@ -18,7 +17,7 @@ flat0 = torch.cat([p[k].reshape(-1) for k in keys]).to(DEV)
 center0 = (torch.randn(R, 3, generator=gen) * 0.1).to(DEV)
 ray0 = (torch.randn(R, 3, generator=gen) * 0.3 + torch.tensor([0., 0., 1.])).to(DEV)
 u = torch.rand(1, R, N, 1, generator=gen)
-depth = ora.stratified_depth(u, N, [1.2, 5.2], "metric")[0, ..., 0].to(DEV)
+depth = F.sample_stratified(u.reshape(-1).to(DEV), R, N, [1.2, 5.2], "metric")      # the product sampler (bit-exact with the reference)
 prog, c2f = 0.3, [0.1, 0.5]
 target = torch.rand(R, 3, generator=gen).to(DEV)
 mode = sys.argv[3] if len(sys.argv) > 3 else "mse"
