@@ -418,6 +418,34 @@ def golden_metrics():
     save("metrics", out)
 
 
+def golden_eval_slices():
+    """Full-frame evaluation render of the reference: ``Graph.forward(mode="eval")`` -> ``render_by_slices``
+    (model/nerf.py:251-274,321-332) on a small frame with a ragged last slice, BARF model with the test poses mapped
+    through a non-trivial sim3 (model/barf.py:235-246), un-stratified sampling (no draws), plus PSNR / SSIM of the frame."""
+    barf = ref_shim.import_reference("model.barf")
+    camera = ref_shim.import_reference("camera")
+    pytorch_ssim = ref_shim.import_reference("external.pohsun_ssim.pytorch_ssim")
+    H, W, B = 13, 18, 2
+    opt = _opt("barf_llff", "barf", parent="nerf_inn_llff", barf_c2f=[0.1, 0.5], data=dict(image_size=[H, W]),
+               nerf=dict(rand_rays=50, sample_intvs=16, sample_stratified=False), optim=dict(test_photo=False))
+    graph = barf.Graph(opt)
+    load_nerf(graph.nerf, syn.nerf_params(95))
+    graph.nerf.progress.data.fill_(0.4)
+    gen = torch.Generator().manual_seed(96)
+    graph.sim3 = ref_shim._AttrDict(t0=torch.randn(1, 3, generator=gen) * 0.1, t1=torch.randn(1, 3, generator=gen) * 0.1,
+                                    s0=torch.tensor(1.2), s1=torch.tensor(0.9),
+                                    R=camera.lie.so3_to_SO3(torch.randn(3, generator=gen) * 0.1))
+    var = _synthetic_var(opt, B, 97)
+    with torch.no_grad():
+        var = graph.forward(opt, var, mode="eval")
+        rgb_map = var.rgb.view(-1, H, W, 3).permute(0, 3, 1, 2)
+        psnr = [(-10 * ((rgb_map[b:b + 1].contiguous() - var.image[b:b + 1]) ** 2).mean().log10()).item() for b in range(B)]
+        ssim = [pytorch_ssim.ssim(rgb_map[b:b + 1], var.image[b:b + 1]).item() for b in range(B)]
+    save("eval_slices", dict(H=H, W=W, B=B, rand_rays=50, N=16, nerf_seed=95, var_seed=97, progress=0.4,
+                             sim3=dict(t0=graph.sim3.t0, t1=graph.sim3.t1, s0=graph.sim3.s0, s1=graph.sim3.s1, R=graph.sim3.R),
+                             rgb=var.rgb.clone(), depth=var.depth.clone(), opacity=var.opacity.clone(), psnr=psnr, ssim=ssim))
+
+
 def golden_options():
     """Hot-path option fields of the YAMLs the target models use (checked against config.py)."""
     out = {}
@@ -436,6 +464,6 @@ def golden_options():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["camera", "sampler", "nerf_mlp", "composite", "nvp", "graph_barf",
-                             "graph_inn_llff", "graph_inn_dtu", "options", "state_dicts", "test_optim", "metrics"]
+                             "graph_inn_llff", "graph_inn_dtu", "options", "state_dicts", "test_optim", "metrics", "eval_slices"]
     for w in which:
         globals()["golden_" + w]()

@@ -320,3 +320,25 @@ def test_evaluate_view_matches_oracle_metrics(eng):
     rgb_map = res.var.rgb.cpu().view(-1, H, W, 3).permute(0, 3, 1, 2)
     assert abs(res.psnr.item() - ora.psnr(rgb_map, var.image.cpu()).item()) < 1e-4
     assert abs(res.ssim.item() - ora.ssim(rgb_map, var.image.cpu()).item()) < 1e-5
+
+
+def test_eval_full_frame_by_slices_golden(eng, golden):
+    """Row a10, eval side: the reference's ``Graph.forward(mode="eval")`` -> ``render_by_slices`` on a whole (small) frame
+    with a ragged last slice and a non-trivial sim3 test-pose alignment, and the frame's PSNR / SSIM (row f3), against
+    the executed reference."""
+    g = golden("eval_slices")
+    H, W, B = g["H"], g["W"], g["B"]
+    opt = cfgmod.builtin_options("barf_llff", model="barf", barf_c2f=[0.1, 0.5], device=DEV, data=dict(image_size=[H, W]),
+                                 nerf=dict(rand_rays=g["rand_rays"], sample_intvs=g["N"], sample_stratified=False),
+                                 optim=dict(test_photo=False), arch=dict(mlp_precision="fp32"))
+    graph = eng.build_graph(opt, B)
+    load_nerf(graph.nerf, syn.nerf_params(g["nerf_seed"]))
+    graph.nerf.progress.data.fill_(g["progress"])
+    graph.sim3 = cfgmod.AttrDict({k: v.to(DEV) for k, v in g["sim3"].items()})
+    var = eng.synthetic_var(opt, B, g["var_seed"])
+    res = eng.evaluate_view(opt, graph, var, test_optim=False)
+    close(res.var.rgb, g["rgb"], rtol=1e-4, atol=2e-5)
+    close(res.var.opacity, g["opacity"], rtol=1e-4, atol=2e-5)
+    close(res.var.depth, g["depth"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(res.psnr.cpu(), torch.tensor(g["psnr"]), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(res.ssim.cpu(), torch.tensor(g["ssim"]), rtol=1e-4, atol=1e-5)
