@@ -262,6 +262,22 @@ def golden_graph_barf():
                             grads=grad_digest({k: v.grad for k, v in graph.nerf.named_parameters() if v.grad is not None})))
 
 
+def golden_graph_nerf():
+    """Plain NeRF with given poses (model/nerf.py Graph :243-365, NeRF :367-483): no pose refinement, no c2f weighting."""
+    nerf = ref_shim.import_reference("model.nerf")
+    opt = _opt("nerf_inn_llff", "nerf", data=dict(image_size=[24, 32]), nerf=dict(rand_rays=40, sample_intvs=16))
+    B = 2
+    graph = nerf.Graph(opt)
+    load_nerf(graph.nerf, syn.nerf_params(55))
+    var = _synthetic_var(opt, B, 56)
+    var, loss, total, log = _finish_graph(graph, opt, var, "train")
+    save("graph_nerf", dict(B=B, H=24, W=32, N=16, rand_rays=40, param_seed=55, var_seed=56,
+                            ray_idx=log["randperm"][0][:40 // B], u=log["rand"][0], rgb=var.rgb.detach(),
+                            depth=var.depth.detach(), opacity=var.opacity.detach(), loss=total.detach(),
+                            keys=sorted(graph.state_dict().keys()),
+                            grads=grad_digest({k: v.grad for k, v in graph.nerf.named_parameters() if v.grad is not None})))
+
+
 def golden_graph_inn_llff():
     mod = ref_shim.import_reference("model.barf_inn_llff")
     nvp = ref_shim.import_reference("model.nvp.nvp_ndr")
@@ -463,7 +479,7 @@ def golden_options():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["camera", "sampler", "nerf_mlp", "composite", "nvp", "graph_barf",
+    which = sys.argv[1:] or ["camera", "sampler", "nerf_mlp", "composite", "nvp", "graph_barf", "graph_nerf",
                              "graph_inn_llff", "graph_inn_dtu", "options", "state_dicts", "test_optim", "metrics", "eval_slices"]
     for w in which:
         globals()["golden_" + w]()
