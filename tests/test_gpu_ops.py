@@ -481,6 +481,25 @@ def test_ops_refuse_cpu_tensors(F):
         F.composite(torch.zeros(2, 3), torch.zeros(2, 4, 3), torch.zeros(2, 4), torch.zeros(2, 4))
 
 
+def test_ops_reject_empty_and_unsupported_shapes(F):
+    """Error behaviour at the edges: the C ABI returns a code (never a silent no-op, never a fallback) and the wrappers
+    raise -- empty batches, a sampler shape beyond its shared-memory budget, a non-8x256 parameter vector, and the
+    single-ray / single-sample corner still computes."""
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    with pytest.raises(RuntimeError):
+        F.composite(z(0, 3), z(0, 4, 3), z(0, 4), z(0, 4))
+    with pytest.raises(RuntimeError):
+        F.sample_stratified(None, 0, 8, [1.0, 2.0], "metric", device=DEV)
+    with pytest.raises(RuntimeError):
+        F.sample_pdf_merge(z(2, 4096), z(2, 4096), 4096, [1.0, 2.0])          # N + Nf beyond the in-kernel sort budget
+    with pytest.raises(RuntimeError):
+        F.nerf_forward_samples(z(1000), z(1, 3), z(1, 3), z(1, 1), None, None, "fp32", training=False)
+    rgb, d, op, prob = F.composite(torch.ones(1, 3, device=DEV), torch.full((1, 1, 3), 0.5, device=DEV), torch.ones(1, 1, device=DEV),
+                                   torch.ones(1, 1, device=DEV))
+    torch.testing.assert_close(op.cpu(), torch.ones(1))                       # one sample: last interval 1e10 -> opaque
+    torch.testing.assert_close(rgb.cpu(), torch.full((1, 3), 0.5))
+
+
 def test_flat_adam_matches_torch_adam():
     """niw_adam_step (row f2) vs torch.optim.Adam + ExponentialLR (model/nerf.py:33-46) on two groups with odd sizes,
     20 steps, weight decay off/on."""
