@@ -186,6 +186,11 @@ int niw_image_metrics(const float* pred_rgb, const float* image, int B, int H, i
 int niw_depth_metrics(const float* pred, const float* gt, const uint8_t* valid, int64_t n, float scale, float* out,
                       void* stream);
 
+/* ---- rigid registration of the global-alignment loss (row f1)   model/nerf_inn_llff.py:563-572, model/pose_models/inn.py:96-102
+ * (roma.rigid_points_registration, roma==1.4.1).  x, y [B,M,3] -> the least-squares proper rotation R [B,3,3] and
+ * translation t [B,3] with y ~ R x + t (Kabsch optimum via Horn's quaternion form, fp64 Jacobi; no host sync). */
+int niw_kabsch(const float* x, const float* y, int B, int M, float* R, float* t, void* stream);
+
 /* ---- optimiser step (row f2): torch.optim.Adam + ExponentialLR over ONE flat fp32 segment
  *      model/nerf.py:33-46,87,92 (optim / sched), model/barf_inn_llff.py:84-120 (optim_pose)
  * params/grads/exp_avg/exp_avg_sq [n] (16-byte aligned).  `state` is a DEVICE array of 2 floats owned by the

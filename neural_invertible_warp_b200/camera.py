@@ -5,8 +5,9 @@ Split of work, following SURVEY.md section 8:
 * everything that is *per ray* runs in CUDA (csrc/raygen.cu) and never materialises the full
   ``B x HW`` pixel grid the reference builds (camera.py:430-443): ``get_center_and_ray`` and
   ``get_unwarped_center_and_ray`` generate only the requested pixels;
-* everything that is *per image* (``B`` poses: Lie algebra, pose composition, Kabsch) stays in
-  PyTorch on the device -- a handful of 3x3 operations whose autograd PyTorch handles.
+* everything that is *per image* (``B`` poses: Lie algebra, pose composition) stays in PyTorch on the
+  device -- a handful of 3x3 operations whose autograd PyTorch handles; the Kabsch fit of the
+  global-alignment loss (no gradient) is one kernel (csrc/kabsch.cu).
 
 Names, argument meaning and return conventions follow the reference (``camera.pose``,
 ``camera.lie``, ``camera.cam2world`` ...), so model code written against it reads the same.
@@ -222,6 +223,8 @@ def rigid_points_registration(x, y):
     """roma's convention: the least-squares R, t with y ~ R x + t (batched Kabsch with the det
     fix).  The reference calls it as (target, source), i.e. it fits the world->camera map
     source ~ R target + t, which ``cam2world`` then inverts.  x, y [B,M,3] -> R [B,3,3], t [B,3]."""
+    if x.is_cuda:
+        return F.kabsch(x, y)          # one kernel, no SVD library call, capturable (csrc/kabsch.cu)
     mu_x = x.mean(dim=1, keepdim=True)
     mu_y = y.mean(dim=1, keepdim=True)
     M = (y - mu_y).transpose(1, 2) @ (x - mu_x)

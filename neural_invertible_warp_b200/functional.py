@@ -505,6 +505,21 @@ def depth_metrics(pred, gt, valid=None, scale=1.0):
     return abs_e, rmse
 
 
+def kabsch(x, y):
+    """roma.rigid_points_registration(x, y) as the reference uses it (model/nerf_inn_llff.py:569,
+    model/pose_models/inn.py:100): the least-squares R [B,3,3], t [B,3] with y ~ R x + t, for x, y [B,M,3].  No gradient
+    (the reference detaches the result), no host synchronisation."""
+    lib = _lib.load()
+    x, y = _f32(x.detach(), "x"), _f32(y.detach(), "y")
+    B, M = x.shape[0], x.shape[1]
+    if x.shape != y.shape or x.shape[-1] != 3:
+        raise RuntimeError("niw_b200: kabsch expects two [B,M,3] point sets")
+    R = torch.empty(B, 3, 3, device=x.device, dtype=torch.float32)
+    t = torch.empty(B, 3, device=x.device, dtype=torch.float32)
+    _lib.check(lib.niw_kabsch(_p(x), _p(y), B, M, _p(R), _p(t), _stream()))
+    return R, t
+
+
 def sample_pixels(n, k, counter, seed=0):
     """First k entries of a random permutation of range(n) (the reference's ``torch.randperm(n)[:k]``,
     model/nerf.py:268) in O(k): int64 [k] on ``counter``'s device.  ``counter`` is a zero-initialised int64 [1]

@@ -481,6 +481,29 @@ def test_ops_refuse_cpu_tensors(F):
         F.composite(torch.zeros(2, 3), torch.zeros(2, 4, 3), torch.zeros(2, 4), torch.zeros(2, 4))
 
 
+def test_kabsch_matches_svd_solution(F):
+    """Row f1: niw_kabsch (Horn's quaternion form, fp64 Jacobi) against the SVD-based batched Kabsch with the det fix
+    (what roma.rigid_points_registration computes) on noisy rigid motions, including a near-reflection case where the
+    det fix matters and the reference's own usage (P grid rows + the centre repeated P times)."""
+    from neural_invertible_warp_b200 import camera
+    gen = torch.Generator().manual_seed(21)
+    B, M = 6, 96
+    x = torch.randn(B, M, 3, generator=gen)
+    x[1, :, 2] *= 1e-3                                                  # nearly planar cloud
+    x[2, M // 2:] = x[2, :1]                                            # half of the rows are one repeated point
+    w = torch.randn(B, 3, generator=gen) * 0.8
+    Rt = camera.lie.so3_to_SO3(w)
+    y = x @ Rt.transpose(1, 2) + torch.randn(B, 1, 3, generator=gen) + 0.01 * torch.randn(B, M, 3, generator=gen)
+    y[3] = y[3] * torch.tensor([1.0, 1.0, -1.0])                       # mirrored target: the unconstrained optimum is a reflection
+    R_ref, t_ref = camera.rigid_points_registration(x, y)              # CPU: torch SVD path
+    R, t = F.kabsch(x.to(DEV), y.to(DEV))
+    torch.testing.assert_close(R.cpu(), R_ref, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(t.cpu(), t_ref, rtol=1e-4, atol=2e-5)
+    assert torch.allclose(torch.linalg.det(R.cpu()), torch.ones(B), atol=1e-5)
+    R2, t2 = camera.rigid_points_registration(x.to(DEV), y.to(DEV))    # the product path dispatches to the kernel
+    assert torch.equal(R2, R) and torch.equal(t2, t)
+
+
 def test_ops_reject_empty_and_unsupported_shapes(F):
     """Error behaviour at the edges: the C ABI returns a code (never a silent no-op, never a fallback) and the wrappers
     raise -- empty batches, a sampler shape beyond its shared-memory budget, a non-8x256 parameter vector, and the
