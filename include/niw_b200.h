@@ -116,6 +116,10 @@ int niw_sample_pixels(int64_t n, int k, uint64_t seed, uint64_t* counter, int64_
  * rounding sequence (no FMA contraction).  u [n_rays*N] or NULL (=0.5, un-stratified). */
 int niw_sample_stratified(const float* u, int64_t n_rays, int N, float scale, float dmin, int inverse,
                           float* depth, void* stream);
+/* same with the depth range [min, max] read from DEVICE memory (the DTU graphs carry it as a tensor, data/dtu.py:110-111):
+ * no host read of the range, so the step can be captured in a CUDA graph */
+int niw_sample_stratified_dev(const float* u, int64_t n_rays, int N, const float* range_dev, int inverse, float* depth,
+                              void* stream);
 
 /* ---- (a5) Graph.sample_depth_from_pdf + cat + sort   model/nerf.py:346-365, :313-315
  * pdf [R,N]; unif [Nf] = 0.5*(grid[:-1]+grid[1:]); bins [N+1] = linspace(dmin,dmax,N+1) (both made

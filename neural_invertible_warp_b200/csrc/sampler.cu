@@ -14,7 +14,8 @@ namespace {
 template <bool POW2>
 __global__ void __launch_bounds__(256)
 stratified_kernel(const float* __restrict__ u, int64_t total, int N, float scale, float dmin, int inverse,
-                  float* __restrict__ depth) {
+                  float* __restrict__ depth, const float* __restrict__ range_dev) {
+    if (range_dev) { dmin = range_dev[0]; scale = __fsub_rn(range_dev[1], range_dev[0]); }   // (max - min) as the reference evaluates it
     const float fN = (float)N, rN = 1.0f / (float)N;
     const int64_t ngroups = (total + 3) >> 2, gstride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gstride) {
@@ -410,20 +411,31 @@ __global__ void sample_pixels_kernel(int64_t n, int k, uint64_t seed, unsigned l
 
 }  // namespace
 
-extern "C" int niw_sample_stratified(const float* u, int64_t n_rays, int N, float scale, float dmin, int inverse,
-                                     float* depth, void* stream) {
-    NIW_CHECK_ARG(depth && n_rays > 0 && N > 0);
+static int launch_stratified(const float* u, int64_t n_rays, int N, float scale, float dmin, const float* range_dev,
+                             int inverse, float* depth, cudaStream_t st) {
     int64_t total = n_rays * N;
     int64_t blocks = niw_blocks((total + 3) / 4, 256);
     const int64_t cap = (int64_t)niw_num_sms() * 16;              // grid-stride: 8 resident CTAs / SM x 2 rounds
     if (blocks > cap) blocks = cap;
     niw::note_launch();
     if ((N & (N - 1)) == 0)
-        stratified_kernel<true><<<(unsigned)blocks, 256, 0, niw_stream(stream)>>>(u, total, N, scale, dmin, inverse, depth);
+        stratified_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(u, total, N, scale, dmin, inverse, depth, range_dev);
     else
-        stratified_kernel<false><<<(unsigned)blocks, 256, 0, niw_stream(stream)>>>(u, total, N, scale, dmin, inverse, depth);
+        stratified_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(u, total, N, scale, dmin, inverse, depth, range_dev);
     NIW_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int niw_sample_stratified(const float* u, int64_t n_rays, int N, float scale, float dmin, int inverse,
+                                     float* depth, void* stream) {
+    NIW_CHECK_ARG(depth && n_rays > 0 && N > 0);
+    return launch_stratified(u, n_rays, N, scale, dmin, nullptr, inverse, depth, niw_stream(stream));
+}
+
+extern "C" int niw_sample_stratified_dev(const float* u, int64_t n_rays, int N, const float* range_dev, int inverse,
+                                         float* depth, void* stream) {
+    NIW_CHECK_ARG(depth && range_dev && n_rays > 0 && N > 0);
+    return launch_stratified(u, n_rays, N, 0.f, 0.f, range_dev, inverse, depth, niw_stream(stream));
 }
 
 template <int CN, int CF>

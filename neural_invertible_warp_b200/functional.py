@@ -206,7 +206,6 @@ def sample_stratified(u, n_rays, N, depth_range, param, device=None):
     """Graph.sample_depth (model/nerf.py:334-344).  u: [n_rays*N] uniforms or None (0.5).
     Returns depth [n_rays, N].  Bit-exact with the reference's fp32 CPU evaluation."""
     lib = _lib.load()
-    dmin, dmax = float(depth_range[0]), float(depth_range[1])
     u = _f32(u, "u")
     device = u.device if u is not None else device
     if u is not None and u.numel() != n_rays * N:
@@ -214,6 +213,12 @@ def sample_stratified(u, n_rays, N, depth_range, param, device=None):
     if param not in ("metric", "inverse"):
         raise KeyError(param)
     depth = torch.empty(n_rays, N, device=device, dtype=torch.float32)
+    if torch.is_tensor(depth_range) and depth_range.is_cuda:
+        # [min, max] stays on the device: no host read, the step remains capturable
+        rng = _f32(depth_range.reshape(-1)[:2], "depth_range")
+        _lib.check(lib.niw_sample_stratified_dev(_p(u), n_rays, N, _p(rng), int(param == "inverse"), _p(depth), _stream()))
+        return depth
+    dmin, dmax = float(depth_range[0]), float(depth_range[1])
     _lib.check(lib.niw_sample_stratified(_p(u), n_rays, N, dmax - dmin, dmin, int(param == "inverse"), _p(depth),
                                          _stream()))
     return depth

@@ -244,7 +244,8 @@ class RenderCore(nn.Module):
         draws come from ``torch.rand`` exactly as in the reference, so a shared seed gives shared
         jitter; the arithmetic runs in one kernel with the reference's rounding sequence."""
         rng = opt.nerf.depth.range if depth_range is None else depth_range
-        rng = [float(rng[0]), float(rng[1])]
+        if not (torch.is_tensor(rng) and rng.is_cuda):           # a device tensor [min, max] is read by the kernel itself
+            rng = [float(rng[0]), float(rng[1])]
         num_rays = num_rays or opt.H * opt.W
         N = opt.nerf.sample_intvs
         u = torch.rand(batch_size, num_rays, N, 1, device=opt.device) if opt.nerf.sample_stratified else None

@@ -23,10 +23,10 @@ class Graph(base.Graph):
         """model/nerf_inn_dtu.py:371-396."""
         batch_size = len(var.idx)
         depth_range = opt.nerf.depth.range if opt.nerf.depth.param == "inverse" else var.depth_range[0]
-        if torch.is_tensor(depth_range):
-            # two floats that parameterise the sampler kernel (the reference unpacks the same
-            # tensor element-wise, nerf_inn_dtu.py:536); one host read per step
+        if torch.is_tensor(depth_range) and not depth_range.is_cuda:
             depth_range = [float(v) for v in depth_range.tolist()]
+        # (a CUDA tensor [min, max] goes to the sampler kernel as it is -- the reference unpacks it element-wise on the
+        # host, nerf_inn_dtu.py:536; here there is no host read, so the step can be captured in a CUDA graph)
         if opt.nerf.rand_rays and mode in ["train", "test-optim"]:
             var.ray_idx = torch.randperm(opt.H * opt.W, device=opt.device)[:opt.nerf.rand_rays // batch_size]
             ray, center, grid_3d = self.get_pose(opt, var, mode=mode, iter=iter)

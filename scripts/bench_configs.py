@@ -67,9 +67,22 @@ def c3(args, flush):
     ms, k = timed(step, args.steps, flush)
     rays = B * P
     evals = rays * (N + N + Nf)                      # coarse net on 64, fine net on 64 + 128
-    return dict(config="c3", workload="barf_inn_dtu train step, 300x400, %d images x %d rays, %d coarse + %d fine samples, fwd+bwd (eager launches)" % (B, P, N, Nf),
-                rays=rays, ms_per_step=ms, rays_per_s=rays / ms * 1e3, mlp_evals_per_s=evals / ms * 1e3,
-                mlp_flop=3 * MLP_FLOP * evals, kernels=k)
+    out = dict(config="c3", workload="barf_inn_dtu train step, 300x400, %d images x %d rays, %d coarse + %d fine samples, fwd+bwd (eager launches)" % (B, P, N, Nf),
+               rays=rays, ms_per_step=ms, rays_per_s=rays / ms * 1e3, mlp_evals_per_s=evals / ms * 1e3,
+               mlp_flop=3 * MLP_FLOP * evals, kernels=k)
+    # the same step as ONE CUDA-graph replay (device RNG, depth range read on the device, Kabsch fit in a kernel: no host sync)
+    try:
+        draws = engine.device_ray_draws(DEV, seed=7)
+
+        def step_dev():
+            with draws:
+                engine.train_step(opt, graph, cfgmod.AttrDict(var0), 5000)
+        captured = engine.CapturedStep(step_dev, warmup=2)
+        ms_g, _ = timed(captured, args.steps, flush)
+        out.update(ms_per_step_graph=ms_g, rays_per_s_graph=rays / ms_g * 1e3)
+    except Exception as e:          # report, do not hide
+        out.update(graph_capture_error=str(e).splitlines()[0])
+    return out
 
 
 def c4(args, flush):
