@@ -444,10 +444,17 @@ constexpr int PACK_THREADS = 1024;
 
 // squared row norm of v[j][0..ld) by one warp (coalesced)
 __device__ __forceinline__ float row_norm2(const float* __restrict__ row, int ld, int lane) {
+    // ld <= EA + DF = 154 < 160: all five loads of a lane are issued before the first is used (the rolled loop paid one
+    // global-memory latency per 32 columns, 40 in sequence for a warp's 8 rows)
+    float t[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { const int c = lane + 32 * i; t[i] = c < ld ? row[c] : 0.f; }
     float a = 0.f;
-    for (int c = lane; c < ld; c += 32) { float t = row[c]; a += t * t; }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) a += t[i] * t[i];
     return warp_sum(a);
 }
+static_assert(EA + DF <= 160 && EB + DF <= 160, "row_norm2 covers 160 columns");
 
 // Grid (coupling block, split): the work of one block is latency-bound in a single CTA (about 270 k warp
 // instructions), so it is spread over `gridDim.y` CTAs.  Every reduction is done by a warp with the lanes along
