@@ -4,7 +4,7 @@
  *
  * The reference has NO native boundary (it is eager PyTorch); each entry point below replaces a
  * chain of ATen ops inside one reference Python function, cited as reference file:line.  The
- * Python mirror of the reference's Graph/NeRF API (neural_invertible_warp_b200/*.py) binds these
+ * Python mirror of the reference's Graph/NeRF API (the .py files of neural_invertible_warp_b200) binds these
  * symbols with ctypes and calls them from torch.autograd.Function.forward/backward; see
  * INTEGRATION.md for the binding a reference maintainer would add.
  *

@@ -49,3 +49,20 @@ def test_ops_fail_loudly_without_cuda():
     from neural_invertible_warp_b200 import functional as F
     with pytest.raises(RuntimeError):
         F.composite(torch.zeros(1, 3), torch.zeros(1, 4, 3), torch.zeros(1, 4), torch.zeros(1, 4))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/niw_b200.h is a C header (no C++ or torch types): a C99 host compiles against it with gcc and links
+    the library -- the binding a non-Python maintainer would write."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "niw_b200.h"\n'
+                   'int main(void) { return (niw_abi_version() == NIW_ABI_VERSION && niw_error_string(0) != 0) ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(build.build())
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                        str(src), "-L", libdir, "-lniw_b200", "-Wl,-rpath," + libdir, "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
