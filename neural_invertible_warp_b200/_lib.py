@@ -48,7 +48,7 @@ SIGNATURES = {
     "niw_image_metrics": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     "niw_depth_metrics": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_float, _P, _P]),
     "niw_kabsch": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _P, _P, _P]),
-    "niw_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64] + [_c.c_float] * 6 + [_P, _P]),
+    "niw_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64] + [_c.c_float] * 8 + [_P, _P, _P, _P]),
     "niw_tc_probe": (_c.c_int, [_c.c_int, _c.c_int, _P, _P]),
     "niw_tc_selftest": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
 }

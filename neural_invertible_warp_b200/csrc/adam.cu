@@ -12,9 +12,12 @@ namespace {
 __global__ void __launch_bounds__(256)
 adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, float lr, float gamma, float beta1, float beta2, float eps, float weight_decay,
+                 float warmup_iters, float max_iter, float* __restrict__ progress0, float* __restrict__ progress1,
                  float* __restrict__ step, unsigned int* __restrict__ ticket) {
     const float t = step[0] + 1.f;                      // every thread reads it before any block can advance it
-    const float lr_t = gamma == 1.f ? lr : lr * powf(gamma, t - 1.f);
+    float lr_t = gamma == 1.f ? lr : lr * powf(gamma, t - 1.f);
+    // pose-LR warm-up (model/barf.py:48-51): lr *= min(1, it / warmup) with it = iterations completed before this one
+    if (warmup_iters > 0.f) lr_t *= fminf(1.f, (t - 1.f) / warmup_iters);
     // torch.optim.Adam (single-tensor form): step_size = lr / (1 - b1^t), denom = sqrt(v) / sqrt(1 - b2^t) + eps
     const float bc1 = 1.f - powf(beta1, t);
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
@@ -51,21 +54,29 @@ adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
         last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) { step[0] = t; *ticket = 0u; }
+    if (last && threadIdx.x == 0) {
+        step[0] = t; *ticket = 0u;
+        // the BARF schedule scalar (model/barf.py:57-59: progress.data.fill_(it / max_iter) after the pose step), kept on
+        // the device so that a captured training loop anneals without a host write
+        const float prog = (float)((double)t / (double)max_iter);
+        if (progress0) progress0[0] = prog;
+        if (progress1) progress1[0] = prog;
+    }
 }
 
 }  // namespace
 
 extern "C" int niw_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                             float lr_gamma, float beta1, float beta2, float eps, float weight_decay, float* state,
-                             void* stream) {
-    NIW_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state && n > 0);
+                             float lr_gamma, float beta1, float beta2, float eps, float weight_decay, float warmup_iters,
+                             float max_iter, float* progress0, float* progress1, float* state, void* stream) {
+    NIW_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state && n > 0 && warmup_iters >= 0.f &&
+                  (!(progress0 || progress1) || max_iter > 0.f));
     if ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
          reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
         return NIW_E_BADARG;                            // segments must be 16-byte aligned
     niw::note_launch(), adam_flat_kernel<<<niw_blocks((n + 3) / 4, 256), 256, 0, niw_stream(stream)>>>(
-        params, grads, exp_avg, exp_avg_sq, n, lr, lr_gamma, beta1, beta2, eps, weight_decay, state,
-        reinterpret_cast<unsigned int*>(state + 1));
+        params, grads, exp_avg, exp_avg_sq, n, lr, lr_gamma, beta1, beta2, eps, weight_decay, warmup_iters, max_iter,
+        progress0, progress1, state, reinterpret_cast<unsigned int*>(state + 1));
     NIW_LAUNCH_CHECK();
     return 0;
 }

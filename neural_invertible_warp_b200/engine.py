@@ -186,10 +186,17 @@ class FlatAdam(SegmentedAllreduce):
     count lives on the device, so ``step`` can be captured in a CUDA graph; ``gamma`` is the per-step
     ExponentialLR factor (lr_t = lr * gamma**(t-1))."""
 
-    def __init__(self, groups):
+    def __init__(self, groups, progress=None, max_iter=None):
+        """``progress``: the BARF schedule scalars (``nerf.progress`` [, ``nerf_fine.progress``]) that the LAST group's
+        kernel sets to step / ``max_iter`` after its update, as the reference's ``train_iteration`` does after the pose
+        step (model/barf.py:57-59).  A group dict may carry ``warmup`` (iterations of linear LR warm-up, model/barf.py:48-51)."""
         from . import _lib
         self._lib = _lib.load()
         self.groups = []
+        self.progress = list(progress or [])
+        self.max_iter = float(max_iter) if max_iter else 0.0
+        if len(self.progress) > 2 or (self.progress and not self.max_iter):
+            raise ValueError("FlatAdam: at most two progress scalars, and max_iter with them")
         dev = groups[0]["params"][0].device
         sizes = []
         for g in groups:
@@ -216,7 +223,7 @@ class FlatAdam(SegmentedAllreduce):
             b1, b2 = g.get("betas", (0.9, 0.999))
             self.groups.append(dict(offset=base, n=size, lr=float(g["lr"]), gamma=float(g.get("gamma", 1.0)), b1=float(b1),
                                     b2=float(b2), eps=float(g.get("eps", 1e-8)), wd=float(g.get("weight_decay", 0.0)),
-                                    params=list(g["params"])))
+                                    warmup=float(g.get("warmup", 0) or 0), params=list(g["params"])))
             base += size
 
     def zero(self):
@@ -230,9 +237,11 @@ class FlatAdam(SegmentedAllreduce):
         for gi, g in enumerate(self.groups):
             o = g["offset"] * 4
             ptr = lambda t: ctypes.c_void_p(t.data_ptr() + o)
+            prog = self.progress if gi == len(self.groups) - 1 else []
+            pp = [ctypes.c_void_p(t.data_ptr()) for t in prog] + [None, None]
             rc = self._lib.niw_adam_step(ptr(self.flat_params), ptr(self.flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                         g["n"], g["lr"], g["gamma"], g["b1"], g["b2"], g["eps"], g["wd"],
-                                         ctypes.c_void_p(self.state.data_ptr() + gi * 8), st)
+                                         g["n"], g["lr"], g["gamma"], g["b1"], g["b2"], g["eps"], g["wd"], g["warmup"],
+                                         self.max_iter, pp[0], pp[1], ctypes.c_void_p(self.state.data_ptr() + gi * 8), st)
             if rc:
                 raise RuntimeError("niw_adam_step: %s" % self._lib.niw_error_string(rc).decode())
 
@@ -260,7 +269,8 @@ def reference_optimizer_groups(opt, graph):
         o = opt.optim
         lr = float(o.get("lr_pose", None) or o.lr)
         lr_end = float(o.get("lr_pose_end", None) or lr)
-        groups.append(dict(params=pose, lr=lr, gamma=(lr_end / lr) ** (1.0 / opt.max_iter) if lr_end != lr else 1.0))
+        groups.append(dict(params=pose, lr=lr, gamma=(lr_end / lr) ** (1.0 / opt.max_iter) if lr_end != lr else 1.0,
+                           warmup=o.get("warmup_pose", None) or 0))
     return groups
 
 

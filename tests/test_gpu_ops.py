@@ -550,3 +550,17 @@ def test_flat_adam_matches_torch_adam():
             torch.testing.assert_close(o.detach().cpu(), r.detach(), rtol=2e-5, atol=2e-6)
         assert fa.state[:, 0].tolist() == [20.0, 20.0]
         assert ours_a[0].data_ptr() == fa.flat_params.data_ptr()
+    # pose-LR warm-up and the BARF progress scalar (model/barf.py:46-60), kept on the device
+    ref = [torch.randn(9, 5, generator=gen).requires_grad_(True)]
+    ours = [torch.nn.Parameter(ref[0].detach().clone().to(DEV))]
+    prog = torch.nn.Parameter(torch.tensor(0.0, device=DEV))
+    o = torch.optim.Adam(ref, lr=3e-3)
+    fa = engine.FlatAdam([dict(params=ours, lr=3e-3, warmup=4)], progress=[prog], max_iter=200000)
+    for it in range(9):
+        g = torch.randn(9, 5, generator=gen)
+        ref[0].grad = g.clone(); ours[0].grad.copy_(g.to(DEV))
+        o.param_groups[0]["lr"] = 3e-3 * min(1, it / 4)
+        o.step()
+        fa.step()
+        assert prog.item() == torch.tensor((it + 1) / 200000).item()        # fp32(it / max_iter), as fill_ stores it
+    torch.testing.assert_close(ours[0].detach().cpu(), ref[0].detach(), rtol=2e-5, atol=2e-6)
