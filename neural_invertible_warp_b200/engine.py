@@ -452,6 +452,24 @@ def evaluate_view(opt, graph, var, test_optim=None, fine=None):
     return AttrDict(psnr=psnr, ssim=ssim, var=var)
 
 
+@torch.no_grad()
+def render_rows(opt, graph, pose, intr, row0, row1, depth_range=None, mode="eval"):
+    """Pixel rows [row0, row1) of a full-frame render: the slice loop of ``render_by_slices`` (reference
+    model/nerf.py:321-332 iterates contiguous ``ray_idx`` ranges of ``rand_rays`` pixels) restricted to one contiguous
+    range, which is how an evaluation frame is sharded over k GPUs (rank r takes rows [r H/k, (r+1) H/k); SURVEY.md 8e:
+    no collective, the rows are independent).  The range is rendered in chunks of ``opt.nerf.rand_rays`` pixels (one
+    chunk when that covers it).  Returns the same edict as ``render`` with [B, (row1-row0) W, K] tensors."""
+    start, stop = int(row0) * opt.W, int(row1) * opt.W
+    chunk = int(opt.nerf.rand_rays) if opt.nerf.rand_rays else stop - start
+    parts = []
+    for c in range(start, stop, chunk):
+        parts.append(graph._render_pose(opt, pose, intr=intr, mode=mode, depth_range=depth_range, idx_start=c,
+                                        num=min(chunk, stop - c)))
+    if len(parts) == 1:
+        return parts[0]
+    return AttrDict({k: torch.cat([p[k] for p in parts], dim=1) for k in parts[0].keys()})
+
+
 class CapturedStep:
     """A whole training step (forward, loss, backward, all-reduce, optimiser) captured once in a CUDA
     graph and replayed: the ~45 kernel launches of a C2 step cost one graph launch instead of ~1 ms of
