@@ -388,6 +388,7 @@ def run_train(args):
     # the reference's two optimisers (Adam + ExponentialLR on nerf, Adam on warp_mlp + warp_latent) as one flat
     # update kernel per group; the same object is the data-parallel gradient bucket
     adam = engine.FlatAdam(engine.reference_optimizer_groups(opt, graph))
+    engine.use_flat_gradients(graph)            # the kernels accumulate straight into the flat gradient bucket
     it = 5000
     P_global = rays_global // IMAGES
     P_local = (P_global + world - 1) // world

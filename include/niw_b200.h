@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NIW_ABI_VERSION 2
+#define NIW_ABI_VERSION 3
 
 #define NIW_E_BADARG   (-1)  /* null pointer / non-positive size */
 #define NIW_E_UNSUPP   (-2)  /* shape or option outside what the kernels implement */
@@ -200,13 +200,16 @@ int niw_kabsch(const float* x, const float* y, int B, int M, float* R, float* t,
  * params/grads/exp_avg/exp_avg_sq [n] (16-byte aligned).  `state` is a DEVICE array of 2 floats owned by the
  * caller and zero-initialised: state[0] = number of steps taken so far (advanced by the kernel, so the call can be
  * replayed from a CUDA graph), state[1] = scratch.  Update (torch's Adam, amsgrad off, maximize off):
- *   t = state[0]+1; lr_t = lr * lr_gamma^(t-1); g += weight_decay*p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *   t = state[0]+1; lr_t = lr * lr_gamma^(t-1) (evaluated in double, as torch's ExponentialLR accumulates it);
+ *   g += weight_decay*p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
  *   p -= lr_t/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
- * warmup_iters > 0: lr_t *= min(1, (t-1)/warmup_iters) (the pose-LR warm-up of model/barf.py:48-51).  progress0/1 (device
- * scalars, may be NULL): set to t / max_iter after the update -- `nerf.progress.data.fill_(it/max_iter)`, model/barf.py:57-59. */
-int niw_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                  float lr_gamma, float beta1, float beta2, float eps, float weight_decay, float warmup_iters,
-                  float max_iter, float* progress0, float* progress1, float* state, void* stream);
+ * warmup_iters > 0: lr_t *= min(1, (t-1)/warmup_iters) for the first warmup_n elements of the segment (the pose-LR warm-up
+ * of model/barf.py:48-51; the reference applies it to optim_pose.param_groups[0] only, i.e. to warp_mlp and not to the
+ * latent codes that follow it in the segment: model/barf_inn_llff.py:108-111).  progress0/1 (device scalars, may be NULL):
+ * set to t / max_iter after the update -- `nerf.progress.data.fill_(it/max_iter)`, model/barf.py:57-59. */
+int niw_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                  double lr_gamma, float beta1, float beta2, float eps, float weight_decay, float warmup_iters,
+                  int64_t warmup_n, float max_iter, float* progress0, float* progress1, float* state, void* stream);
 
 /* ---- tcgen05 self-test: D[128,N] = A[128,K] . B[N,K]^T with BF16 operands staged exactly as the
  * MLP kernel stages them.  variant selects the operand form under test (see csrc/tc_selftest.cu); variant 4 is the

@@ -17,7 +17,7 @@ NIW_PREC_BF16 = 1
 NIW_NERF_PREPACKED = 2
 NIW_NERF_PARAMS = 530052
 NIW_NVP_BLOCK_FLOATS = ((128 * 27 + 128 + 1 + 128 * 13 + 3 * 128 + 3) + 3) // 4 * 4   # 5636, include/niw_b200.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/niw_b200.h one to one
 SIGNATURES = {
@@ -48,7 +48,7 @@ SIGNATURES = {
     "niw_image_metrics": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     "niw_depth_metrics": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_float, _P, _P]),
     "niw_kabsch": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _P, _P, _P]),
-    "niw_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64] + [_c.c_float] * 8 + [_P, _P, _P, _P]),
+    "niw_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_double, _c.c_double] + [_c.c_float] * 5 + [_c.c_int64, _c.c_float, _P, _P, _P, _P]),
     "niw_tc_probe": (_c.c_int, [_c.c_int, _c.c_int, _P, _P]),
     "niw_tc_selftest": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
 }
@@ -72,6 +72,14 @@ def load(build_if_missing=True):
         except Exception as e:  # no nvcc on this box: fall through to the prebuilt file
             if not os.path.exists(path):
                 raise RuntimeError("libniw_b200.so is missing and could not be built: %s" % e)
+            # a prebuilt library older than its sources that cannot be rebuilt: usable only if the caller says so
+            if not os.environ.get("NIW_B200_ALLOW_STALE"):
+                raise RuntimeError("libniw_b200.so is older than csrc/*.cu / include/niw_b200.h and the rebuild failed (%s); "
+                                   "fix the build, or set NIW_B200_ALLOW_STALE=1 to load the stale library anyway"
+                                   % str(e).splitlines()[0])
+            import warnings
+            warnings.warn("niw_b200: loading a STALE libniw_b200.so (sources are newer, rebuild failed: %s)"
+                          % str(e).splitlines()[0])
     if not os.path.exists(path):
         raise RuntimeError("libniw_b200.so not found at %s -- run `python -m neural_invertible_warp_b200.build`; "
                            "there is no CPU fallback" % path)

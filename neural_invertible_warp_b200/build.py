@@ -25,13 +25,28 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+STAMP = LIB + ".srchash"
+
+
+def source_hash():
+    """sha256 over the sources, the header and the compile flags: what the built library is a function of.  (File
+    times do not survive the snapshot to the GPU box, contents do.)"""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
     deps.append(os.path.join(os.path.dirname(HERE), "include", "niw_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def needs_build():
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+        return True
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False, extra_flags=(), out=None):
@@ -61,6 +76,9 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    if out is None and not extra_flags:
+        with open(STAMP, "w") as f:
+            f.write(source_hash())
     return out or LIB
 
 

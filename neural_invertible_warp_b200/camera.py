@@ -223,14 +223,4 @@ def rigid_points_registration(x, y):
     """roma's convention: the least-squares R, t with y ~ R x + t (batched Kabsch with the det
     fix).  The reference calls it as (target, source), i.e. it fits the world->camera map
     source ~ R target + t, which ``cam2world`` then inverts.  x, y [B,M,3] -> R [B,3,3], t [B,3]."""
-    if x.is_cuda:
-        return F.kabsch(x, y)          # one kernel, no SVD library call, capturable (csrc/kabsch.cu)
-    mu_x = x.mean(dim=1, keepdim=True)
-    mu_y = y.mean(dim=1, keepdim=True)
-    M = (y - mu_y).transpose(1, 2) @ (x - mu_x)
-    U, _, Vh = torch.linalg.svd(M)
-    d = torch.det(U @ Vh)
-    D = torch.diag_embed(torch.stack([torch.ones_like(d), torch.ones_like(d), d], dim=-1))
-    R = U @ D @ Vh
-    t = mu_y[:, 0] - (R @ mu_x[:, 0, :, None])[..., 0]
-    return R, t
+    return F.kabsch(x, y)              # one kernel, no SVD library call, capturable (csrc/kabsch.cu); CPU tensors raise

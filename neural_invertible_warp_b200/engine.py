@@ -78,6 +78,17 @@ def summarize_loss(opt, loss):
     return loss
 
 
+def use_flat_gradients(graph, enabled=True):
+    """Opt the graph's NeRF modules (and warp networks) in to in-kernel gradient accumulation: their backward kernels
+    add into the ``.grad`` buffers directly and return None to autograd.  Meant for training loops that own a flat
+    gradient bucket (``GradBucket`` / ``FlatAdam``) and call plain ``loss.backward()``; leave it off when gradients are
+    consumed through ``torch.autograd.grad`` / ``backward(inputs=...)`` / hooks."""
+    from .model._core import NeRFCore
+    for m in graph.modules():
+        if isinstance(m, (NeRFCore, DeformNetwork)):
+            m.accumulate_grads_in_place = bool(enabled)
+
+
 class GradBucket:
     """One flat fp32 buffer holding every trainable gradient.  ``attach`` points each ``p.grad`` at
     its slice, so backward accumulates straight into the bucket and ``allreduce`` is a single
@@ -135,9 +146,20 @@ class SegmentedAllreduce:
         if not pending:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             return
-        for gi in range(len(self.groups)):
-            if gi not in pending:
-                dist.all_reduce(self._segment(gi), op=dist.ReduceOp.SUM, group=group)
+        # what is left goes out as ONE collective per run of adjacent segments (normally a single one: everything
+        # behind the early NeRF segment)
+        gi, n = 0, len(self.groups)
+        while gi < n:
+            if gi in pending:
+                gi += 1
+                continue
+            gj = gi
+            while gj + 1 < n and gj + 1 not in pending and \
+                    self.groups[gj + 1]["offset"] == self.groups[gj]["offset"] + self.groups[gj]["n"]:
+                gj += 1
+            lo, hi = self.groups[gi]["offset"], self.groups[gj]["offset"] + self.groups[gj]["n"]
+            dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+            gi = gj + 1
         for work in pending.values():
             work.wait()                       # the current stream waits for the collective; no host block
         self._pending = {}
@@ -159,11 +181,16 @@ class overlap_allreduce:
 
     def __enter__(self):
         if self.ok:
-            waiting = {id(m) for m in self.mods}
+            # a module may have been evaluated several times in this step with gradients enabled (slices, several views
+            # in one loss): functional._NerfSamples counts those forward calls in ``_pending_backward`` and reports a
+            # module only when its LAST backward node has run -- an earlier reduce would race with the later nodes'
+            # accumulation into the same segment
+            waiting = {id(m) for m in self.mods if getattr(m, "_pending_backward", 0) > 0}
+            fire = bool(waiting)
 
             def ready(m):
                 waiting.discard(id(m))
-                if not waiting:
+                if fire and not waiting:
                     self.bucket.allreduce_group_async(0, self.group)
             for m in self.mods:
                 m._grads_ready = ready
@@ -172,6 +199,7 @@ class overlap_allreduce:
     def __exit__(self, *exc):
         for m in self.mods:
             m._grads_ready = None
+            m._pending_backward = 0      # forward calls whose backward never ran (unused outputs) do not leak into the next step
 
 
 class FlatAdam(SegmentedAllreduce):
@@ -179,7 +207,10 @@ class FlatAdam(SegmentedAllreduce):
     ``optim_pose`` on ``warp_mlp`` + ``warp_latent`` / ``se3_refine``: model/barf_inn_llff.py:84-104,
     model/barf.py:46-60) as ONE kernel launch per parameter group (csrc/adam.cu, ``niw_adam_step``).
 
-    ``groups`` = [dict(params=[...], lr=, gamma=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0), ...].
+    ``groups`` = [dict(params=[...], lr=, gamma=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, warmup=0,
+    warmup_params=None, torch_groups=None), ...].  ``warmup_params``: how many leading tensors of ``params`` the linear
+    LR warm-up applies to (default: all); ``torch_groups``: tensor counts of the ``param_groups`` the reference's
+    torch optimiser has for this group (state_dict interchange, default one group).
     Every group becomes a contiguous fp32 segment of one flat parameter buffer and of one flat gradient buffer
     (the parameters / their ``.grad`` are re-pointed at views, names and shapes untouched), so this object is
     also the data-parallel gradient bucket: ``zero`` / ``allreduce`` have GradBucket's meaning.  The step
@@ -221,10 +252,19 @@ class FlatAdam(SegmentedAllreduce):
                 p.grad = self.flat[off:off + n].view_as(p)
                 off += n
             b1, b2 = g.get("betas", (0.9, 0.999))
+            wp = g.get("warmup_params", None)
+            warmup_n = size if wp is None else sum(p.numel() for p in g["params"][:wp])
+            tg = list(g.get("torch_groups", None) or [len(g["params"])])
+            if sum(tg) != len(g["params"]):
+                raise ValueError("FlatAdam: torch_groups must partition the group's parameter list")
             self.groups.append(dict(offset=base, n=size, lr=float(g["lr"]), gamma=float(g.get("gamma", 1.0)), b1=float(b1),
                                     b2=float(b2), eps=float(g.get("eps", 1e-8)), wd=float(g.get("weight_decay", 0.0)),
-                                    warmup=float(g.get("warmup", 0) or 0), params=list(g["params"])))
+                                    warmup=float(g.get("warmup", 0) or 0), warmup_n=int(warmup_n), torch_groups=tg,
+                                    params=list(g["params"])))
             base += size
+        for p in self.progress:
+            if not p.is_cuda:
+                raise RuntimeError("niw_b200 FlatAdam: progress scalars must live on the device")
 
     def zero(self):
         self.flat.zero_()
@@ -241,36 +281,137 @@ class FlatAdam(SegmentedAllreduce):
             pp = [ctypes.c_void_p(t.data_ptr()) for t in prog] + [None, None]
             rc = self._lib.niw_adam_step(ptr(self.flat_params), ptr(self.flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                                          g["n"], g["lr"], g["gamma"], g["b1"], g["b2"], g["eps"], g["wd"], g["warmup"],
-                                         self.max_iter, pp[0], pp[1], ctypes.c_void_p(self.state.data_ptr() + gi * 8), st)
+                                         g["warmup_n"], self.max_iter, pp[0], pp[1],
+                                         ctypes.c_void_p(self.state.data_ptr() + gi * 8), st)
             if rc:
                 raise RuntimeError("niw_adam_step: %s" % self._lib.niw_error_string(rc).decode())
+
+    # -- checkpointing (reference util.py:124-163 persists every optim* / sched* state_dict) ------------------------
+    _HYPER = ("offset", "n", "lr", "gamma", "b1", "b2", "eps", "wd", "warmup", "warmup_n")
+
+    def state_dict(self):
+        """Both Adam moments, the device step counters (which drive lr * gamma**(t-1), the pose warm-up and the BARF
+        ``progress`` scalar) and the group hyper-parameters.  Parameters and ``progress`` belong to the graph's own
+        ``state_dict``."""
+        return dict(version=1, exp_avg=self.exp_avg.detach().clone(), exp_avg_sq=self.exp_avg_sq.detach().clone(),
+                    steps=self.state[:, 0].detach().clone(), max_iter=self.max_iter,
+                    groups=[{k: g[k] for k in self._HYPER} for g in self.groups])
+
+    def load_state_dict(self, sd):
+        """In place (buffers captured in a CUDA graph stay valid).  The layout must match; learning-rate
+        hyper-parameters are taken from the checkpoint, as ``torch.optim.Optimizer.load_state_dict`` does."""
+        if len(sd["groups"]) != len(self.groups) or any(a["n"] != b["n"] or a["offset"] != b["offset"]
+                                                        for a, b in zip(sd["groups"], self.groups)):
+            raise ValueError("FlatAdam.load_state_dict: parameter groups do not match this optimiser")
+        with torch.no_grad():
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            self.state.zero_()
+            self.state[:, 0].copy_(sd["steps"])
+        for g, saved in zip(self.groups, sd["groups"]):
+            for k in self._HYPER:
+                g[k] = saved[k]
+
+    def _group_slices(self, gi):
+        g, off, out = self.groups[gi], self.groups[gi]["offset"], []
+        for p in g["params"]:
+            out.append((p, off, off + p.numel()))
+            off += p.numel()
+        return out
+
+    def to_torch(self, gi):
+        """Group ``gi`` as the reference's own optimiser objects: (torch.optim.Adam, ExponentialLR or None) over the same
+        parameter tensors, carrying this optimiser's moments, step count and decayed learning rate -- what
+        ``util.save_checkpoint`` (util.py:147-163) stores as ``optim`` / ``sched`` (``optim_pose`` / ``sched_pose``).
+        Reads the step counter (one host sync)."""
+        g = self.groups[gi]
+        t = int(round(float(self.state[gi, 0])))
+        ps, k, pgs = g["params"], 0, []
+        for cnt in g["torch_groups"]:
+            pgs.append(dict(params=ps[k:k + cnt], lr=g["lr"]))
+            k += cnt
+        optim = torch.optim.Adam(pgs, betas=(g["b1"], g["b2"]), eps=g["eps"], weight_decay=g["wd"])
+        if t > 0:
+            for p, lo, hi in self._group_slices(gi):
+                optim.state[p] = dict(step=torch.tensor(float(t)), exp_avg=self.exp_avg[lo:hi].clone().view_as(p),
+                                      exp_avg_sq=self.exp_avg_sq[lo:hi].clone().view_as(p))
+        sched = None
+        if g["gamma"] != 1.0:
+            sched = torch.optim.lr_scheduler.ExponentialLR(optim, gamma=g["gamma"])
+            sched.last_epoch = t
+            sched._step_count = t + 1
+            lr_t = g["lr"] * g["gamma"] ** t
+            for pg in optim.param_groups:
+                pg["lr"] = lr_t
+            sched._last_lr = [lr_t for _ in optim.param_groups]
+        return optim, sched
+
+    def load_torch(self, gi, optim_sd, sched_sd=None):
+        """Adopt the state of a reference checkpoint's ``optim`` (+ ``sched``) ``state_dict`` for group ``gi``."""
+        g = self.groups[gi]
+        slices = self._group_slices(gi)
+        state = optim_sd["state"]
+        t = 0
+        with torch.no_grad():
+            for i, (p, lo, hi) in enumerate(slices):
+                st = state.get(i, None)
+                if st is None:
+                    self.exp_avg[lo:hi].zero_(); self.exp_avg_sq[lo:hi].zero_()
+                    continue
+                self.exp_avg[lo:hi].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[lo:hi].copy_(st["exp_avg_sq"].reshape(-1))
+                t = max(t, int(round(float(st["step"]))))
+            if sched_sd is not None:
+                if int(sched_sd["last_epoch"]) != t and t > 0:
+                    raise ValueError("FlatAdam.load_torch: optimiser took %d steps, scheduler %d" % (t, sched_sd["last_epoch"]))
+                t = int(sched_sd["last_epoch"])
+                g["gamma"] = float(sched_sd["gamma"])
+                g["lr"] = float(sched_sd["base_lrs"][0])
+            else:
+                g["lr"] = float(optim_sd["param_groups"][0].get("initial_lr", optim_sd["param_groups"][0]["lr"]))
+            pg0 = optim_sd["param_groups"][0]
+            g["b1"], g["b2"] = (float(b) for b in pg0["betas"])
+            g["eps"], g["wd"] = float(pg0["eps"]), float(pg0["weight_decay"])
+            self.state[gi, 0] = float(t)
 
 
 def reference_optimizer_groups(opt, graph):
     """The parameter groups of the reference's optimisers for the target models (model/nerf.py:33-46,
-    model/barf.py:46-60, model/barf_inn_llff.py:84-104), as FlatAdam group dicts.  ExponentialLR:
-    gamma = (lr_end / lr) ** (1 / max_iter)."""
-    def sched(o):
-        lr, lr_end = float(o.lr), float(o.get("lr_end", None) or o.lr)
-        return dict(lr=lr, gamma=(lr_end / lr) ** (1.0 / opt.max_iter) if lr_end != lr else 1.0)
-    nerf_params = list(graph.nerf.parameters())
+    model/barf.py:46-60, model/barf_inn_llff.py:84-104, model/barf_inn_dtu.py:338-351), as FlatAdam group dicts.
+    ExponentialLR only when ``optim.sched`` / ``optim.sched_pose`` is set, gamma = (lr_end / lr) ** (1 / max_iter)
+    when ``lr_end`` is given (else the YAML's own gamma); the pose warm-up covers the reference's
+    ``optim_pose.param_groups[0]`` only (the warp network / ``se3_refine``), not the latent codes added as a second
+    param group (model/barf_inn_llff.py:108-111)."""
+    def sched(lr, lr_end, sc):
+        lr = float(lr)
+        if not sc:
+            return dict(lr=lr, gamma=1.0)
+        if lr_end:
+            return dict(lr=lr, gamma=(float(lr_end) / lr) ** (1.0 / opt.max_iter))
+        g = sc.get("gamma", None) if hasattr(sc, "get") else None
+        return dict(lr=lr, gamma=float(g) if g else 1.0)
+    o = opt.optim
     nerf_params = [p for n, p in graph.nerf.named_parameters() if not n.endswith("progress")]
+    tg = [len(nerf_params)]
     if opt.nerf.fine_sampling:
-        nerf_params += [p for n, p in graph.nerf_fine.named_parameters() if not n.endswith("progress")]
-    groups = [dict(params=nerf_params, **sched(opt.optim))]
-    pose = []
+        fine = [p for n, p in graph.nerf_fine.named_parameters() if not n.endswith("progress")]
+        nerf_params += fine
+        tg.append(len(fine))
+    groups = [dict(params=nerf_params, torch_groups=tg, **sched(o.lr, o.get("lr_end", None), o.get("sched", None)))]
+    first, second = [], []           # optim_pose.param_groups[0] / [1]
     if hasattr(graph, "se3_refine"):
-        pose += list(graph.se3_refine.parameters())
+        first += list(graph.se3_refine.parameters())
     if hasattr(graph, "warp_mlp"):
-        pose += list(graph.warp_mlp.parameters()) + list(graph.warp_latent.parameters())
+        first += list(graph.warp_mlp.parameters())
+        second += list(graph.warp_latent.parameters())
     if hasattr(graph, "pose_net"):
-        pose += [p for n, p in graph.pose_net.named_parameters() if "pose_global" not in n]
-    if pose:
-        o = opt.optim
-        lr = float(o.get("lr_pose", None) or o.lr)
-        lr_end = float(o.get("lr_pose_end", None) or lr)
-        groups.append(dict(params=pose, lr=lr, gamma=(lr_end / lr) ** (1.0 / opt.max_iter) if lr_end != lr else 1.0,
-                           warmup=o.get("warmup_pose", None) or 0))
+        first += list(graph.pose_net.pose_embedding.parameters())
+        second += list(graph.pose_net.pose_latent.parameters())
+    if first or second:
+        lr = o.get("lr_pose", None) or o.lr
+        groups.append(dict(params=first + second, warmup=o.get("warmup_pose", None) or 0, warmup_params=len(first),
+                           torch_groups=[n for n in (len(first), len(second)) if n],
+                           **sched(lr, o.get("lr_pose_end", None), o.get("sched_pose", None))))
     return groups
 
 
@@ -391,6 +532,9 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1):
     takes_iter = opt.model in ("barf_inn_llff", "nerf_inn_llff", "barf_inn_dtu", "nerf_inn_dtu")
     if bucket is not None:
         bucket.zero()
+        if not getattr(graph, "_flat_gradients", False):
+            use_flat_gradients(graph)          # the bucket owns every .grad: let the kernels accumulate into it
+            graph._flat_gradients = True
     else:
         graph.zero_grad(set_to_none=True)
     if world > 1:
@@ -441,9 +585,16 @@ def evaluate_view(opt, graph, var, test_optim=None, fine=None):
     ``AttrDict(psnr [B], ssim [B], var)`` with device tensors: nothing is read back to the host here."""
     from . import functional as F
     if test_optim is None:
-        test_optim = opt.model in ("barf",) and bool(opt.optim.get("test_photo", False))
+        # model/nerf.py:172 (barf) and model/nerf_inn_dtu.py:217 ('barf' in opt.model).  model/nerf_inn_llff.py:202 lists
+        # model names that do not exist in the reference, so barf_inn_llff never refines there and its next line,
+        # get_pose(mode="eval"), then reads the unset var.pose_refine_test (barf_inn_llff.py:395-396): the evident
+        # intent -- refine whenever optim.test_photo is set -- is implemented for all three
+        test_optim = "barf" in opt.model.lower() and bool(opt.optim.get("test_photo", False))
     if test_optim:
         var = test_time_photometric_optim(opt, graph, var)
+    elif opt.optim.get("test_photo", False) and "pose_refine_test" not in var:
+        # refinement explicitly skipped although the eval pose composes it: the identity is the unrefined pose
+        var.pose_refine_test = torch.eye(3, 4, device=opt.device)[None].repeat(len(var.idx), 1, 1)
     takes_iter = opt.model in ("barf_inn_llff", "nerf_inn_llff", "barf_inn_dtu", "nerf_inn_dtu")
     var = graph.forward(opt, var, mode="eval", iter=None) if takes_iter else graph.forward(opt, var, mode="eval")
     use_fine = opt.nerf.fine_sampling if fine is None else fine

@@ -334,9 +334,14 @@ def band_weights(progress, c2f, L):
 class _NerfSamples(torch.autograd.Function):
     """``flat`` is the 530 052-float parameter vector the kernels read.  Two ways to receive its
     gradient: (a) ``flat`` itself requires grad (functional use, tests) -> returned through autograd;
-    (b) ``module`` is a NeRFCore whose ``nn.Linear`` parameters (passed as ``*params`` so autograd knows
-    the output depends on them) own a flat gradient buffer -> the kernels accumulate straight into it
-    and None is returned for the parameters (no per-parameter accumulate launches)."""
+    (b) ``module`` is a NeRFCore whose ``nn.Linear`` parameters are passed as ``*params`` so autograd knows
+    the output depends on them.  Their gradients are returned through autograd as well (so
+    ``torch.autograd.grad``, ``backward(inputs=...)`` and gradient hooks behave) UNLESS the engine has opted the
+    module in to in-kernel accumulation (``module.accumulate_grads_in_place``, set by ``engine.train_step`` /
+    ``engine.use_flat_gradients`` when the parameters' ``.grad`` are slices of one flat bucket): then the kernels
+    accumulate straight into that bucket and None is returned (no per-parameter accumulate launches).  Every
+    training-mode forward call of such a module is counted in ``module._pending_backward``; the module is reported
+    to ``_grads_ready`` (engine.overlap_allreduce) only when the last of those calls has been back-propagated."""
 
     @staticmethod
     def forward(ctx, flat, center, ray, depth, progress, c2f, precision, training, module, prepacked, *params):
@@ -366,6 +371,8 @@ class _NerfSamples(torch.autograd.Function):
         if training:
             ctx.save_for_backward(flat, center, ray, depth, ws)
             ctx.cfg = (precision, nbytes, module, len(params))
+            if module is not None and params:
+                module._pending_backward = getattr(module, "_pending_backward", 0) + 1
         return rgb, sigma
 
     @staticmethod
@@ -373,7 +380,8 @@ class _NerfSamples(torch.autograd.Function):
         flat, center, ray, depth, ws = ctx.saved_tensors
         precision, nbytes, module, n_params = ctx.cfg
         R, N = depth.shape
-        target = module.flat_grad_pointer() if (module is not None and n_params) else None
+        in_place = module is not None and n_params and getattr(module, "accumulate_grads_in_place", False)
+        target = module.flat_grad_pointer() if in_place else None
         if target is None:
             d_params = torch.zeros_like(flat)
             dp = _p(d_params)
@@ -391,9 +399,10 @@ class _NerfSamples(torch.autograd.Function):
             _lib.check(_lib.load().niw_nerf_bwd(_p(flat), _p(center), _p(ray), _p(depth), R, N, precision,
                                                 _p(ws), nbytes, _p(d_rgb), _p(d_sigma), dp, _p(d_center),
                                                 _p(d_ray), _stream()))
-        if target is not None:
+        if module is not None and n_params:
+            module._pending_backward = max(getattr(module, "_pending_backward", 1) - 1, 0)
             ready = getattr(module, "_grads_ready", None)       # engine.overlap_allreduce: this module's gradients are final
-            if ready is not None:
+            if target is not None and ready is not None and module._pending_backward == 0:
                 ready(module)
         if n_params and d_params is not None:
             # slow path: the module's gradients are not one flat buffer -> hand slices back to autograd

@@ -42,6 +42,9 @@ class NeRFCore(nn.Module):
     """Parameter-compatible with reference ``model.nerf.NeRF`` (model/nerf.py:367-483)."""
 
     has_progress = False   # BARF variants own a ``progress`` Parameter (model/barf.py:254)
+    # opt-in of the engine (engine.use_flat_gradients): the MLP kernels accumulate parameter gradients straight into the
+    # flat bucket the parameters' ``.grad`` are slices of, instead of returning them through autograd
+    accumulate_grads_in_place = False
 
     def __init__(self, opt):
         super().__init__()

@@ -29,6 +29,14 @@ class Graph(base.Graph):
         # host, nerf_inn_dtu.py:536; here there is no host read, so the step can be captured in a CUDA graph)
         if opt.nerf.rand_rays and mode in ["train", "test-optim"]:
             var.ray_idx = torch.randperm(opt.H * opt.W, device=opt.device)[:opt.nerf.rand_rays // batch_size]
+            if mode == "test-optim":
+                # the reference unpacks (ray, center, grid) from get_pose here as well, but in this mode get_pose returns
+                # the aligned test POSE (barf_inn_dtu.py:546-564) and the unpack raises; the evident intent -- the BARF
+                # test-time refinement (barf_inn_dtu.py:468-483), rendering the drawn pixels from that pose -- is implemented
+                pose_w2c = self.get_pose(opt, var, mode=mode)
+                ret = self.render(opt, pose_w2c, intr=var.intr, ray_idx=var.ray_idx, mode=mode, depth_range=depth_range)
+                var.update(ret)
+                return var
             ray, center, grid_3d = self.get_pose(opt, var, mode=mode, iter=iter)
             ret = self.render_local(opt, ray, center, intr=var.intr, mode=mode, depth_range=depth_range)
             ret.update(grid_local=grid_3d, center_local=center, grid_init=self.pose_net.grid_init,

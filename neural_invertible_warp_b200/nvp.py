@@ -51,10 +51,11 @@ def pack_effective(p, code, n_blocks=3, n_freq=N_FREQ, prefix=""):
 
 class _NvpNetwork(torch.autograd.Function):
     """DeformNetwork.forward as four kernels: pack (weight-norm + code projection + per-image biases),
-    warp; warp backward, pack backward.  The parameter gradients are accumulated by the pack-backward
-    kernel straight into the parameters' ``.grad`` buffers (allocated zero-filled when absent) instead
-    of being returned through autograd: that saves ~30 tiny accumulate launches per step.  The latent
-    code's gradient is returned normally."""
+    warp; warp backward, pack backward.  With ``module.accumulate_grads_in_place`` (engine.use_flat_gradients) the
+    parameter gradients are accumulated by the pack-backward kernel straight into the parameters' ``.grad``
+    buffers (allocated zero-filled when absent) instead of being returned through autograd: that saves ~30 tiny
+    accumulate launches per step.  Otherwise they are returned through autograd.  The latent code's gradient is
+    always returned normally."""
 
     @staticmethod
     def forward(ctx, code, pts, alpha_ratio, module, index_map, *params):
@@ -89,20 +90,28 @@ class _NvpNetwork(torch.autograd.Function):
         _lib.check(lib.niw_nvp_warp_bwd(F._p(wpack), F._p(code_bias), F._p(pts), ctx.alpha, B, Pt, *ctx.im, F._p(d_out),
                                         F._p(d_w), F._p(d_cb), F._stream()))
         params = ctx.module.ordered_parameters()
-        for p in params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
+        in_place = getattr(ctx.module, "accumulate_grads_in_place", False)
+        if in_place:
+            for p in params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            grads = [p.grad for p in params]
+        else:
+            # gradients go back through autograd (torch.autograd.grad, backward(inputs=...), hooks all behave)
+            grads = [torch.zeros_like(p) for p in params]
         ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
-        gptrs = (ctypes.c_void_p * len(params))(*[p.grad.data_ptr() for p in params])
+        gptrs = (ctypes.c_void_p * len(params))(*[g.data_ptr() for g in grads])
         d_code = torch.empty_like(code)
         _lib.check(lib.niw_nvp_pack_bwd(ptrs, gptrs, F._p(code), F._p(cb), F._p(d_w), F._p(d_cb), B, F._p(d_code), F._stream()))
-        return (d_code, None, None, None, None) + (None,) * len(params)
+        return (d_code, None, None, None, None) + ((None,) * len(params) if in_place else tuple(grads))
 
 
 class DeformNetwork(nn.Module):
     """Drop-in for ``model.nvp.nvp_ndr.DeformNetwork`` restricted to what the target models
     instantiate (barf_inn_llff.py:54-55, pose_models/inn.py:23-27): d_in=3, n_blocks=3,
     n_layers=1, skip_in=[], multires=6, weight_norm=True, softplus.  Anything else raises."""
+
+    accumulate_grads_in_place = False      # engine.use_flat_gradients
 
     def __init__(self, d_feature, d_in, d_out_1, d_out_2, n_blocks, d_hidden, n_layers, skip_in=(4,),
                  multires=0, weight_norm=True, actfn="softplus"):

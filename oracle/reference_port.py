@@ -395,6 +395,20 @@ def warped_rays(nvp_p, code, H, W, intr, ray_idx, alpha_ratio, pose_init=None, *
     return grid_3D - center_3D, center_3D, grid_3D, grid_cam, center_cam
 
 
+def kabsch(x, y):
+    """roma.rigid_points_registration(x, y) (roma==1.4.1, requirements.txt:1; absent from /root/reference): the
+    least-squares rigid motion y ~ R x + t by the published Kabsch/Umeyama construction -- centroids,
+    M = sum (y - ym)(x - xm)^T, SVD, determinant fix.  The reference calls it as (target, source):
+    model/nerf_inn_llff.py:569, model/pose_models/inn.py:100.  x, y [B,M,3] -> R [B,3,3], t [B,3]."""
+    xm, ym = x.mean(dim=-2, keepdim=True), y.mean(dim=-2, keepdim=True)
+    M = (y - ym).transpose(-1, -2) @ (x - xm)
+    U, _, Vh = torch.linalg.svd(M)
+    d = torch.det(U @ Vh)
+    D = torch.diag_embed(torch.stack([torch.ones_like(d), torch.ones_like(d), d], dim=-1))
+    R = U @ D @ Vh
+    return R, ym.squeeze(-2) - (R @ xm.transpose(-1, -2)).squeeze(-1)
+
+
 def mse(pred, label):
     """model/base.py:209-211."""
     return ((pred.contiguous() - label) ** 2).mean()

@@ -495,7 +495,10 @@ def test_kabsch_matches_svd_solution(F):
     Rt = camera.lie.so3_to_SO3(w)
     y = x @ Rt.transpose(1, 2) + torch.randn(B, 1, 3, generator=gen) + 0.01 * torch.randn(B, M, 3, generator=gen)
     y[3] = y[3] * torch.tensor([1.0, 1.0, -1.0])                       # mirrored target: the unconstrained optimum is a reflection
-    R_ref, t_ref = camera.rigid_points_registration(x, y)              # CPU: torch SVD path
+    from oracle import reference_port as ora
+    R_ref, t_ref = ora.kabsch(x, y)                                    # CPU oracle: SVD with the determinant fix
+    with pytest.raises(RuntimeError):                                  # the product has no CPU path
+        camera.rigid_points_registration(x, y)
     R, t = F.kabsch(x.to(DEV), y.to(DEV))
     torch.testing.assert_close(R.cpu(), R_ref, rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(t.cpu(), t_ref, rtol=1e-4, atol=2e-5)
