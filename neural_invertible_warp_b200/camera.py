@@ -125,14 +125,15 @@ class Lie:
 
 pose = Pose()
 lie = Lie()
+_POSE = pose      # functions below take a ``pose`` argument (the reference's name), which shadows the module-level object
 
 
 def to_hom(X):
     return torch.cat([X, torch.ones_like(X[..., :1])], dim=-1)
 
 
-def world2cam(X, pose_):
-    return to_hom(X) @ pose_.transpose(-1, -2)
+def world2cam(X, pose):
+    return to_hom(X) @ pose.transpose(-1, -2)
 
 
 def cam2img(X, cam_intr):
@@ -143,8 +144,8 @@ def img2cam(X, cam_intr):
     return X @ torch.linalg.inv(cam_intr).transpose(-1, -2)
 
 
-def cam2world(X, pose_):
-    return to_hom(X) @ pose.invert(pose_).transpose(-1, -2)
+def cam2world(X, pose):
+    return to_hom(X) @ _POSE.invert(pose).transpose(-1, -2)
 
 
 # --------------------------------------------------------------------------------------------
@@ -160,18 +161,18 @@ def _bcast_intr(intr, B):
     return intr if intr.shape[0] == B else intr.expand(B, 3, 3)
 
 
-def get_center_and_ray(opt, pose_, intr=None, ray_idx=None, idx_start=0, num=None):
+def get_center_and_ray(opt, pose, intr=None, ray_idx=None, idx_start=0, num=None):
     """reference camera.py:419-443 followed by the ``[:, ray_idx]`` of model/nerf.py:298-300.
 
-    pose_ [B,3,4] (or [3,4], broadcast over the images of ``intr``), intr [B,3,3] ->
+    pose [B,3,4] (or [3,4], broadcast over the images of ``intr``), intr [B,3,3] ->
     center, ray [B,P,3].  ``ray_idx=None`` renders pixels ``idx_start .. idx_start+num-1``
-    (whole frame by default).  Differentiable with respect to ``pose_``.
+    (whole frame by default).  Differentiable with respect to ``pose``.
     """
     _check_perspective(opt)
-    B = max(pose_.shape[0] if pose_.dim() == 3 else 1, intr.shape[0])
-    if pose_.dim() == 2 or pose_.shape[0] != B:
-        pose_ = pose_.expand(B, 3, 4)
-    return F.raygen_pose(pose_, _bcast_intr(intr, B), opt.H, opt.W, ray_idx=ray_idx, idx_start=idx_start, num=num)
+    B = max(pose.shape[0] if pose.dim() == 3 else 1, intr.shape[0])
+    if pose.dim() == 2 or pose.shape[0] != B:
+        pose = pose.expand(B, 3, 4)
+    return F.raygen_pose(pose, _bcast_intr(intr, B), opt.H, opt.W, ray_idx=ray_idx, idx_start=idx_start, num=num)
 
 
 def get_unwarped_center_and_ray(opt, intr=None, ray_idx=None, pose_init=None, idx_start=0, num=None):

@@ -43,6 +43,18 @@ class Graph(nerf_inn_llff.Graph):
         if mode == "train":
             return self._initial_pose(opt, var)[0]
 
+    def _warp_network(self):
+        """``self.warp_mlp`` is attached by the engine (model/barf_inn_llff.py:54-55).  Behind the reference's engine it must be
+        this package's fused ``DeformNetwork`` -- ``dropin.install_dropin`` swaps ``model.nvp.nvp_ndr.DeformNetwork`` -- not the
+        reference's eager module: there is no non-CUDA-kernel path."""
+        from ..nvp import DeformNetwork
+        if not isinstance(self.warp_mlp, DeformNetwork):
+            raise RuntimeError("niw_b200: graph.warp_mlp is %s.%s, not neural_invertible_warp_b200.nvp.DeformNetwork -- call "
+                               "neural_invertible_warp_b200.dropin.install_dropin(reference_root) before the engine builds its "
+                               "networks (it swaps model.nvp.nvp_ndr.DeformNetwork)"
+                               % (type(self.warp_mlp).__module__, type(self.warp_mlp).__name__))
+        return self.warp_mlp
+
     def _latent(self, opt):
         if opt.warp_latent.enc_type == "l2fbarf":
             return self.warp_latent.weight
@@ -67,8 +79,8 @@ class Graph(nerf_inn_llff.Graph):
             # the warp sees [grid rows ; centre] with the centre evaluated once per image when that is exact, and a ray
             # shard's rows at their positions in the global list (functional.warp_point_list)
             wpts, index_map, shared = F.warp_point_list(pts, P, F.ray_shard)
-            warped = self.warp_mlp.forward(self._latent(opt), wpts.unsqueeze(2), alpha_ratio=alpha_ratio,
-                                           index_map=index_map)[:, :, 0]
+            warped = self._warp_network().forward(self._latent(opt), wpts.unsqueeze(2), alpha_ratio=alpha_ratio,
+                                                  index_map=index_map)[:, :, 0]
             ray, center_3D = F.rays_from_warp_shared(warped, P) if shared else F.rays_from_warp(warped, P)
             return ray, center_3D, warped[:, :P], alpha_ratio
         if mode == "render_train":
@@ -77,7 +89,7 @@ class Graph(nerf_inn_llff.Graph):
             with torch.no_grad():
                 pts = camera.unwarped_points(opt, var.intr[ind][None])
             P = pts.shape[1] // 2
-            warped = self.warp_mlp.forward(self._latent(opt)[ind][None], pts.unsqueeze(2), alpha_ratio=1)[:, :, 0]
+            warped = self._warp_network().forward(self._latent(opt)[ind][None], pts.unsqueeze(2), alpha_ratio=1)[:, :, 0]
             return warped[:, :P] - warped[:, P:], warped[:, P:]
         if mode in ["val", "eval", "test-optim"]:
             return barf.Graph._aligned_test_pose(self, opt, var, mode)
