@@ -36,6 +36,10 @@ extern "C" {
 /* precision of the MLP GEMMs */
 #define NIW_PREC_FP32 0 /* CUDA-core fp32 (parity / high-precision path)          */
 #define NIW_PREC_BF16 1 /* tcgen05 BF16 operands, FP32 accumulate in TMEM (fast)  */
+#define NIW_PREC_BF16X3 2 /* tcgen05, every operand a hi + lo BF16 pair and every product 3 MMAs (hi.hi + lo.hi + hi.lo), FP32
+                           * accumulate: ~fp32 operand accuracy on the tensor cores -- the path that meets the 1e-3 max-abs
+                           * contract on rendered rgb / depth / opacity.  Forward only; niw_nerf_bwd runs the BF16 backward
+                           * on the tile records this forward saves (gradient contract: 1e-2 relative, BF16 operands). */
 
 int niw_abi_version(void);
 const char* niw_error_string(int code);
@@ -161,7 +165,7 @@ size_t niw_nerf_workspace_bytes(int64_t R, int N, int precision, int training);
 int niw_nerf_fwd(const float* params, const float* center, const float* ray, const float* depth,
                  int64_t R, int N, const float* progress, float c2f_start, float c2f_end, int precision, int training,
                  void* workspace, size_t workspace_bytes, float* rgb, float* sigma, void* stream);
-/* The parameter-only part of niw_nerf_fwd for NIW_PREC_BF16 (fp32 parameters -> BF16 weight streams and constants in
+/* The parameter-only part of niw_nerf_fwd for NIW_PREC_BF16 / NIW_PREC_BF16X3 (fp32 parameters -> BF16 weight streams and constants in
  * `workspace`): it does not depend on the rays, so a caller may run it early on another stream; pass
  * `training | NIW_NERF_PREPACKED` to the following niw_nerf_fwd on the same workspace to skip it there. */
 #define NIW_NERF_PREPACKED 2

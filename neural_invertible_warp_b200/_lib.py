@@ -14,6 +14,7 @@ _LIB = None
 
 NIW_PREC_FP32 = 0
 NIW_PREC_BF16 = 1
+NIW_PREC_BF16X3 = 2
 NIW_NERF_PREPACKED = 2
 NIW_NERF_PARAMS = 530052
 NIW_NVP_BLOCK_FLOATS = ((128 * 27 + 128 + 1 + 128 * 13 + 3 * 128 + 3) + 3) // 4 * 4   # 5636, include/niw_b200.h

@@ -24,7 +24,9 @@ extern "C" const char* niw_error_string(int code) {
 extern "C" size_t niw_nerf_workspace_bytes(int64_t R, int N, int precision, int training) {
     if (R <= 0 || N <= 0) return 0;
     training &= 1;
-    return precision == NIW_PREC_BF16 ? tc_workspace_bytes(R, N, training) : fp32_workspace_bytes(R, N, training);
+    if (precision == NIW_PREC_BF16) return tc_workspace_bytes(R, N, training);
+    if (precision == NIW_PREC_BF16X3) return tc_x3_workspace_bytes(R, N, training);
+    return precision == NIW_PREC_FP32 ? fp32_workspace_bytes(R, N, training) : 0;
 }
 
 // `progress` is the DEVICE scalar of the BARF schedule (model/barf.py:254); the band weights of
@@ -41,6 +43,9 @@ extern "C" int niw_nerf_fwd(const float* params, const float* center, const floa
     if (precision == NIW_PREC_BF16)
         return tc_fwd(params, center, ray, depth, R, N, c2f, training, workspace, workspace_bytes, rgb, sigma,
                       niw_stream(stream));
+    if (precision == NIW_PREC_BF16X3)
+        return tc_x3_fwd(params, center, ray, depth, R, N, c2f, training, workspace, workspace_bytes, rgb, sigma,
+                         niw_stream(stream));
     return NIW_E_UNSUPP;
 }
 
@@ -48,8 +53,10 @@ extern "C" int niw_nerf_pack(const float* params, const float* progress, float c
                              int training, int64_t R, int N, void* workspace, size_t workspace_bytes, void* stream) {
     NIW_CHECK_ARG(params && workspace && R > 0 && N > 0);
     if (progress && !(c2f_end != c2f_start)) return NIW_E_BADARG;
-    if (precision != NIW_PREC_BF16) return NIW_E_UNSUPP;      // the FP32 path reads the parameters in place
     C2F c2f{progress, c2f_start, c2f_end};
+    if (precision == NIW_PREC_BF16X3)
+        return tc_x3_pack(params, c2f, training & 1, R, N, workspace, workspace_bytes, niw_stream(stream));
+    if (precision != NIW_PREC_BF16) return NIW_E_UNSUPP;      // the FP32 path reads the parameters in place
     return tc_pack(params, c2f, training & 1, R, N, workspace, workspace_bytes, niw_stream(stream));
 }
 
@@ -62,7 +69,7 @@ extern "C" int niw_nerf_bwd(const float* params, const float* center, const floa
     if (precision == NIW_PREC_FP32)
         return fp32_bwd(params, center, ray, depth, R, N, workspace, workspace_bytes, d_rgb, d_sigma, d_params,
                         d_center, d_ray, niw_stream(stream));
-    if (precision == NIW_PREC_BF16)
+    if (precision == NIW_PREC_BF16 || precision == NIW_PREC_BF16X3)     // the split-precision forward saves BF16 tile records too
         return tc_bwd(params, center, ray, depth, R, N, workspace, workspace_bytes, d_rgb, d_sigma, d_params,
                       d_center, d_ray, niw_stream(stream));
     return NIW_E_UNSUPP;

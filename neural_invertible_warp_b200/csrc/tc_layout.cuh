@@ -82,6 +82,16 @@ __host__ __device__ constexpr int64_t stream_off(int l) {
 }
 constexpr int64_t STREAM_BYTES = stream_off(NLAYER);
 static_assert(STREAM_BYTES == 1126400, "weight stream size");
+// split-precision forward (mlp_tc_x3.cu): every main chunk carries a hi and a lo BF16 image of the weights
+__host__ __device__ constexpr int64_t layer_stream_x3_bytes(int l) {
+    return (int64_t)layer_rows(l) * (2 * layer_chunks(l) * CHUNK_K + BIAS_K) * 2;
+}
+__host__ __device__ constexpr int64_t stream_x3_off(int l) {
+    int64_t o = 0;
+    for (int i = 0; i < l; ++i) o += layer_stream_x3_bytes(i);
+    return o;
+}
+constexpr int64_t STREAM_X3_BYTES = stream_x3_off(NLAYER);
 
 // ---- dX-pass weight stream (transposed weights): D[samples, N = inputs] = G[samples, K = outputs] . B^T ----
 // step:        0 view   1 rgb0   2 L7    3 L6    4 L5    5 L4enc  6 L4    7 L3    8 L2    9 L1    10 L0
@@ -135,11 +145,12 @@ struct Workspace {
     uint8_t* save;        // [tiles] x SAVE_TILE_BYTES
     float* scratch;       // [SMs*2 slots][64][128] fp32: skip-connection gradient parked between steps 5 and 10
     float* partial;       // [max_slices][NPARAMS] fp32 weight-gradient partial sums
+    uint8_t* wstream_x3;  // split-precision forward weight stream (hi / lo bf16), carved last: the other offsets do not move
     size_t bytes;
 };
 constexpr int PARTIAL_SLICES = 16;
 
-inline Workspace carve(void* base, int64_t S, bool training) {
+inline Workspace carve(void* base, int64_t S, bool training, bool x3 = false) {
     Workspace w;
     size_t off = 0;
     auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += (n + 255) & ~size_t(255); return p; };
@@ -152,6 +163,7 @@ inline Workspace carve(void* base, int64_t S, bool training) {
     w.save = take(training ? tiles * SAVE_TILE_BYTES : 0);
     w.scratch = (float*)take(training ? (size_t)niw_num_sms() * 2 * ENC3_PAD * TILE * 4 : 0);
     w.partial = (float*)take(training ? (size_t)PARTIAL_SLICES * NPARAMS * 4 : 0);
+    w.wstream_x3 = take(x3 ? STREAM_X3_BYTES : 0);
     w.bytes = off;
     return w;
 }

@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import NIW_PREC_BF16, NIW_PREC_FP32, NIW_NERF_PARAMS, NIW_NVP_BLOCK_FLOATS  # noqa: F401
+from ._lib import NIW_PREC_BF16, NIW_PREC_BF16X3, NIW_PREC_FP32, NIW_NERF_PARAMS, NIW_NVP_BLOCK_FLOATS  # noqa: F401
 
 _c = ctypes
 
@@ -41,7 +41,7 @@ def _idx(ray_idx, device):
     return ray_idx.to(torch.int64).contiguous()
 
 
-PRECISIONS = {"fp32": NIW_PREC_FP32, "bf16": NIW_PREC_BF16}
+PRECISIONS = {"fp32": NIW_PREC_FP32, "bf16": NIW_PREC_BF16, "bf16x3": NIW_PREC_BF16X3}
 
 
 class KernelTimer:
@@ -91,7 +91,7 @@ def precision_code(p):
     try:
         return PRECISIONS[str(p).lower()]
     except KeyError:
-        raise RuntimeError("niw_b200: unknown arch.mlp_precision %r (fp32 | bf16)" % (p,))
+        raise RuntimeError("niw_b200: unknown arch.mlp_precision %r (fp32 | bf16 | bf16x3)" % (p,))
 
 
 # --------------------------------------------------------------------------------------------
@@ -357,7 +357,7 @@ class _NerfSamples(torch.autograd.Function):
         flags = int(training)
         if prepacked is not None:
             # weight streams already packed into this workspace (nerf_prepack, possibly on another stream)
-            if prepacked.numel() != nbytes or precision != NIW_PREC_BF16:
+            if prepacked.numel() != nbytes or precision not in (NIW_PREC_BF16, NIW_PREC_BF16X3):
                 raise RuntimeError("niw_b200: prepacked workspace does not match this call")
             ws, flags = prepacked, flags | _lib.NIW_NERF_PREPACKED
         else:
@@ -445,7 +445,7 @@ def nerf_prepack(params, R, N, progress=None, c2f=None, precision=NIW_PREC_BF16,
     produced.  Returns the workspace to pass as ``prepacked`` (``training`` must be what that call will use), or None
     when there is nothing to hoist (FP32 path)."""
     precision = precision_code(precision)
-    if precision != NIW_PREC_BF16:
+    if precision not in (NIW_PREC_BF16, NIW_PREC_BF16X3):
         return None
     lib = _lib.load()
     params = _f32(params, "params")

@@ -170,9 +170,33 @@ class NeRFCore(nn.Module):
             return self.progress.data, tuple(opt.barf_c2f)
         return None, None
 
+    _warned_default = False
+
     @staticmethod
-    def precision(opt):
-        return opt.arch.get("mlp_precision", "bf16") if hasattr(opt.arch, "get") else "bf16"
+    def precision(opt, mode=None):
+        """MLP operand precision of a call.  ``arch.mlp_precision`` (fp32 | bf16 | bf16x3), when the YAML sets it, rules
+        every mode (``arch.mlp_precision_eval`` overrides it for val / eval renders).  An unmodified reference YAML sets
+        neither; then the defaults follow the contract of BASELINE.json: rendering whose outputs are the product
+        (val / eval / direct calls) runs the split-precision tensor-core path (bf16x3: rgb / depth / opacity within 1e-3
+        of the reference's fp32), optimisation steps (train / test-optim) run BF16 operands (gradients within 1e-2
+        relative) -- announced once, because training numerics then differ from the reference's fp32 GEMMs."""
+        a = opt.arch
+        get = a.get if hasattr(a, "get") else (lambda k, d=None: getattr(a, k, d))
+        p = get("mlp_precision", None)
+        if mode in ("val", "eval") and get("mlp_precision_eval", None) is not None:
+            return get("mlp_precision_eval")
+        if p is not None:
+            return p
+        if mode in ("train", "test-optim"):
+            if not NeRFCore._warned_default:
+                NeRFCore._warned_default = True
+                import warnings
+                warnings.warn("niw_b200: arch.mlp_precision is not set: optimisation steps run the MLP with BF16 tensor-core "
+                              "operands (FP32 accumulate; parameter gradients within 1e-2 relative of the reference's fp32 "
+                              "path), val / eval renders with split BF16 operands (bf16x3, outputs within 1e-3).  Set "
+                              "arch.mlp_precision=bf16x3 or fp32 for reference-tight training numerics.", stacklevel=3)
+            return "bf16"
+        return "bf16x3"
 
     def _check_mode(self, opt, mode):
         if opt.nerf.density_noise_reg and mode == "train":
@@ -190,8 +214,8 @@ class NeRFCore(nn.Module):
         view = ray_unit.expand_as(points_3D).reshape(-1, 3)
         depth = torch.zeros(pts.shape[0], 1, device=pts.device)
         progress, c2f = self.c2f_schedule(opt)
-        rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), pts, view, depth, progress, c2f, self.precision(opt),
-                                            module=self)
+        rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), pts, view, depth, progress, c2f,
+                                            self.precision(opt, mode), module=self)
         return rgb.view(*shape, 3), sigma.view(*shape)
 
     def forward_samples(self, opt, center, ray, depth_samples, mode=None, prepacked=None):
@@ -201,16 +225,16 @@ class NeRFCore(nn.Module):
         B, P, N = depth_samples.shape[:3]
         progress, c2f = self.c2f_schedule(opt)
         rgb, sigma = F.nerf_forward_samples(self.flat_parameters(), center.reshape(B * P, 3), ray.reshape(B * P, 3),
-                                            depth_samples.reshape(B * P, N), progress, c2f, self.precision(opt),
+                                            depth_samples.reshape(B * P, N), progress, c2f, self.precision(opt, mode),
                                             module=self, prepacked=prepacked)
         return rgb.view(B, P, N, 3), sigma.view(B, P, N)
 
-    def prepack(self, opt, n_rays, n_samples):
+    def prepack(self, opt, n_rays, n_samples, mode="train"):
         """Workspace of the coming ``forward_samples`` call with the weight streams already packed (current stream);
         None when the precision has nothing to hoist.  Training-ness is decided as that call will decide it."""
         training = torch.is_grad_enabled() and any(p.requires_grad for p in self.mlp_parameters())
         progress, c2f = self.c2f_schedule(opt)
-        return F.nerf_prepack(self.flat_parameters(), n_rays, n_samples, progress, c2f, self.precision(opt), training), training
+        return F.nerf_prepack(self.flat_parameters(), n_rays, n_samples, progress, c2f, self.precision(opt, mode), training), training
 
     def composite(self, opt, ray, rgb_samples, density_samples, depth_samples, want_prob=True):
         """model/nerf.py:458-474 -> rgb [B,P,3], depth [B,P,1], opacity [B,P,1], prob [B,P,N,1]

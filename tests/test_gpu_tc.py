@@ -197,3 +197,125 @@ def test_tc_full_size_equals_sum_of_chunks(F):
     for i in (3, 4):      # per-ray input gradients: same atomics per ray in both runs, order within a ray may differ
         a, b = whole[i].double(), torch.cat([q[i] for q in parts]).double()
         assert ((a - b).norm() / b.norm()).item() < 1e-4
+
+
+# --------------------------------------------------------------------------------------------
+# tensor-core paths DIRECTLY against the CPU oracle (reference model/nerf.py:416-474), C2 batch
+# --------------------------------------------------------------------------------------------
+
+# tolerances (BASELINE.json north_star): rendered rgb / depth / opacity within 1e-3 max abs for the 1e-3 path (bf16x3:
+# split BF16 operands, FP32 accumulate); MLP parameter gradients within 1e-2 relative (per-tensor rel-L2) for BF16
+# operands.  Plain BF16 operands do NOT meet 1e-3 on the forward: they are held to the measured level.
+# Inverse-depth (LLFF) composited depths reach ~1e1..1e3 (weights x 1/(u+1e-8)): depth is compared as
+# |d - d_ref| <= atol + rtol |d_ref|.
+OUT_TOL = {"bf16": dict(rgb=5e-3, opacity=1e-3, depth_atol=2e-2, depth_rtol=5e-3),
+           "bf16x3": dict(rgb=1e-3, opacity=1e-3, depth_atol=1e-3, depth_rtol=1e-3)}
+GRAD_TOL = 1e-2
+
+
+def _oracle_c2(p, center, ray, depth, target, prog, c2f):
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    c, r = center.clone().requires_grad_(True), ray.clone().requires_grad_(True)
+    d = depth[None, ..., None]
+    pts, unit = ora.sample_points(c[None], r[None], d)
+    rgb_s, sig_s = ora.nerf_mlp(q, pts, unit, progress=prog, c2f=c2f)
+    rgb, dep, op, _ = ora.composite(r[None], rgb_s, sig_s, d)
+    loss = ((rgb[0] - target) ** 2).mean()
+    loss.backward()
+    return dict(rgb=rgb[0].detach(), depth=dep[0, :, 0].detach(), opacity=op[0, :, 0].detach(), loss=loss.detach(),
+                grads={k: v.grad for k, v in q.items()}, d_center=c.grad, d_ray=r.grad)
+
+
+@pytest.mark.parametrize("param", ["metric", "inverse"])
+def test_tc_paths_vs_oracle_c2(F, param):
+    """BF16 and split-BF16 (bf16x3) tensor-core paths against the CPU oracle at the C2 batch (1 024 rays x 128 samples),
+    both depth parametrisations: composited rgb / DEPTH / opacity and every MLP parameter gradient, errors printed."""
+    R, N = 1024, 128
+    gen = torch.Generator().manual_seed(2024 + (param == "inverse"))
+    p = syn.nerf_params(13)
+    center = torch.randn(R, 3, generator=gen) * 0.1
+    ray = torch.randn(R, 3, generator=gen) * 0.3 + torch.tensor([0., 0., 1.])
+    u = torch.rand(1, R, N, 1, generator=gen)
+    rng = [1.2, 5.2] if param == "metric" else [1, 0]
+    depth = ora.stratified_depth(u, N, rng, param)[0, ..., 0]
+    target = torch.rand(R, 3, generator=gen)
+    prog, c2f = 0.3, [0.1, 0.5]
+    ref = _oracle_c2(p, center, ray, depth, target, prog, c2f)
+    for prec in ("bf16", "bf16x3"):
+        flat = _flat(p).to(DEV).requires_grad_(True)
+        c, r = center.to(DEV).requires_grad_(True), ray.to(DEV).requires_grad_(True)
+        d = depth.to(DEV)
+        rgb_s, sig_s = F.nerf_forward_samples(flat, c, r, d, prog, c2f, prec, training=True)
+        rgb, dep, op, _ = F.composite(r, rgb_s, sig_s, d)
+        ((rgb - target.to(DEV)) ** 2).mean().backward()
+        torch.cuda.synchronize()
+        tol = OUT_TOL[prec]
+        e_rgb = (rgb.detach().cpu() - ref["rgb"]).abs().max().item()
+        e_op = (op.detach().cpu() - ref["opacity"]).abs().max().item()
+        dd = (dep.detach().cpu() - ref["depth"]).abs()
+        e_dep = dd.max().item()
+        dep_excess = (dd - tol["depth_rtol"] * ref["depth"].abs()).max().item()
+        print("[%s %s] vs oracle: rgb %.3e  opacity %.3e  depth abs %.3e (max |depth| %.3e, excess over rtol %.3e)"
+              % (prec, param, e_rgb, e_op, e_dep, ref["depth"].abs().max().item(), dep_excess))
+        assert e_rgb <= tol["rgb"], (prec, "rgb", e_rgb)
+        assert e_op <= tol["opacity"], (prec, "opacity", e_op)
+        assert dep_excess <= tol["depth_atol"], (prec, "depth", e_dep, dep_excess)
+        g = _split(flat.grad.detach().cpu(), p)
+        worst = ("", 0.0)
+        for k in _nerf_keys():
+            a, b = g[k].double(), ref["grads"][k].double().reshape(-1)
+            rel = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+            worst = max(worst, (k, rel), key=lambda t: t[1])
+            assert rel < GRAD_TOL, (prec, k, rel)
+        rel_c = ((c.grad.cpu().double() - ref["d_center"].double()).norm() / ref["d_center"].double().norm()).item()
+        rel_r = ((r.grad.cpu().double() - ref["d_ray"].double()).norm() / ref["d_ray"].double().norm()).item()
+        print("[%s %s] gradients vs oracle: worst MLP tensor %s rel-L2 %.3e (bar %.0e); d_center %.3e  d_ray %.3e "
+              "(ill-conditioned input path, SURVEY.md H10: reported, bound 0.5)" % (prec, param, worst[0], worst[1], GRAD_TOL, rel_c, rel_r))
+        assert rel_c < 0.5 and rel_r < 0.5
+
+
+@pytest.mark.parametrize("R,N", [(4, 128), (37, 16), (64, 192), (333, 128)])
+def test_tc_x3_forward_meets_1e3(F, R, N):
+    """The split-precision tensor-core forward (row n1: the 1e-3 path, replacing the CUDA-core FP32 kernels in that role)
+    on ragged shapes (partial tiles, a lone CTA pair, N not a multiple of 32), per-sample and composited, inference mode."""
+    gen = torch.Generator().manual_seed(3 * R + N)
+    p = syn.nerf_params(11)
+    flat = _flat(p).to(DEV)
+    center = torch.randn(R, 3, generator=gen) * 0.1
+    ray = torch.randn(R, 3, generator=gen) * 0.3 + torch.tensor([0., 0., 1.])
+    u = torch.rand(1, R, N, 1, generator=gen)
+    depth = ora.stratified_depth(u, N, [1.2, 5.2], "metric")[0, ..., 0]
+    prog, c2f = 0.3, [0.1, 0.5]
+    d = depth[None, ..., None]
+    pts, unit = ora.sample_points(center[None], ray[None], d)
+    rgb_ref, sig_ref = ora.nerf_mlp(p, pts, unit, progress=prog, c2f=c2f)
+    out_ref = ora.composite(ray[None], rgb_ref, sig_ref, d)
+    rgb, sig = F.nerf_forward_samples(flat, center.to(DEV), ray.to(DEV), depth.to(DEV), prog, c2f, "bf16x3", training=False)
+    e_rgb = (rgb.cpu() - rgb_ref[0]).abs().max().item()
+    e_sig = ((sig.cpu() - sig_ref[0]).abs() / (1 + sig_ref[0].abs())).max().item()
+    out = F.composite(ray.to(DEV), rgb, sig, depth.to(DEV))
+    errs = [(a.cpu().reshape(-1) - b[0].reshape(-1)).abs().max().item() for a, b in zip(out[:3], out_ref[:3])]
+    print("bf16x3 vs oracle R=%d N=%d: per-sample rgb %.3e sigma(rel) %.3e | composited rgb %.3e depth %.3e opacity %.3e"
+          % (R, N, e_rgb, e_sig, *errs))
+    assert e_rgb < 1e-3 and e_sig < 1e-3 and max(errs) < 1e-3
+
+
+def test_tc_x3_training_records_feed_the_bf16_backward(F):
+    """bf16x3 forward in training mode writes the same tile records as the BF16 forward (hi images, ReLU masks): its
+    backward is the BF16 backward and must agree with the BF16 path's gradients up to the forward's rounding."""
+    R, N = 256, 128
+    gen = torch.Generator().manual_seed(99)
+    p = syn.nerf_params(13)
+    center = (torch.randn(R, 3, generator=gen) * 0.1).to(DEV)
+    ray = (torch.randn(R, 3, generator=gen) * 0.3 + torch.tensor([0., 0., 1.])).to(DEV)
+    depth = (torch.rand(R, N, generator=gen) * 4 + 1).sort(-1).values.to(DEV)
+    w_rgb = (torch.rand(R, N, 3, generator=gen) - 0.5).to(DEV)
+    grads = {}
+    for prec in ("bf16", "bf16x3"):
+        flat = _flat(p).to(DEV).requires_grad_(True)
+        rgb, sig = F.nerf_forward_samples(flat, center, ray, depth, 0.3, [0.1, 0.5], prec, training=True)
+        ((rgb * w_rgb).sum() + sig.sum() * 0.01).backward()
+        grads[prec] = flat.grad.double()
+    rel = ((grads["bf16"] - grads["bf16x3"]).norm() / grads["bf16x3"].norm()).item()
+    print("bf16 vs bf16x3 parameter gradient rel-L2 %.3e" % rel)
+    assert rel < 2e-2
