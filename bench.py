@@ -428,30 +428,34 @@ def run_train(args):
             with engine.feed_draws(ray_idx=static["ray_idx"], u=static["u"]):
                 v = graph.forward(opt, v, mode="train", iter=it)
             loss = engine.summarize_loss(opt, graph.compute_loss(opt, v, mode="train"))
-            if world > 1:
-                with engine.overlap_allreduce(graph, adam):
-                    (loss.all * (1.0 / world)).backward()
-                adam.allreduce()
-            else:
-                loss.all.backward()
+            with engine.backward_schedule(graph):          # dW on a side stream under the pose / warp backward (as train_step)
+                if world > 1:
+                    with engine.overlap_allreduce(graph, adam):
+                        (loss.all * (1.0 / world)).backward()
+                    adam.allreduce()
+                else:
+                    loss.all.backward()
             adam.step()
             return loss.all.detach()
         return step_static
 
     e2e_body = [make_step_static(statics[0]), make_step_static(statics[1])]
 
-    class HostLoader:
-        """The host side of the e2e leg: loader threads draw every step's pixel indices (k distinct pixels of the frame,
-        what ``torch.randperm(H*W)[:k]`` yields, in O(k)) and stratified uniforms into pinned staging sets while the GPU
-        works on earlier steps -- inside the timed region, like a prefetching data loader."""
+    CHUNK = 8          # steps per staging set: one GIL-free numpy fill per 8 steps keeps the loader threads off the main thread's back
 
-        def __init__(self, n_sets=4, n_threads=2):
+    class HostLoader:
+        """The host side of the e2e leg: loader threads draw the pixel indices (k distinct pixels of the frame, what
+        ``torch.randperm(H*W)[:k]`` yields, in O(k)) and stratified uniforms of the coming steps into pinned staging sets
+        (CHUNK steps per set) while the GPU works on earlier steps -- inside the timed region, like a prefetching data
+        loader."""
+
+        def __init__(self, n_sets=3, n_threads=2):
             import queue
             import numpy as np
             self.free, self.ready = queue.Queue(), queue.Queue()
             for _ in range(n_sets):
-                self.free.put(dict(ridx=torch.empty(P_local, dtype=torch.int64).pin_memory(),
-                                   u=torch.empty(IMAGES, P_local, N_SAMPLES, 1).pin_memory(), copied=None))
+                self.free.put(dict(ridx=torch.empty(CHUNK, P_local, dtype=torch.int64).pin_memory(),
+                                   u=torch.empty(CHUNK, IMAGES, P_local, N_SAMPLES, 1).pin_memory(), copied=None))
             self.threads = [threading.Thread(target=self._work, args=(np.random.default_rng(1234 + 97 * rank + t), np),
                                              daemon=True) for t in range(n_threads)]
             for t in self.threads:
@@ -464,7 +468,9 @@ def run_train(args):
                     return
                 if s["copied"] is not None:
                     s["copied"].synchronize()              # the H2D copies out of this staging set have completed
-                s["ridx"].numpy()[:] = rng.choice(H * W, P_local, replace=False)
+                ridx = s["ridx"].numpy()
+                for k in range(CHUNK):
+                    ridx[k] = rng.choice(H * W, P_local, replace=False)
                 rng.random(out=s["u"].numpy().reshape(-1), dtype=np.float32)
                 self.ready.put(s)
 
@@ -477,21 +483,24 @@ def run_train(args):
         main = torch.cuda.current_stream()
         loader = HostLoader()
         losses = []
+        batch = None
         for i in range(steps):
-            b = i & 1
-            batch = loader.ready.get()                           # host-side batch of this step (pinned memory)
+            b, k = i & 1, i % CHUNK
+            if k == 0:
+                batch = loader.ready.get()                       # host-side batches of the next CHUNK steps (pinned memory)
             with torch.cuda.stream(copy_stream):
                 if i >= 2:
                     copy_stream.wait_event(consumed[b])          # step i-2 is done with this buffer set
                 st = statics[b]
-                st["ray_idx"].copy_(batch["ridx"], non_blocking=True)
-                st["u"].copy_(batch["u"], non_blocking=True)
-                for k in ("idx", "intr", "pose"):
-                    st[k].copy_(pin[k], non_blocking=True)
+                st["ray_idx"].copy_(batch["ridx"][k], non_blocking=True)
+                st["u"].copy_(batch["u"][k], non_blocking=True)
+                for key in ("idx", "intr", "pose"):
+                    st[key].copy_(pin[key], non_blocking=True)
                 ready[b].record(copy_stream)
-                batch["copied"] = torch.cuda.Event()
-                batch["copied"].record(copy_stream)
-            loader.free.put(batch)
+                if k == CHUNK - 1 or i == steps - 1:
+                    batch["copied"] = torch.cuda.Event()
+                    batch["copied"].record(copy_stream)
+                    loader.free.put(batch)
             main.wait_event(ready[b])
             loss = e2e_body[b]()
             loss_host[b].copy_(loss, non_blocking=True)

@@ -103,11 +103,13 @@ int niw_nvp_pack_bwd(const float* const* params, float* const* grads, const floa
 /* idx_offset / idx_split / idx_jump: position of local point n of an image in the point list the reference would have
  * built, n < idx_split ? n + idx_offset : n + idx_offset + idx_jump (the embedder's annealing quirk, embedder.py:46-49,
  * is keyed on it).  Identity: (0, Pt, 0).  A ray shard passes its first ray's index in the global per-image list. */
+/* (max_ctas of the backward: 0 = one CTA per SM; > 0 caps the grid, each warp then walks more points -- for callers that
+ * run it next to another kernel, e.g. niw_nerf_bwd_dw on a second stream) */
 int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                      int B, int Pt, int idx_offset, int idx_split, int idx_jump, float* out, void* stream);
 int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                      int B, int Pt, int idx_offset, int idx_split, int idx_jump, const float* d_out, float* d_wpack,
-                     float* d_code_bias, void* stream);
+                     float* d_code_bias, int max_ctas, void* stream);
 
 /* ---- random pixel subset   model/nerf.py:268 (`torch.randperm(H*W)[:rand_rays//B]`)
  * out[i] = pi(i), i < k, for a keyed random bijection pi of [0,n): the first k entries of a random permutation
@@ -175,6 +177,17 @@ int niw_nerf_bwd(const float* params, const float* center, const float* ray, con
                  int64_t R, int N, int precision,
                  void* workspace, size_t workspace_bytes, const float* d_rgb, const float* d_sigma,
                  float* d_params, float* d_center, float* d_ray, void* stream);
+/* niw_nerf_bwd as two calls (NIW_PREC_BF16 / NIW_PREC_BF16X3): _dx runs the activation-gradient chain (d_center, d_ray, the
+ * gradient images of the tile records), _dw the weight-gradient GEMMs over those records (d_params += ...).  _dw is
+ * HBM-bound and independent of everything downstream of d_center / d_ray, so a training step may enqueue it on a second
+ * stream -- ordered after _dx by the caller -- while the pose / warp backward runs on the first.  max_ctas > 0 caps its
+ * grid (one CTA per SM) so that the concurrent kernels find free SMs; 0 = all SMs. */
+int niw_nerf_bwd_dx(const float* params, const float* center, const float* ray, const float* depth, int64_t R, int N,
+                    int precision, void* workspace, size_t workspace_bytes, const float* d_rgb, const float* d_sigma,
+                    float* d_params, float* d_center, float* d_ray, void* stream);
+int niw_nerf_bwd_dw(int64_t R, int N, int precision, void* workspace, size_t workspace_bytes, float* d_params,
+                    int max_ctas, void* stream);
+
 
 /* ---- loss head: image gather + MSE   model/nerf.py:276-288, model/base.py:209-211
  * image [B,3,H,W], rgb [B,P,3]; loss += scale * sum((rgb - image[:, :, pix])^2) (scale = 1/(B*P*3)

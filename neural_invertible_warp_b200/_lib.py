@@ -33,7 +33,7 @@ SIGNATURES = {
     "niw_nvp_pack_fwd": (_c.c_int, [_P, _P, _c.c_int, _P, _P, _P, _P]),
     "niw_nvp_pack_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int, _P, _P]),
     "niw_nvp_warp_fwd": (_c.c_int, [_P, _P, _P, _c.c_float] + [_c.c_int] * 5 + [_P, _P]),
-    "niw_nvp_warp_bwd": (_c.c_int, [_P, _P, _P, _c.c_float] + [_c.c_int] * 5 + [_P, _P, _P, _P]),
+    "niw_nvp_warp_bwd": (_c.c_int, [_P, _P, _P, _c.c_float] + [_c.c_int] * 5 + [_P, _P, _P, _c.c_int, _P]),
     "niw_sample_pixels": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_uint64, _P, _P, _P]),
     "niw_sample_stratified": (_c.c_int, [_P, _c.c_int64, _c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P]),
     "niw_sample_stratified_dev": (_c.c_int, [_P, _c.c_int64, _c.c_int, _P, _c.c_int, _P, _P]),
@@ -45,6 +45,8 @@ SIGNATURES = {
                                 _c.c_size_t, _P, _P, _P]),
     "niw_nerf_pack": (_c.c_int, [_P, _P, _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _P, _c.c_size_t, _P]),
     "niw_nerf_bwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _P, _P, _P, _P, _P]),
+    "niw_nerf_bwd_dx": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _P, _P, _P, _P, _P]),
+    "niw_nerf_bwd_dw": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _c.c_int, _P]),
     "niw_mse_gather": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),
     "niw_image_metrics": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     "niw_depth_metrics": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_float, _P, _P]),

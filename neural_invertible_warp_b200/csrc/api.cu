@@ -75,6 +75,25 @@ extern "C" int niw_nerf_bwd(const float* params, const float* center, const floa
     return NIW_E_UNSUPP;
 }
 
+// niw_nerf_bwd in two calls (tensor-core precisions only): the activation-gradient chain, then the weight-gradient pass,
+// which may be enqueued on a different stream once the first has been (the caller orders the streams)
+extern "C" int niw_nerf_bwd_dx(const float* params, const float* center, const float* ray, const float* depth, int64_t R,
+                               int N, int precision, void* workspace, size_t workspace_bytes, const float* d_rgb,
+                               const float* d_sigma, float* d_params, float* d_center, float* d_ray, void* stream) {
+    NIW_CHECK_ARG(params && center && ray && depth && workspace && d_rgb && d_sigma && d_params &&
+                  d_center && d_ray && R > 0 && N > 0);
+    if (precision != NIW_PREC_BF16 && precision != NIW_PREC_BF16X3) return NIW_E_UNSUPP;
+    return tc_bwd_dx(params, center, ray, depth, R, N, workspace, workspace_bytes, d_rgb, d_sigma, d_params, d_center,
+                     d_ray, niw_stream(stream));
+}
+
+extern "C" int niw_nerf_bwd_dw(int64_t R, int N, int precision, void* workspace, size_t workspace_bytes, float* d_params,
+                               int max_ctas, void* stream) {
+    NIW_CHECK_ARG(workspace && d_params && R > 0 && N > 0 && max_ctas >= 0);
+    if (precision != NIW_PREC_BF16 && precision != NIW_PREC_BF16X3) return NIW_E_UNSUPP;
+    return tc_bwd_dw(R, N, workspace, workspace_bytes, d_params, max_ctas, niw_stream(stream));
+}
+
 // ---- loss head: pixel gather + squared error  (model/nerf.py:276-288, model/base.py:209-211) ----
 namespace {
 __global__ void mse_gather_kernel(const float* __restrict__ image, const float* __restrict__ rgb,

@@ -51,6 +51,12 @@ int tc_bwd(const float* P, const float* center, const float* ray, const float* d
            void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma,
            float* dP, float* d_center, float* d_ray, cudaStream_t st);
 
+// the two halves of tc_bwd, for callers that run the HBM-bound weight-gradient pass on another stream
+int tc_bwd_dx(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
+              void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma,
+              float* dP, float* d_center, float* d_ray, cudaStream_t st);
+int tc_bwd_dw(int64_t R, int N, void* ws, size_t ws_bytes, float* dP, int max_ctas, cudaStream_t st);
+
 // split-precision (hi + lo BF16 operands, 3 MMAs per product) tcgen05 forward, mlp_tc_x3.cu; its backward is tc_bwd
 size_t tc_x3_workspace_bytes(int64_t R, int N, int training);
 int tc_x3_pack(const float* P, const C2F& c2f, int training, int64_t R, int N, void* ws, size_t ws_bytes, cudaStream_t st);

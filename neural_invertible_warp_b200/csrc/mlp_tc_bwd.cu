@@ -637,9 +637,10 @@ static DwPlan make_plan(int64_t ntiles, int n_sms) {
 
 }  // namespace tc
 
-int tc_bwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
-           void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma, float* dP,
-           float* d_center, float* d_ray, cudaStream_t st) {
+// activation-gradient chain: G images into the tile records, d_center / d_ray, the CUDA-core heads' bias gradients
+int tc_bwd_dx(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
+              void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma, float* dP,
+              float* d_center, float* d_ray, cudaStream_t st) {
     using namespace tc;
     (void)P;
     const int64_t S = R * (int64_t)N;
@@ -656,10 +657,23 @@ int tc_bwd(const float* P, const float* center, const float* ray, const float* d
     niw::note_launch(), tc_dx_kernel<<<grid, 384, BX_TOTAL, st>>>(w.bstream, w.consts, center, ray, depth, S, N, d_rgb, d_sigma,
                                                                  w.sig_pre, w.rgb_keep, w.save, w.scratch, dP, d_center, d_ray);
     NIW_LAUNCH_CHECK();
-    // CTAs of the dW pass (one per SM by default).  The pass is HBM-bound, so fewer CTAs can carry it: NIW_DW_CTAS leaves
-    // the other SMs to a concurrent kernel (tuning knob)
-    static const int dw_ctas = getenv("NIW_DW_CTAS") ? atoi(getenv("NIW_DW_CTAS")) : 0;
-    DwPlan plan = make_plan(ntiles, dw_ctas > 0 && dw_ctas < niw_num_sms() ? dw_ctas : niw_num_sms());
+    return 0;
+}
+
+// weight gradients from the tile records (after tc_bwd_dx on the same workspace): dP += G^T X.  `max_ctas` (0 = one per
+// SM): the pass is HBM-bound, so fewer CTAs carry it at nearly the same speed and leave the other SMs to kernels running
+// concurrently on another stream (the pose / warp backward of the training step)
+int tc_bwd_dw(int64_t R, int N, void* ws, size_t ws_bytes, float* dP, int max_ctas, cudaStream_t st) {
+    using namespace tc;
+    const int64_t S = R * (int64_t)N;
+    Workspace w = carve(ws, S, true);
+    if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
+    const int64_t ntiles = (S + TILE - 1) / TILE;
+    // NIW_DW_CTAS overrides the CTA budget (tuning knob)
+    static const int env_ctas = getenv("NIW_DW_CTAS") ? atoi(getenv("NIW_DW_CTAS")) : 0;
+    int budget = env_ctas > 0 ? env_ctas : max_ctas;
+    if (budget <= 0 || budget > niw_num_sms()) budget = niw_num_sms();
+    DwPlan plan = make_plan(ntiles, budget);
     NIW_CUDA(cudaMemsetAsync(w.partial, 0, sizeof(float) * (size_t)plan.max_slices * NPARAMS, st));
     NIW_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_TOTAL));
     // NIW_DW_DEBUG=1: per-CTA start / end times of the dW pass on stderr (synchronises; diagnostics only)
@@ -685,6 +699,14 @@ int tc_bwd(const float* P, const float* center, const float* ray, const float* d
     niw::note_launch(), tc_dw_reduce_kernel<<<niw_blocks(NPARAMS, 256), 256, 0, st>>>(w.partial, plan.max_slices, dP);
     NIW_LAUNCH_CHECK();
     return 0;
+}
+
+int tc_bwd(const float* P, const float* center, const float* ray, const float* depth, int64_t R, int N,
+           void* ws, size_t ws_bytes, const float* d_rgb, const float* d_sigma, float* dP,
+           float* d_center, float* d_ray, cudaStream_t st) {
+    int e = tc_bwd_dx(P, center, ray, depth, R, N, ws, ws_bytes, d_rgb, d_sigma, dP, d_center, d_ray, st);
+    if (e) return e;
+    return tc_bwd_dw(R, N, ws, ws_bytes, dP, 0, st);
 }
 
 }  // namespace niw

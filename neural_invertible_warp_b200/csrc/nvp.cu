@@ -689,9 +689,9 @@ extern "C" int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, cons
 
 extern "C" int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                                 int B, int Pt, int idx_offset, int idx_split, int idx_jump, const float* d_out,
-                                float* d_wpack, float* d_code_bias, void* stream) {
+                                float* d_wpack, float* d_code_bias, int max_ctas, void* stream) {
     NIW_CHECK_ARG(wpack && code_bias && pts && d_out && d_wpack && d_code_bias && B > 0 && Pt > 0 && idx_offset >= 0 &&
-                  idx_split >= 0 && idx_jump >= 0);
+                  idx_split >= 0 && idx_jump >= 0 && max_ctas >= 0);
     const IndexMap im{idx_offset, idx_split, idx_jump};
     cudaStream_t st = niw_stream(stream);
     NIW_CUDA(cudaMemsetAsync(d_wpack, 0, sizeof(float) * NB * BLOCK_FLOATS, st));
@@ -700,7 +700,9 @@ extern "C" int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, cons
     const int64_t total = (int64_t)B * Pt;
     // points per warp: the pass is a latency chain per warp (blocks in sequence, points in sequence), so as few as one
     // wave of CTAs allows (one CTA per SM: its gradient accumulators fill shared memory)
-    const int64_t warps_max = (int64_t)niw_num_sms() * BWD_WARPS;
+    // (max_ctas > 0: the caller keeps the other SMs for a kernel running concurrently on another stream)
+    const int sms = max_ctas > 0 && max_ctas < niw_num_sms() ? max_ctas : niw_num_sms();
+    const int64_t warps_max = (int64_t)sms * BWD_WARPS;
     int64_t ppw = (total + warps_max - 1) / warps_max;
     if (ppw < 1) ppw = 1;
     if (ppw > MAX_PTS_PER_WARP) ppw = MAX_PTS_PER_WARP;

@@ -13,6 +13,7 @@ lacks (it asserts a single GPU, options.py:103).
 * ``GradBucket``       -- flat fp32 bucket of every trainable gradient: ONE NCCL all-reduce per step
                           (SURVEY.md section 8e); rays shard, parameters replicate.
 """
+import contextlib
 import importlib
 
 import torch
@@ -519,13 +520,28 @@ class feed_draws:
         torch.rand, torch.randperm = self._rand, self._perm
 
 
-def train_step(opt, graph, var, it, bucket=None, rank=0, world=1):
+def backward_schedule(graph):
+    """The graph's functional.BackwardOverlap (made once): opts the network whose backward runs LAST (the coarse NeRF) in
+    to the side-stream weight-gradient pass when there is a pose / warp backward to hide it under."""
+    from . import functional as F
+    ov = getattr(graph, "_backward_overlap", None)
+    if ov is None:
+        has_warp = hasattr(graph, "warp_mlp") or hasattr(graph, "pose_net") or hasattr(graph, "se3_refine")
+        graph.nerf.overlap_weight_gradients = bool(has_warp)
+        ov = graph._backward_overlap = F.BackwardOverlap()
+    return ov
+
+
+def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=True):
     """One optimisation step minus the optimiser: forward, loss, backward (+ all-reduce).
 
     With ``world > 1`` the rank renders a contiguous 1/world slice of the global ray batch; local
     losses are means over the local rays, so they are scaled by ``n_local / n_global`` before the
     summed all-reduce -- the reduced gradient equals the single-GPU gradient of the
     same global batch.  Returns the loss dict (``all`` is the local, scaled value).
+
+    With a flat gradient ``bucket`` (the engine owns every ``.grad``) the backward is scheduled on two streams
+    (``overlap_dw``): see functional.BackwardOverlap.  The streams are joined before this function returns.
     """
     B = len(var.idx)
     n_global = opt.nerf.rand_rays // B
@@ -546,10 +562,16 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1):
     scale = 1.0
     if world > 1:
         scale = len(var.ray_idx) / float(n_global)
-    if bucket is not None and world > 1:
-        with overlap_allreduce(graph, bucket):
-            (loss.all * scale).backward()
-        bucket.allreduce()
+    if bucket is not None:
+        # the weight-gradient pass of the (last) NeRF network runs on a side stream under the pose / warp backward
+        sched = backward_schedule(graph) if overlap_dw else contextlib.nullcontext()
+        with sched:
+            if world > 1:
+                with overlap_allreduce(graph, bucket):
+                    (loss.all * scale).backward()
+                bucket.allreduce()
+            else:
+                loss.all.backward()
     else:
         (loss.all if scale == 1.0 else loss.all * scale).backward()
     return loss

@@ -188,7 +188,7 @@ class _NvpWarp(torch.autograd.Function):
         d_w = torch.empty_like(wpack)
         d_cb = torch.empty_like(code_bias)
         _lib.check(_lib.load().niw_nvp_warp_bwd(_p(wpack), _p(code_bias), _p(pts), ctx.alpha, B, Pt, *ctx.im,
-                                                _p(d_out.contiguous()), _p(d_w), _p(d_cb), _stream()))
+                                                _p(d_out.contiguous()), _p(d_w), _p(d_cb), 0, _stream()))
         return d_w, d_cb, None, None, None
 
 
@@ -331,6 +331,42 @@ def band_weights(progress, c2f, L):
     return [float(x) for x in w]
 
 
+class BackwardOverlap:
+    """Step-level scheduling of the training backward (engine.train_step): the MLP weight-gradient pass (niw_nerf_bwd_dw:
+    streams the tile records, HBM-bound, nothing downstream of it but the optimiser) is enqueued on a side stream with
+    ``dw_ctas`` CTAs, while the pose / warp backward that consumes d_center / d_ray continues on the launching stream on
+    the remaining SMs (``side_ctas`` caps the warp backward's grid to them).  Only for a module the engine has opted in
+    (``module.overlap_weight_gradients``: the LAST NeRF network of the backward pass; an earlier one would push the next
+    network's persistent dX kernel onto the few free SMs).  ``join()`` makes the current stream wait for the side work."""
+
+    def __init__(self, dw_ctas=None, side_ctas=None):
+        import os
+        self.stream = torch.cuda.Stream()
+        n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        self.side_ctas = int(os.environ.get("NIW_OVERLAP_SIDE_CTAS", side_ctas if side_ctas is not None else 24))
+        self.dw_ctas = int(os.environ.get("NIW_OVERLAP_DW_CTAS", dw_ctas if dw_ctas is not None else n - self.side_ctas))
+        self.used = False
+
+    def __enter__(self):
+        global backward_overlap
+        self.used = False
+        backward_overlap = self
+        return self
+
+    def __exit__(self, *exc):
+        global backward_overlap
+        backward_overlap = None
+        self.join()
+
+    def join(self):
+        if self.used:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.used = False
+
+
+backward_overlap = None
+
+
 class _NerfSamples(torch.autograd.Function):
     """``flat`` is the 530 052-float parameter vector the kernels read.  Two ways to receive its
     gradient: (a) ``flat`` itself requires grad (functional use, tests) -> returned through autograd;
@@ -395,15 +431,35 @@ class _NerfSamples(torch.autograd.Function):
         if d_sigma is None:
             d_sigma = torch.zeros(R, N, device=depth.device)
         d_rgb, d_sigma = d_rgb.contiguous(), d_sigma.contiguous()
-        with _timed("nerf_bwd"):
-            _lib.check(_lib.load().niw_nerf_bwd(_p(flat), _p(center), _p(ray), _p(depth), R, N, precision,
-                                                _p(ws), nbytes, _p(d_rgb), _p(d_sigma), dp, _p(d_center),
-                                                _p(d_ray), _stream()))
+        lib = _lib.load()
+        ov = backward_overlap
+        split = (ov is not None and target is not None and precision in (NIW_PREC_BF16, NIW_PREC_BF16X3)
+                 and getattr(module, "overlap_weight_gradients", False) and KernelTimer.active is None)
+        if split:
+            # dX on this stream; dW on the side stream, ordered after it, while this stream goes on to the pose / warp backward
+            _lib.check(lib.niw_nerf_bwd_dx(_p(flat), _p(center), _p(ray), _p(depth), R, N, precision, _p(ws), nbytes,
+                                           _p(d_rgb), _p(d_sigma), dp, _p(d_center), _p(d_ray), _stream()))
+            cur = torch.cuda.current_stream()
+            ov.stream.wait_stream(cur)
+            ov.used = True
+            with torch.cuda.stream(ov.stream):
+                _lib.check(lib.niw_nerf_bwd_dw(R, N, precision, _p(ws), nbytes, dp, ov.dw_ctas, _stream()))
+                if not torch.cuda.is_current_stream_capturing():
+                    ws.record_stream(ov.stream)
+        else:
+            with _timed("nerf_bwd"):
+                _lib.check(lib.niw_nerf_bwd(_p(flat), _p(center), _p(ray), _p(depth), R, N, precision,
+                                            _p(ws), nbytes, _p(d_rgb), _p(d_sigma), dp, _p(d_center),
+                                            _p(d_ray), _stream()))
         if module is not None and n_params:
             module._pending_backward = max(getattr(module, "_pending_backward", 1) - 1, 0)
             ready = getattr(module, "_grads_ready", None)       # engine.overlap_allreduce: this module's gradients are final
             if target is not None and ready is not None and module._pending_backward == 0:
-                ready(module)
+                if split:
+                    with torch.cuda.stream(ov.stream):          # "final" once the side stream's dW has run: order the reduce after it
+                        ready(module)
+                else:
+                    ready(module)
         if n_params and d_params is not None:
             # slow path: the module's gradients are not one flat buffer -> hand slices back to autograd
             pg = tuple(g.view_as(p) for g, p in zip(torch.split(d_params, [p.numel() for p in module.mlp_parameters()]),

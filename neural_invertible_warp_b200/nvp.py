@@ -87,8 +87,10 @@ class _NvpNetwork(torch.autograd.Function):
         d_w = torch.empty_like(wpack)
         d_cb = torch.empty_like(code_bias)
         d_out = d_out.contiguous()
+        ov = F.backward_overlap                 # engine: the MLP weight-gradient pass is running on another stream
         _lib.check(lib.niw_nvp_warp_bwd(F._p(wpack), F._p(code_bias), F._p(pts), ctx.alpha, B, Pt, *ctx.im, F._p(d_out),
-                                        F._p(d_w), F._p(d_cb), F._stream()))
+                                        F._p(d_w), F._p(d_cb), int(ov.side_ctas) if ov is not None and ov.used else 0,
+                                        F._stream()))
         params = ctx.module.ordered_parameters()
         in_place = getattr(ctx.module, "accumulate_grads_in_place", False)
         if in_place:

@@ -29,6 +29,12 @@ fi
 if has c5; then
   timeout 600 python bench.py --config c5 --steps 10 --no-micro > $O/${TAG}_bench_c5.json 2> $O/${TAG}_bench_c5.err; echo "bench c5 exit $?"; cat $O/${TAG}_bench_c5.json; tail -3 $O/${TAG}_bench_c5.err
 fi
+if has sweep; then
+  for side in 12 16 24 32 48; do
+    NIW_OVERLAP_SIDE_CTAS=$side timeout 300 python bench.py --steps 30 --no-cpu-baseline --no-micro > $O/${TAG}_sweep_$side.json 2> $O/${TAG}_sweep_$side.err
+    python -c "import json,sys; d=json.load(open('$O/${TAG}_sweep_$side.json')); print('side_ctas $side: ms/step %.4f value %.0f e2e %.0f mlp_ms %.4f' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['mlp_ms_per_step']))"
+  done
+fi
 if has ref; then
   timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $O/${TAG}_bench_ref.json 2>&1; cat $O/${TAG}_bench_ref.json
 fi

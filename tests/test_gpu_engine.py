@@ -249,3 +249,34 @@ def test_evaluate_view_defaults_for_inn_models(eng, model):
     assert res.var.se3_refine_test.shape == (1, 6) and torch.isfinite(res.psnr).all() and torch.isfinite(res.ssim).all()
     res2 = eng.evaluate_view(opt, graph, cfgmod.AttrDict(var), test_optim=False)
     assert torch.equal(res2.var.pose_refine_test, torch.eye(3, 4, device=DEV)[None]) and torch.isfinite(res2.psnr).all()
+
+
+def test_backward_overlap_matches_sequential_backward(eng):
+    """engine.train_step with a flat bucket runs the MLP weight-gradient pass on a side stream under the pose / warp
+    backward (functional.BackwardOverlap): same gradients as the single-stream backward (the dW slices are partitioned over
+    fewer CTAs, so only the fp32 summation order differs), streams joined on return, also when captured in a CUDA graph."""
+    d = draws(1, seed=12)[0]
+    grads = {}
+    for overlap in (False, True):
+        opt, g, var = make(eng, precision="bf16")
+        bucket = eng.GradBucket(g)
+        with eng.feed_draws(ray_idx=d[0], u=d[1]):
+            eng.train_step(opt, g, cfgmod.AttrDict(var), 5000, bucket=bucket, overlap_dw=overlap)
+        torch.cuda.synchronize()
+        grads[overlap] = bucket.flat.clone()
+        if overlap:
+            assert g.nerf.overlap_weight_gradients and not g._backward_overlap.used      # joined
+            s_ridx, s_u = d[0].clone(), d[1].clone()
+
+            def body():
+                with eng.feed_draws(ray_idx=s_ridx, u=s_u):
+                    eng.train_step(opt, g, cfgmod.AttrDict(var), 5000, bucket=bucket)
+                return bucket.flat
+            captured = eng.CapturedStep(body, warmup=1)
+            captured()
+            torch.cuda.synchronize()
+            grads["graph"] = bucket.flat.clone()
+    for k in (True, "graph"):
+        rel = ((grads[k].double() - grads[False].double()).norm() / grads[False].double().norm()).item()
+        assert rel < 1e-4, (k, rel)
+        assert (grads[k] != 0).sum() == (grads[False] != 0).sum()
