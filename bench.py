@@ -25,6 +25,7 @@ Prints ONE JSON line (see DESIGN.md "Measurement" for every field):
 ``--impl reference`` times that CPU implementation alone (all host threads) and prints the same line shape.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -425,9 +426,10 @@ def run_train(args):
         def step_static():
             v = cfgmod.AttrDict(idx=static["idx"], intr=static["intr"], pose=static["pose"], image=var_dev.image)
             adam.zero()
-            with engine.feed_draws(ray_idx=static["ray_idx"], u=static["u"]):
+            with engine.feed_draws(ray_idx=static["ray_idx"], u=static["u"]), \
+                    (engine.data_parallel() if world > 1 else contextlib.nullcontext()):
                 v = graph.forward(opt, v, mode="train", iter=it)
-            loss = engine.summarize_loss(opt, graph.compute_loss(opt, v, mode="train"))
+                loss = engine.summarize_loss(opt, graph.compute_loss(opt, v, mode="train"))
             with engine.backward_schedule(graph):          # dW on a side stream under the pose / warp backward (as train_step)
                 if world > 1:
                     with engine.overlap_allreduce(graph, adam):

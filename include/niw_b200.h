@@ -211,6 +211,12 @@ int niw_depth_metrics(const float* pred, const float* gt, const uint8_t* valid, 
  * (roma.rigid_points_registration, roma==1.4.1).  x, y [B,M,3] -> the least-squares proper rotation R [B,3,3] and
  * translation t [B,3] with y ~ R x + t (Kabsch optimum via Horn's quaternion form, fp64 Jacobi; no host sync). */
 int niw_kabsch(const float* x, const float* y, int B, int M, float* R, float* t, void* stream);
+/* The same fit in two steps for point lists sharded over data-parallel ranks (the reference fits each image's WHOLE list,
+ * model/nerf_inn_llff.py:566-572): _stats writes stats [B,16] doubles = (rows, sum x [3], sum y [3], sum x_a y_c [9]) of this
+ * rank's rows; the caller sums the stats over the ranks (one all-reduce of 16 doubles per image); _solve fits from the sums.
+ * With one rank, _stats followed by _solve equals niw_kabsch up to fp64 rounding of the un-centred sums. */
+int niw_kabsch_stats(const float* x, const float* y, int B, int M, double* stats, void* stream);
+int niw_kabsch_solve(const double* stats, int B, float* R, float* t, void* stream);
 
 /* ---- optimiser step (row f2): torch.optim.Adam + ExponentialLR over ONE flat fp32 segment
  *      model/nerf.py:33-46,87,92 (optim / sched), model/barf_inn_llff.py:84-120 (optim_pose)

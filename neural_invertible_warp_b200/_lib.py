@@ -51,6 +51,8 @@ SIGNATURES = {
     "niw_image_metrics": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     "niw_depth_metrics": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_float, _P, _P]),
     "niw_kabsch": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _P, _P, _P]),
+    "niw_kabsch_stats": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _P, _P]),
+    "niw_kabsch_solve": (_c.c_int, [_P, _c.c_int, _P, _P, _P]),
     "niw_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_double, _c.c_double] + [_c.c_float] * 5 + [_c.c_int64, _c.c_float, _P, _P, _P, _P]),
     "niw_tc_probe": (_c.c_int, [_c.c_int, _c.c_int, _P, _P]),
     "niw_tc_selftest": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),

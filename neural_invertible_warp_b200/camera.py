@@ -224,4 +224,9 @@ def rigid_points_registration(x, y):
     """roma's convention: the least-squares R, t with y ~ R x + t (batched Kabsch with the det
     fix).  The reference calls it as (target, source), i.e. it fits the world->camera map
     source ~ R target + t, which ``cam2world`` then inverts.  x, y [B,M,3] -> R [B,3,3], t [B,3]."""
+    if F.data_parallel_group is not None:
+        # the rows of every image's list are sharded over data-parallel ranks: fit the WHOLE list (15 sums per image
+        # all-reduced, SURVEY.md H8), not this rank's shard
+        group = None if F.data_parallel_group is True else F.data_parallel_group
+        return F.kabsch_sharded(x, y, group)
     return F.kabsch(x, y)              # one kernel, no SVD library call, capturable (csrc/kabsch.cu); CPU tensors raise

@@ -532,7 +532,27 @@ def backward_schedule(graph):
     return ov
 
 
-def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=True):
+class data_parallel:
+    """``with data_parallel(group):`` -- forward + loss of a step whose per-image ray / point lists are sharded over the
+    ranks of ``group`` (None = the default group).  Everything on the path is per-ray except the rigid fit behind the
+    ``global_alignment`` loss (reference model/nerf_inn_llff.py:563-572, model/pose_models/inn.py:96-102), which must see an
+    image's whole list: inside this context it is computed from rank-summed sufficient statistics."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def __enter__(self):
+        from . import functional as F
+        self._old = F.data_parallel_group
+        F.data_parallel_group = True if self.group is None else self.group
+        return self
+
+    def __exit__(self, *exc):
+        from . import functional as F
+        F.data_parallel_group = self._old
+
+
+def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=True, group=None):
     """One optimisation step minus the optimiser: forward, loss, backward (+ all-reduce).
 
     With ``world > 1`` the rank renders a contiguous 1/world slice of the global ray batch; local
@@ -554,11 +574,14 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=Tru
     else:
         graph.zero_grad(set_to_none=True)
     if world > 1:
-        with _ShardedRandperm(rank, world, n_global):
+        # (the per-image rigid fit of the global-alignment loss spans the WHOLE list of an image's points, which is now
+        # spread over the ranks: data_parallel makes camera.rigid_points_registration all-reduce its 15 sums per image)
+        with _ShardedRandperm(rank, world, n_global), data_parallel(group):
             var = graph.forward(opt, var, mode="train", iter=it) if takes_iter else graph.forward(opt, var, mode="train")
+            loss = summarize_loss(opt, graph.compute_loss(opt, var, mode="train"))
     else:
         var = graph.forward(opt, var, mode="train", iter=it) if takes_iter else graph.forward(opt, var, mode="train")
-    loss = summarize_loss(opt, graph.compute_loss(opt, var, mode="train"))
+        loss = summarize_loss(opt, graph.compute_loss(opt, var, mode="train"))
     scale = 1.0
     if world > 1:
         scale = len(var.ray_idx) / float(n_global)
@@ -567,9 +590,9 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=Tru
         sched = backward_schedule(graph) if overlap_dw else contextlib.nullcontext()
         with sched:
             if world > 1:
-                with overlap_allreduce(graph, bucket):
+                with overlap_allreduce(graph, bucket, group):
                     (loss.all * scale).backward()
-                bucket.allreduce()
+                bucket.allreduce(group)
             else:
                 loss.all.backward()
     else:

@@ -590,6 +590,46 @@ def kabsch(x, y):
     return R, t
 
 
+# process group over which per-image point lists are sharded (data-parallel ray shards); set by the engine for the
+# duration of a sharded forward + loss.  While set, ``kabsch_sharded`` sums the fit's sufficient statistics over it.
+data_parallel_group = None
+
+
+def kabsch_stats(x, y):
+    """Per-image sufficient statistics of the rigid fit over THIS rank's rows: [B,16] float64 =
+    (rows, sum x, sum y, sum x_a y_c).  Summed over ranks they determine the fit of the whole list."""
+    lib = _lib.load()
+    x, y = _f32(x.detach(), "x"), _f32(y.detach(), "y")
+    B, M = x.shape[0], x.shape[1]
+    if x.shape != y.shape or x.shape[-1] != 3:
+        raise RuntimeError("niw_b200: kabsch expects two [B,M,3] point sets")
+    stats = torch.empty(B, 16, device=x.device, dtype=torch.float64)
+    _lib.check(lib.niw_kabsch_stats(_p(x), _p(y), B, M, _p(stats), _stream()))
+    return stats
+
+
+def kabsch_solve(stats):
+    """R [B,3,3], t [B,3] from (rank-summed) ``kabsch_stats``."""
+    lib = _lib.load()
+    if not stats.is_cuda or stats.dtype != torch.float64 or stats.shape[-1] != 16:
+        raise RuntimeError("niw_b200: kabsch_solve expects a CUDA float64 [B,16] statistics tensor")
+    stats = stats.contiguous()
+    B = stats.shape[0]
+    R = torch.empty(B, 3, 3, device=stats.device, dtype=torch.float32)
+    t = torch.empty(B, 3, device=stats.device, dtype=torch.float32)
+    _lib.check(lib.niw_kabsch_solve(_p(stats), B, _p(R), _p(t), _stream()))
+    return R, t
+
+
+def kabsch_sharded(x, y, group=None):
+    """``kabsch`` of point lists whose rows are spread over the ranks of ``group``: statistics, ONE all-reduce of 16
+    doubles per image, solve -- every rank obtains the fit of the whole list, as the single-GPU step computes it."""
+    import torch.distributed as dist
+    stats = kabsch_stats(x, y)
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return kabsch_solve(stats)
+
+
 def sample_pixels(n, k, counter, seed=0):
     """First k entries of a random permutation of range(n) (the reference's ``torch.randperm(n)[:k]``,
     model/nerf.py:268) in O(k): int64 [k] on ``counter``'s device.  ``counter`` is a zero-initialised int64 [1]

@@ -409,6 +409,27 @@ def kabsch(x, y):
     return R, ym.squeeze(-2) - (R @ xm.transpose(-1, -2)).squeeze(-1)
 
 
+def kabsch_stats(x, y):
+    """Sufficient statistics of ``kabsch`` over the given rows, [B,16] float64 = (rows, sum x, sum y, sum x_a y_c): additive
+    over any partition of the rows (the data-parallel form of the fit)."""
+    xd, yd = x.double(), y.double()
+    n = torch.full((x.shape[0], 1), float(x.shape[1]), dtype=torch.float64)
+    return torch.cat([n, xd.sum(1), yd.sum(1), (xd.transpose(1, 2) @ yd).reshape(-1, 9)], dim=1)
+
+
+def kabsch_from_stats(stats):
+    """``kabsch`` from (summed) ``kabsch_stats``: M = sum y x^T - n ym xm^T."""
+    n = stats[:, 0]
+    xm, ym = stats[:, 1:4] / n[:, None], stats[:, 4:7] / n[:, None]
+    Sxy = stats[:, 7:16].reshape(-1, 3, 3)                               # [a][c] = sum x_a y_c
+    M = Sxy.transpose(1, 2) - n[:, None, None] * ym[:, :, None] * xm[:, None, :]
+    U, _, Vh = torch.linalg.svd(M)
+    d = torch.det(U @ Vh)
+    D = torch.diag_embed(torch.stack([torch.ones_like(d), torch.ones_like(d), d], dim=-1))
+    R = U @ D @ Vh
+    return R.float(), (ym - (R @ xm[..., None])[..., 0]).float()
+
+
 def mse(pred, label):
     """model/base.py:209-211."""
     return ((pred.contiguous() - label) ** 2).mean()

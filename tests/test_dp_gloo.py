@@ -161,3 +161,52 @@ def test_early_segment_allreduce_equals_one_collective(tmp_path):
     want = torch.arange(24.0) * 3
     for early, flat in res.items():
         assert torch.equal(flat, want), early
+
+
+def _kabsch_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from neural_invertible_warp_b200 import camera, engine, functional as F
+    from oracle import reference_port as ora
+    # the host path under test is the product's (camera.rigid_points_registration -> F.kabsch_sharded -> all_reduce -> solve);
+    # only the two CUDA kernels are stood in for by the oracle, as everywhere in this CPU suite
+    F.kabsch_stats, F.kabsch_solve = ora.kabsch_stats, ora.kabsch_from_stats
+    x, y = _kabsch_points()
+    per = x.shape[1] // world
+    xs, ys = x[:, rank * per:(rank + 1) * per], y[:, rank * per:(rank + 1) * per]
+    assert F.data_parallel_group is None
+    with engine.data_parallel():
+        R, t = camera.rigid_points_registration(xs, ys)
+    assert F.data_parallel_group is None
+    if rank == 1:
+        torch.save(dict(R=R, t=t), out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _kabsch_points():
+    gen = torch.Generator().manual_seed(31)
+    Bk, M = 3, 40
+    x = torch.randn(Bk, M, 3, generator=gen) + torch.tensor([0.5, -2.0, 4.0])
+    w = torch.randn(Bk, 3, generator=gen) * 0.6
+    from oracle import reference_port as ora
+    Rt = ora.se3_to_SE3(torch.cat([w, torch.zeros(Bk, 3)], dim=-1))[..., :3]
+    y = x @ Rt.transpose(1, 2) + torch.randn(Bk, 1, 3, generator=gen) + 0.02 * torch.randn(Bk, M, 3, generator=gen)
+    return x, y
+
+
+@pytest.mark.timeout(300)
+def test_sharded_rigid_fit_equals_whole_list_fit(tmp_path):
+    """the global-alignment fit (reference model/nerf_inn_llff.py:566-572) spans all of an image's points; with
+    the rows sharded over two ranks, the statistics all-reduce inside ``engine.data_parallel`` must give every rank the fit
+    of the whole list -- not the fit of its own shard."""
+    from oracle import reference_port as ora
+    out = str(tmp_path / "kabsch.pt")
+    mp.spawn(_kabsch_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    x, y = _kabsch_points()
+    R, t = ora.kabsch(x, y)
+    torch.testing.assert_close(got["R"], R, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got["t"], t, rtol=1e-5, atol=1e-5)
+    R_shard, _ = ora.kabsch(x[:, 20:], y[:, 20:])                    # what rank 1 would have fitted on its own
+    assert (R_shard - R).abs().max() > 1e-4

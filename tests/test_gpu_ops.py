@@ -505,6 +505,17 @@ def test_kabsch_matches_svd_solution(F):
     assert torch.allclose(torch.linalg.det(R.cpu()), torch.ones(B), atol=1e-5)
     R2, t2 = camera.rigid_points_registration(x.to(DEV), y.to(DEV))    # the product path dispatches to the kernel
     assert torch.equal(R2, R) and torch.equal(t2, t)
+    # the two-step form used under data parallelism (statistics -> [all-reduce] -> solve): same fit, and the statistics
+    # are additive over a split of the rows
+    st = F.kabsch_stats(x.to(DEV), y.to(DEV))
+    torch.testing.assert_close(st.cpu(), ora.kabsch_stats(x, y), rtol=1e-12, atol=1e-12)
+    R3, t3 = F.kabsch_solve(st)
+    torch.testing.assert_close(R3.cpu(), R_ref, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(t3.cpu(), t_ref, rtol=1e-4, atol=2e-5)
+    st2 = F.kabsch_stats(x[:, :40].to(DEV), y[:, :40].to(DEV)) + F.kabsch_stats(x[:, 40:].to(DEV), y[:, 40:].to(DEV))
+    R4, t4 = F.kabsch_solve(st2)
+    torch.testing.assert_close(R4, R3, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(t4, t3, rtol=1e-6, atol=1e-6)
 
 
 def test_ops_reject_empty_and_unsupported_shapes(F):
