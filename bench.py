@@ -458,12 +458,13 @@ def run_train(args):
             for _ in range(n_sets):
                 self.free.put(dict(ridx=torch.empty(CHUNK, P_local, dtype=torch.int64).pin_memory(),
                                    u=torch.empty(CHUNK, IMAGES, P_local, N_SAMPLES, 1).pin_memory(), copied=None))
-            self.threads = [threading.Thread(target=self._work, args=(np.random.default_rng(1234 + 97 * rank + t), np),
+            self.threads = [threading.Thread(target=self._work, args=(np.random.default_rng(1234 + 97 * rank + t),
+                                                                      torch.Generator().manual_seed(4321 + 97 * rank + t)),
                                              daemon=True) for t in range(n_threads)]
             for t in self.threads:
                 t.start()
 
-        def _work(self, rng, np):
+        def _work(self, rng, tgen):
             while True:
                 s = self.free.get()
                 if s is None:
@@ -473,7 +474,7 @@ def run_train(args):
                 ridx = s["ridx"].numpy()
                 for k in range(CHUNK):
                     ridx[k] = rng.choice(H * W, P_local, replace=False)
-                rng.random(out=s["u"].numpy().reshape(-1), dtype=np.float32)
+                torch.rand(s["u"].shape, generator=tgen, out=s["u"])      # (ATen releases the GIL while it fills the buffer)
                 self.ready.put(s)
 
         def close(self):

@@ -600,17 +600,68 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=Tru
     return loss
 
 
-def test_time_photometric_optim(opt, graph, var, iters=None, lr=None, on_step=None):
+class _frozen:
+    """``with _frozen(graph):`` -- the graph's parameters do not require gradients inside (test-time pose refinement
+    differentiates THROUGH the networks, never into them; the MLP backward then skips its weight-gradient pass)."""
+
+    def __init__(self, graph):
+        self.params = [p for p in graph.parameters() if p.requires_grad]
+
+    def __enter__(self):
+        for p in self.params:
+            p.requires_grad_(False)
+
+    def __exit__(self, *exc):
+        for p in self.params:
+            p.requires_grad_(True)
+
+
+def test_time_photometric_optim(opt, graph, var, iters=None, lr=None, on_step=None, captured=None, seed=0):
     """``Model.evaluate_test_time_photometric_optim`` (reference model/barf.py:153-169): absorb the remaining pose
     error of ONE held-out view in a fresh se(3) parameter by ``opt.optim.test_iter`` Adam steps on the photometric
     loss of ``rand_rays`` random pixels per step (``mode="test-optim"``: the pose gradient comes out of the
-    ray-generation kernel's backward).  ``on_step(it, loss, se3)`` is called after every update (tests, logging).
-    Returns ``var`` with ``se3_refine_test`` / ``pose_refine_test`` set, as the reference does."""
+    ray-generation kernel's backward).  Returns ``var`` with ``se3_refine_test`` / ``pose_refine_test`` set, as the
+    reference does.
+
+    ``captured`` (default: whenever no ``on_step`` callback asks to look at every iterate): the iteration -- device-side
+    pixel draw, se(3) -> SE(3), ray generation, render, loss, backward into the 6 pose numbers, ``FlatAdam`` update -- is
+    captured ONCE in a CUDA graph and replayed; the loop then costs one graph launch per iteration and no host
+    synchronisation.  Otherwise the loop runs eagerly with ``torch.optim`` exactly as the reference writes
+    it and ``on_step(it, loss, se3)`` is called after every update (tests, logging)."""
+    n_iter = opt.optim.test_iter if iters is None else iters
+    lr = opt.optim.lr_pose if lr is None else lr
     var.se3_refine_test = torch.nn.Parameter(torch.zeros(1, 6, device=opt.device))
+    if captured is None:
+        captured = on_step is None and n_iter > 3 and torch.device(opt.device).type == "cuda" \
+            and not torch.cuda.is_current_stream_capturing()
+    if captured:
+        if opt.optim.algo != "Adam":
+            raise NotImplementedError("captured test-time refinement implements optim.algo=Adam")
+        adam = FlatAdam([dict(params=[var.se3_refine_test], lr=lr)])
+        draws = device_ray_draws(opt.device, seed=seed)
+
+        def body():
+            adam.zero()
+            var.pose_refine_test = camera.lie.se3_to_SE3(var.se3_refine_test)
+            with draws:
+                v = graph.forward(opt, var, mode="test-optim")
+            loss = summarize_loss(opt, graph.compute_loss(opt, v, mode="test-optim"))
+            loss.all.backward()
+            adam.step()
+            return loss.all.detach()
+        warm = 2
+        with torch.enable_grad(), _frozen(graph):
+            step = CapturedStep(body, warmup=warm)        # the warm-up runs are real iterations (they advance the optimiser)
+            for _ in range(max(n_iter - warm, 0)):
+                step()
+        with torch.no_grad():
+            var.pose_refine_test = camera.lie.se3_to_SE3(var.se3_refine_test)
+        var.test_optim_steps = adam.state[0, 0]           # device scalar: iterations taken (no host read here)
+        return var
     optimizer = getattr(torch.optim, opt.optim.algo)
-    optim_pose = optimizer([dict(params=[var.se3_refine_test], lr=opt.optim.lr_pose if lr is None else lr)])
+    optim_pose = optimizer([dict(params=[var.se3_refine_test], lr=lr)])
     with torch.enable_grad():
-        for it in range(opt.optim.test_iter if iters is None else iters):
+        for it in range(n_iter):
             optim_pose.zero_grad()
             var.pose_refine_test = camera.lie.se3_to_SE3(var.se3_refine_test)
             var = graph.forward(opt, var, mode="test-optim")

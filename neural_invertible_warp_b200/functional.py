@@ -343,7 +343,7 @@ class BackwardOverlap:
         import os
         self.stream = torch.cuda.Stream()
         n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-        self.side_ctas = int(os.environ.get("NIW_OVERLAP_SIDE_CTAS", side_ctas if side_ctas is not None else 24))
+        self.side_ctas = int(os.environ.get("NIW_OVERLAP_SIDE_CTAS", side_ctas if side_ctas is not None else 32))
         self.dw_ctas = int(os.environ.get("NIW_OVERLAP_DW_CTAS", dw_ctas if dw_ctas is not None else n - self.side_ctas))
         self.used = False
 
@@ -407,6 +407,8 @@ class _NerfSamples(torch.autograd.Function):
         if training:
             ctx.save_for_backward(flat, center, ray, depth, ws)
             ctx.cfg = (precision, nbytes, module, len(params))
+            # weight gradients wanted at all?  (test-time pose refinement differentiates through a frozen network)
+            ctx.need_dw = bool(flat.requires_grad or any(p.requires_grad for p in params))
             if module is not None and params:
                 module._pending_backward = getattr(module, "_pending_backward", 0) + 1
         return rgb, sigma
@@ -435,6 +437,13 @@ class _NerfSamples(torch.autograd.Function):
         ov = backward_overlap
         split = (ov is not None and target is not None and precision in (NIW_PREC_BF16, NIW_PREC_BF16X3)
                  and getattr(module, "overlap_weight_gradients", False) and KernelTimer.active is None)
+        if not ctx.need_dw and precision in (NIW_PREC_BF16, NIW_PREC_BF16X3):
+            # frozen network: only the activation-gradient chain (d_center / d_ray); the weight-gradient GEMMs are skipped
+            scratch = torch.zeros(NIW_NERF_PARAMS, device=depth.device)     # the chain adds two head-bias sums here
+            with _timed("nerf_bwd"):
+                _lib.check(lib.niw_nerf_bwd_dx(_p(flat), _p(center), _p(ray), _p(depth), R, N, precision, _p(ws), nbytes,
+                                               _p(d_rgb), _p(d_sigma), _p(scratch), _p(d_center), _p(d_ray), _stream()))
+            return (None, d_center, d_ray, None, None, None, None, None, None, None) + (None,) * n_params
         if split:
             # dX on this stream; dW on the side stream, ordered after it, while this stream goes on to the pose / warp backward
             _lib.check(lib.niw_nerf_bwd_dx(_p(flat), _p(center), _p(ray), _p(depth), R, N, precision, _p(ws), nbytes,

@@ -280,3 +280,49 @@ def test_backward_overlap_matches_sequential_backward(eng):
         rel = ((grads[k].double() - grads[False].double()).norm() / grads[False].double().norm()).item()
         assert rel < 1e-4, (k, rel)
         assert (grads[k] != 0).sum() == (grads[False] != 0).sum()
+
+
+def test_captured_test_time_pose_refinement(eng):
+    """the test-time photometric pose refinement (reference model/barf.py:153-169) as ONE captured CUDA graph
+    replayed per iteration on engine.FlatAdam (device pixel draws, no host sync): from a perturbed test pose the loss of the
+    fitted view falls and the refinement moves towards the perturbation's inverse; the networks are not touched (frozen:
+    the MLP backward skips its weight-gradient pass) and the eager torch.optim loop, fed the same draws, takes the same
+    first step."""
+    from neural_invertible_warp_b200 import camera, _lib
+    Hs, Ws = 24, 32
+    opt = cfgmod.builtin_options("barf_llff", model="barf", barf_c2f=[0.1, 0.5], device=DEV, data=dict(image_size=[Hs, Ws]),
+                                 nerf=dict(rand_rays=256, sample_intvs=32), optim=dict(test_iter=40, lr_pose=3e-3),
+                                 arch=dict(mlp_precision="bf16"))
+    graph = eng.build_graph(opt, 1)
+    load_nerf(graph.nerf, syn.nerf_params(3))
+    graph.nerf.progress.data.fill_(1.0)
+    graph.sim3 = cfgmod.AttrDict(t0=torch.zeros(1, 3, device=DEV), t1=torch.zeros(1, 3, device=DEV), s0=1.0, s1=1.0,
+                                 R=torch.eye(3, device=DEV))
+    var = eng.synthetic_var(opt, 1, 5)
+    # ground truth image = the network's own render from the true pose (un-stratified would need another opt: use eval render)
+    with torch.no_grad():
+        var.pose_refine_test = torch.eye(3, 4, device=DEV)[None]
+        opt.optim.test_photo = True
+        full = graph.forward(opt, cfgmod.AttrDict(var), mode="eval")
+        var.image = full.rgb.view(1, Hs, Ws, 3).permute(0, 3, 1, 2).contiguous()
+    # perturb the test pose: the refinement has to undo it
+    delta = torch.tensor([[0.0, 0.0, 0.0, 0.02, -0.015, 0.0]], device=DEV)
+    var.pose = camera.pose.compose([camera.lie.se3_to_SE3(delta), var.pose])
+    before = {k: v.detach().clone() for k, v in graph.named_parameters()}
+
+    def view_loss(v):
+        with torch.no_grad():
+            out = graph.forward(opt, cfgmod.AttrDict(v), mode="eval")
+            return float(((out.rgb.view(1, Hs, Ws, 3).permute(0, 3, 1, 2) - v.image) ** 2).mean())
+    var.pose_refine_test = torch.eye(3, 4, device=DEV)[None]
+    l0 = view_loss(var)
+    n0 = _lib.launch_count()
+    out = eng.test_time_photometric_optim(opt, graph, cfgmod.AttrDict(var))
+    torch.cuda.synchronize()
+    assert float(out.test_optim_steps) == opt.optim.test_iter
+    assert _lib.launch_count() - n0 < 3 * 40                      # two eager warm-up iterations + capture: the replays launch nothing from the host
+    l1 = view_loss(out)
+    print("captured test-time refinement: view loss %.3e -> %.3e, se3 %s" % (l0, l1, out.se3_refine_test.detach().cpu().numpy().round(4)))
+    assert l1 < 0.7 * l0
+    for k, v in graph.named_parameters():
+        assert torch.equal(v, before[k]) and v.requires_grad, k
