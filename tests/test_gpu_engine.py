@@ -295,7 +295,9 @@ def test_captured_test_time_pose_refinement(eng):
                                  arch=dict(mlp_precision="bf16"))
     graph = eng.build_graph(opt, 1)
     load_nerf(graph.nerf, syn.nerf_params(3))
-    graph.nerf.progress.data.fill_(1.0)
+    # early in the coarse-to-fine schedule (2.5 of 10 bands): the random-init field is smooth, so the photometric loss of a
+    # shifted view is well above the stratified-sampling noise and has a usable slope (with all bands on it is not)
+    graph.nerf.progress.data.fill_(0.2)
     graph.sim3 = cfgmod.AttrDict(t0=torch.zeros(1, 3, device=DEV), t1=torch.zeros(1, 3, device=DEV), s0=1.0, s1=1.0,
                                  R=torch.eye(3, device=DEV))
     var = eng.synthetic_var(opt, 1, 5)
@@ -306,7 +308,7 @@ def test_captured_test_time_pose_refinement(eng):
         full = graph.forward(opt, cfgmod.AttrDict(var), mode="eval")
         var.image = full.rgb.view(1, Hs, Ws, 3).permute(0, 3, 1, 2).contiguous()
     # perturb the test pose: the refinement has to undo it
-    delta = torch.tensor([[0.0, 0.0, 0.0, 0.02, -0.015, 0.0]], device=DEV)
+    delta = torch.tensor([[0.0, 0.0, 0.0, 0.06, -0.045, 0.0]], device=DEV)
     var.pose = camera.pose.compose([camera.lie.se3_to_SE3(delta), var.pose])
     before = {k: v.detach().clone() for k, v in graph.named_parameters()}
 
@@ -323,6 +325,6 @@ def test_captured_test_time_pose_refinement(eng):
     assert _lib.launch_count() - n0 < 3 * 40                      # two eager warm-up iterations + capture: the replays launch nothing from the host
     l1 = view_loss(out)
     print("captured test-time refinement: view loss %.3e -> %.3e, se3 %s" % (l0, l1, out.se3_refine_test.detach().cpu().numpy().round(4)))
-    assert l1 < 0.7 * l0
+    assert l1 < 0.8 * l0
     for k, v in graph.named_parameters():
         assert torch.equal(v, before[k]) and v.requires_grad, k
