@@ -28,7 +28,6 @@
 // writes 512 contiguous bytes (bank-conflict free).
 #include "tc_layout.cuh"
 #include "tc_epilogue.cuh"
-#include <cstdlib>
 #ifndef NIW_NSTAGE
 #define NIW_NSTAGE 7
 #endif
@@ -440,12 +439,6 @@ int tc_fwd(const float* P, const float* center, const float* ray, const float* d
     if (!prepacked) {
         int e = tc_pack(P, c2f, training, R, N, ws, ws_bytes, st);
         if (e) return e;
-    }
-    // training: the streaming form (tile records double as the operand store, mlp_tc_stream.cu); NIW_FWD_STREAM=0 keeps
-    // the slot form
-    if (training) {
-        const char* e = getenv("NIW_FWD_STREAM");
-        if (!(e && e[0] == '0')) return tc_fwd_stream(w, center, ray, depth, S, N, rgb, sigma, st);
     }
     NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     const int64_t nquads = ((S + TILE - 1) / TILE + 3) / 4;     // four tiles per CTA pair and round

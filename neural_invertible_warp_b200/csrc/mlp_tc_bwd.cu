@@ -421,24 +421,21 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // producer warp: a 64-sample half of an image is one 1 KB piece per 8-column group (group stride 2 KB in the
-        // record, 1 KB in the stage); lane g copies group g, g + 32, ...
-        const uint32_t stage_bytes = (uint32_t)(U.a_half + U.a2_half + U.b_half + U.b2_half + SMALL_BYTES / 2);
-        const int gA = U.a_half / HROW, gA2 = U.a2_half / HROW, gB = U.b_half / HROW, gB2 = U.b2_half / HROW;
-        for (int64_t it = 0; it < nstages; ++it) {
-            const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
-            const uint8_t* rec = save + (slice + (my_tiles - 1 - (it >> 1)) * U.n_slices) * SAVE_TILE_BYTES + (it & 1) * HROW;
-            uint8_t* dst = smem + st * BW_STAGE;
-            if (lane == 0) {
+        if (lane == 0) {
+            const uint32_t stage_bytes = (uint32_t)(U.a_half + U.a2_half + U.b_half + U.b2_half + SMALL_BYTES / 2);
+            for (int64_t it = 0; it < nstages; ++it) {
+                const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
+                const uint8_t* rec = save + (slice + (my_tiles - 1 - (it >> 1)) * U.n_slices) * SAVE_TILE_BYTES;
+                const int half = (int)(it & 1);
+                uint8_t* dst = smem + st * BW_STAGE;
                 ptx::mbar_wait(&empty[st], ph ^ 1);
                 ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+                ptx::bulk_g2s(dst + BW_A, rec + U.a_off + half * U.a_half, (uint32_t)U.a_half, &full[st]);
+                if (U.a2_half) ptx::bulk_g2s(dst + BW_A + HR_BYTES / 2, rec + U.a2_off + half * U.a2_half, (uint32_t)U.a2_half, &full[st]);
+                if (U.b_half) ptx::bulk_g2s(dst + BW_B, rec + U.b_off + half * U.b_half, (uint32_t)U.b_half, &full[st]);
+                if (U.b2_half) ptx::bulk_g2s(dst + BW_B2, rec + U.b2_off + half * U.b2_half, (uint32_t)U.b2_half, &full[st]);
+                ptx::bulk_g2s(dst + BW_S, rec + SV_SMALL + half * (SMALL_BYTES / 2), SMALL_BYTES / 2, &full[st]);
             }
-            __syncwarp();
-            for (int g = lane; g < gA; g += 32) ptx::bulk_g2s(dst + BW_A + g * HROW, rec + U.a_off + g * KROW, HROW, &full[st]);
-            for (int g = lane; g < gA2; g += 32) ptx::bulk_g2s(dst + BW_A + HR_BYTES / 2 + g * HROW, rec + U.a2_off + g * KROW, HROW, &full[st]);
-            for (int g = lane; g < gB; g += 32) ptx::bulk_g2s(dst + BW_B + g * HROW, rec + U.b_off + g * KROW, HROW, &full[st]);
-            for (int g = lane; g < gB2; g += 32) ptx::bulk_g2s(dst + BW_B2 + g * HROW, rec + U.b2_off + g * KROW, HROW, &full[st]);
-            if (lane == 31) ptx::bulk_g2s(dst + BW_S, rec + SV_SMALL, SMALL_BYTES / 2, &full[st]);
         }
     } else if (warp == 1) {
         if (lane == 0) {

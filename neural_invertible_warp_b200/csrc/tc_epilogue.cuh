@@ -1,4 +1,4 @@
-// Per-row epilogue helpers shared by the tcgen05 forward kernels (mlp_tc.cu slot form, mlp_tc_stream.cu streaming form):
+// Per-row epilogue helpers of the tcgen05 forward kernel (mlp_tc.cu):
 // positional encoding straight into an operand image, and the ReLU + BF16 re-pack of one 32-column accumulator chunk.
 #pragma once
 #include "tc_layout.cuh"
@@ -68,15 +68,8 @@ __device__ __forceinline__ void write_venc_row(uint8_t* enc_tile, uint8_t* save_
 //   act      next layer's A image in shared memory (nullptr: not needed, rgb0)
 //   save_img this layer's image in the tile record (nullptr: inference); C = image columns
 //   flags    this layer's ReLU-flag words of the tile record (nullptr: inference)
-// 16-byte record store, optionally with an L2 eviction-priority policy (createpolicy); pol = 0: plain store
-__device__ __forceinline__ void store_record16(uint8_t* p, const uint4& o, uint64_t pol) {
-    if (pol)
-        asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w), "l"(pol) : "memory");
-    else
-        *reinterpret_cast<uint4*>(p) = o;
-}
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int cc, int row, int C, uint8_t* act,
-                                               uint8_t* save_img, uint32_t* flags, uint32_t (&pk)[16], uint64_t pol = 0) {
+                                               uint8_t* save_img, uint32_t* flags, uint32_t (&pk)[16]) {
     uint32_t bits = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -87,7 +80,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int cc, 
     for (int q = 0; q < 4; ++q) {
         const uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         if (act) *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
-        if (save_img) store_record16(save_img + hbm_img_off(C, row, cc * 4 + q), o, pol);
+        if (save_img) *reinterpret_cast<uint4*>(save_img + hbm_img_off(C, row, cc * 4 + q)) = o;
     }
     if (flags) flags[cc * TILE + row] = bits;
 }

@@ -6,11 +6,11 @@
 //     [C/8 groups][128 rows][8 bf16]      (C = feature columns, rows = samples of the tile)
 // i.e. element (row r, column c) lives at (c/8)*2048 + r*16 + (c%8)*2 bytes: a K-major A operand with
 // K = features, LBO = 2048, SBO = 128.
-// The copy saved in HBM (tile record) has the SAME layout, so the streaming kernels (mlp_tc_stream.cu) bring a
-// whole image -- or a K range of it -- back as an A operand with one bulk copy.  The weight-gradient pass stages
-// 64-sample halves of it, [C/8 groups][64 rows][8 bf16] (one 1 KB bulk copy per group), an MN-major operand with
-// K = samples: LBO = 128 (8 samples), SBO = 1024 (8 features).  A warp of epilogue threads (32 rows, one 16-byte
-// group each) writes 512 contiguous bytes.
+// The copy saved in HBM for the weight-gradient pass is split into two 64-sample halves,
+//     [2 halves][C/8 groups][64 rows][8 bf16]     (hbm_img_off below)
+// so that a half image is one contiguous block (one bulk copy) and, in shared memory, an MN-major operand
+// with K = samples: LBO = 128 (8 samples), SBO = 1024 (8 features).  A warp of epilogue threads (32 rows,
+// one 16-byte group each) writes 512 contiguous bytes in either layout.
 // (no swizzle; both conventions verified on hardware by tests/test_gpu_tc.py::test_tc_selftest_variants).
 #pragma once
 #include "common.cuh"
@@ -61,8 +61,8 @@ constexpr int64_t SV_SMALL = SV_G8 + HR_BYTES;               // 8-column image, 
 constexpr int64_t SAVE_TILE_BYTES = SV_SMALL + SMALL_BYTES;
 static_assert(SAVE_TILE_BYTES % 256 == 0, "tile record alignment");
 // byte offset of the 16-byte group (row, column group cg) inside a saved image of C columns
-__host__ __device__ constexpr int hbm_img_off(int /*C*/, int row, int cg) {
-    return cg * KROW + row * 16;
+__host__ __device__ constexpr int hbm_img_off(int C, int row, int cg) {
+    return (row >> 6) * (C / 8) * HROW + cg * HROW + (row & (HALF - 1)) * 16;
 }
 
 // ---- forward weight stream ----------------------------------------------------------------------
@@ -154,7 +154,7 @@ inline Workspace carve(void* base, int64_t S, bool training, bool x3 = false) {
     Workspace w;
     size_t off = 0;
     auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += (n + 255) & ~size_t(255); return p; };
-    int64_t tiles = ((S + TILE - 1) / TILE + 1) & ~int64_t(1);   // even: the streaming kernels work on tile PAIRS
+    int64_t tiles = (S + TILE - 1) / TILE;
     w.wstream = take(STREAM_BYTES);
     w.bstream = take(BSTREAM_BYTES);
     w.consts = (float*)take(C_FLOATS * 4);
@@ -184,9 +184,4 @@ __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 
 }  // namespace tc
-
-// streaming-form training forward (mlp_tc_stream.cu)
-int tc_fwd_stream(const tc::Workspace& w, const float* center, const float* ray, const float* depth, int64_t S, int N,
-                  float* rgb, float* sigma, cudaStream_t st);
-
 }  // namespace niw
