@@ -390,6 +390,9 @@ def run_train(args):
     # update kernel per group; the same object is the data-parallel gradient bucket
     adam = engine.FlatAdam(engine.reference_optimizer_groups(opt, graph))
     engine.use_flat_gradients(graph)            # the kernels accumulate straight into the flat gradient bucket
+    # N > 1: the gradient sum runs through our own peer-memory kernels (csrc/p2p.cu) when the ranks share a node
+    # (NIW_P2P_ALLREDUCE=0: NCCL all-reduce)
+    p2p_on = adam.enable_p2p() if world > 1 else False
     it = 5000
     P_global = rays_global // IMAGES
     P_local = (P_global + world - 1) // world
@@ -659,6 +662,12 @@ def run_train(args):
                              "sets -> CUDA-graph replay -> loss to pinned memory; the host reads every step's loss, one step "
                              "late; wall clock over all steps"),
                 gpu_launches=launches, roofline=roof, hbm_kernels=hbm, cpu_baseline=cpu, clocks=clk, loss_check=loss_check)
+    if world > 1:
+        line["collective"] = ("gradient sum by this repo's peer-memory kernels over NVLink (csrc/p2p.cu: publish + rank-order "
+                              "reduce, one channel per segment); torch.distributed/NCCL for rendezvous and the scalar checks only"
+                              if p2p_on else "NCCL all-reduce of the flat gradient bucket (two segments)")
+        if p2p_on:
+            line["collective_errors"] = [ch.error() for ch in adam._p2p]
     print(json.dumps(line))
     _leave(world)
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NIW_ABI_VERSION 3
+#define NIW_ABI_VERSION 4
 
 #define NIW_E_BADARG   (-1)  /* null pointer / non-positive size */
 #define NIW_E_UNSUPP   (-2)  /* shape or option outside what the kernels implement */
@@ -243,6 +243,25 @@ int niw_tc_selftest(const float* A, const float* Bm, int N, int K, int variant, 
  * M = 128, N = 256, K = 16 into TMEM columns 0-255) and of four warps draining TMEM columns 256-511 (what & 2: iters x
  * 128 KB), alone or concurrently, on one SM.  out[0] = MMA cycles, out[1] = slowest reader's cycles (device int64[2]). */
 int niw_tc_probe(int what, int iters, long long* out, void* stream);
+
+/* ---- data-parallel gradient exchange over NVLink peer memory (no counterpart in the reference, which
+ * asserts a single GPU at options.py:103) ------------------------------------------------------------------------------
+ * The only exchange step of a training step is the sum of the flat gradient bucket (0.53 M + 0.17 M floats): at that size
+ * a library all-reduce is launch + protocol latency, so the sum is two kernels of our own over CUDA-IPC-mapped buffers
+ * (csrc/p2p.cu): publish (copy into this rank's exchange buffer, raise its flag in every peer) and reduce (wait for all
+ * flags, sum the `world` buffers in rank order -- bit-identical on all ranks -- straight from peer memory).
+ * niw_p2p_alloc: a device block of `bytes` (zeroed) and its 64-byte IPC handle; niw_p2p_open maps a peer's handle into
+ * this process.  Block layout: 64-byte flag block, at byte 256 the exchange buffer of 2 * half_floats floats (double
+ * buffered on the sequence number kept in the block, so the call is CUDA-graph capturable).
+ * niw_allreduce_p2p: in-place sum of n floats (n % 4 == 0, n <= half_floats) over `world` <= 8 ranks of one node;
+ * blocks[r] = rank r's block as mapped here.  All ranks make the same sequence of calls.  niw_p2p_error reads the
+ * time-out flag of a block (a wait for a peer that never arrived gives up after ~2 s instead of hanging the GPU). */
+int niw_p2p_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int niw_p2p_open(const void* handle64, void** dev_ptr);
+int niw_p2p_close(void* dev_ptr);
+int niw_p2p_free(void* dev_ptr);
+int niw_allreduce_p2p(float* data, int64_t n, void* const* blocks, int rank, int world, int64_t half_floats, void* stream);
+int niw_p2p_error(const void* block, unsigned int* error);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ NIW_PREC_BF16X3 = 2
 NIW_NERF_PREPACKED = 2
 NIW_NERF_PARAMS = 530052
 NIW_NVP_BLOCK_FLOATS = ((128 * 27 + 128 + 1 + 128 * 13 + 3 * 128 + 3) + 3) // 4 * 4   # 5636, include/niw_b200.h
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); mirrors include/niw_b200.h one to one
 SIGNATURES = {
@@ -50,6 +50,12 @@ SIGNATURES = {
     "niw_mse_gather": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),
     "niw_image_metrics": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     "niw_depth_metrics": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_float, _P, _P]),
+    "niw_p2p_alloc": (_c.c_int, [_c.c_size_t, _c.POINTER(_c.c_void_p), _P]),
+    "niw_p2p_open": (_c.c_int, [_P, _c.POINTER(_c.c_void_p)]),
+    "niw_p2p_close": (_c.c_int, [_P]),
+    "niw_p2p_free": (_c.c_int, [_P]),
+    "niw_allreduce_p2p": (_c.c_int, [_P, _c.c_int64, _c.POINTER(_c.c_void_p), _c.c_int, _c.c_int, _c.c_int64, _P]),
+    "niw_p2p_error": (_c.c_int, [_P, _c.POINTER(_c.c_uint)]),
     "niw_kabsch": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _P, _P, _P]),
     "niw_kabsch_stats": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _P, _P]),
     "niw_kabsch_solve": (_c.c_int, [_P, _c.c_int, _P, _P, _P]),

@@ -123,6 +123,17 @@ class SegmentedAllreduce:
     collective over the whole buffer."""
 
     _pending = None
+    _p2p = None
+
+    def enable_p2p(self, group=None):
+        """Route the sums through the peer-memory kernels (p2p.P2PChannel, csrc/p2p.cu; one channel per segment, so an
+        early segment on the side stream and the rest on the main stream never share flags) when all ranks are GPUs of
+        one node; otherwise keep the NCCL collectives.  Collective call: every rank of ``group`` makes it.  Returns
+        whether the peer path is on."""
+        from . import p2p
+        if self._p2p is None and p2p.available(group):
+            self._p2p = [p2p.P2PChannel(g["n"], group) for g in self.groups]
+        return self._p2p is not None
 
     @staticmethod
     def _active(group):
@@ -138,12 +149,22 @@ class SegmentedAllreduce:
         if self._pending is None:
             self._pending = {}
         if gi not in self._pending:
-            self._pending[gi] = dist.all_reduce(self._segment(gi), op=dist.ReduceOp.SUM, group=group, async_op=True)
+            if self._p2p is not None:
+                self._p2p[gi].allreduce_(self._segment(gi))       # two launches on the current stream; nothing to wait for
+                self._pending[gi] = None
+            else:
+                self._pending[gi] = dist.all_reduce(self._segment(gi), op=dist.ReduceOp.SUM, group=group, async_op=True)
 
     def allreduce(self, group=None):
         if not self._active(group):
             return
         pending = self._pending or {}
+        if self._p2p is not None:
+            for gi in range(len(self.groups)):
+                if gi not in pending:
+                    self._p2p[gi].allreduce_(self._segment(gi))
+            self._pending = {}
+            return
         if not pending:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             return
@@ -162,7 +183,8 @@ class SegmentedAllreduce:
             dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
             gi = gj + 1
         for work in pending.values():
-            work.wait()                       # the current stream waits for the collective; no host block
+            if work is not None:
+                work.wait()                   # the current stream waits for the collective; no host block
         self._pending = {}
 
 
