@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-micro", action="store_true", help="skip the standalone HBM-kernel timings (hbm_kernels)")
+    ap.add_argument("--timeline", default=None, metavar="PREFIX",
+                    help="after the timed region, record ONE more step under the CUPTI activity tracer and write every rank's "
+                         "kernel timeline (stream, start, duration) to PREFIX.rank<r>.txt (not a bench value)")
     ap.add_argument("--no-loss-check", action="store_true", help="N>1: skip the global-loss check against one rank")
     a = ap.parse_args()
     if a.rays is None:
@@ -320,6 +323,11 @@ class Harness:
                 # the flush is rank-local work outside the timed region: re-align the ranks on the device before the start
                 # event, or its jitter shows up inside the step as time spent waiting in the gradient all-reduce
                 self.dist.all_reduce(self.sync_token)
+            # the token all-reduce drains the queue: without a short device-side delay in front of the start event the GPU
+            # would idle between the event and the step's first kernel for as long as the HOST needs to launch the step
+            # (20-45 us seen in the N = 2 timeline, profiles/r2_timeline_*), which a training loop that enqueues ahead of
+            # the device never pays.  ~100 us of spinning on the device, outside the event pair, at every N alike.
+            torch.cuda._sleep(200000)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); step_fn(); b.record()
             evs.append((a, b))
@@ -338,6 +346,43 @@ class Harness:
     def free_flush(self):
         del self.flush, self.drain
         torch.cuda.empty_cache()
+
+
+def write_timeline(prefix, hs, step_fn):
+    """One step under the CUPTI activity tracer (torch.profiler, kernels inside a CUDA-graph replay included): every rank
+    writes its kernels as `stream start_us dur_us name`, times relative to the first kernel of the step.  The ranks are
+    re-aligned by a token all-reduce right before the step, as in the timed region."""
+    from torch.profiler import profile, ProfilerActivity
+    for _ in range(2):
+        step_fn()
+    hs.barrier()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        hs.flush.zero_()
+        hs.drain.view(torch.int32).sum()
+        if hs.world > 1:
+            hs.dist.all_reduce(hs.sync_token)
+        marker = torch.cuda.Event(enable_timing=True)
+        step_fn()
+        torch.cuda.synchronize()
+    rows = []
+    for e in prof.profiler.kineto_results.events():
+        if str(e.device_type()).endswith("CUDA") and e.duration_ns() > 0:
+            rows.append((e.start_ns(), e.duration_ns(), e.device_resource_id(), e.name()))
+    rows.sort()
+    # the step = everything after the flush (a fill, then torch's sum over the drain buffer) and the token all-reduce
+    cut = 0
+    for i, r in enumerate(rows):
+        if "at::native::reduce_kernel" in r[3]:
+            cut = i + 1
+    if hs.world > 1 and cut < len(rows) and "nccl" in rows[cut][3].lower():
+        cut += 1
+    rows = rows[cut:]
+    t0 = rows[0][0] if rows else 0
+    with open("%s.rank%d.txt" % (prefix, hs.rank), "w") as f:
+        f.write("# stream start_us dur_us end_us kernel   (rank %d of %d; t = 0 at the step's first kernel)\n" % (hs.rank, hs.world))
+        for st, du, sid, name in rows:
+            f.write("%3d %9.1f %8.1f %9.1f %s\n" % (sid, (st - t0) / 1e3, du / 1e3, (st - t0 + du) / 1e3, name[:90]))
+    hs.barrier()
 
 
 def mlp_roofline(pk, kernel_ms, flop_per_call_pair, traffic, what, timed_note, ms_total):
@@ -403,8 +448,7 @@ def run_train(args):
     def step_device():
         v = cfgmod.AttrDict(var_dev)
         with ray_draws:
-            loss = engine.train_step(opt, graph, v, it, bucket=adam, rank=rank, world=world)
-        adam.step()
+            loss = engine.train_step(opt, graph, v, it, bucket=adam, rank=rank, world=world, optimizer=adam)
         return loss
 
     # ---- e2e leg: the step's host-side inputs (camera batch, pixel indices, stratified uniforms) are DRAWN ON THE HOST
@@ -440,7 +484,8 @@ def run_train(args):
                     adam.allreduce()
                 else:
                     loss.all.backward()
-            adam.step()
+                adam.step(groups=range(1, len(adam.groups)))    # pose / warp groups: final before the side stream is joined
+            adam.step(groups=[0])
             return loss.all.detach()
         return step_static
 
@@ -577,6 +622,8 @@ def run_train(args):
     rays_per_step = rays_local * world
     value = rays_per_step / (ms_per_step * 1e-3)
     e2e_value = rays_per_step * args.steps / e2e_s
+    if args.timeline:
+        write_timeline(args.timeline, hs, step_value)
 
     # ---- N > 1: the sharded step's global loss against the same batch rendered by rank 0 alone ----
     loss_check = None

@@ -50,10 +50,10 @@ __global__ void p2p_publish_kernel(const float* __restrict__ data, int64_t n4, i
     float4* dst = reinterpret_cast<float4*>(peers.buf[rank] + (seq & 1) * half_floats);
     const float4* src = reinterpret_cast<const float4*>(data);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicAdd(&me->blocks_done, 1u);
+        __threadfence();                                      // the block's copies (ordered before this by the barrier): released at GPU
+        const unsigned int ticket = atomicAdd(&me->blocks_done, 1u);   // scope through the counter; the last block carries them to system scope
         if (ticket == gridDim.x - 1) {
             me->blocks_done = 0;
             __threadfence_system();                           // every block's copy (observed through the counter) before the flags

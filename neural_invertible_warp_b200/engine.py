@@ -294,10 +294,15 @@ class FlatAdam(SegmentedAllreduce):
 
     zero_grad = zero
 
-    def step(self):
+    def step(self, groups=None):
+        """One update of every group (``groups``: indices, default all) on the current stream.  The groups are independent,
+        so a training step may update the pose / warp groups as soon as their gradients are final and the NeRF group
+        after the side-stream weight-gradient pass has been joined (``train_step(optimizer=...)``)."""
         import ctypes
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         for gi, g in enumerate(self.groups):
+            if groups is not None and gi not in groups:
+                continue
             o = g["offset"] * 4
             ptr = lambda t: ctypes.c_void_p(t.data_ptr() + o)
             prog = self.progress if gi == len(self.groups) - 1 else []
@@ -574,7 +579,7 @@ class data_parallel:
         F.data_parallel_group = self._old
 
 
-def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=True, group=None):
+def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=True, group=None, optimizer=None):
     """One optimisation step minus the optimiser: forward, loss, backward (+ all-reduce).
 
     With ``world > 1`` the rank renders a contiguous 1/world slice of the global ray batch; local
@@ -584,6 +589,10 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=Tru
 
     With a flat gradient ``bucket`` (the engine owns every ``.grad``) the backward is scheduled on two streams
     (``overlap_dw``): see functional.BackwardOverlap.  The streams are joined before this function returns.
+
+    ``optimizer`` (a ``FlatAdam`` that is also the ``bucket``): the update is part of the step -- the pose / warp groups are
+    updated on the launching stream as soon as their gradients are summed, while the weight-gradient pass (and the sum of
+    the NeRF segment behind it) still runs on the side stream; the NeRF group follows after the join.
     """
     B = len(var.idx)
     n_global = opt.nerf.rand_rays // B
@@ -610,6 +619,7 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=Tru
     if bucket is not None:
         # the weight-gradient pass of the (last) NeRF network runs on a side stream under the pose / warp backward
         sched = backward_schedule(graph) if overlap_dw else contextlib.nullcontext()
+        early = optimizer is not None and optimizer is bucket and len(optimizer.groups) > 1
         with sched:
             if world > 1:
                 with overlap_allreduce(graph, bucket, group):
@@ -617,8 +627,14 @@ def train_step(opt, graph, var, it, bucket=None, rank=0, world=1, overlap_dw=Tru
                 bucket.allreduce(group)
             else:
                 loss.all.backward()
+            if early:
+                optimizer.step(groups=range(1, len(optimizer.groups)))
+        if optimizer is not None:
+            optimizer.step(groups=[0] if early else None)
     else:
         (loss.all if scale == 1.0 else loss.all * scale).backward()
+        if optimizer is not None:
+            optimizer.step()
     return loss
 
 
