@@ -251,8 +251,9 @@ int niw_tc_probe(int what, int iters, long long* out, void* stream);
  * (csrc/p2p.cu): publish (copy into this rank's exchange buffer, raise its flag in every peer) and reduce (wait for all
  * flags, sum the `world` buffers in rank order -- bit-identical on all ranks -- straight from peer memory).
  * niw_p2p_alloc: a device block of `bytes` (zeroed) and its 64-byte IPC handle; niw_p2p_open maps a peer's handle into
- * this process.  Block layout: 64-byte flag block, at byte 256 the exchange buffer of 2 * half_floats floats (double
- * buffered on the sequence number kept in the block, so the call is CUDA-graph capturable).
+ * this process.  Block layout: flag block, at byte 256 the exchange buffer of 2 * half_floats floats (double buffered on
+ * the sequence number kept in the block, so the call is CUDA-graph capturable), then 2 * half_floats floats of result area:
+ * bytes >= 256 + 16 * half_floats.  From 4 ranks up the sum is two-shot (reduce-scatter into the result areas, all-gather).
  * niw_allreduce_p2p: in-place sum of n floats (n % 4 == 0, n <= half_floats) over `world` <= 8 ranks of one node;
  * blocks[r] = rank r's block as mapped here.  All ranks make the same sequence of calls.  niw_p2p_error reads the
  * time-out flag of a block (a wait for a peer that never arrived gives up after ~2 s instead of hanging the GPU). */

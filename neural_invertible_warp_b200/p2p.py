@@ -48,7 +48,7 @@ class P2PChannel:
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.half = (int(max_floats) + 3) // 4 * 4
-        nbytes = 256 + 2 * self.half * 4
+        nbytes = 256 + 4 * self.half * 4        # flag block, two exchange halves, two result halves (two-shot)
         mine, handle = _c.c_void_p(), _c.create_string_buffer(64)
         _lib.check(self.lib.niw_p2p_alloc(nbytes, _c.byref(mine), handle))
         self.mine = mine
