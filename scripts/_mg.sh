@@ -1,6 +1,8 @@
-for ts in 1 0; do
-  echo "== NIW_P2P_TWO_SHOT=$ts"
-  NIW_P2P_TWO_SHOT=$ts timeout 400 python -m pytest tests/test_gpu_multi.py -q -x -s -k "p2p" 2>&1 | grep -E "passed|failed|rel-L2|Error" | head
-  NIW_P2P_TWO_SHOT=$ts timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 --no-loss-check > gpurun_out/r2y_n2_ts$ts.json 2> gpurun_out/r2y_n2_ts$ts.err
-  python -c "import json; d=json.load(open('gpurun_out/r2y_n2_ts$ts.json')); print('N=2 two_shot=$ts ms/step %.4f value %.0f' % (d['ms_per_step'], d['value']), d.get('collective_errors'))" || tail -5 gpurun_out/r2y_n2_ts$ts.err
+N=${1:-2}; shift
+for cfg in "$@"; do
+  extra=""; [ "$cfg" = "c2" ] && extra="--timeline gpurun_out/r2z_tl_n${N}"
+  steps=20; [ "$cfg" = "c5" ] && steps=10; [ "$cfg" = "c4" ] && steps=5
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --config $cfg --steps $steps --warmup 5 $extra > gpurun_out/r2z_bench_${cfg}_n${N}.json 2> gpurun_out/r2z_bench_${cfg}_n${N}.err
+  python -c "import json; d=json.load(open('gpurun_out/r2z_bench_${cfg}_n${N}.json')); print('$cfg N=$N ms/step %.4f value %.0f e2e %.0f' % (d['ms_per_step'], d['value'], d['e2e']['value']), d.get('collective_errors'), (d.get('loss_check') or {}).get('abs_diff'))" || tail -5 gpurun_out/r2z_bench_${cfg}_n${N}.err
 done
+timeout 300 python -m pytest tests/test_gpu_multi.py -q -x -k p2p_allreduce 2>&1 | tail -2
