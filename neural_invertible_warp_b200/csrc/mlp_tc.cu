@@ -2,7 +2,8 @@
 // SURVEY.md section 8 rows a6+a7+a8; reference model/nerf.py:416-456, model/barf.py:256-268.
 //
 // Forward (tc_fwd_kernel): persistent, CTA PAIRS (clusters of 2 on neighbouring SMs, tcgen05 cta_group::2),
-// 384 threads per CTA.  A pair works on four 128-sample tiles at a time: slot s of CTA r holds tile 4q + 2s + r,
+// 384 threads per CTA.  A pair works on up to four 128-sample tiles at a time: slot s of CTA r holds tile 2*hq + r of the
+// tile pair hq assigned to the slot (round k: hq = (2k + s) * pairs + pair; the last round may use slot 0 only),
 // and every MMA is an M = 256 instruction over the two tiles of one slot (rows 0-127 in the leader, 128-255 in
 // its peer), so each CTA only stages HALF of every weight chunk.  That halving pays for streaming the weights
 // once per SLOT instead of once per pair of slots, which is what lets the two slots run a layer apart: while the
@@ -169,8 +170,13 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const int64_t ntiles = (S + TILE - 1) / TILE;
-    const int64_t nquads = (ntiles + 3) / 4;
-    const int64_t quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
+    // Work unit = one SLOT of a CTA pair = one tile pair (tiles 2*hq + rank).  In round k slot s of pair p holds tile pair
+    // (2k + s) * npairs + p, so the last round of a pair may use slot 0 only: 1 024 tiles over 74 pairs are 6.92 tile pairs per
+    // CTA pair -- three rounds of two slots and one of a single slot (which runs its layers back to back, ~25 % faster than a
+    // shared round) instead of four full rounds for half of the pairs and three for the rest.
+    const int64_t nhq = (ntiles + 1) / 2;
+    const int64_t pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    auto hq_of = [&](int64_t k, int s) { return (2 * k + s) * npairs + pair0; };
 
     if (threadIdx.x == 0) {
         // leader: a stage is full when its own copy has landed (expect_tx arrive) and the peer has reported its half
@@ -199,11 +205,12 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
         // ================= weight producer (this CTA's half of every chunk, once per slot) =================
         if (lane == 0) {
             uint32_t st = 0, cyc = 0;                  // ring stage, trips round the ring
-            for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+            for (int64_t k = 0; hq_of(k, 0) < nhq; ++k) {
+                const int nslots = hq_of(k, 1) < nhq ? 2 : 1;
                 const uint8_t* lsrc = wstream;
                 for (int l = 0; l < NLAYER; ++l) {
                     const int nch = layer_chunks(l), hrows = layer_rows(l) / 2;
-                    for (int s = 0; s < 2; ++s) {
+                    for (int s = 0; s < nslots; ++s) {
                         const uint8_t* src = lsrc;
                         for (int c = 0; c <= nch; ++c) {                // chunk nch is the K = 16 bias chunk
                             const uint32_t bytes = (uint32_t)hrows * (c < nch ? CHUNK_K : BIAS_K) * 2;
@@ -224,9 +231,9 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
         if (lane == 0) {
             uint32_t st = 0, cyc = 0;
             const uint32_t full0 = ptx::mapa(&w_full[0], 0);
-            for (int64_t quad = quad0; quad < nquads; quad += quad_step)
+            for (int64_t k = 0; hq_of(k, 0) < nhq; ++k)
                 for (int l = 0; l < NLAYER; ++l)
-                    for (int c = 0; c < 2 * (layer_chunks(l) + 1); ++c) {
+                    for (int c = 0; c < (hq_of(k, 1) < nhq ? 2 : 1) * (layer_chunks(l) + 1); ++c) {
                         const uint32_t fb = (cyc & 1) * NSTAGE + st;
                         ptx::mbar_wait(&w_full[fb], (cyc >> 1) & 1);
                         ptx::mbar_arrive_cluster(full0 + fb * 8);
@@ -252,7 +259,8 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
             const uint32_t ring_a = ptx::smem_addr(smem + SM_RING) >> 4;
             const uint32_t desc_hi = ptx::smem_desc_hi(128);
             const uint32_t tacc = tmem_base + s * WIDTH;
-            for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+            for (int64_t k = 0; hq_of(k, s) < nhq; ++k) {
+                const bool both = hq_of(k, 1) < nhq;                 // the other slot works in this round too
                 for (int l = 0; l < NLAYER; ++l) {
                     const int hrows = layer_rows(l) / 2, nch = layer_chunks(l);
                     const uint32_t idesc = ptx::idesc_bf16(2 * TILE, 2 * hrows, 0, 0);
@@ -289,7 +297,7 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                         __syncwarp();
                         if (++st == NSTAGE) { st = 0; ++cyc; }
                     }
-                    if (s == 0) skip(nch + 1);
+                    if (s == 0 && both) skip(nch + 1);
                 }
             }
         }
@@ -302,8 +310,8 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
         const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * WIDTH;
         const uint32_t ready_bar = ptx::mapa(&a_ready[slot], 0);     // the leader's barrier
         uint32_t full_uses = 0;
-        for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
-            const int64_t tile = quad * 4 + slot * 2 + rank;
+        for (int64_t k = 0; hq_of(k, slot) < nhq; ++k) {
+            const int64_t tile = hq_of(k, slot) * 2 + rank;
             const int64_t g = tile * TILE + row;
             const bool valid = tile < ntiles && g < S;
             uint8_t* save_tile = (save && tile < ntiles) ? save + tile * SAVE_TILE_BYTES : nullptr;
@@ -441,9 +449,9 @@ int tc_fwd(const float* P, const float* center, const float* ray, const float* d
         if (e) return e;
     }
     NIW_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    const int64_t nquads = ((S + TILE - 1) / TILE + 3) / 4;     // four tiles per CTA pair and round
+    const int64_t nhq = ((S + TILE - 1) / TILE + 1) / 2;        // tile pairs: one per slot of a CTA pair and round
     int64_t pairs = niw_num_sms() / 2;
-    if (pairs > nquads) pairs = nquads;
+    if (pairs > nhq) pairs = nhq;
     const int grid = (int)(2 * (pairs < 1 ? 1 : pairs));
     niw::note_launch(), tc_fwd_kernel<<<grid, 384, SM_TOTAL, st>>>(w.wstream, w.consts, center, ray, depth, S, N, rgb, sigma,
                                              training ? w.sig_pre : nullptr, training ? w.rgb_keep : nullptr,

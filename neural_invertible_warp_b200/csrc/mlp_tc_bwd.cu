@@ -51,8 +51,8 @@ __device__ __forceinline__ void ray_atomic_add3(float* dst, int64_t r, const flo
     }
 }
 
-// CTA pairs (cta_group::2), same organisation as the forward kernel (mlp_tc.cu): slot s of CTA r holds tile
-// 4q + 2s + r, every MMA is M = 256 over the two tiles of a slot, each CTA stages half of every transposed-weight
+// CTA pairs (cta_group::2), same organisation as the forward kernel (mlp_tc.cu): slot s of CTA r holds tile 2*hq + r of
+// the slot's tile pair hq, every MMA is M = 256 over the two tiles of a slot, each CTA stages half of every transposed-weight
 // chunk, the two slots run one step apart, one issuer thread per slot in the leader CTA.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ consts_g, const float* __restrict__ center,
@@ -72,8 +72,13 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const int64_t ntiles = (S + TILE - 1) / TILE;
-    const int64_t nquads = (ntiles + 3) / 4;
-    const int64_t quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
+    // Work unit = one SLOT of a CTA pair = one tile pair (tiles 2*hq + rank).  In round k slot s of pair p holds tile pair
+    // (2k + s) * npairs + p, so the last round of a pair may use slot 0 only: 1 024 tiles over 74 pairs are 6.92 tile pairs per
+    // CTA pair -- three rounds of two slots and one of a single slot (which runs its layers back to back, ~25 % faster than a
+    // shared round) instead of four full rounds for half of the pairs and three for the rest.
+    const int64_t nhq = (ntiles + 1) / 2;
+    const int64_t pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    auto hq_of = [&](int64_t k, int s) { return (2 * k + s) * npairs + pair0; };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * BX_NSTAGE; ++i) ptx::mbar_init(&w_full[i], rank == 0 ? 2 : 1);
@@ -98,11 +103,12 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
         // ================= transposed-weight producer (this CTA's half of every chunk, once per slot) =================
         if (lane == 0) {
             uint32_t st = 0, cyc = 0;
-            for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+            for (int64_t k = 0; hq_of(k, 0) < nhq; ++k) {
+                const int nslots = hq_of(k, 1) < nhq ? 2 : 1;
                 const uint8_t* ssrc = bstream;
                 for (int s = 0; s < NSTEP; ++s) {
                     const uint32_t bytes = (uint32_t)(step_n(s) / 2) * CHUNK_K * 2;
-                    for (int sl = 0; sl < 2; ++sl) {
+                    for (int sl = 0; sl < nslots; ++sl) {
                         const uint8_t* src = ssrc + rank * bytes;
                         for (int c = 0; c < step_chunks(s); ++c) {
                             uint64_t* full = &w_full[(cyc & 1) * BX_NSTAGE + st];
@@ -122,9 +128,9 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
         if (lane == 0) {
             uint32_t st = 0, cyc = 0;
             const uint32_t full0 = ptx::mapa(&w_full[0], 0);
-            for (int64_t quad = quad0; quad < nquads; quad += quad_step)
+            for (int64_t k = 0; hq_of(k, 0) < nhq; ++k)
                 for (int s = 0; s < NSTEP; ++s)
-                    for (int c = 0; c < 2 * step_chunks(s); ++c) {
+                    for (int c = 0; c < (hq_of(k, 1) < nhq ? 2 : 1) * step_chunks(s); ++c) {
                         const uint32_t fb = (cyc & 1) * BX_NSTAGE + st;
                         ptx::mbar_wait(&w_full[fb], (cyc >> 1) & 1);
                         ptx::mbar_arrive_cluster(full0 + fb * 8);
@@ -142,7 +148,8 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
             const uint32_t ring_a = ptx::smem_addr(smem + BX_RING) >> 4;
             const uint32_t desc_hi = ptx::smem_desc_hi(128);
             const uint32_t tacc = tmem_base + sl * WIDTH;
-            for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
+            for (int64_t k = 0; hq_of(k, sl) < nhq; ++k) {
+                const bool both = hq_of(k, 1) < nhq;                 // the other slot works in this round too
                 for (int s = 0; s < NSTEP; ++s) {
                     const int hrows = step_n(s) / 2, nch = step_chunks(s);
                     const uint32_t idesc = ptx::idesc_bf16(2 * TILE, 2 * hrows, 0, 0);
@@ -165,7 +172,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                         __syncwarp();
                         if (++st == BX_NSTAGE) { st = 0; ++cyc; }
                     }
-                    if (sl == 0) skip(nch);
+                    if (sl == 0 && both) skip(nch);
                 }
             }
         }
@@ -179,8 +186,8 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
         const bool uniform = (N % 32) == 0;       // the 32 rows of a warp then share one ray
         const uint32_t ready_bar = ptx::mapa(&a_ready[slot], 0);     // the leader's barrier
         uint32_t full_uses = 0;
-        for (int64_t quad = quad0; quad < nquads; quad += quad_step) {
-            const int64_t tile = quad * 4 + slot * 2 + rank;
+        for (int64_t k = 0; hq_of(k, slot) < nhq; ++k) {
+            const int64_t tile = hq_of(k, slot) * 2 + rank;
             const int64_t g = tile * TILE + row;
             const bool valid = tile < ntiles && g < S;
             const int64_t r = valid ? g / N : -1;
@@ -650,9 +657,9 @@ int tc_bwd_dx(const float* P, const float* center, const float* ray, const float
     NIW_CUDA(cudaMemsetAsync(d_center, 0, sizeof(float) * R * 3, st));
     NIW_CUDA(cudaMemsetAsync(d_ray, 0, sizeof(float) * R * 3, st));
     NIW_CUDA(cudaFuncSetAttribute(tc_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_TOTAL));
-    const int64_t nquads = (ntiles + 3) / 4;      // four tiles per CTA pair and round
+    const int64_t nhq = (ntiles + 1) / 2;         // tile pairs: one per slot of a CTA pair and round
     int64_t pairs = niw_num_sms() / 2;
-    if (pairs > nquads) pairs = nquads;
+    if (pairs > nhq) pairs = nhq;
     const int grid = (int)(2 * (pairs < 1 ? 1 : pairs));
     niw::note_launch(), tc_dx_kernel<<<grid, 384, BX_TOTAL, st>>>(w.bstream, w.consts, center, ray, depth, S, N, d_rgb, d_sigma,
                                                                  w.sig_pre, w.rgb_keep, w.save, w.scratch, dP, d_center, d_ray);
