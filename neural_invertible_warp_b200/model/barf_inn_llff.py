@@ -55,6 +55,20 @@ class Graph(nerf_inn_llff.Graph):
                                % (type(self.warp_mlp).__module__, type(self.warp_mlp).__name__))
         return self.warp_mlp
 
+    def _prefetch_pose(self, opt, var):
+        """The warp network's weight pack depends on its parameters and the latent codes only: it runs on the render side
+        stream while the pixel draw and the un-warped grid are produced (``DeformNetwork.prepack``)."""
+        from ..nvp import DeformNetwork
+        if not isinstance(getattr(self, "warp_mlp", None), DeformNetwork) or not torch.is_grad_enabled() \
+                or opt.warp_latent.enc_type != "l2fbarf":      # (other encodings build a new code tensor per call)
+            return
+        cur = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream()
+        side.wait_stream(cur)
+        self.warp_mlp.prepack(self._latent(opt), side)
+
     def _latent(self, opt):
         if opt.warp_latent.enc_type == "l2fbarf":
             return self.warp_latent.weight

@@ -29,11 +29,16 @@ class Graph(base.Graph):
         opt.nerf.depth.range = [(depth_min / (depth_max + depth_min)) * diameter,
                                 (depth_max / (depth_max + depth_min)) * diameter]
 
+    def _prefetch_pose(self, opt, var):
+        """Hook: work of ``get_pose`` that depends neither on the pixel draw nor on the rays (none here)."""
+
     def forward(self, opt, var, mode=None, iter=None):
         """model/nerf_inn_llff.py:493-546."""
         if opt.data.dataset == "blender" and opt.camera.noise_type == "l2g":
             self._rescale_depth_range_l2g(opt)
         batch_size = len(var.idx)
+        if opt.nerf.rand_rays and mode == "train":
+            self._prefetch_pose(opt, var)           # (barf_inn_llff: the warp network's weight pack, on the side stream)
         if opt.nerf.rand_rays and mode in ["train", "test-optim"]:
             var.ray_idx = torch.randperm(opt.H * opt.W, device=opt.device)[:opt.nerf.rand_rays // batch_size]
             if mode == "train":

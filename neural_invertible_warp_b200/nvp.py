@@ -49,6 +49,15 @@ def pack_effective(p, code, n_blocks=3, n_freq=N_FREQ, prefix=""):
     return torch.cat(chunks), torch.stack(biases).view(n_blocks, 2, B, -1)
 
 
+def _pack_forward(lib, params, code, B, dev):
+    wpack = torch.empty(3 * F.NIW_NVP_BLOCK_FLOATS, device=dev)
+    code_bias = torch.empty(3, 2, B, HID, device=dev)
+    cb = torch.empty(3, B, HID, device=dev)
+    ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    _lib.check(lib.niw_nvp_pack_fwd(ptrs, F._p(code), B, F._p(wpack), F._p(code_bias), F._p(cb), F._stream()))
+    return wpack, code_bias, cb
+
+
 class _NvpNetwork(torch.autograd.Function):
     """DeformNetwork.forward as four kernels: pack (weight-norm + code projection + per-image biases),
     warp; warp backward, pack backward.  With ``module.accumulate_grads_in_place`` (engine.use_flat_gradients) the
@@ -66,11 +75,16 @@ class _NvpNetwork(torch.autograd.Function):
         if code.shape != (B, HID):
             raise RuntimeError("niw_b200 DeformNetwork: latent code must be [B=%d, %d], got %s" % (B, HID, tuple(code.shape)))
         dev = pts.device
-        wpack = torch.empty(3 * F.NIW_NVP_BLOCK_FLOATS, device=dev)
-        code_bias = torch.empty(3, 2, B, HID, device=dev)
-        cb = torch.empty(3, B, HID, device=dev)
-        ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
-        _lib.check(lib.niw_nvp_pack_fwd(ptrs, F._p(code), B, F._p(wpack), F._p(code_bias), F._p(cb), F._stream()))
+        pre = module._take_prepacked(code) if module is not None else None
+        if pre is not None:
+            # the pack ran earlier on a side stream (DeformNetwork.prepack): wait for it here, nothing to launch
+            wpack, code_bias, cb, done = pre
+            torch.cuda.current_stream().wait_event(done)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in (wpack, code_bias, cb):
+                    t.record_stream(torch.cuda.current_stream())
+        else:
+            wpack, code_bias, cb = _pack_forward(lib, params, code, B, dev)
         out = torch.empty_like(pts)
         im = F.index_map_args(index_map, Pt)
         _lib.check(lib.niw_nvp_warp_fwd(F._p(wpack), F._p(code_bias), F._p(pts), float(alpha_ratio), B, Pt, *im, F._p(out),
@@ -175,6 +189,25 @@ class DeformNetwork(nn.Module):
             lc = getattr(self, f"lin{b}_c")
             p[f"lin{b}_c.weight"], p[f"lin{b}_c.bias"] = lc.weight, lc.bias
         return p
+
+    def prepack(self, deformation_code, stream):
+        """The part of ``forward`` that depends on the parameters and the latent codes only (weight-norm resolution, code
+        projection, per-image first-layer biases: ``niw_nvp_pack_fwd``, ~15 us) launched on ``stream`` NOW, so that it
+        overlaps whatever produces the points (pixel draw, un-warped grid).  The next ``forward`` with the same code
+        tensor picks the result up and waits for it on its own stream; its backward is unchanged."""
+        code = F._f32(deformation_code, "deformation_code")
+        params = self.ordered_parameters()
+        with torch.cuda.stream(stream):
+            packed = _pack_forward(_lib.load(), params, code.detach(), code.shape[0], code.device)
+            done = torch.cuda.Event()
+            done.record(stream)
+        self._prepacked = (code.data_ptr(), code._version, tuple(code.shape)) + (packed + (done,),)
+
+    def _take_prepacked(self, code):
+        pre, self._prepacked = getattr(self, "_prepacked", None), None
+        if pre is not None and pre[:3] == (code.data_ptr(), code._version, tuple(code.shape)):
+            return pre[3]
+        return None
 
     def forward(self, deformation_code, input_pts, alpha_ratio=0, index_map=None):
         """deformation_code [B,D], input_pts [B,P,1,3] -> [B,P,1,3]  (nvp_ndr.py:365).  ``index_map`` (offset, split,
