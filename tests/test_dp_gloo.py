@@ -136,14 +136,31 @@ def _seg_worker(rank, world, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     res = {}
-    for early in ((), (0,), (0, 1), (1,)):
+
+    class _Chan:                                 # stands in for p2p.P2PChannel (peer memory needs GPUs): same interface
+        calls = 0
+
+        def allreduce_(self, t):
+            _Chan.calls += 1
+            dist.all_reduce(t)
+            return t
+
+    for early in ((), (0,), (0, 1), (1,), ("p2p",), ("p2p", 0)):
         b = _Segments([8, 4, 12])
+        if early and early[0] == "p2p":
+            assert b.enable_p2p() is False       # gloo / CPU ranks: the peer-memory path is not available, NCCL / gloo stays
+            b._p2p = [_Chan() for _ in b.groups]  # the routing with channels in place: one channel call per segment
+            early_groups, calls0 = early[1:], _Chan.calls
+        else:
+            early_groups = early
         b.flat.copy_(torch.arange(24.0) * (rank + 1))
-        for gi in early:
+        for gi in early_groups:
             b.allreduce_group_async(gi)          # "this segment's gradients are final": reduced while backward continues
             b.allreduce_group_async(gi)          # idempotent within a step
         b.allreduce()                            # the rest + join
         assert not b._pending
+        if early and early[0] == "p2p":
+            assert _Chan.calls - calls0 == len(b.groups)
         res[early] = b.flat.clone()
     if rank == 0:
         torch.save(res, out_path)
