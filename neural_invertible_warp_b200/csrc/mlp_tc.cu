@@ -270,32 +270,40 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                     ptx::mbar_wait_fast(&a_ready[s], ready_ph);
                     ready_ph ^= 1;
                     ptx::tc_fence_after();
-                    for (int c = 0; c < nch; ++c) {
-                        wait_full();
+                    // ring entries 0 .. nch-1 are the K = 32 weight chunks, entry nch the K = 16 bias chunk
+                    // (D += ones[256 x 16] . [bf16(b), b - bf16(b), 0 ...]^T); two entries per elected region: every
+                    // elect / reconverge round trip costs issue time (profiles/r2_stream_experiment.md)
+                    for (int e = 0; e <= nch; e += 2) {
+                        const bool two = e + 1 <= nch;
+                        const uint32_t st0 = st, fb0 = (cyc & 1) * NSTAGE + st, ph0 = (cyc >> 1) & 1;
+                        if (++st == NSTAGE) { st = 0; ++cyc; }
+                        const uint32_t st1 = st, fb1 = (cyc & 1) * NSTAGE + st, ph1 = (cyc >> 1) & 1;
+                        if (two) { if (++st == NSTAGE) { st = 0; ++cyc; } }
+                        ptx::mbar_wait(&w_full[fb0], ph0);
+                        if (two) ptx::mbar_wait(&w_full[fb1], ph1);
                         ptx::tc_fence_after();
-                        // which A tile region does this chunk multiply?
-                        const bool from_enc = (l == 0) || (c >= 8);
-                        const uint32_t a_lo = (from_enc ? enc_lo : act_lo) + (uint32_t)((l == 0 || c < 8) ? c : c - 8) * (CHUNK_K / 8) * (KROW >> 4);
-                        const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
+                        uint32_t a_lo[2], b_lo[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int c = e + i;
+                            // which A tile region does this chunk multiply?
+                            const bool from_enc = (l == 0) || (c >= 8);
+                            a_lo[i] = c >= nch ? ones_lo
+                                               : (from_enc ? enc_lo : act_lo) + (uint32_t)((l == 0 || c < 8) ? c : c - 8) * (CHUNK_K / 8) * (KROW >> 4);
+                            b_lo[i] = (ring_a + (i ? st1 : st0) * (HSTAGE_BYTES >> 4)) | b_lbo;
+                        }
                         if (ptx::elect_one()) {
-                            ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, c != 0);
-                            ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
-                            ptx::mma2_commit(&w_empty[st]);
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const int c = e + i;
+                                if (i == 1 && !two) break;
+                                ptx::mma2_bf16_w(tacc, a_lo[i], desc_hi, b_lo[i], desc_hi, idesc, c != 0);
+                                if (c < nch) ptx::mma2_bf16_w(tacc, a_lo[i] + 2 * (KROW >> 4), desc_hi, b_lo[i] + b_kstep, desc_hi, idesc, 1u);
+                                ptx::mma2_commit(&w_empty[i ? st1 : st0]);
+                                if (c == nch) ptx::mma2_commit(&acc_full[s]);
+                            }
                         }
                         __syncwarp();
-                        if (++st == NSTAGE) { st = 0; ++cyc; }
-                    }
-                    {   // bias: D += ones[256 x 16] . [bf16(b), b - bf16(b), 0 ...]^T
-                        wait_full();
-                        ptx::tc_fence_after();
-                        const uint32_t b_lo = (ring_a + st * (HSTAGE_BYTES >> 4)) | b_lbo;
-                        if (ptx::elect_one()) {
-                            ptx::mma2_bf16_w(tacc, ones_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
-                            ptx::mma2_commit(&w_empty[st]);
-                            ptx::mma2_commit(&acc_full[s]);
-                        }
-                        __syncwarp();
-                        if (++st == NSTAGE) { st = 0; ++cyc; }
                     }
                     if (s == 0 && both) skip(nch + 1);
                 }
