@@ -38,6 +38,11 @@ namespace niw {
 namespace tc {
 
 constexpr int NSTAGE = NIW_NSTAGE;
+#ifndef NIW_ISSUE_GROUP
+#define NIW_ISSUE_GROUP 2
+#endif
+constexpr int ISSUE_GROUP = NIW_ISSUE_GROUP;     // ring entries (2 MMAs each) per elected region of an issuer
+static_assert(ISSUE_GROUP >= 1 && ISSUE_GROUP <= NSTAGE - 2, "an issuer waits for a whole group of ring stages");
 
 // shared memory map of the forward kernel
 constexpr int SM_ACT = 0;
@@ -271,36 +276,38 @@ tc_fwd_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ con
                     ready_ph ^= 1;
                     ptx::tc_fence_after();
                     // ring entries 0 .. nch-1 are the K = 32 weight chunks, entry nch the K = 16 bias chunk
-                    // (D += ones[256 x 16] . [bf16(b), b - bf16(b), 0 ...]^T); two entries per elected region: every
+                    // (D += ones[256 x 16] . [bf16(b), b - bf16(b), 0 ...]^T); ISSUE_GROUP entries per elected region: every
                     // elect / reconverge round trip costs issue time (profiles/r2_stream_experiment.md)
-                    for (int e = 0; e <= nch; e += 2) {
-                        const bool two = e + 1 <= nch;
-                        const uint32_t st0 = st, fb0 = (cyc & 1) * NSTAGE + st, ph0 = (cyc >> 1) & 1;
-                        if (++st == NSTAGE) { st = 0; ++cyc; }
-                        const uint32_t st1 = st, fb1 = (cyc & 1) * NSTAGE + st, ph1 = (cyc >> 1) & 1;
-                        if (two) { if (++st == NSTAGE) { st = 0; ++cyc; } }
-                        ptx::mbar_wait(&w_full[fb0], ph0);
-                        if (two) ptx::mbar_wait(&w_full[fb1], ph1);
-                        ptx::tc_fence_after();
-                        uint32_t a_lo[2], b_lo[2];
+                    for (int e = 0; e <= nch; e += ISSUE_GROUP) {
+                        const int n_in = nch + 1 - e < ISSUE_GROUP ? nch + 1 - e : ISSUE_GROUP;
+                        uint32_t stg[ISSUE_GROUP], a_lo[ISSUE_GROUP], b_lo[ISSUE_GROUP];
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
+                        for (int i = 0; i < ISSUE_GROUP; ++i) {
+                            if (i < n_in) {
+                                stg[i] = st;
+                                ptx::mbar_wait(&w_full[(cyc & 1) * NSTAGE + st], (cyc >> 1) & 1);
+                                if (++st == NSTAGE) { st = 0; ++cyc; }
+                            } else {
+                                stg[i] = 0;
+                            }
                             const int c = e + i;
                             // which A tile region does this chunk multiply?
                             const bool from_enc = (l == 0) || (c >= 8);
                             a_lo[i] = c >= nch ? ones_lo
                                                : (from_enc ? enc_lo : act_lo) + (uint32_t)((l == 0 || c < 8) ? c : c - 8) * (CHUNK_K / 8) * (KROW >> 4);
-                            b_lo[i] = (ring_a + (i ? st1 : st0) * (HSTAGE_BYTES >> 4)) | b_lbo;
+                            b_lo[i] = (ring_a + stg[i] * (HSTAGE_BYTES >> 4)) | b_lbo;
                         }
+                        ptx::tc_fence_after();
                         if (ptx::elect_one()) {
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) {
+                            for (int i = 0; i < ISSUE_GROUP; ++i) {
                                 const int c = e + i;
-                                if (i == 1 && !two) break;
-                                ptx::mma2_bf16_w(tacc, a_lo[i], desc_hi, b_lo[i], desc_hi, idesc, c != 0);
-                                if (c < nch) ptx::mma2_bf16_w(tacc, a_lo[i] + 2 * (KROW >> 4), desc_hi, b_lo[i] + b_kstep, desc_hi, idesc, 1u);
-                                ptx::mma2_commit(&w_empty[i ? st1 : st0]);
-                                if (c == nch) ptx::mma2_commit(&acc_full[s]);
+                                if (i < n_in) {
+                                    ptx::mma2_bf16_w(tacc, a_lo[i], desc_hi, b_lo[i], desc_hi, idesc, c != 0);
+                                    if (c < nch) ptx::mma2_bf16_w(tacc, a_lo[i] + 2 * (KROW >> 4), desc_hi, b_lo[i] + b_kstep, desc_hi, idesc, 1u);
+                                    ptx::mma2_commit(&w_empty[stg[i]]);
+                                    if (c == nch) ptx::mma2_commit(&acc_full[s]);
+                                }
                             }
                         }
                         __syncwarp();

@@ -33,7 +33,11 @@ namespace tc {
 // ==========================================================================================
 
 constexpr int BX_NSTAGE = 10;
-static_assert(step_chunks(0) % 2 == 0 && step_chunks(2) % 2 == 0, "the issuer takes the weight chunks in pairs");
+#ifndef NIW_BX_GROUP
+#define NIW_BX_GROUP 2
+#endif
+constexpr int BX_GROUP = NIW_BX_GROUP;           // weight chunks (2 MMAs each) per elected region of an issuer
+static_assert(step_chunks(0) % BX_GROUP == 0 && step_chunks(2) % BX_GROUP == 0, "the issuer takes the weight chunks in groups");
 constexpr int BX_ACT = 0;                                   // 2 x 64 KB G tiles
 constexpr int BX_RING = BX_ACT + 2 * ACT_BYTES;
 constexpr int BX_CONST = BX_RING + BX_NSTAGE * HSTAGE_BYTES; // W7 row 0 [256] + Wrgb1 [3][128]
@@ -159,25 +163,26 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                     ptx::mbar_wait_fast(&a_ready[sl], ready_ph);
                     ready_ph ^= 1;
                     ptx::tc_fence_after();
-                    // two weight chunks (nch is even: 4 or 8) per elected region, as in the forward kernel
-                    for (int c = 0; c < nch; c += 2) {
-                        const uint32_t st0 = st, fb0 = (cyc & 1) * BX_NSTAGE + st, ph0 = (cyc >> 1) & 1;
-                        if (++st == BX_NSTAGE) { st = 0; ++cyc; }
-                        const uint32_t st1 = st, fb1 = (cyc & 1) * BX_NSTAGE + st, ph1 = (cyc >> 1) & 1;
-                        if (++st == BX_NSTAGE) { st = 0; ++cyc; }
-                        ptx::mbar_wait(&w_full[fb0], ph0);
-                        ptx::mbar_wait(&w_full[fb1], ph1);
+                    // BX_GROUP weight chunks (nch is 4 or 8) per elected region, as in the forward kernel
+                    for (int c = 0; c < nch; c += BX_GROUP) {
+                        uint32_t stg[BX_GROUP];
+#pragma unroll
+                        for (int i = 0; i < BX_GROUP; ++i) {
+                            stg[i] = st;
+                            ptx::mbar_wait(&w_full[(cyc & 1) * BX_NSTAGE + st], (cyc >> 1) & 1);
+                            if (++st == BX_NSTAGE) { st = 0; ++cyc; }
+                        }
                         ptx::tc_fence_after();
                         const uint32_t a_lo = act_lo + (uint32_t)c * (CHUNK_K / 8) * (KROW >> 4);
-                        const uint32_t b0 = (ring_a + st0 * (HSTAGE_BYTES >> 4)) | b_lbo, b1 = (ring_a + st1 * (HSTAGE_BYTES >> 4)) | b_lbo;
                         if (ptx::elect_one()) {
-                            ptx::mma2_bf16_w(tacc, a_lo, desc_hi, b0, desc_hi, idesc, c != 0);
-                            ptx::mma2_bf16_w(tacc, a_lo + 2 * (KROW >> 4), desc_hi, b0 + b_kstep, desc_hi, idesc, 1u);
-                            ptx::mma2_commit(&w_empty[st0]);
-                            ptx::mma2_bf16_w(tacc, a_lo + 4 * (KROW >> 4), desc_hi, b1, desc_hi, idesc, 1u);
-                            ptx::mma2_bf16_w(tacc, a_lo + 6 * (KROW >> 4), desc_hi, b1 + b_kstep, desc_hi, idesc, 1u);
-                            ptx::mma2_commit(&w_empty[st1]);
-                            if (c == nch - 2) ptx::mma2_commit(&acc_full[sl]);
+#pragma unroll
+                            for (int i = 0; i < BX_GROUP; ++i) {
+                                const uint32_t b_lo = (ring_a + stg[i] * (HSTAGE_BYTES >> 4)) | b_lbo;
+                                ptx::mma2_bf16_w(tacc, a_lo + (4 * i) * (KROW >> 4), desc_hi, b_lo, desc_hi, idesc, (c + i) != 0);
+                                ptx::mma2_bf16_w(tacc, a_lo + (4 * i + 2) * (KROW >> 4), desc_hi, b_lo + b_kstep, desc_hi, idesc, 1u);
+                                ptx::mma2_commit(&w_empty[stg[i]]);
+                            }
+                            if (c + BX_GROUP >= nch) ptx::mma2_commit(&acc_full[sl]);
                         }
                         __syncwarp();
                     }
