@@ -459,32 +459,37 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = ptx::idesc_bf16(TILE, U.n_main > 0 ? U.n_main : 16, 1, 1);
-            const uint32_t idesc2 = ptx::idesc_bf16(TILE, U.n2 > 0 ? U.n2 : 16, 1, 1);
-            for (int64_t it = 0; it < nstages; ++it) {
-                const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
-                ptx::mbar_wait(&full[st], ph);
-                ptx::tc_fence_after();
-                const uint32_t base = ptx::smem_addr(smem + st * BW_STAGE);
+        // MMA issuer: the warp stays converged (loop state and descriptor words uniform), one elected lane issues a whole
+        // stage -- a single-thread issuer computes every descriptor in per-thread registers and pays register-to-uniform
+        // moves per MMA, which made the ISSUE (not the memory system) the limit of a dW CTA (~40 GB/s)
+        const uint32_t idesc = ptx::idesc_bf16(TILE, U.n_main > 0 ? U.n_main : 16, 1, 1);
+        const uint32_t idesc2 = ptx::idesc_bf16(TILE, U.n2 > 0 ? U.n2 : 16, 1, 1);
+        const uint32_t desc_hi = ptx::smem_desc_hi(HROW);          // MN-major operands, K = samples: LBO = 128 (8 samples), SBO = HROW
+        const int m_halves = U.m_halves;
+        const bool second = U.n2 > 0;
+        for (int64_t it = 0; it < nstages; ++it) {
+            const uint32_t st = (uint32_t)(it % BW_NSTAGE), ph = (uint32_t)(it / BW_NSTAGE) & 1;
+            ptx::mbar_wait(&full[st], ph);
+            ptx::tc_fence_after();
+            const uint32_t base = ptx::smem_addr(smem + st * BW_STAGE);
+            const uint32_t a_lo = ptx::smem_desc_lo(base + BW_A, 128), b_lo = ptx::smem_desc_lo(base + BW_B, 128);
+            const uint32_t b2_lo = ptx::smem_desc_lo(base + BW_B2, 128);
+            const uint32_t first = it != 0;
+            if (ptx::elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < HALF / 16; ++ks) {
-                    // MN-major operands, K = samples: 16 samples = 256 B along a feature group
-                    const uint64_t bd = ptx::smem_desc(base + BW_B + ks * 256, 128, HROW);
-                    for (int h = 0; h < U.m_halves; ++h) {
-                        const uint64_t ad = ptx::smem_desc(base + BW_A + h * 16 * HROW + ks * 256, 128, HROW);
-                        ptx::mma_bf16(tmem_base + h * WIDTH, ad, bd, idesc, (it | ks) != 0);
-                    }
-                    if (U.n2 > 0) {
-                        const uint64_t ad = ptx::smem_desc(base + BW_A + ks * 256, 128, HROW);
-                        const uint64_t b2 = ptx::smem_desc(base + BW_B2 + ks * 256, 128, HROW);
-                        ptx::mma_bf16(tmem_base + WIDTH, ad, b2, idesc2, (it | ks) != 0);
-                    }
+                    // 16 samples = 256 B along a feature group
+                    const uint32_t k = (uint32_t)(ks * 256) >> 4, acc = first | (uint32_t)(ks != 0);
+                    ptx::mma_bf16_w(tmem_base, a_lo + k, desc_hi, b_lo + k, desc_hi, idesc, acc);
+                    if (m_halves > 1) ptx::mma_bf16_w(tmem_base + WIDTH, a_lo + ((16 * HROW) >> 4) + k, desc_hi, b_lo + k, desc_hi, idesc, acc);
+                    if (second) ptx::mma_bf16_w(tmem_base + WIDTH, a_lo + k, desc_hi, b2_lo + k, desc_hi, idesc2, acc);
                 }
                 ptx::mma_commit(&empty[st]);
             }
-            ptx::mma_commit(done);
+            __syncwarp();
         }
+        if (ptx::elect_one()) ptx::mma_commit(done);
+        __syncwarp();
     } else if (warp >= 4) {
         const int wq = warp & 3;
         // ---- thin products on the warp-level tensor path while the tiles stream ----
