@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libniw_b200.so")
-SOURCES = ["api.cu", "raygen.cu", "nvp.cu", "sampler.cu", "composite.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_tc_x3.cu", "mlp_tc_bwd.cu", "mlp_tc_bwd_stream.cu", "tc_selftest.cu", "adam.cu", "metrics.cu", "kabsch.cu", "p2p.cu"]
+SOURCES = ["api.cu", "raygen.cu", "nvp.cu", "sampler.cu", "composite.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_tc_x3.cu", "mlp_tc_bwd.cu", "tc_selftest.cu", "adam.cu", "metrics.cu", "kabsch.cu", "p2p.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -64,7 +64,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
              const float* __restrict__ ray, const float* __restrict__ depth, int64_t S, int N,
              const float* __restrict__ d_rgb, const float* __restrict__ d_sigma, const float* __restrict__ sig_pre,
              const float* __restrict__ rgb_keep, uint8_t* __restrict__ save, float* __restrict__ scratch,
-             float* __restrict__ dP, float* __restrict__ d_center, float* __restrict__ d_ray, int nstep, int g_unsplit) {
+             float* __restrict__ dP, float* __restrict__ d_center, float* __restrict__ d_ray) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BX_BAR);
     uint64_t* w_full = bars;                    // [2][BX_NSTAGE] (alternating trips round the ring, see mlp_tc.cu)
@@ -111,7 +111,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
             for (int64_t k = 0; hq_of(k, 0) < nhq; ++k) {
                 const int nslots = hq_of(k, 1) < nhq ? 2 : 1;
                 const uint8_t* ssrc = bstream;
-                for (int s = 0; s < nstep; ++s) {
+                for (int s = 0; s < NSTEP; ++s) {
                     const uint32_t bytes = (uint32_t)(step_n(s) / 2) * CHUNK_K * 2;
                     for (int sl = 0; sl < nslots; ++sl) {
                         const uint8_t* src = ssrc + rank * bytes;
@@ -134,7 +134,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
             uint32_t st = 0, cyc = 0;
             const uint32_t full0 = ptx::mapa(&w_full[0], 0);
             for (int64_t k = 0; hq_of(k, 0) < nhq; ++k)
-                for (int s = 0; s < nstep; ++s)
+                for (int s = 0; s < NSTEP; ++s)
                     for (int c = 0; c < (hq_of(k, 1) < nhq ? 2 : 1) * step_chunks(s); ++c) {
                         const uint32_t fb = (cyc & 1) * BX_NSTAGE + st;
                         ptx::mbar_wait(&w_full[fb], (cyc >> 1) & 1);
@@ -155,7 +155,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
             const uint32_t tacc = tmem_base + sl * WIDTH;
             for (int64_t k = 0; hq_of(k, sl) < nhq; ++k) {
                 const bool both = hq_of(k, 1) < nhq;                 // the other slot works in this round too
-                for (int s = 0; s < nstep; ++s) {
+                for (int s = 0; s < NSTEP; ++s) {
                     const int hrows = step_n(s) / 2, nch = step_chunks(s);
                     const uint32_t idesc = ptx::idesc_bf16(2 * TILE, 2 * hrows, 0, 0);
                     const uint32_t b_lbo = (uint32_t)hrows << 16, b_kstep = (uint32_t)hrows * 2;
@@ -248,7 +248,7 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
             ptx::fence_proxy_async();
             ptx::warp_arrive_cluster(ready_bar);
 
-            for (int s = 0; s < nstep; ++s, ++full_uses) {
+            for (int s = 0; s < NSTEP; ++s, ++full_uses) {
                 const int lo = step_out_layer(s);
                 uint32_t mw[MASK_WORDS];
                 if (lo >= 0) {   // the ReLU flags do not depend on the products: fetch them while the MMAs run
@@ -287,13 +287,12 @@ tc_dx_kernel(const uint8_t* __restrict__ bstream, const float* __restrict__ cons
                         for (int q = 0; q < 4; ++q) {
                             uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
                             *reinterpret_cast<uint4*>(act + (cc * 4 + q) * KROW + row * 16) = o;
-                            // (g_unsplit: the streaming continuation of the chain reads the image back as an A operand, mlp_tc_bwd_stream.cu)
-                            if (save_img) *reinterpret_cast<uint4*>(save_img + (g_unsplit ? (cc * 4 + q) * KROW + row * 16 : hbm_img_off(WIDTH, row, cc * 4 + q))) = o;
+                            if (save_img) *reinterpret_cast<uint4*>(save_img + hbm_img_off(WIDTH, row, cc * 4 + q)) = o;
                         }
                     }
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    if (s + 1 < nstep) ptx::warp_arrive_cluster(ready_bar);      // (head mode ends here: the next arrival is the next tile's step -1)
+                    ptx::warp_arrive_cluster(ready_bar);
                 } else if (s == 0) {
                     // ---- view branch: d(encoded view) -> d(unit view) -> d ray through normalize ----
                     uint32_t v[32];
@@ -681,14 +680,9 @@ int tc_bwd_dx(const float* P, const float* center, const float* ray, const float
     int64_t pairs = niw_num_sms() / 2;
     if (pairs > nhq) pairs = nhq;
     const int grid = (int)(2 * (pairs < 1 ? 1 : pairs));
-    // NIW_DX_STREAM=1 (experiment): the head steps (-1, 0, 1) here, steps 2 .. 10 in streaming form (mlp_tc_bwd_stream.cu)
-    const char* env = getenv("NIW_DX_STREAM");
-    const bool stream = env && env[0] == '1';
     niw::note_launch(), tc_dx_kernel<<<grid, 384, BX_TOTAL, st>>>(w.bstream, w.consts, center, ray, depth, S, N, d_rgb, d_sigma,
-                                                                 w.sig_pre, w.rgb_keep, w.save, w.scratch, dP, d_center, d_ray,
-                                                                 stream ? 2 : NSTEP, stream ? 1 : 0);
+                                                                 w.sig_pre, w.rgb_keep, w.save, w.scratch, dP, d_center, d_ray);
     NIW_LAUNCH_CHECK();
-    if (stream) return tc_dx_stream(w, center, ray, depth, S, N, d_sigma, d_center, d_ray, st);
     return 0;
 }
 

@@ -146,7 +146,6 @@ struct Workspace {
     float* scratch;       // [SMs*2 slots][64][128] fp32: skip-connection gradient parked between steps 5 and 10
     float* partial;       // [max_slices][NPARAMS] fp32 weight-gradient partial sums
     uint8_t* wstream_x3;  // split-precision forward weight stream (hi / lo bf16), carved last: the other offsets do not move
-    float* park;          // [tiles][64][128] fp32: skip-connection gradient per tile (streaming chain, mlp_tc_bwd_stream.cu)
     size_t bytes;
 };
 constexpr int PARTIAL_SLICES = 16;
@@ -155,7 +154,7 @@ inline Workspace carve(void* base, int64_t S, bool training, bool x3 = false) {
     Workspace w;
     size_t off = 0;
     auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += (n + 255) & ~size_t(255); return p; };
-    int64_t tiles = ((S + TILE - 1) / TILE + 1) & ~int64_t(1);   // even: the streaming kernels work on tile PAIRS
+    int64_t tiles = (S + TILE - 1) / TILE;
     w.wstream = take(STREAM_BYTES);
     w.bstream = take(BSTREAM_BYTES);
     w.consts = (float*)take(C_FLOATS * 4);
@@ -165,7 +164,6 @@ inline Workspace carve(void* base, int64_t S, bool training, bool x3 = false) {
     w.scratch = (float*)take(training ? (size_t)niw_num_sms() * 2 * ENC3_PAD * TILE * 4 : 0);
     w.partial = (float*)take(training ? (size_t)PARTIAL_SLICES * NPARAMS * 4 : 0);
     w.wstream_x3 = take(x3 ? STREAM_X3_BYTES : 0);
-    w.park = (float*)take(training ? (size_t)tiles * ENC3_PAD * TILE * 4 : 0);
     w.bytes = off;
     return w;
 }
@@ -186,9 +184,4 @@ __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 
 }  // namespace tc
-
-// steps 2 .. 10 of the activation-gradient chain in streaming form (mlp_tc_bwd_stream.cu)
-int tc_dx_stream(const tc::Workspace& w, const float* center, const float* ray, const float* depth, int64_t S, int N,
-                 const float* d_sigma, float* d_center, float* d_ray, cudaStream_t st);
-
 }  // namespace niw
