@@ -282,6 +282,69 @@ def test_backward_overlap_matches_sequential_backward(eng):
         assert (grads[k] != 0).sum() == (grads[False] != 0).sum()
 
 
+def test_train_step_with_optimizer_equals_step_then_update(eng):
+    """engine.train_step(optimizer=FlatAdam) updates the pose / warp groups before the side stream is joined and the NeRF group
+    after it.  The groups are independent: on the SAME gradients, FlatAdam.step(groups=...) group by group in that order is
+    bit-identical to one FlatAdam.step(); and the fused call takes exactly one step in every group."""
+    d = draws(1, seed=31)[0]
+    opt, g, var = make(eng, precision="bf16")
+    fa = eng.FlatAdam(eng.reference_optimizer_groups(opt, g))
+    with eng.feed_draws(ray_idx=d[0], u=d[1]):
+        eng.train_step(opt, g, cfgmod.AttrDict(var), 0, bucket=fa)
+    torch.cuda.synchronize()
+    grads, p0 = fa.flat.clone(), fa.flat_params.clone()
+    fa.step()
+    torch.cuda.synchronize()
+    whole = (fa.flat_params.clone(), fa.exp_avg.clone(), fa.exp_avg_sq.clone(), fa.state.clone())
+    # same start, same gradients, group by group in the order train_step(optimizer=) uses
+    fa.flat_params.copy_(p0); fa.exp_avg.zero_(); fa.exp_avg_sq.zero_(); fa.state.zero_(); fa.flat.copy_(grads)
+    fa.step(groups=range(1, len(fa.groups)))
+    fa.step(groups=[0])
+    torch.cuda.synchronize()
+    for a, b in zip(whole, (fa.flat_params, fa.exp_avg, fa.exp_avg_sq, fa.state)):
+        assert torch.equal(a, b)
+    # the fused call: one more step in every group, parameters move
+    before = fa.flat_params.clone()
+    with eng.feed_draws(ray_idx=d[0], u=d[1]):
+        eng.train_step(opt, g, cfgmod.AttrDict(var), 1, bucket=fa, optimizer=fa)
+    torch.cuda.synchronize()
+    assert torch.equal(fa.state[:, 0], torch.full_like(fa.state[:, 0], 2.0))
+    for gr in fa.groups:
+        seg = slice(gr["offset"], gr["offset"] + gr["n"])
+        assert not torch.equal(fa.flat_params[seg], before[seg])
+
+
+def test_warp_network_prepack_on_a_side_stream_is_the_same_forward(eng):
+    """DeformNetwork.prepack (the weight pack launched early on a side stream, barf_inn_llff._prefetch_pose): the following
+    forward picks it up -- same output bits and same gradients as the forward that packs for itself; a prepack for another
+    code tensor is ignored."""
+    opt, g, var = make(eng)
+    net, code = g.warp_mlp, g.warp_latent.weight
+    gen = torch.Generator().manual_seed(5)
+    pts = (torch.randn(B, 40, 1, 3, generator=gen) * 0.5).to(DEV)
+    w = torch.randn(B, 40, 1, 3, generator=gen).to(DEV)
+    outs, grads = [], []
+    side = torch.cuda.Stream()
+    for mode in ("plain", "prepacked", "stale"):
+        for p in list(net.parameters()) + [code]:
+            p.grad = None
+        if mode == "prepacked":
+            side.wait_stream(torch.cuda.current_stream())
+            net.prepack(code, side)
+        elif mode == "stale":
+            net.prepack(code.detach().clone(), side)          # another tensor: must not be used
+        out = net.forward(code, pts, alpha_ratio=0.4)
+        (out * w).sum().backward()
+        torch.cuda.synchronize()
+        assert getattr(net, "_prepacked", None) is None
+        outs.append(out.detach().clone())
+        grads.append(torch.cat([p.grad.reshape(-1) for p in net.parameters()] + [code.grad.reshape(-1)]).clone())
+    for o, gr in zip(outs[1:], grads[1:]):
+        assert torch.equal(o, outs[0])
+        rel = ((gr.double() - grads[0].double()).norm() / grads[0].double().norm()).item()
+        assert rel < 1e-5, rel
+
+
 def test_captured_test_time_pose_refinement(eng):
     """the test-time photometric pose refinement (reference model/barf.py:153-169) as ONE captured CUDA graph
     replayed per iteration on engine.FlatAdam (device pixel draws, no host sync): from a perturbed test pose the loss of the
