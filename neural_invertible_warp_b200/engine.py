@@ -132,7 +132,16 @@ class SegmentedAllreduce:
         whether the peer path is on."""
         from . import p2p
         if self._p2p is None and p2p.available(group):
-            self._p2p = [p2p.P2PChannel(g["n"], group) for g in self.groups]
+            chans = []
+            try:
+                for g in self.groups:
+                    chans.append(p2p.P2PChannel(g["n"], group))      # raises on every rank alike when any rank failed
+                self._p2p = chans
+            except RuntimeError as e:
+                import warnings
+                warnings.warn("niw_b200: peer-memory gradient sum unavailable (%s); using the NCCL all-reduce" % e)
+                for c in chans:
+                    c.close()
         return self._p2p is not None
 
     @staticmethod

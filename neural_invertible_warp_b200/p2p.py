@@ -44,27 +44,53 @@ class P2PChannel:
     """In-place sum of fp32 tensors of up to ``max_floats`` elements over the ranks of ``group`` (one node)."""
 
     def __init__(self, max_floats, group=None):
+        """Collective: every rank of ``group`` constructs its channel at the same point.  Raises ``RuntimeError`` on ALL ranks
+        when any rank could not allocate or map a block (the outcome of each stage is agreed on before the next), so a
+        caller can fall back to NCCL consistently."""
         self.lib = _lib.load()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.half = (int(max_floats) + 3) // 4 * 4
         nbytes = 256 + 4 * self.half * 4        # flag block, two exchange halves, two result halves (two-shot)
-        mine, handle = _c.c_void_p(), _c.create_string_buffer(64)
-        _lib.check(self.lib.niw_p2p_alloc(nbytes, _c.byref(mine), handle))
+        mine, handle, err = _c.c_void_p(), _c.create_string_buffer(64), None
+        rc = self.lib.niw_p2p_alloc(nbytes, _c.byref(mine), handle)
+        if rc:
+            mine, err = None, "niw_p2p_alloc: %s" % self.lib.niw_error_string(rc).decode()
+        elif os.environ.get("NIW_P2P_TEST_FAIL") == str(self.rank):      # tests: this rank pretends its allocation failed
+            self.lib.niw_p2p_free(mine)
+            mine, err = None, "simulated allocation failure (NIW_P2P_TEST_FAIL)"
         self.mine = mine
-        handles = [None] * self.world
-        dist.all_gather_object(handles, handle.raw, group=group)
-        self.blocks = (_c.c_void_p * self.world)()
         self._opened = []
-        for r, h in enumerate(handles):
+        stage = [None] * self.world
+        dist.all_gather_object(stage, (err, handle.raw), group=group)
+        if any(e is not None for e, _ in stage):
+            self._release()
+            raise RuntimeError("P2PChannel: " + "; ".join("rank %d: %s" % (r, e) for r, (e, _) in enumerate(stage) if e))
+        self.blocks = (_c.c_void_p * self.world)()
+        for r, (_, h) in enumerate(stage):
             if r == self.rank:
                 self.blocks[r] = mine.value
-            else:
-                p = _c.c_void_p()
-                _lib.check(self.lib.niw_p2p_open(_c.create_string_buffer(h, 64), _c.byref(p)))
-                self.blocks[r] = p.value
-                self._opened.append(p)
-        dist.barrier(group=group)        # every rank has mapped every block before the first flag is raised
+                continue
+            p = _c.c_void_p()
+            rc = self.lib.niw_p2p_open(_c.create_string_buffer(h, 64), _c.byref(p))
+            if rc:
+                err = "niw_p2p_open(rank %d): %s" % (r, self.lib.niw_error_string(rc).decode())
+                break
+            self.blocks[r] = p.value
+            self._opened.append(p)
+        stage = [None] * self.world
+        dist.all_gather_object(stage, err, group=group)      # (also: every rank has mapped every block before the first flag is raised)
+        if any(e is not None for e in stage):
+            self._release()
+            raise RuntimeError("P2PChannel: " + "; ".join("rank %d: %s" % (r, e) for r, e in enumerate(stage) if e))
+
+    def _release(self):
+        for p in self._opened:
+            self.lib.niw_p2p_close(p)
+        self._opened = []
+        if self.mine is not None:
+            self.lib.niw_p2p_free(self.mine)
+            self.mine = None
 
     def allreduce_(self, t):
         """Sum ``t`` (contiguous CUDA fp32, numel % 4 == 0, 16-byte aligned) over the ranks, in place, on the current stream."""
@@ -89,5 +115,4 @@ class P2PChannel:
             self.lib.niw_p2p_close(p)
         self._opened = []
         dist.barrier(group=self.group)
-        self.lib.niw_p2p_free(self.mine)
-        self.mine = None
+        self._release()

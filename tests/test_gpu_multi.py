@@ -50,6 +50,15 @@ def _worker(rank, world, port, precision, out_path, collective="nccl"):
     adam = engine.FlatAdam(engine.reference_optimizer_groups(opt, graph))
     if collective == "p2p":
         assert adam.enable_p2p(), "peer-memory all-reduce unavailable on this box"
+    elif collective == "p2p-fails":
+        # one rank cannot set its exchange block up: EVERY rank must fall back to NCCL (no hang, no mixed collectives)
+        import warnings
+        os.environ["NIW_P2P_TEST_FAIL"] = "1"
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter("always")
+            assert adam.enable_p2p() is False and adam._p2p is None
+        assert any("NCCL" in str(w.message) for w in caught)
+        del os.environ["NIW_P2P_TEST_FAIL"]
     ridx, u = _draws(dev)
     per = (P_GLOBAL + world - 1) // world
     for rep in range(3 if collective == "p2p" else 1):      # p2p: the exchange buffers are double-buffered on a sequence number
@@ -76,7 +85,7 @@ def _free_port():
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("precision,collective", [("fp32", "nccl"), ("bf16", "nccl"), ("bf16", "p2p")])
+@pytest.mark.parametrize("precision,collective", [("fp32", "nccl"), ("bf16", "nccl"), ("bf16", "p2p"), ("bf16", "p2p-fails")])
 def test_two_gpu_sharded_step_equals_single_gpu_step(tmp_path, precision, collective):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
