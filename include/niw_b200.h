@@ -126,6 +126,13 @@ int niw_sample_stratified(const float* u, int64_t n_rays, int N, float scale, fl
  * no host read of the range, so the step can be captured in a CUDA graph */
 int niw_sample_stratified_dev(const float* u, int64_t n_rays, int N, const float* range_dev, int inverse, float* depth,
                               void* stream);
+/* The same depths with the uniforms drawn INSIDE the kernel (Philox4x32-10, 24-bit uniforms in [0, 1) as torch.rand; counter =
+ * (sample group, call number), key = seed): what `torch.rand` + niw_sample_stratified give in distribution, without the torch
+ * RNG op in a captured step (its graph-safe generator state costs two fill launches in front of every replay).  `rng`: two
+ * zero-initialised 64-bit device words owned by the caller; the kernel advances the call number, so every launch / replay
+ * draws afresh.  range_dev (device [min, max]) or NULL -> scale = max - min, dmin. */
+int niw_sample_stratified_rng(int64_t n_rays, int N, float scale, float dmin, const float* range_dev, int inverse,
+                              unsigned long long seed, unsigned long long* rng, float* depth, void* stream);
 
 /* ---- (a5) Graph.sample_depth_from_pdf + cat + sort   model/nerf.py:346-365, :313-315
  * pdf [R,N]; unif [Nf] = 0.5*(grid[:-1]+grid[1:]); bins [N+1] = linspace(dmin,dmax,N+1) (both made

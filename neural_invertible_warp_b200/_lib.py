@@ -37,6 +37,7 @@ SIGNATURES = {
     "niw_sample_pixels": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_uint64, _P, _P, _P]),
     "niw_sample_stratified": (_c.c_int, [_P, _c.c_int64, _c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P]),
     "niw_sample_stratified_dev": (_c.c_int, [_P, _c.c_int64, _c.c_int, _P, _c.c_int, _P, _P]),
+    "niw_sample_stratified_rng": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_float, _c.c_float, _P, _c.c_int, _c.c_uint64, _P, _P, _P]),
     "niw_sample_pdf_merge": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     "niw_composite_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P, _P]),
     "niw_composite_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P, _P, _P]),

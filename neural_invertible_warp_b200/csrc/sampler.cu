@@ -9,12 +9,30 @@
 
 namespace {
 
+// Philox4x32-10 (Salmon et al. 2011): four 32-bit words per (counter, key) -- the generator behind the uniforms of the
+// device-RNG path (niw_sample_stratified_rng): counter = (group index, call number), key = seed.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
 // ((u+k)/N)*scale + dmin ; inverse: 1/(d+1e-8).  One thread per 4 consecutive samples (128-bit accesses), grid-stride.
 // POW2: N is a power of two, so (u+k)/N == (u+k)*(1/N) bit for bit and the sample index is a mask.
+// rng != nullptr: the uniforms are drawn here (24-bit, [0, 1), as torch.rand) from Philox4x32-10 keyed by `seed`, counter
+// (group, call number rng[0]); the last block to finish advances rng[0] (ticket in rng[1]), so every launch -- and every
+// replay of a captured graph -- draws afresh without a torch RNG op (whose graph-safe state costs two fill launches per replay).
 template <bool POW2>
 __global__ void __launch_bounds__(256)
 stratified_kernel(const float* __restrict__ u, int64_t total, int N, float scale, float dmin, int inverse,
-                  float* __restrict__ depth, const float* __restrict__ range_dev) {
+                  float* __restrict__ depth, const float* __restrict__ range_dev, unsigned long long* __restrict__ rng,
+                  unsigned long long seed) {
+    const unsigned long long call = rng ? rng[0] : 0ull;
     if (range_dev) { dmin = range_dev[0]; scale = __fsub_rn(range_dev[1], range_dev[0]); }   // (max - min) as the reference evaluates it
     const float fN = (float)N, rN = 1.0f / (float)N;
     const int64_t ngroups = (total + 3) >> 2, gstride = (int64_t)gridDim.x * blockDim.x;
@@ -22,7 +40,12 @@ stratified_kernel(const float* __restrict__ u, int64_t total, int N, float scale
         const int64_t i0 = gi * 4;
         float uu[4] = {0.5f, 0.5f, 0.5f, 0.5f};
         const bool vec = (i0 + 3 < total);
-        if (u) {
+        if (rng) {
+            const uint4 x = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)((uint64_t)gi >> 32), (uint32_t)call, (uint32_t)(call >> 32)),
+                                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            uu[0] = (float)(x.x >> 8) * 5.9604644775390625e-08f; uu[1] = (float)(x.y >> 8) * 5.9604644775390625e-08f;
+            uu[2] = (float)(x.z >> 8) * 5.9604644775390625e-08f; uu[3] = (float)(x.w >> 8) * 5.9604644775390625e-08f;
+        } else if (u) {
             if (vec) {
                 const float4 v = __ldcs(reinterpret_cast<const float4*>(u + i0));
                 uu[0] = v.x; uu[1] = v.y; uu[2] = v.z; uu[3] = v.w;
@@ -46,6 +69,10 @@ stratified_kernel(const float* __restrict__ u, int64_t total, int N, float scale
         } else {
             for (int j = 0; j < 4 && i0 + j < total; ++j) depth[i0 + j] = out[j];
         }
+    }
+    if (rng) {      // every block has read rng[0] before it gets here: the last one to arrive moves on to the next call number
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(rng + 1, 1ull) == gridDim.x - 1) { rng[1] = 0ull; __threadfence(); rng[0] = call + 1; }
     }
 }
 
@@ -412,16 +439,17 @@ __global__ void sample_pixels_kernel(int64_t n, int k, uint64_t seed, unsigned l
 }  // namespace
 
 static int launch_stratified(const float* u, int64_t n_rays, int N, float scale, float dmin, const float* range_dev,
-                             int inverse, float* depth, cudaStream_t st) {
+                             int inverse, float* depth, cudaStream_t st, unsigned long long* rng = nullptr,
+                             unsigned long long seed = 0) {
     int64_t total = n_rays * N;
     int64_t blocks = niw_blocks((total + 3) / 4, 256);
     const int64_t cap = (int64_t)niw_num_sms() * 16;              // grid-stride: 8 resident CTAs / SM x 2 rounds
     if (blocks > cap) blocks = cap;
     niw::note_launch();
     if ((N & (N - 1)) == 0)
-        stratified_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(u, total, N, scale, dmin, inverse, depth, range_dev);
+        stratified_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(u, total, N, scale, dmin, inverse, depth, range_dev, rng, seed);
     else
-        stratified_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(u, total, N, scale, dmin, inverse, depth, range_dev);
+        stratified_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(u, total, N, scale, dmin, inverse, depth, range_dev, rng, seed);
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -436,6 +464,14 @@ extern "C" int niw_sample_stratified_dev(const float* u, int64_t n_rays, int N, 
                                          float* depth, void* stream) {
     NIW_CHECK_ARG(depth && range_dev && n_rays > 0 && N > 0);
     return launch_stratified(u, n_rays, N, 0.f, 0.f, range_dev, inverse, depth, niw_stream(stream));
+}
+
+// stratified depths with the uniforms drawn inside the kernel; range_dev (device [min, max]) may be NULL: then scale / dmin.
+// rng: two zero-initialised 64-bit device words owned by the caller (call number, block ticket)
+extern "C" int niw_sample_stratified_rng(int64_t n_rays, int N, float scale, float dmin, const float* range_dev, int inverse,
+                                         unsigned long long seed, unsigned long long* rng, float* depth, void* stream) {
+    NIW_CHECK_ARG(depth && rng && n_rays > 0 && N > 0);
+    return launch_stratified(nullptr, n_rays, N, scale, dmin, range_dev, inverse, depth, niw_stream(stream), rng, seed);
 }
 
 template <int CN, int CF>

@@ -488,7 +488,8 @@ class _ShardedRandperm:
 
 
 class device_ray_draws:
-    """Makes ``torch.randperm(n, device=cuda)[:k]`` inside ``Graph.forward`` an O(k) kernel: the reference sorts
+    """Device-side random draws of a training step without torch RNG ops (a captured step then needs no generator-state
+    fills in front of every replay).  Makes ``torch.randperm(n, device=cuda)[:k]`` inside ``Graph.forward`` an O(k) kernel: the reference sorts
     H*W random keys to keep ``rand_rays // B`` of them (model/nerf.py:268; five radix-sort passes per step).
     ``torch.randperm`` is replaced by a lazy stand-in whose ``[:k]`` slice launches ``F.sample_pixels`` -- the
     first k entries of a random permutation, drawn from the library's own counter-based stream (capturable:
@@ -507,10 +508,11 @@ class device_ray_draws:
 
     def __init__(self, device, seed=0):
         self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+        self.rng = torch.zeros(2, dtype=torch.int64, device=device)     # stratified uniforms: call number, block ticket
         self.seed = seed
 
     def __enter__(self):
-        self._perm = torch.randperm
+        self._perm, self._rand = torch.randperm, torch.rand
         me = self
 
         def randperm(n, **k):
@@ -518,11 +520,20 @@ class device_ray_draws:
             if dev is None or torch.device(dev).type != "cuda":
                 return me._perm(n, **k)
             return device_ray_draws._Lazy(int(n), me.counter, me.seed)
-        torch.randperm = randperm
+
+        def rand(*shape, **k):
+            # the stratified jitter torch.rand(B, P, N, 1, device=cuda) of Graph.sample_depth (model/nerf.py:338): drawn inside
+            # the sampling kernel instead (functional.DeviceUniform) -- no torch RNG op in the captured step
+            dev = k.get("device", None)
+            if dev is None or torch.device(dev).type != "cuda" or len(shape) != 4 or shape[-1] != 1 or k.get("generator") is not None:
+                return me._rand(*shape, **k)
+            from . import functional as F
+            return F.DeviceUniform(shape, me.rng, me.seed + 0x9E3779B97F4A7C15)
+        torch.randperm, torch.rand = randperm, rand
         return self
 
     def __exit__(self, *exc):
-        torch.randperm = self._perm
+        torch.randperm, torch.rand = self._perm, self._rand
 
 
 class feed_draws:

@@ -202,10 +202,44 @@ def nvp_warp(wpack, code_bias, pts, alpha_ratio, index_map=None):
 # depth sampling
 # --------------------------------------------------------------------------------------------
 
+class DeviceUniform:
+    """Stand-in for ``torch.rand(B, P, N, 1, device=cuda)`` inside ``engine.device_ray_draws``: no tensor is drawn; the
+    stratified-sampling kernel that consumes it draws its uniforms itself (``niw_sample_stratified_rng``, Philox4x32-10)
+    from ``seed`` and the caller-owned device counter ``rng`` (int64 [2], advanced by the kernel).  Anything but
+    ``view`` / ``numel`` / ``shape`` is unsupported on purpose: another consumer of the draw would need real numbers."""
+
+    def __init__(self, shape, rng, seed):
+        self.shape, self.rng, self.seed = tuple(int(x) for x in shape), rng, int(seed) & (2 ** 64 - 1)
+        self.device = rng.device
+
+    def numel(self):
+        n = 1
+        for x in self.shape:
+            n *= x
+        return n
+
+    def view(self, *shape):
+        return self
+
+
 def sample_stratified(u, n_rays, N, depth_range, param, device=None):
-    """Graph.sample_depth (model/nerf.py:334-344).  u: [n_rays*N] uniforms or None (0.5).
-    Returns depth [n_rays, N].  Bit-exact with the reference's fp32 CPU evaluation."""
+    """Graph.sample_depth (model/nerf.py:334-344).  u: [n_rays*N] uniforms, None (0.5) or a ``DeviceUniform`` (drawn inside
+    the kernel).  Returns depth [n_rays, N].  Bit-exact with the reference's fp32 CPU evaluation of the same uniforms."""
     lib = _lib.load()
+    if isinstance(u, DeviceUniform):
+        if u.numel() != n_rays * N:
+            raise RuntimeError("niw_b200: uniforms have %d elements, expected %d" % (u.numel(), n_rays * N))
+        if param not in ("metric", "inverse"):
+            raise KeyError(param)
+        depth = torch.empty(n_rays, N, device=u.device, dtype=torch.float32)
+        if torch.is_tensor(depth_range) and depth_range.is_cuda:
+            rng_dev, scale, dmin = _f32(depth_range.reshape(-1)[:2], "depth_range"), 0.0, 0.0
+        else:
+            rng_dev, dmin = None, float(depth_range[0])
+            scale = float(depth_range[1]) - dmin
+        _lib.check(lib.niw_sample_stratified_rng(n_rays, N, scale, dmin, _p(rng_dev), int(param == "inverse"), u.seed, _p(u.rng),
+                                                 _p(depth), _stream()))
+        return depth
     u = _f32(u, "u")
     device = u.device if u is not None else device
     if u is not None and u.numel() != n_rays * N:

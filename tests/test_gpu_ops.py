@@ -578,3 +578,42 @@ def test_flat_adam_matches_torch_adam():
         fa.step()
         assert prog.item() == torch.tensor((it + 1) / 200000).item()        # fp32(it / max_iter), as fill_ stores it
     torch.testing.assert_close(ours[0].detach().cpu(), ref[0].detach(), rtol=2e-5, atol=2e-6)
+
+
+def test_stratified_depths_with_in_kernel_uniforms(F):
+    """niw_sample_stratified_rng (functional.DeviceUniform): the uniforms of Graph.sample_depth (model/nerf.py:334-344) drawn
+    inside the kernel.  Every depth lies in its own stratum, the implied uniforms are uniform (mean, variance, no value
+    outside [0, 1)), every call draws afresh, the same seed and call number reproduce the draw, and a CUDA-graph replay
+    advances the call number on the device."""
+    R, N = 4096, 128
+    dmin, dmax = 1.2, 5.2
+    rng = torch.zeros(2, dtype=torch.int64, device=DEV)
+    a = F.sample_stratified(F.DeviceUniform((1, R, N, 1), rng, 7), R, N, [dmin, dmax], "metric")
+    b = F.sample_stratified(F.DeviceUniform((1, R, N, 1), rng, 7), R, N, [dmin, dmax], "metric")
+    torch.cuda.synchronize()
+    assert rng.tolist() == [2, 0]
+    k = torch.arange(N, device=DEV, dtype=torch.float64)
+    for d in (a, b):
+        u = (d.double() - dmin) / (dmax - dmin) * N - k
+        assert u.min().item() > -1e-4 and u.max().item() < 1 + 1e-4            # inside the stratum (fp32 rounding of the affine map)
+        assert abs(u.mean().item() - 0.5) < 2e-3 and abs(u.var().item() - 1 / 12) < 2e-3
+    assert not torch.equal(a, b)
+    rng2 = torch.zeros(2, dtype=torch.int64, device=DEV)
+    a2 = F.sample_stratified(F.DeviceUniform((1, R, N, 1), rng2, 7), R, N, [dmin, dmax], "metric")
+    assert torch.equal(a, a2)                                                  # same seed, same call number
+    other = F.sample_stratified(F.DeviceUniform((1, R, N, 1), torch.zeros(2, dtype=torch.int64, device=DEV), 8), R, N, [dmin, dmax], "metric")
+    assert not torch.equal(a, other)
+    # against the product sampler fed the same uniforms: recover u from the metric depths, feed it back
+    inv = F.sample_stratified(F.DeviceUniform((1, R, N, 1), torch.zeros(2, dtype=torch.int64, device=DEV), 7), R, N,
+                              torch.tensor([dmin, dmax], device=DEV), "inverse")
+    torch.testing.assert_close(inv, 1.0 / (a + 1e-8), rtol=2e-6, atol=0)          # same draw through the inverse parametrisation
+    # captured: the call number advances on replay
+    static = torch.zeros(2, dtype=torch.int64, device=DEV)
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        out = F.sample_stratified(F.DeviceUniform((1, R, N, 1), static, 7), R, N, [dmin, dmax], "metric")
+    g.replay(); torch.cuda.synchronize()
+    first = out.clone()
+    g.replay(); torch.cuda.synchronize()
+    assert static.tolist() == [2, 0] and not torch.equal(first, out) and torch.equal(first, a)
