@@ -202,6 +202,8 @@ int niw_nerf_bwd_dw(int64_t R, int N, int precision, void* workspace, size_t wor
  * that the caller zeroes. */
 int niw_mse_gather(const float* image, const float* rgb, const int64_t* ray_idx, int64_t idx_start,
                    int B, int P, int H, int W, float scale, float* loss, float* d_rgb, void* stream);
+/* 1: `loss` accumulates over several blocks and must be zeroed by the caller; 0 (B*P <= 1024): one block writes it. */
+int niw_mse_gather_needs_zero(int B, int P);
 
 /* ---- evaluation metrics (row f3)   model/nerf.py:176-183, external/pohsun_ssim/pytorch_ssim/__init__.py:7-37
  * pred_rgb [B,H*W,3] (the renderer's layout), image [B,3,H,W] -> out [B,2] = per image (sum of squared errors,

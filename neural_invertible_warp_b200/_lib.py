@@ -49,6 +49,7 @@ SIGNATURES = {
     "niw_nerf_bwd_dx": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _P, _P, _P, _P, _P]),
     "niw_nerf_bwd_dw": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_int, _P, _c.c_size_t, _P, _c.c_int, _P]),
     "niw_mse_gather": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),
+    "niw_mse_gather_needs_zero": (_c.c_int, [_c.c_int, _c.c_int]),
     "niw_image_metrics": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     "niw_depth_metrics": (_c.c_int, [_P, _P, _P, _c.c_int64, _c.c_float, _P, _P]),
     "niw_p2p_alloc": (_c.c_int, [_c.c_size_t, _c.POINTER(_c.c_void_p), _P]),

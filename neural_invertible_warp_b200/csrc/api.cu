@@ -98,7 +98,7 @@ extern "C" int niw_nerf_bwd_dw(int64_t R, int N, int precision, void* workspace,
 namespace {
 __global__ void mse_gather_kernel(const float* __restrict__ image, const float* __restrict__ rgb,
                                   const int64_t* __restrict__ ray_idx, int64_t idx_start, int B, int P, int HW,
-                                  float scale, float* __restrict__ loss, float* __restrict__ d_rgb) {
+                                  float scale, float* __restrict__ loss, float* __restrict__ d_rgb, int direct) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float acc = 0.f;
     if (t < (int64_t)B * P) {
@@ -112,24 +112,33 @@ __global__ void mse_gather_kernel(const float* __restrict__ image, const float* 
         }
     }
     acc = warp_sum(acc);
-    __shared__ float red[8];
+    __shared__ float red[32];
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) red[warp] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         float v = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
-        atomicAdd(loss, v * scale);
+        if (direct) *loss = v * scale;          // the only block: no accumulation, `loss` need not be zeroed
+        else atomicAdd(loss, v * scale);
     }
 }
 }  // namespace
+
+extern "C" int niw_mse_gather_needs_zero(int B, int P) { return (int64_t)B * P > 1024 ? 1 : 0; }
 
 extern "C" int niw_mse_gather(const float* image, const float* rgb, const int64_t* ray_idx, int64_t idx_start, int B,
                               int P, int H, int W, float scale, float* loss, float* d_rgb, void* stream) {
     NIW_CHECK_ARG(image && rgb && loss && B > 0 && P > 0 && H > 0 && W > 0);
     int64_t n = (int64_t)B * P;
-    niw::note_launch(), mse_gather_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(image, rgb, ray_idx, idx_start, B, P, H * W,
-                                                                         scale, loss, d_rgb);
+    // up to 1 024 rays: ONE block that writes the loss (no zero-fill launch in front, no atomics); more: `loss` accumulates
+    // over the blocks and the caller zeroes it first (niw_mse_gather_needs_zero)
+    if (n <= 1024)
+        niw::note_launch(), mse_gather_kernel<<<1, (unsigned)((n + 31) / 32 * 32), 0, niw_stream(stream)>>>(image, rgb, ray_idx, idx_start, B, P,
+                                                                                       H * W, scale, loss, d_rgb, 1);
+    else
+        niw::note_launch(), mse_gather_kernel<<<niw_blocks(n, 256), 256, 0, niw_stream(stream)>>>(image, rgb, ray_idx, idx_start, B, P, H * W,
+                                                                             scale, loss, d_rgb, 0);
     NIW_LAUNCH_CHECK();
     return 0;
 }

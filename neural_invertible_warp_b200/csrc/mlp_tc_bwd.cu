@@ -673,8 +673,12 @@ int tc_bwd_dx(const float* P, const float* center, const float* ray, const float
     Workspace w = carve(ws, S, true);
     if (ws_bytes < w.bytes) return NIW_E_WORKSPACE;
     const int64_t ntiles = (S + TILE - 1) / TILE;
-    NIW_CUDA(cudaMemsetAsync(d_center, 0, sizeof(float) * R * 3, st));
-    NIW_CUDA(cudaMemsetAsync(d_ray, 0, sizeof(float) * R * 3, st));
+    if (d_ray == d_center + R * 3) {          // adjacent buffers (functional.py allocates them so): one memset node
+        NIW_CUDA(cudaMemsetAsync(d_center, 0, sizeof(float) * R * 6, st));
+    } else {
+        NIW_CUDA(cudaMemsetAsync(d_center, 0, sizeof(float) * R * 3, st));
+        NIW_CUDA(cudaMemsetAsync(d_ray, 0, sizeof(float) * R * 3, st));
+    }
     NIW_CUDA(cudaFuncSetAttribute(tc_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_TOTAL));
     const int64_t nhq = (ntiles + 1) / 2;         // tile pairs: one per slot of a CTA pair and round
     int64_t pairs = niw_num_sms() / 2;

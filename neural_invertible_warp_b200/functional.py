@@ -460,8 +460,8 @@ class _NerfSamples(torch.autograd.Function):
         else:
             d_params = None
             dp = _c.c_void_p(target)
-        d_center = torch.empty_like(center)
-        d_ray = torch.empty_like(ray)
+        both = torch.empty((2,) + tuple(center.shape), device=center.device, dtype=center.dtype)     # adjacent: one memset
+        d_center, d_ray = both[0], both[1]
         if d_rgb is None:
             d_rgb = torch.zeros(R, N, 3, device=depth.device)
         if d_sigma is None:
@@ -568,7 +568,7 @@ class _MseGather(torch.autograd.Function):
         rgb, image = _f32(rgb, "rgb"), _f32(image, "image")
         B, P = rgb.shape[0], rgb.shape[1]
         H, W = image.shape[-2:]
-        loss = torch.zeros((), device=rgb.device)
+        loss = (torch.zeros if lib.niw_mse_gather_needs_zero(B, P) else torch.empty)((), device=rgb.device)
         d_rgb = torch.empty_like(rgb)
         scale = 1.0 / (B * P * 3)
         _lib.check(lib.niw_mse_gather(_p(image), _p(rgb), _p(ray_idx), idx_start, B, P, H, W, scale, _p(loss), _p(d_rgb),
