@@ -319,15 +319,16 @@ class Harness:
             # are written back before the step starts (cold and clean L2)
             self.flush.zero_()
             self.drain.view(torch.int32).sum()
-            if self.world > 1:
-                # the flush is rank-local work outside the timed region: re-align the ranks on the device before the start
-                # event, or its jitter shows up inside the step as time spent waiting in the gradient all-reduce
-                self.dist.all_reduce(self.sync_token)
-            # the token all-reduce drains the queue: without a short device-side delay in front of the start event the GPU
-            # would idle between the event and the step's first kernel for as long as the HOST needs to launch the step
-            # (20-45 us seen in the N = 2 timeline, profiles/r2_timeline_*), which a training loop that enqueues ahead of
-            # the device never pays.  ~100 us of spinning on the device, outside the event pair, at every N alike.
+            # ~100 us of spinning on the device in front of the step: the host enqueues the token all-reduce, the start event
+            # and the step's graph launch meanwhile, so the GPU never idles between the event and the step's first kernel for
+            # as long as the HOST needs to launch the step (20-45 us seen in the N = 2 timeline, profiles/r2_timeline_*),
+            # which a training loop that enqueues ahead of the device never pays.  Outside the event pair, at every N alike.
             torch.cuda._sleep(200000)
+            if self.world > 1:
+                # the flush and the delay are rank-local work outside the timed region (and last a different time on GPUs at
+                # different clocks): re-align the ranks on the device right before the start event, or that jitter shows up
+                # inside the step as time spent waiting in the gradient sum
+                self.dist.all_reduce(self.sync_token)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); step_fn(); b.record()
             evs.append((a, b))
