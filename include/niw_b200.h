@@ -110,6 +110,15 @@ int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pt
 int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                      int B, int Pt, int idx_offset, int idx_split, int idx_jump, const float* d_out, float* d_wpack,
                      float* d_code_bias, int max_ctas, void* stream);
+/* Warped ray generation in ONE launch (model/barf_inn_llff.py:325-364 + camera.py:359-390): pixel index -> un-warped grid
+ * point (K^-1, pose_init [B,3,4] or NULL) -> coupling blocks -> ray = warped grid - warped camera centre, the centre warped
+ * once per image (valid when no centre row of the image's point list is an annealed row: P_global >= 26).  Outputs: pts and
+ * warped [B, P+1, 3] = [grid rows ; the centre row] (pts is what niw_nvp_warp_bwd takes; warped may be NULL), ray and
+ * center [B, P, 3].  Backward: niw_rays_from_warp_bwd (n_center = 1) -> niw_nvp_warp_bwd -> niw_nvp_pack_bwd. */
+int niw_nvp_rays_fwd(const float* wpack, const float* code_bias, const float* intr, const float* pose_init,
+                     const int64_t* ray_idx, int64_t idx_start, float alpha_ratio, int B, int P, int H, int W,
+                     int idx_offset, int idx_split, int idx_jump, float* pts, float* warped, float* ray, float* center,
+                     void* stream);
 
 /* ---- random pixel subset   model/nerf.py:268 (`torch.randperm(H*W)[:rand_rays//B]`)
  * out[i] = pi(i), i < k, for a keyed random bijection pi of [0,n): the first k entries of a random permutation

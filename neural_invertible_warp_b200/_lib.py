@@ -34,6 +34,7 @@ SIGNATURES = {
     "niw_nvp_pack_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int, _P, _P]),
     "niw_nvp_warp_fwd": (_c.c_int, [_P, _P, _P, _c.c_float] + [_c.c_int] * 5 + [_P, _P]),
     "niw_nvp_warp_bwd": (_c.c_int, [_P, _P, _P, _c.c_float] + [_c.c_int] * 5 + [_P, _P, _P, _c.c_int, _P]),
+    "niw_nvp_rays_fwd": (_c.c_int, [_P, _P, _P, _P, _P, _c.c_int64, _c.c_float] + [_c.c_int] * 7 + [_P, _P, _P, _P, _P]),
     "niw_sample_pixels": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_uint64, _P, _P, _P]),
     "niw_sample_stratified": (_c.c_int, [_P, _c.c_int64, _c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P]),
     "niw_sample_stratified_dev": (_c.c_int, [_P, _c.c_int64, _c.c_int, _P, _c.c_int, _P, _P]),

@@ -195,6 +195,85 @@ nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
 }
 
 // ------------------------------------------------------------------------------------------
+// Warped ray generation in ONE kernel (north_star (1); reference model/barf_inn_llff.py:325-364, camera.py:359-390):
+// pixel index -> un-warped grid point (K^-1, initial pose) -> three coupling blocks -> ray = warped grid - warped centre.
+// Grid (chunks of 8 pixels, images).  Warps 0-7 of a CTA warp one grid point each; warp 8 warps the image's camera centre
+// (the same point for every ray of the image, evaluated once per CTA instead of once per ray: it runs next to the grid
+// points, so it adds no latency), and after one barrier every grid warp subtracts it.  Also written: the un-warped list
+// [grid ; centre] (the backward kernel's input, var.grid_cam / var.center_cam) and the warped list.
+// ------------------------------------------------------------------------------------------
+struct PoseInvW { float R[9]; float tinv[3]; };
+constexpr size_t RAYS_SMEM = sizeof(float) * ((size_t)NB * S_BLOCK + (FWD_WARPS + 1) * 32 + 4);
+
+__global__ void __launch_bounds__((FWD_WARPS + 1) * 32)
+nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ intr,
+                    const float* __restrict__ pose_init, const int64_t* __restrict__ ray_idx, int64_t idx_start, Bands bw,
+                    IndexMap im, int B, int P, int W, float* __restrict__ pts, float* __restrict__ warped,
+                    float* __restrict__ ray, float* __restrict__ center) {
+    extern __shared__ float smem[];
+    float* sw = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* es = smem + (size_t)NB * S_BLOCK + warp * 32;
+    float* s_c = smem + (size_t)NB * S_BLOCK + (FWD_WARPS + 1) * 32;
+    load_weights_smem(sw, wpack, NB);
+    const int b = blockIdx.y;
+    const bool is_center = warp == FWD_WARPS;
+    const int p = is_center ? P : blockIdx.x * FWD_WARPS + warp;          // local row of the [grid ; centre] list
+    const bool active = is_center || p < P;
+    float x[3] = {0.f, 0.f, 0.f};
+    if (active) {
+        // world-frame quantities of the initial pose: Rinv = R^T, tinv = -R^T t   (camera.py:89-95, :343-346)
+        float R[9], tinv[3] = {0.f, 0.f, 0.f};
+        if (pose_init) {
+            const float* q = pose_init + b * 12;
+            float t3[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) R[i * 3 + j] = q[i * 4 + j];
+                t3[i] = q[i * 4 + 3];
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) tinv[j] = -(R[0 * 3 + j] * t3[0] + R[1 * 3 + j] * t3[1] + R[2 * 3 + j] * t3[2]);
+        }
+        if (is_center) {
+            x[0] = tinv[0]; x[1] = tinv[1]; x[2] = tinv[2];
+        } else {
+            const Mat3 Ki = inverse3x3(intr + b * 9);
+            const int64_t pix = ray_idx ? ray_idx[p] : idx_start + p;
+            float g[3];
+            pixel_to_cam(Ki, pix, W, g);
+            if (pose_init) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) x[j] = R[0 * 3 + j] * g[0] + R[1 * 3 + j] * g[1] + R[2 * 3 + j] * g[2] + tinv[j];
+            } else {
+                x[0] = g[0]; x[1] = g[1]; x[2] = g[2];
+            }
+        }
+        if (lane < 3 && (!is_center || blockIdx.x == 0)) pts[((int64_t)b * (P + 1) + p) * 3 + lane] = sel3(x, lane);
+    }
+    __syncthreads();                                                      // weights in shared memory
+    if (active) {
+        const int n = list_index(im, p);
+        const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
+#pragma unroll 1
+        for (int blk = 0; blk < NB; ++blk) {
+            const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
+            const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
+            block_forward(sw + (size_t)blk * S_BLOCK, biasA, biasB, sa, sb, x, blk, es, lane);
+        }
+        if (is_center && lane < 3) s_c[lane] = sel3(x, lane);
+        if (lane < 3 && warped && (!is_center || blockIdx.x == 0)) warped[((int64_t)b * (P + 1) + p) * 3 + lane] = sel3(x, lane);
+    }
+    __syncthreads();                                                      // the image's warped centre
+    if (active && !is_center && lane < 3) {
+        const float c = s_c[lane];
+        ray[((int64_t)b * P + p) * 3 + lane] = sel3(x, lane) - c;
+        center[((int64_t)b * P + p) * 3 + lane] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward: block-outer order; each warp owns a private gradient accumulator in shared memory
 // (plain read-modify-write, no atomics, odd row strides), reduced across the CTA at the end of a
 // block pass and flushed with one global atomic per weight per CTA
@@ -683,6 +762,23 @@ extern "C" int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, cons
     if (blocks > cap) blocks = cap;
     niw::note_launch(), nvp_fwd_kernel<<<(unsigned)blocks, FWD_WARPS * 32, FWD_SMEM, niw_stream(stream)>>>(
         wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, out);
+    NIW_LAUNCH_CHECK();
+    return 0;
+}
+
+// pixel indices -> warped rays in one launch (shared centre row: the caller has checked that no centre row of the image's
+// list is an annealed one).  pts / warped: [B, P+1, 3] = [grid rows ; the centre row]; ray, center: [B, P, 3].
+extern "C" int niw_nvp_rays_fwd(const float* wpack, const float* code_bias, const float* intr, const float* pose_init,
+                                const int64_t* ray_idx, int64_t idx_start, float alpha_ratio, int B, int P, int H, int W,
+                                int idx_offset, int idx_split, int idx_jump, float* pts, float* warped, float* ray,
+                                float* center, void* stream) {
+    NIW_CHECK_ARG(wpack && code_bias && intr && pts && ray && center && B > 0 && P > 0 && H > 0 && W > 0 && idx_offset >= 0 &&
+                  idx_split >= 0 && idx_jump >= 0);
+    const IndexMap im{idx_offset, idx_split, idx_jump};
+    NIW_CUDA(cudaFuncSetAttribute(nvp_rays_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RAYS_SMEM));
+    const dim3 grid((unsigned)((P + FWD_WARPS - 1) / FWD_WARPS), (unsigned)B);
+    niw::note_launch(), nvp_rays_fwd_kernel<<<grid, (FWD_WARPS + 1) * 32, RAYS_SMEM, niw_stream(stream)>>>(
+        wpack, code_bias, intr, pose_init, ray_idx, idx_start, make_bands(alpha_ratio), im, B, P, W, pts, warped, ray, center);
     NIW_LAUNCH_CHECK();
     return 0;
 }

@@ -5,6 +5,7 @@ PyTorch is used for device memory, streams and autograd bookkeeping only; all ar
 ray/sample axes happens in the library.  Non-CUDA inputs raise: there is no CPU fallback.
 """
 import ctypes
+import os
 import math
 
 import torch
@@ -728,6 +729,14 @@ def rays_from_warp_shared(warped, P):
 # rows of the per-image point list that the embedder's annealing quirk touches (embedder.py:46-49: [d, d (2 NF + 1)),
 # d = 2 or 1, NF = 6): a centre row may be shared only if every centre row of the full list lies beyond them
 NVP_QUIRK_ROWS = 2 * (2 * 6 + 1)
+
+
+# train-mode warped ray generation as ONE launch (nvp.DeformNetwork.warped_rays, csrc/nvp.cu niw_nvp_rays_fwd) instead of
+# raygen_unwarped -> warp -> rays_from_warp.  Off by default: inside the captured C2 step it measured 3.6 us SLOWER
+# (0.6725 vs 0.6688 ms, three alternating runs of 100 steps) -- the un-warped grid kernel already runs
+# beside the weight pack of the side stream, and the centre row costs every CTA a ninth warp.  NIW_FUSED_RAYS=1 turns it on
+# (two launches fewer per step where the host's launch rate is the limit: eager calls from the reference's engine).
+fused_warped_rays = os.environ.get("NIW_FUSED_RAYS", "0") == "1"
 
 
 def shared_center_ok(P, shard=None):

@@ -81,15 +81,23 @@ class Graph(nerf_inn_llff.Graph):
         if mode == "train":
             _, pose_init = self._initial_pose(opt, var)
             P = len(var.ray_idx)
-            # [grid ; centre] rows for the sampled pixels only, no gradient (:325-330, :348)
-            shared = F.shared_center_ok(P, F.ray_shard)
-            with torch.no_grad():
-                pts = camera.unwarped_points(opt, var.intr, ray_idx=var.ray_idx, pose_init=pose_init, shared_center=shared)
-            var.grid_cam, var.center_cam = pts[:, :P], (pts[:, P:].expand(-1, P, -1) if shared else pts[:, P:])
             if opt.inn.real_nvp.c2f == True:   # noqa: E712  (the reference compares with == True)
                 alpha_ratio = max(min(iter / opt.inn.real_nvp.max_pe_iter, 1), 0)
             else:
                 alpha_ratio = 1
+            shared = F.shared_center_ok(P, F.ray_shard)
+            if shared and F.fused_warped_rays:
+                # grid points, warp and ray construction in one launch (csrc/nvp.cu niw_nvp_rays_fwd)
+                offset, P_global = F.ray_shard if F.ray_shard is not None else (0, P)
+                ray, center_3D, grid_3D, pts = self._warp_network().warped_rays(
+                    self._latent(opt), var.intr, pose_init, var.ray_idx, opt.H, opt.W, alpha_ratio=alpha_ratio,
+                    index_map=(offset, P, P_global - P))
+                var.grid_cam, var.center_cam = pts[:, :P], pts[:, P:].expand(-1, P, -1)
+                return ray, center_3D, grid_3D, alpha_ratio
+            # [grid ; centre] rows for the sampled pixels only, no gradient (:325-330, :348)
+            with torch.no_grad():
+                pts = camera.unwarped_points(opt, var.intr, ray_idx=var.ray_idx, pose_init=pose_init, shared_center=shared)
+            var.grid_cam, var.center_cam = pts[:, :P], (pts[:, P:].expand(-1, P, -1) if shared else pts[:, P:])
             # the warp sees [grid rows ; centre] with the centre evaluated once per image when that is exact, and a ray
             # shard's rows at their positions in the global list (functional.warp_point_list)
             wpts, index_map, shared = F.warp_point_list(pts, P, F.ray_shard)

@@ -95,31 +95,89 @@ class _NvpNetwork(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
-        lib = _lib.load()
         code, pts, wpack, code_bias, cb = ctx.saved_tensors
-        B, Pt = pts.shape[0], pts.shape[1]
-        d_w = torch.empty_like(wpack)
-        d_cb = torch.empty_like(code_bias)
-        d_out = d_out.contiguous()
-        ov = F.backward_overlap                 # engine: the MLP weight-gradient pass is running on another stream
-        _lib.check(lib.niw_nvp_warp_bwd(F._p(wpack), F._p(code_bias), F._p(pts), ctx.alpha, B, Pt, *ctx.im, F._p(d_out),
-                                        F._p(d_w), F._p(d_cb), int(ov.side_ctas) if ov is not None and ov.used else 0,
-                                        F._stream()))
-        params = ctx.module.ordered_parameters()
-        in_place = getattr(ctx.module, "accumulate_grads_in_place", False)
-        if in_place:
-            for p in params:
-                if p.grad is None:
-                    p.grad = torch.zeros_like(p)
-            grads = [p.grad for p in params]
+        d_code, grads = _warp_backward(ctx.module, ctx.alpha, ctx.im, code, pts, wpack, code_bias, cb, d_out)
+        return (d_code, None, None, None, None) + grads
+
+
+def _warp_backward(module, alpha, im, code, pts, wpack, code_bias, cb, d_out):
+    """Warp backward + pack backward for the gradient ``d_out`` of the warped point list; returns d_code and the tuple of
+    parameter gradients (Nones when the engine opted into accumulation in place into ``.grad``)."""
+    lib = _lib.load()
+    B, Pt = pts.shape[0], pts.shape[1]
+    d_w = torch.empty_like(wpack)
+    d_cb = torch.empty_like(code_bias)
+    d_out = d_out.contiguous()
+    ov = F.backward_overlap                 # engine: the MLP weight-gradient pass is running on another stream
+    _lib.check(lib.niw_nvp_warp_bwd(F._p(wpack), F._p(code_bias), F._p(pts), alpha, B, Pt, *im, F._p(d_out),
+                                    F._p(d_w), F._p(d_cb), int(ov.side_ctas) if ov is not None and ov.used else 0,
+                                    F._stream()))
+    params = module.ordered_parameters()
+    in_place = getattr(module, "accumulate_grads_in_place", False)
+    if in_place:
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in params]
+    else:
+        # gradients go back through autograd (torch.autograd.grad, backward(inputs=...), hooks all behave)
+        grads = [torch.zeros_like(p) for p in params]
+    ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    gptrs = (ctypes.c_void_p * len(params))(*[g.data_ptr() for g in grads])
+    d_code = torch.empty_like(code)
+    _lib.check(lib.niw_nvp_pack_bwd(ptrs, gptrs, F._p(code), F._p(cb), F._p(d_w), F._p(d_cb), B, F._p(d_code), F._stream()))
+    return d_code, ((None,) * len(params) if in_place else tuple(grads))
+
+
+class _NvpRays(torch.autograd.Function):
+    """Warped ray generation in ONE launch (csrc/nvp.cu ``niw_nvp_rays_fwd``; model/barf_inn_llff.py:325-364): pixel indices
+    -> (ray, warped centre, warped grid points, un-warped [grid ; centre] list).  Backward: the three kernels of the
+    separate path (rays-from-warp backward, warp backward, pack backward)."""
+
+    @staticmethod
+    def forward(ctx, code, intr, pose_init, ray_idx, alpha_ratio, module, index_map, H, W, *params):
+        lib = _lib.load()
+        code = F._f32(code, "deformation_code")
+        intr, pose_init = F._f32(intr, "intr"), F._f32(pose_init, "pose_init")
+        ray_idx = F._idx(ray_idx, intr.device)
+        B, P = intr.shape[0], int(ray_idx.numel())
+        dev = intr.device
+        pre = module._take_prepacked(code)
+        if pre is not None:
+            wpack, code_bias, cb, done = pre
+            torch.cuda.current_stream().wait_event(done)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in (wpack, code_bias, cb):
+                    t.record_stream(torch.cuda.current_stream())
         else:
-            # gradients go back through autograd (torch.autograd.grad, backward(inputs=...), hooks all behave)
-            grads = [torch.zeros_like(p) for p in params]
-        ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
-        gptrs = (ctypes.c_void_p * len(params))(*[g.data_ptr() for g in grads])
-        d_code = torch.empty_like(code)
-        _lib.check(lib.niw_nvp_pack_bwd(ptrs, gptrs, F._p(code), F._p(cb), F._p(d_w), F._p(d_cb), B, F._p(d_code), F._stream()))
-        return (d_code, None, None, None, None) + ((None,) * len(params) if in_place else tuple(grads))
+            wpack, code_bias, cb = _pack_forward(lib, params, code, B, dev)
+        pts = torch.empty(B, P + 1, 3, device=dev)
+        warped = torch.empty(B, P + 1, 3, device=dev)
+        ray = torch.empty(B, P, 3, device=dev)
+        center = torch.empty(B, P, 3, device=dev)
+        im = F.index_map_args(index_map, P + 1)
+        _lib.check(lib.niw_nvp_rays_fwd(F._p(wpack), F._p(code_bias), F._p(intr), F._p(pose_init), F._p(ray_idx), 0,
+                                        float(alpha_ratio), B, P, int(H), int(W), *im, F._p(pts), F._p(warped), F._p(ray),
+                                        F._p(center), F._stream()))
+        ctx.save_for_backward(code, pts, wpack, code_bias, cb)
+        ctx.module, ctx.alpha, ctx.im, ctx.P = module, float(alpha_ratio), im, P
+        ctx.mark_non_differentiable(pts)
+        return ray, center, warped[:, :P], pts
+
+    @staticmethod
+    def backward(ctx, d_ray, d_center, d_grid, _d_pts):
+        code, pts, wpack, code_bias, cb = ctx.saved_tensors
+        B, P = pts.shape[0], ctx.P
+        d_warped = torch.empty(B, P + 1, 3, device=pts.device)
+        c = lambda t: None if t is None else t.contiguous()
+        if d_ray is None and d_center is None:
+            d_warped.zero_()
+        else:
+            _lib.check(_lib.load().niw_rays_from_warp_bwd(F._p(c(d_ray)), F._p(c(d_center)), B, P, 1, F._p(d_warped), F._stream()))
+        if d_grid is not None:
+            d_warped[:, :P] += d_grid
+        d_code, grads = _warp_backward(ctx.module, ctx.alpha, ctx.im, code, pts, wpack, code_bias, cb, d_warped)
+        return (d_code, None, None, None, None, None, None, None, None) + grads
 
 
 class DeformNetwork(nn.Module):
@@ -208,6 +266,17 @@ class DeformNetwork(nn.Module):
         if pre is not None and pre[:3] == (code.data_ptr(), code._version, tuple(code.shape)):
             return pre[3]
         return None
+
+    def warped_rays(self, deformation_code, intr, pose_init, ray_idx, H, W, alpha_ratio=0, index_map=None):
+        """The train-mode ray generation of model/barf_inn_llff.py:325-364 in one launch: un-warped grid points of the pixels
+        ``ray_idx`` (camera.py:359-390, initial pose ``pose_init`` [B,3,4] or None), this network's warp, ray = warped grid -
+        warped camera centre.  The centre is warped once per image, so ``functional.shared_center_ok`` must hold.  Returns
+        (ray [B,P,3], center [B,P,3], warped grid [B,P,3], un-warped list [B,P+1,3] = [grid ; centre], no gradient)."""
+        params = self.ordered_parameters()
+        for p in params:
+            if not p.is_contiguous():
+                raise RuntimeError("niw_b200 DeformNetwork: parameters must be contiguous")
+        return _NvpRays.apply(deformation_code, intr, pose_init, ray_idx, alpha_ratio, self, index_map, H, W, *params)
 
     def forward(self, deformation_code, input_pts, alpha_ratio=0, index_map=None):
         """deformation_code [B,D], input_pts [B,P,1,3] -> [B,P,1,3]  (nvp_ndr.py:365).  ``index_map`` (offset, split,

@@ -391,3 +391,54 @@ def test_captured_test_time_pose_refinement(eng):
     assert l1 < 0.8 * l0
     for k, v in graph.named_parameters():
         assert torch.equal(v, before[k]) and v.requires_grad, k
+
+
+@pytest.mark.parametrize("shard,dataset", [(None, "llff"), ((40, 200), "llff"), (None, "blender")])
+def test_one_launch_warped_ray_generation_equals_the_three_launch_path(eng, shard, dataset):
+    """csrc/nvp.cu niw_nvp_rays_fwd (pixels -> un-warped grid -> NVP warp -> ray / centre in one launch;
+    model/barf_inn_llff.py:325-364) against raygen_unwarped -> warp -> rays_from_warp: same outputs, same gradients to the
+    warp network and the latent codes, same un-warped points left in ``var``; also as a ray shard at its position in the
+    global point list, and with an initial pose (blender branch, :309-323)."""
+    from neural_invertible_warp_b200 import functional as F
+    opt, g, var = make(eng)
+    var = cfgmod.AttrDict(var)
+    if dataset == "blender":
+        opt.data.dataset, opt.camera.noise_type = "blender", None
+        gen = torch.Generator().manual_seed(3)
+        rot = torch.linalg.qr(torch.randn(B, 3, 3, generator=gen))[0]
+        var.pose = torch.cat([rot, torch.randn(B, 3, 1, generator=gen)], dim=-1).to(DEV)
+    Pn = 72
+    gen = torch.Generator().manual_seed(9)
+    var.ray_idx = torch.randperm(H * W, generator=gen)[:Pn].to(DEV)
+    wr, wc, wg = (torch.randn(B, Pn, 3, generator=gen).to(DEV) for _ in range(3))
+    params = list(g.warp_mlp.parameters()) + [g.warp_latent.weight]
+    res = {}
+    saved = F.fused_warped_rays, F.ray_shard
+    try:
+        F.ray_shard = shard
+        for fused in (False, True):
+            F.fused_warped_rays = fused
+            for p in params:
+                p.grad = None
+            launches0 = _lib_launches()
+            ray, center, grid, alpha = g.get_pose(opt, var, mode="train", iter=20)
+            n_launch = _lib_launches() - launches0
+            ((ray * wr).sum() + (center * wc).sum() + (grid * wg).sum()).backward()
+            torch.cuda.synchronize()
+            res[fused] = dict(out=[t.detach().clone() for t in (ray, center, grid, var.grid_cam, var.center_cam)], alpha=alpha,
+                              grad=torch.cat([p.grad.reshape(-1) for p in params]).clone(), launches=n_launch)
+    finally:
+        F.fused_warped_rays, F.ray_shard = saved
+    assert res[True]["alpha"] == res[False]["alpha"]
+    for a, b in zip(res[True]["out"], res[False]["out"]):
+        assert a.shape == b.shape
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-6)   # (one ulp: the two kernels contract the pixel -> world arithmetic differently)
+    rel = ((res[True]["grad"].double() - res[False]["grad"].double()).norm() / res[False]["grad"].double().norm()).item()
+    assert rel < 1e-5, rel
+    assert res[True]["launches"] == res[False]["launches"] - 2, (res[True]["launches"], res[False]["launches"])
+
+
+def _lib_launches():
+    import ctypes
+    from neural_invertible_warp_b200 import _lib
+    return int(_lib.load().niw_launch_count())
