@@ -409,7 +409,7 @@ __device__ __forceinline__ void mma_16816_top(float (&d)[4], uint32_t a0, uint32
 }
 
 __global__ void __launch_bounds__(256, 1)
-tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, float* __restrict__ partial,
+tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, float* __restrict__ partial, int direct,
              unsigned long long* __restrict__ dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     unsigned long long t_start = 0;
@@ -540,7 +540,10 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
         ptx::mbar_wait(done, 0);
         ptx::tc_fence_after();
         asm volatile("bar.sync 1, 128;" ::: "memory");   // all four warps are done with the stage buffers
-        float* out = partial + (size_t)slice * NPARAMS;
+        // direct: `partial` is the gradient vector itself and every slice adds its product with reductions at the L2
+        // (RED.ADD.F32, warp-coalesced) -- no partial rows to clear before and no reduction pass after this kernel
+        float* out = direct ? partial : partial + (size_t)slice * NPARAMS;
+        auto put = [&](int64_t i, float v) { if (direct) atomicAdd(out + i, v); else out[i] = v; };
         if (my_tiles > 0) {
             float* tr = reinterpret_cast<float*>(smem) + wq * (32 * 33);   // stage buffers are idle now
             for (int h = 0; h < U.m_halves + (U.n2 > 0 ? 1 : 0); ++h) {
@@ -559,7 +562,7 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
                     const int col = c0 + lane;
                     if (col < ncols) {
                         for (int rr = 0; rr < 32; ++rr)
-                            out[U.w_base + (int64_t)(frow + wq * 32 + rr) * U.ld + col0 + col] = tr[rr * 33 + lane];
+                            put(U.w_base + (int64_t)(frow + wq * 32 + rr) * U.ld + col0 + col, tr[rr * 33 + lane]);
                     }
                     __syncwarp();
                 }
@@ -575,8 +578,8 @@ tc_dw_kernel(const uint8_t* __restrict__ save, int64_t ntiles, DwPlan plan, floa
                     if (i < gq) {
                         const int f = (wq * gq + i) * 8 + n0;
                         const float x0 = j == 0 ? acc0[i][0] : acc1[i][0], x1 = j == 0 ? acc0[i][1] : acc1[i][1];
-                        if ((sd.kind == 1 && m == 4) || (sd.kind == 3 && m == 3)) { out[sd.base + f] = x0; out[sd.base + f + 1] = x1; }
-                        if (sd.kind == 2 && m < 3) { out[sd.base + m * RGBW + f] = x0; out[sd.base + m * RGBW + f + 1] = x1; }
+                        if ((sd.kind == 1 && m == 4) || (sd.kind == 3 && m == 3)) { put(sd.base + f, x0); put(sd.base + f + 1, x1); }
+                        if (sd.kind == 2 && m < 3) { put(sd.base + m * RGBW + f, x0); put(sd.base + m * RGBW + f + 1, x1); }
                     }
                 }
             }
@@ -704,13 +707,16 @@ int tc_bwd_dw(int64_t R, int N, void* ws, size_t ws_bytes, float* dP, int max_ct
     int budget = env_ctas > 0 ? env_ctas : max_ctas;
     if (budget <= 0 || budget > niw_num_sms()) budget = niw_num_sms();
     DwPlan plan = make_plan(ntiles, budget);
-    NIW_CUDA(cudaMemsetAsync(w.partial, 0, sizeof(float) * (size_t)plan.max_slices * NPARAMS, st));
+    // NIW_DW_PARTIALS=1: the first form of the cross-slice sum (each slice stores a row of partial sums, cleared before and
+    // reduced after the kernel: 30 MB written, 30 MB cleared and 30 MB read again, 16 us of the C2 step on its critical path)
+    static const bool direct = !(getenv("NIW_DW_PARTIALS") && atoi(getenv("NIW_DW_PARTIALS")) != 0);
+    if (!direct) NIW_CUDA(cudaMemsetAsync(w.partial, 0, sizeof(float) * (size_t)plan.max_slices * NPARAMS, st));
     NIW_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_TOTAL));
     // NIW_DW_DEBUG=1: per-CTA start / end times of the dW pass on stderr (synchronises; diagnostics only)
     static const bool dw_debug = getenv("NIW_DW_DEBUG") != nullptr;
     unsigned long long* dbg = nullptr;
     if (dw_debug) NIW_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 2 * plan.n_ctas));
-    niw::note_launch(), tc_dw_kernel<<<plan.n_ctas, 256, BW_TOTAL, st>>>(w.save, ntiles, plan, w.partial, dbg);
+    niw::note_launch(), tc_dw_kernel<<<plan.n_ctas, 256, BW_TOTAL, st>>>(w.save, ntiles, plan, direct ? dP : w.partial, direct ? 1 : 0, dbg);
     NIW_LAUNCH_CHECK();
     if (dbg) {
         std::vector<unsigned long long> h(2 * plan.n_ctas);
@@ -726,8 +732,10 @@ int tc_bwd_dw(int64_t R, int N, void* ws, size_t ws_bytes, float* dP, int max_ct
                         (h[2 * c] - t0) * 1e-3, (h[2 * c + 1] - h[2 * c]) * 1e-3);
             }
     }
-    niw::note_launch(), tc_dw_reduce_kernel<<<niw_blocks(NPARAMS, 256), 256, 0, st>>>(w.partial, plan.max_slices, dP);
-    NIW_LAUNCH_CHECK();
+    if (!direct) {
+        niw::note_launch(), tc_dw_reduce_kernel<<<niw_blocks(NPARAMS, 256), 256, 0, st>>>(w.partial, plan.max_slices, dP);
+        NIW_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -53,13 +53,25 @@ struct Bands { float w[NF]; };
 struct IndexMap { int offset, split, jump; };
 __device__ __forceinline__ int list_index(const IndexMap& m, int n) { return n < m.split ? n + m.offset : n + m.offset + m.jump; }
 
-__device__ __forceinline__ float softplus100(float x) {
-    float bx = BETA * x;
-    return bx > 20.f ? x : log1pf(expf(bx)) / BETA;
+// softplus(beta = 100, threshold 20) and its derivative from one ex2, one lg2 and one reciprocal of the special-function
+// unit (the libm log1pf(expf()) pair was 22 % of the backward kernel's instructions): with y = fl(1 + e),
+// log1p(e) = log(y) - ((y - 1) - e) / y compensates the rounding of 1 + e to first order, so small e keeps its relative
+// accuracy; MUFU.LG2 is within 2^-21.4 absolute on [0.5, 2] and 3 ulp elsewhere, i.e. h is within 5e-9 absolute + 4e-7
+// relative of the reference's value (tests: 5e-6 on the warped points).  Forward and backward use the same function.
+__device__ __forceinline__ void softplus100_both(float x, float& h, float& g) {
+    const float bx = BETA * x;
+    const float e = __expf(fminf(bx, 20.f));
+    const float y = 1.f + e;
+    const float ry = __fdividef(1.f, y);
+    const float l = __logf(y) - ((y - 1.f) - e) * ry;
+    const bool lin = bx > 20.f;
+    h = lin ? x : l * (1.f / BETA);
+    g = lin ? 1.f : e * ry;
 }
-__device__ __forceinline__ float softplus100_grad(float x) {
-    float bx = BETA * x;
-    return bx > 20.f ? 1.f : 1.f / (1.f + expf(-bx));
+__device__ __forceinline__ float softplus100(float x) {
+    float h, g;
+    softplus100_both(x, h, g);
+    return h;
 }
 
 // the reference anneals `output[:, a:b]` of a [B,P,1,C] tensor, i.e. along the point axis
@@ -103,30 +115,13 @@ __device__ __forceinline__ void embed_coop(const float* x, float scale, float* e
     __syncwarp();
 }
 
-// d(embedding)/dx contracted with de (every lane holds the full, already reduced de)
-template <int D>
-__device__ __forceinline__ void embed_bwd(const float* x, float scale, const float* de, float* dx) {
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-        float acc = de[c];
-#pragma unroll
-        for (int k = 0; k < NF; ++k) {
-            const float f = (float)(1 << k) * PI_F;
-            float s, co;
-            sincosf(x[c] * f, &s, &co);
-            acc += f * (co * de[D + k * 2 * D + c] - s * de[D + k * 2 * D + D + c]);
-        }
-        dx[c] += scale * acc;
-    }
-}
-
 struct BlockFwd { float xo[2]; float xf; float y[2]; float c, s; };
 
 // forward of one coupling block for the warp's point; x is replicated in every lane.
 // es: per-warp scratch in shared memory (EA floats)
-__device__ __forceinline__ BlockFwd block_forward(const float* sw, const float* __restrict__ biasA,
-                                                  const float* __restrict__ biasB, float sa, float sb, float x[3], int blk,
-                                                  float* es, int lane) {
+// biasA / biasB: the lane's U per-image first-layer biases (code_bias rows), loaded by the caller ahead of the chain
+__device__ __forceinline__ BlockFwd block_forward(const float* sw, const float biasA[U], const float biasB[U], float sa,
+                                                  float sb, float x[3], int blk, float* es, int lane) {
     int foc, o0, o1;
     axes(blk, foc, o0, o1);
     BlockFwd r;
@@ -137,7 +132,7 @@ __device__ __forceinline__ BlockFwd block_forward(const float* sw, const float* 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int j = lane + 32 * u;
-        float pre = biasA[j];
+        float pre = biasA[u];
         const float* w = sw + S_W1A + j * SA;
 #pragma unroll
         for (int i = 0; i < EA; ++i) pre += w[i] * es[i];
@@ -151,7 +146,7 @@ __device__ __forceinline__ BlockFwd block_forward(const float* sw, const float* 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int j = lane + 32 * u;
-        float pre = biasB[j];
+        float pre = biasB[u];
         const float* w = sw + S_W1B + j * EB;
 #pragma unroll
         for (int i = 0; i < EB; ++i) pre += w[i] * es[i];
@@ -167,6 +162,19 @@ __device__ __forceinline__ BlockFwd block_forward(const float* sw, const float* 
     return r;
 }
 
+// the lane's first-layer biases of image b: all blocks and both parts at once, so that ONE global-memory latency is paid
+// ahead of the chain (loaded inside the chain, the six loads were 43 % of the forward kernel's stall samples)
+struct LaneBias { float a[NB][U], b[NB][U]; };
+__device__ __forceinline__ void load_lane_bias(LaneBias& lb, const float* __restrict__ code_bias, int B, int b, int lane) {
+#pragma unroll
+    for (int blk = 0; blk < NB; ++blk)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            lb.a[blk][u] = code_bias[((size_t)(blk * 2 + 0) * B + b) * HID + lane + 32 * u];
+            lb.b[blk][u] = code_bias[((size_t)(blk * 2 + 1) * B + b) * HID + lane + 32 * u];
+        }
+}
+
 constexpr int FWD_WARPS = 8;
 constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)NB * S_BLOCK + FWD_WARPS * 32);
 
@@ -177,20 +185,27 @@ nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
     float* sw = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* es = smem + (size_t)NB * S_BLOCK + warp * 32;
+    const int64_t total = (int64_t)B * Pt;
+    int64_t t = (int64_t)blockIdx.x * FWD_WARPS + warp;
+    LaneBias lb;
+    float x[3] = {0.f, 0.f, 0.f};
+    if (t < total) {                                                      // in flight while the weights arrive
+        load_lane_bias(lb, code_bias, B, (int)(t / Pt), lane);
+        x[0] = pts[t * 3]; x[1] = pts[t * 3 + 1]; x[2] = pts[t * 3 + 2];
+    }
     load_weights_smem(sw, wpack, NB);
     __syncthreads();
-    const int64_t total = (int64_t)B * Pt;
-    for (int64_t t = (int64_t)blockIdx.x * FWD_WARPS + warp; t < total; t += (int64_t)gridDim.x * FWD_WARPS) {
-        const int b = (int)(t / Pt), n = list_index(im, (int)(t % Pt));
-        float x[3] = {pts[t * 3], pts[t * 3 + 1], pts[t * 3 + 2]};
+    while (t < total) {
+        const int n = list_index(im, (int)(t % Pt));
         const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
-#pragma unroll 1
-        for (int blk = 0; blk < NB; ++blk) {
-            const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
-            const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
-            block_forward(sw + (size_t)blk * S_BLOCK, biasA, biasB, sa, sb, x, blk, es, lane);
-        }
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) block_forward(sw + (size_t)blk * S_BLOCK, lb.a[blk], lb.b[blk], sa, sb, x, blk, es, lane);
         if (lane < 3) out[t * 3 + lane] = sel3(x, lane);
+        t += (int64_t)gridDim.x * FWD_WARPS;
+        if (t < total) {
+            load_lane_bias(lb, code_bias, B, (int)(t / Pt), lane);
+            x[0] = pts[t * 3]; x[1] = pts[t * 3 + 1]; x[2] = pts[t * 3 + 2];
+        }
     }
 }
 
@@ -215,8 +230,10 @@ nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* es = smem + (size_t)NB * S_BLOCK + warp * 32;
     float* s_c = smem + (size_t)NB * S_BLOCK + (FWD_WARPS + 1) * 32;
-    load_weights_smem(sw, wpack, NB);
     const int b = blockIdx.y;
+    LaneBias lb;
+    load_lane_bias(lb, code_bias, B, b, lane);                            // in flight while the weights arrive
+    load_weights_smem(sw, wpack, NB);
     const bool is_center = warp == FWD_WARPS;
     const int p = is_center ? P : blockIdx.x * FWD_WARPS + warp;          // local row of the [grid ; centre] list
     const bool active = is_center || p < P;
@@ -256,12 +273,8 @@ nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ c
     if (active) {
         const int n = list_index(im, p);
         const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
-#pragma unroll 1
-        for (int blk = 0; blk < NB; ++blk) {
-            const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
-            const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
-            block_forward(sw + (size_t)blk * S_BLOCK, biasA, biasB, sa, sb, x, blk, es, lane);
-        }
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) block_forward(sw + (size_t)blk * S_BLOCK, lb.a[blk], lb.b[blk], sa, sb, x, blk, es, lane);
         if (is_center && lane < 3) s_c[lane] = sel3(x, lane);
         if (lane < 3 && warped && (!is_center || blockIdx.x == 0)) warped[((int64_t)b * (P + 1) + p) * 3 + lane] = sel3(x, lane);
     }
@@ -274,17 +287,37 @@ nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ c
 }
 
 // ------------------------------------------------------------------------------------------
-// backward: block-outer order; each warp owns a private gradient accumulator in shared memory
-// (plain read-modify-write, no atomics, odd row strides), reduced across the CTA at the end of a
-// block pass and flushed with one global atomic per weight per CTA
+// backward: block-outer order, one warp per point and round.  A warp's pass over a point is a long dependent chain
+// (~1 500 instructions per block), so the kernel lives on warps per SM.  The weight gradients are outer products
+// dpre (x) e summed over points; they are NOT accumulated by the warp that owns the point (a private accumulator image
+// per warp is 22 KB of shared memory and capped the CTA at 8 warps): phase 1 leaves dpre, the activations and the
+// embedding of its point in a small record, and after one barrier per round phase 2 adds the round's records into
+// accumulators that every thread keeps in REGISTERS for its fixed slice of the weight image (thread = hidden unit x
+// 13 embedding columns), flushed with one global atomic per weight per CTA at the end of the block pass.
 // ------------------------------------------------------------------------------------------
-constexpr int BWD_WARPS = 8;
-constexpr int MAX_PTS_PER_WARP = 32;      // per-point state kept in shared memory: xin[3][3] + dx[3]
+#ifndef NIW_NVP_BWD_WARPS
+#define NIW_NVP_BWD_WARPS 16
+#endif
+constexpr int BWD_WARPS = NIW_NVP_BWD_WARPS;
+constexpr int BWD_THREADS = BWD_WARPS * 32;
+static_assert(BWD_THREADS >= 384 && BWD_THREADS % 128 == 0, "phase 2 maps 3 x 128 threads onto the first-layer gradients");
+constexpr int MAX_ROUNDS = 32;             // points per warp; per-point state kept in shared memory: xin[3][3] + dx[3]
 constexpr int PT_STATE = 12;
 constexpr int ES_FLOATS = 2 * (EA + EB) + 2;   // scaled + raw embeddings of both parts
-constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)S_BLOCK + (size_t)BWD_WARPS * S_BLOCK + BWD_WARPS * ES_FLOATS +
-                                             (size_t)BWD_WARPS * MAX_PTS_PER_WARP * PT_STATE);
+// record of one point and block (phase 1 -> phase 2), floats
+constexpr int R_DA = 0;                    // dpre of part a        [128]
+constexpr int R_DB = HID;                  // dpre of part b        [128]
+constexpr int R_VA = 2 * HID;              // ddelta * h_a          [128]   (gradient of W2a)
+constexpr int R_HB = 3 * HID;              // h_b                   [128]   (x dout[m] = gradient of W2b)
+constexpr int R_EA = 4 * HID;              // scaled embedding a, two halves of 13 padded to 16
+constexpr int R_EB = R_EA + 32;            // scaled embedding b, 13 padded to 16
+constexpr int R_MISC = R_EB + 16;          // dout[3], ddelta
+constexpr int R_IMG = R_MISC + 4;          // image index (bits)
+constexpr int REC = R_IMG + 4;             // 568 floats, a multiple of 4
+constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)S_BLOCK + 2 * (size_t)BWD_WARPS * REC + BWD_WARPS * ES_FLOATS +
+                                             (size_t)MAX_ROUNDS * BWD_WARPS * PT_STATE);
 static_assert(BWD_SMEM <= 227 * 1024, "shared memory budget (NVP backward)");
+static_assert(S_BLOCK % 4 == 0 && REC % 4 == 0 && (BWD_WARPS * ES_FLOATS) % 4 == 0, "16-byte alignment of the records");
 
 // scaled embedding e (what the MLP sees) and the raw sin/cos (needed by the derivative)
 template <int D>
@@ -300,44 +333,58 @@ __device__ __forceinline__ void embed_coop2(const float* x, float scale, float* 
     }
     __syncwarp();
 }
-template <int D>
-__device__ __forceinline__ void embed_bwd_raw(const float* raw, float scale, const float* de, float* dx) {
+// Sums over the lanes of several per-lane values, transposed: after log2 halving steps lane l holds the total of v[l]
+// (31 shuffles for 32 values, where one butterfly per value costs 160).  The 16-value form leaves v[l & 15] in lanes
+// l and l ^ 16.
+__device__ __forceinline__ float warp_sum_scatter32(float (&v)[32], int lane) {
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
-        float acc = de[c];
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool hi = (lane & o) != 0;
 #pragma unroll
-        for (int k = 0; k < NF; ++k) {
-            const float f = (float)(1 << k) * PI_F;
-            acc += f * (raw[D + k * 2 * D + D + c] * de[D + k * 2 * D + c] - raw[D + k * 2 * D + c] * de[D + k * 2 * D + D + c]);
+        for (int i = 0; i < o; ++i) {
+            const float send = hi ? v[i] : v[i + o], keep = hi ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
-        dx[c] += scale * acc;
     }
+    return v[0];
 }
-// softplus(beta=100) value and derivative from one exponential
-__device__ __forceinline__ void softplus100_both(float x, float& h, float& g) {
-    const float bx = BETA * x;
-    if (bx > 20.f) { h = x; g = 1.f; return; }
-    const float e = expf(bx);
-    h = log1pf(e) / BETA;
-    g = e / (1.f + e);
+__device__ __forceinline__ float warp_sum_scatter16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const bool hi = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = hi ? v[i] : v[i + o], keep = hi ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+// element q of the embedding's backward: d(e . de)/dx_c = de[c] + sum_k f_k (cos_kc de[sin_kc] - sin_kc de[cos_kc]); the lane
+// holding de[q] contributes its term to coordinate q % D (raw: the un-scaled sin / cos values, embed_coop2)
+template <int D>
+__device__ __forceinline__ float embed_bwd_term(const float* raw, float de_q, int q) {
+    if (q >= D * (1 + 2 * NF)) return 0.f;
+    if (q < D) return de_q;
+    const int r = q - D, k = r / (2 * D), m = r % (2 * D);
+    const float f = (float)(1 << k) * PI_F;
+    return m < D ? f * raw[q + D] * de_q : -f * raw[q - D] * de_q;
 }
 
-__global__ void __launch_bounds__(BWD_WARPS * 32, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
-               Bands bw, IndexMap im, int B, int Pt, int pts_per_warp, const float* __restrict__ d_out, float* __restrict__ d_wpack,
+               Bands bw, IndexMap im, int B, int Pt, int rounds, const float* __restrict__ d_out, float* __restrict__ d_wpack,
                float* __restrict__ d_code_bias) {
-    extern __shared__ float smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* sw = smem;                                            // one block's weights (padded image)
-    float* acc = smem + S_BLOCK + (size_t)warp * S_BLOCK;        // this warp's gradient accumulator (same padded layout)
-    float* es = smem + S_BLOCK + (size_t)BWD_WARPS * S_BLOCK + warp * ES_FLOATS;
+    float* recs = smem + S_BLOCK;                                // [2][BWD_WARPS][REC]
+    float* es = recs + 2 * (size_t)BWD_WARPS * REC + warp * ES_FLOATS;
     float* eA = es, *rawA = es + EA, *eB = es + 2 * EA, *rawB = es + 2 * EA + EB;
-    float* state = smem + S_BLOCK + (size_t)BWD_WARPS * S_BLOCK + BWD_WARPS * ES_FLOATS + (size_t)warp * MAX_PTS_PER_WARP * PT_STATE;
+    float* state = recs + 2 * (size_t)BWD_WARPS * REC + BWD_WARPS * ES_FLOATS;       // [rounds * BWD_WARPS][PT_STATE]
     const int64_t total = (int64_t)B * Pt;
-    const int64_t gw = (int64_t)blockIdx.x * BWD_WARPS + warp;
-    const int64_t p0 = gw * pts_per_warp;
-    int np = (int)(total - p0 < pts_per_warp ? total - p0 : pts_per_warp);
-    if (np < 0) np = 0;
+    const int64_t cta0 = (int64_t)blockIdx.x * rounds * BWD_WARPS;   // the CTA's points: cta0 + round * BWD_WARPS + warp
+    const int n_cta = (int)(total - cta0 < (int64_t)rounds * BWD_WARPS ? total - cta0 : (int64_t)rounds * BWD_WARPS);
 
     // per-point state in shared memory: stt[3*blk .. 3*blk+2] = input of block blk, stt[9..11] = running gradient
     // ---- pass 0: forward through blocks 0 .. NB-2 remembering each block's input; dx <- d_out ----
@@ -345,8 +392,8 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
         __syncthreads();
         load_weights_smem(sw, wpack + (size_t)blk * BLOCK_FLOATS, 1);
         __syncthreads();
-        for (int i = 0; i < np; ++i) {
-            const int64_t t = p0 + i;
+        for (int i = warp; i < n_cta; i += BWD_WARPS) {
+            const int64_t t = cta0 + i;
             const int b = (int)(t / Pt), n = list_index(im, (int)(t % Pt));
             float* stt = state + i * PT_STATE;
             float x[3];
@@ -357,146 +404,198 @@ nvp_bwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
                 x[0] = stt[blk * 3]; x[1] = stt[blk * 3 + 1]; x[2] = stt[blk * 3 + 2];
             }
             const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
-            const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
-            const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
+            float biasA[U], biasB[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                biasA[u] = code_bias[((size_t)(blk * 2 + 0) * B + b) * HID + lane + 32 * u];
+                biasB[u] = code_bias[((size_t)(blk * 2 + 1) * B + b) * HID + lane + 32 * u];
+            }
             block_forward(sw, biasA, biasB, sa, sb, x, blk, eA, lane);
             if (lane < 3) stt[(blk + 1) * 3 + lane] = sel3(x, lane);
             __syncwarp();
         }
     }
 
-    // ---- passes NB-1 .. 0: backward of one block for all points of the warp ----
+    // phase-2 roles: threads 0..383 own 13 columns of one hidden unit's first-layer gradient row (part 0, 1: the two halves
+    // of W1a; part 2: W1b); the last 128 threads also own the unit's second-layer gradients and the per-image bias sums
+    const int j = tid & (HID - 1), part = tid >> 7;
+    const bool heavy = tid < 3 * HID, light = tid >= BWD_THREADS - HID;
+    const int doff = part < 2 ? R_DA : R_DB, eoff = part < 2 ? R_EA + part * 16 : R_EB;
+
+    // ---- passes NB-1 .. 0: backward of one block for all points of the CTA ----
     for (int blk = NB - 1; blk >= 0; --blk) {
         __syncthreads();
         load_weights_smem(sw, wpack + (size_t)blk * BLOCK_FLOATS, 1);
-        for (int i = lane; i < S_BLOCK / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
         int foc, o0, o1;
         axes(blk, foc, o0, o1);
-        float abA[U], abB[U];
+        float a[EB];                                             // heavy: 13 columns
+        float a2[4] = {0.f, 0.f, 0.f, 0.f}, ab[2] = {0.f, 0.f}, amisc = 0.f;   // light: W2a, W2b[3]; bias sums; b2b / b2a
 #pragma unroll
-        for (int u = 0; u < U; ++u) { abA[u] = 0.f; abB[u] = 0.f; }
+        for (int q = 0; q < EB; ++q) a[q] = 0.f;
         int cur_img = -1;
         float* dbA = d_code_bias + (size_t)(blk * 2 + 0) * B * HID;
         float* dbB = d_code_bias + (size_t)(blk * 2 + 1) * B * HID;
-        for (int i = 0; i < np; ++i) {
-            const int64_t t = p0 + i;
-            const int b = (int)(t / Pt), n = list_index(im, (int)(t % Pt));
-            if (b != cur_img) {
-                if (cur_img >= 0) {
+        for (int r = 0; r * BWD_WARPS < n_cta; ++r) {
+            float* rbuf = recs + (size_t)(r & 1) * BWD_WARPS * REC;
+            const int i = r * BWD_WARPS + warp;
+            if (i < n_cta) {
+                // ================= phase 1: this warp's point =================
+                float* rc = rbuf + (size_t)warp * REC;
+                const int64_t t = cta0 + i;
+                const int b = (int)(t / Pt), n = list_index(im, (int)(t % Pt));
+                float* stt = state + i * PT_STATE;
+                const float x[3] = {stt[blk * 3], stt[blk * 3 + 1], stt[blk * 3 + 2]};
+                const float dx[3] = {stt[9], stt[10], stt[11]};
+                const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
+                float biasA[U], biasB[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        atomicAdd(dbA + (size_t)cur_img * HID + lane + 32 * u, abA[u]);
-                        atomicAdd(dbB + (size_t)cur_img * HID + lane + 32 * u, abB[u]);
-                        abA[u] = 0.f; abB[u] = 0.f;
-                    }
+                for (int u = 0; u < U; ++u) {
+                    biasA[u] = code_bias[((size_t)(blk * 2 + 0) * B + b) * HID + lane + 32 * u];
+                    biasB[u] = code_bias[((size_t)(blk * 2 + 1) * B + b) * HID + lane + 32 * u];
                 }
-                cur_img = b;
+                // ---------------- forward, keeping activations ----------------
+                const float xo[2] = {sel3(x, o0), sel3(x, o1)};
+                embed_coop2<2>(xo, sa, eA, rawA, lane);
+                float hA[U], gA[U], part_sum = 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int jj = lane + 32 * u;
+                    float pre = biasA[u];
+                    const float* w = sw + S_W1A + jj * SA;
+#pragma unroll
+                    for (int q = 0; q < EA; ++q) pre += w[q] * eA[q];
+                    softplus100_both(pre, hA[u], gA[u]);
+                    part_sum += sw[S_W2A + jj] * hA[u];
+                }
+                const float xf = sel3(x, foc) - (sw[S_B2A] + warp_sum(part_sum));
+                embed_coop2<1>(&xf, sb, eB, rawB, lane);
+                float hB[U], gB[U], q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int jj = lane + 32 * u;
+                    float pre = biasB[u];
+                    const float* w = sw + S_W1B + jj * EB;
+#pragma unroll
+                    for (int q = 0; q < EB; ++q) pre += w[q] * eB[q];
+                    softplus100_both(pre, hB[u], gB[u]);
+                    q0 += sw[S_W2B + jj] * hB[u]; q1 += sw[S_W2B + HID + jj] * hB[u]; q2 += sw[S_W2B + 2 * HID + jj] * hB[u];
+                }
+                const float th = sw[S_B2B] + warp_sum(q0), t1 = sw[S_B2B + 1] + warp_sum(q1), t2 = sw[S_B2B + 2] + warp_sum(q2);
+                float sn, cs;
+                sincosf(th, &sn, &cs);
+                const float y0 = xo[0] - t1, y1 = xo[1] - t2;
+                // ---------------- part b backward ----------------
+                const float g0 = sel3(dx, o0), g1 = sel3(dx, o1);
+                const float dy0 = cs * g0 - sn * g1, dy1 = sn * g0 + cs * g1;
+                const float dth = g0 * (-sn * y0 + cs * y1) + g1 * (-cs * y0 - sn * y1);
+                const float dout[3] = {dth, -dy0, -dy1};
+                float dxo[2] = {dy0, dy1};
+                float dxf = sel3(dx, foc);
+                float de2[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) de2[q] = 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int jj = lane + 32 * u;
+                    const float* w = sw + S_W1B + jj * EB;
+                    const float dh = sw[S_W2B + jj] * dout[0] + sw[S_W2B + HID + jj] * dout[1] + sw[S_W2B + 2 * HID + jj] * dout[2];
+                    const float dpre = dh * gB[u];
+                    rc[R_DB + jj] = dpre;
+                    rc[R_HB + jj] = hB[u];
+#pragma unroll
+                    for (int q = 0; q < EB; ++q) de2[q] += w[q] * dpre;
+                }
+                {
+                    float tb = embed_bwd_term<1>(rawB, warp_sum_scatter16(de2, lane), lane & 15);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) tb += __shfl_xor_sync(0xffffffffu, tb, o);
+                    dxf += sb * tb;
+                }
+                // ---------------- part a backward ----------------
+                const float ddelta = -dxf;
+                float de[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) de[q] = 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int jj = lane + 32 * u;
+                    const float* w = sw + S_W1A + jj * SA;
+                    const float dpre = sw[S_W2A + jj] * ddelta * gA[u];
+                    rc[R_DA + jj] = dpre;
+                    rc[R_VA + jj] = ddelta * hA[u];
+#pragma unroll
+                    for (int q = 0; q < EA; ++q) de[q] += w[q] * dpre;
+                }
+                {
+                    // coordinate of element q is q % 2: the butterfly over lane bits 4..1 sums each parity class
+                    float ta = embed_bwd_term<2>(rawA, warp_sum_scatter32(de, lane), lane);
+#pragma unroll
+                    for (int o = 16; o > 1; o >>= 1) ta += __shfl_xor_sync(0xffffffffu, ta, o);
+                    dxo[0] += sa * __shfl_sync(0xffffffffu, ta, 0);
+                    dxo[1] += sa * __shfl_sync(0xffffffffu, ta, 1);
+                }
+                if (lane < EA) rc[R_EA + (lane / EB) * 16 + lane % EB] = eA[lane];
+                if (lane < EB) rc[R_EB + lane] = eB[lane];
+                if (lane < 3) rc[R_MISC + lane] = sel3(dout, lane);
+                if (lane == 3) rc[R_MISC + 3] = ddelta;
+                if (lane == 4) rc[R_IMG] = __int_as_float(b);
+                __syncwarp();
+                if (lane == 0) { stt[9 + foc] = dxf; stt[9 + o0] = dxo[0]; stt[9 + o1] = dxo[1]; }
             }
-            float* stt = state + i * PT_STATE;
-            __syncwarp();
-            const float x[3] = {stt[blk * 3], stt[blk * 3 + 1], stt[blk * 3 + 2]};
-            const float dx[3] = {stt[9], stt[10], stt[11]};
-            const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
-            const float* biasA = code_bias + ((size_t)(blk * 2 + 0) * B + b) * HID;
-            const float* biasB = code_bias + ((size_t)(blk * 2 + 1) * B + b) * HID;
-            // ---------------- forward, keeping activations ----------------
-            const float xo[2] = {sel3(x, o0), sel3(x, o1)};
-            embed_coop2<2>(xo, sa, eA, rawA, lane);
-            float hA[U], gA[U], part = 0.f;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = lane + 32 * u;
-                float pre = biasA[j];
-                const float* w = sw + S_W1A + j * SA;
-#pragma unroll
-                for (int q = 0; q < EA; ++q) pre += w[q] * eA[q];
-                softplus100_both(pre, hA[u], gA[u]);
-                part += sw[S_W2A + j] * hA[u];
+            __syncthreads();
+            // ================= phase 2: the round's records into the register accumulators =================
+            const int nv = n_cta - r * BWD_WARPS < BWD_WARPS ? n_cta - r * BWD_WARPS : BWD_WARPS;
+            if (heavy) {
+#pragma unroll 4
+                for (int p = 0; p < nv; ++p) {
+                    const float* rp = rbuf + (size_t)p * REC;
+                    const float d = rp[doff + j];
+                    const float4* e4 = reinterpret_cast<const float4*>(rp + eoff);
+                    const float4 e0 = e4[0], e1 = e4[1], e2 = e4[2];
+                    const float e12 = rp[eoff + 12];
+                    a[0] += d * e0.x; a[1] += d * e0.y; a[2] += d * e0.z; a[3] += d * e0.w;
+                    a[4] += d * e1.x; a[5] += d * e1.y; a[6] += d * e1.z; a[7] += d * e1.w;
+                    a[8] += d * e2.x; a[9] += d * e2.y; a[10] += d * e2.z; a[11] += d * e2.w;
+                    a[12] += d * e12;
+                }
             }
-            const float xf = sel3(x, foc) - (sw[S_B2A] + warp_sum(part));
-            embed_coop2<1>(&xf, sb, eB, rawB, lane);
-            float hB[U], gB[U], q0 = 0.f, q1 = 0.f, q2 = 0.f;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = lane + 32 * u;
-                float pre = biasB[j];
-                const float* w = sw + S_W1B + j * EB;
-#pragma unroll
-                for (int q = 0; q < EB; ++q) pre += w[q] * eB[q];
-                softplus100_both(pre, hB[u], gB[u]);
-                q0 += sw[S_W2B + j] * hB[u]; q1 += sw[S_W2B + HID + j] * hB[u]; q2 += sw[S_W2B + 2 * HID + j] * hB[u];
+            if (light) {
+                for (int p = 0; p < nv; ++p) {
+                    const float* rp = rbuf + (size_t)p * REC;
+                    const int img = __float_as_int(rp[R_IMG]);
+                    if (img != cur_img) {
+                        if (cur_img >= 0) {
+                            atomicAdd(dbA + (size_t)cur_img * HID + j, ab[0]);
+                            atomicAdd(dbB + (size_t)cur_img * HID + j, ab[1]);
+                            ab[0] = 0.f; ab[1] = 0.f;
+                        }
+                        cur_img = img;
+                    }
+                    ab[0] += rp[R_DA + j]; ab[1] += rp[R_DB + j];
+                    a2[0] += rp[R_VA + j];
+                    const float hb = rp[R_HB + j];
+                    a2[1] += rp[R_MISC] * hb; a2[2] += rp[R_MISC + 1] * hb; a2[3] += rp[R_MISC + 2] * hb;
+                    if (j < 4) amisc += rp[R_MISC + j];
+                }
             }
-            const float th = sw[S_B2B] + warp_sum(q0), t1 = sw[S_B2B + 1] + warp_sum(q1), t2 = sw[S_B2B + 2] + warp_sum(q2);
-            float sn, cs;
-            sincosf(th, &sn, &cs);
-            const float y0 = xo[0] - t1, y1 = xo[1] - t2;
-            // ---------------- part b backward ----------------
-            const float g0 = sel3(dx, o0), g1 = sel3(dx, o1);
-            const float dy0 = cs * g0 - sn * g1, dy1 = sn * g0 + cs * g1;
-            const float dth = g0 * (-sn * y0 + cs * y1) + g1 * (-cs * y0 - sn * y1);
-            const float dout[3] = {dth, -dy0, -dy1};
-            float dxo[2] = {dy0, dy1};
-            float dxf = sel3(dx, foc);
-            float de2[EB];
-#pragma unroll
-            for (int q = 0; q < EB; ++q) de2[q] = 0.f;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = lane + 32 * u;
-                const float* w = sw + S_W1B + j * EB;
-                const float dh = sw[S_W2B + j] * dout[0] + sw[S_W2B + HID + j] * dout[1] + sw[S_W2B + 2 * HID + j] * dout[2];
-                const float dpre = dh * gB[u];
-#pragma unroll
-                for (int m = 0; m < 3; ++m) acc[S_W2B + m * HID + j] += dout[m] * hB[u];
-                abB[u] += dpre;
-                float* a1 = acc + S_W1B + j * EB;
-#pragma unroll
-                for (int q = 0; q < EB; ++q) { a1[q] += dpre * eB[q]; de2[q] += w[q] * dpre; }
-            }
-            if (lane < 3) acc[S_B2B + lane] += sel3(dout, lane);
-#pragma unroll
-            for (int q = 0; q < EB; ++q) de2[q] = warp_sum(de2[q]);
-            embed_bwd_raw<1>(rawB, sb, de2, &dxf);
-            // ---------------- part a backward ----------------
-            const float ddelta = -dxf;
-            float de[EA];
-#pragma unroll
-            for (int q = 0; q < EA; ++q) de[q] = 0.f;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = lane + 32 * u;
-                const float* w = sw + S_W1A + j * SA;
-                const float dpre = sw[S_W2A + j] * ddelta * gA[u];
-                acc[S_W2A + j] += ddelta * hA[u];
-                abA[u] += dpre;
-                float* a1 = acc + S_W1A + j * SA;
-#pragma unroll
-                for (int q = 0; q < EA; ++q) { a1[q] += dpre * eA[q]; de[q] += w[q] * dpre; }
-            }
-            if (lane == 0) acc[S_B2A] += ddelta;
-#pragma unroll
-            for (int q = 0; q < EA; ++q) de[q] = warp_sum(de[q]);
-            embed_bwd_raw<2>(rawA, sa, de, dxo);
-            __syncwarp();
-            if (lane == 0) { stt[9 + foc] = dxf; stt[9 + o0] = dxo[0]; stt[9 + o1] = dxo[1]; }
+            // (no second barrier: the next round writes the other record buffer)
         }
-        if (cur_img >= 0) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                atomicAdd(dbA + (size_t)cur_img * HID + lane + 32 * u, abA[u]);
-                atomicAdd(dbB + (size_t)cur_img * HID + lane + 32 * u, abB[u]);
-            }
-        }
-        // ---- CTA-level reduction of the warps' accumulators, then one global atomic per weight ----
-        __syncthreads();
+        // ---- one global atomic per weight per CTA ----
         float* dW = d_wpack + (size_t)blk * BLOCK_FLOATS;
-        const float* accs = smem + S_BLOCK;
-        for (int i = threadIdx.x; i < BLOCK_FLOATS; i += blockDim.x) {
-            float v = 0.f;
+        if (heavy && n_cta > 0) {
+            float* row = part < 2 ? dW + OFF_W1A + j * SA + part * EB : dW + OFF_W1B + j * EB;
 #pragma unroll
-            for (int w = 0; w < BWD_WARPS; ++w) v += accs[(size_t)w * S_BLOCK + i];
-            if (v != 0.f) atomicAdd(dW + i, v);
+            for (int q = 0; q < EB; ++q) if (a[q] != 0.f) atomicAdd(row + q, a[q]);
+        }
+        if (light && cur_img >= 0) {
+            atomicAdd(dbA + (size_t)cur_img * HID + j, ab[0]);
+            atomicAdd(dbB + (size_t)cur_img * HID + j, ab[1]);
+            atomicAdd(dW + OFF_W2A + j, a2[0]);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) atomicAdd(dW + OFF_W2B + m * HID + j, a2[1 + m]);
+            if (j < 3) atomicAdd(dW + OFF_B2B + j, amisc);
+            if (j == 3) atomicAdd(dW + OFF_B2A, amisc);
         }
     }
 }
@@ -794,18 +893,17 @@ extern "C" int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, cons
     NIW_CUDA(cudaMemsetAsync(d_code_bias, 0, sizeof(float) * NB * 2 * (size_t)B * HID, st));
     NIW_CUDA(cudaFuncSetAttribute(nvp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     const int64_t total = (int64_t)B * Pt;
-    // points per warp: the pass is a latency chain per warp (blocks in sequence, points in sequence), so as few as one
-    // wave of CTAs allows (one CTA per SM: its gradient accumulators fill shared memory)
+    // rounds (points per warp): the pass is a latency chain per warp (blocks in sequence, points in sequence), so as few as
+    // one wave of CTAs allows
     // (max_ctas > 0: the caller keeps the other SMs for a kernel running concurrently on another stream)
     const int sms = max_ctas > 0 && max_ctas < niw_num_sms() ? max_ctas : niw_num_sms();
     const int64_t warps_max = (int64_t)sms * BWD_WARPS;
-    int64_t ppw = (total + warps_max - 1) / warps_max;
-    if (ppw < 1) ppw = 1;
-    if (ppw > MAX_PTS_PER_WARP) ppw = MAX_PTS_PER_WARP;
-    const int64_t warps = (total + ppw - 1) / ppw;
-    const int64_t blocks = (warps + BWD_WARPS - 1) / BWD_WARPS;
-    niw::note_launch(), nvp_bwd_kernel<<<(unsigned)blocks, BWD_WARPS * 32, BWD_SMEM, st>>>(
-        wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, (int)ppw, d_out, d_wpack, d_code_bias);
+    int64_t rounds = (total + warps_max - 1) / warps_max;
+    if (rounds < 1) rounds = 1;
+    if (rounds > MAX_ROUNDS) rounds = MAX_ROUNDS;
+    const int64_t blocks = (total + rounds * BWD_WARPS - 1) / (rounds * BWD_WARPS);
+    niw::note_launch(), nvp_bwd_kernel<<<(unsigned)blocks, BWD_THREADS, BWD_SMEM, st>>>(
+        wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, (int)rounds, d_out, d_wpack, d_code_bias);
     NIW_LAUNCH_CHECK();
     return 0;
 }

@@ -378,7 +378,7 @@ class BackwardOverlap:
         import os
         self.stream = torch.cuda.Stream()
         n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-        self.side_ctas = int(os.environ.get("NIW_OVERLAP_SIDE_CTAS", side_ctas if side_ctas is not None else 26))
+        self.side_ctas = int(os.environ.get("NIW_OVERLAP_SIDE_CTAS", side_ctas if side_ctas is not None else 20))
         self.dw_ctas = int(os.environ.get("NIW_OVERLAP_DW_CTAS", dw_ctas if dw_ctas is not None else n - self.side_ctas))
         self.used = False
 
