@@ -15,7 +15,16 @@ adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
                  int64_t n, double lr, double log_gamma, float beta1, float beta2, float eps, float weight_decay,
                  float warmup_iters, int64_t warmup_n, float max_iter, float* __restrict__ progress0,
                  float* __restrict__ progress1, float* __restrict__ step, unsigned int* __restrict__ ticket) {
-    const float t = step[0] + 1.f;                      // every thread reads it before any block can advance it
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const bool vec = i0 + 3 < n && (i0 + 3 < warmup_n || i0 >= warmup_n);     // a straddling float4 is handled per element
+    // the element loads go out first: the scalar chain below (step counter -> double exp -> two powf) would otherwise sit
+    // in front of them, two dependent memory round trips in a kernel that is all latency
+    float4 pp, gg, mm, vv;
+    if (vec) {
+        pp = *reinterpret_cast<float4*>(p + i0); gg = *reinterpret_cast<const float4*>(g + i0);
+        mm = *reinterpret_cast<float4*>(m + i0); vv = *reinterpret_cast<float4*>(v + i0);
+    }
+    const float t = *reinterpret_cast<volatile float*>(step) + 1.f;   // every thread reads it before any block can advance it
     // ExponentialLR: torch multiplies the (double) learning rate by gamma once per step; gamma^(t-1) is evaluated in
     // double here as well -- an fp32 gamma drifts by ~0.5 % over the 200 000 iterations of the target schedules
     const float lr_full = (float)(log_gamma == 0.0 ? lr : lr * exp(log_gamma * (double)(t - 1.f)));
@@ -26,11 +35,8 @@ adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     // torch.optim.Adam (single-tensor form): step_size = lr / (1 - b1^t), denom = sqrt(v) / sqrt(1 - b2^t) + eps
     const float bc1 = 1.f - powf(beta1, t);
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
-    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const float step_size = (i0 + 3 < warmup_n ? lr_warm : lr_full) / bc1;     // a straddling float4 is handled per element
-    if (i0 + 3 < n && (i0 + 3 < warmup_n || i0 >= warmup_n)) {
-        float4 pp = *reinterpret_cast<float4*>(p + i0), gg = *reinterpret_cast<const float4*>(g + i0);
-        float4 mm = *reinterpret_cast<float4*>(m + i0), vv = *reinterpret_cast<float4*>(v + i0);
+    const float step_size = (i0 + 3 < warmup_n ? lr_warm : lr_full) / bc1;
+    if (vec) {
         float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -17,6 +17,7 @@
 //   nvp_pack_bwd_kernel   (3 CTAs)  back through the biases, the code projector and weight-norm,
 //                                   accumulating straight into the parameters' .grad buffers
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <math.h>
 
 namespace {
@@ -99,6 +100,27 @@ __device__ __forceinline__ void load_weights_smem(float* sw, const float* __rest
     for (int i = threadIdx.x; i < nblocks * (S_BLOCK / 4); i += blockDim.x) dst[i] = src[i];
 }
 
+// the forward kernels' form: all blocks' weights with one thread's bulk async copies (TMA engine, one mbarrier) while the
+// other threads compute their points' inputs; `bulk` = 0 (wpack not 16-byte aligned) keeps the copy loop.  Every thread
+// calls weights_arrive() before its first read.
+__device__ __forceinline__ void weights_issue(float* sw, const float* __restrict__ wpack, int nblocks, uint64_t* bar, int bulk) {
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            niw::ptx::mbar_init(bar, 1);
+            niw::ptx::fence_mbar_init();
+            niw::ptx::mbar_arrive_expect_tx(bar, (uint32_t)(nblocks * S_BLOCK * sizeof(float)));
+            for (int b = 0; b < nblocks; ++b)
+                niw::ptx::bulk_g2s(sw + (size_t)b * S_BLOCK, wpack + (size_t)b * S_BLOCK, (uint32_t)(S_BLOCK * sizeof(float)), bar);
+        }
+    } else {
+        load_weights_smem(sw, wpack, nblocks);
+    }
+}
+__device__ __forceinline__ void weights_arrive(uint64_t* bar, int bulk) {
+    __syncthreads();                                  // the barrier's initialisation / the copy loop's stores
+    if (bulk) niw::ptx::mbar_wait(bar, 0);
+}
+
 // embedding of D coordinates into e[D*(1+2NF)], computed cooperatively: lane i < D*NF evaluates
 // one (frequency, coordinate) sin/cos pair; every lane then reads the whole vector from shared memory
 template <int D>
@@ -176,15 +198,18 @@ __device__ __forceinline__ void load_lane_bias(LaneBias& lb, const float* __rest
 }
 
 constexpr int FWD_WARPS = 8;
-constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)NB * S_BLOCK + FWD_WARPS * 32);
+constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)NB * S_BLOCK + FWD_WARPS * 32) + 8;    // + the weights' mbarrier
+static_assert((FWD_SMEM - 8) % 8 == 0, "mbarrier alignment");
 
 __global__ void __launch_bounds__(FWD_WARPS * 32)
 nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
-               Bands bw, IndexMap im, int B, int Pt, float* __restrict__ out) {
-    extern __shared__ float smem[];
+               Bands bw, IndexMap im, int B, int Pt, int bulk, float* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
     float* sw = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* es = smem + (size_t)NB * S_BLOCK + warp * 32;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)NB * S_BLOCK + FWD_WARPS * 32);
+    weights_issue(sw, wpack, NB, bar, bulk);
     const int64_t total = (int64_t)B * Pt;
     int64_t t = (int64_t)blockIdx.x * FWD_WARPS + warp;
     LaneBias lb;
@@ -193,8 +218,7 @@ nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
         load_lane_bias(lb, code_bias, B, (int)(t / Pt), lane);
         x[0] = pts[t * 3]; x[1] = pts[t * 3 + 1]; x[2] = pts[t * 3 + 2];
     }
-    load_weights_smem(sw, wpack, NB);
-    __syncthreads();
+    weights_arrive(bar, bulk);
     while (t < total) {
         const int n = list_index(im, (int)(t % Pt));
         const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
@@ -218,22 +242,24 @@ nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
 // [grid ; centre] (the backward kernel's input, var.grid_cam / var.center_cam) and the warped list.
 // ------------------------------------------------------------------------------------------
 struct PoseInvW { float R[9]; float tinv[3]; };
-constexpr size_t RAYS_SMEM = sizeof(float) * ((size_t)NB * S_BLOCK + (FWD_WARPS + 1) * 32 + 4);
+constexpr size_t RAYS_SMEM = sizeof(float) * ((size_t)NB * S_BLOCK + (FWD_WARPS + 1) * 32 + 4) + 8;   // + the weights' mbarrier
+static_assert((RAYS_SMEM - 8) % 8 == 0, "mbarrier alignment");
 
 __global__ void __launch_bounds__((FWD_WARPS + 1) * 32)
 nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ intr,
                     const float* __restrict__ pose_init, const int64_t* __restrict__ ray_idx, int64_t idx_start, Bands bw,
-                    IndexMap im, int B, int P, int W, float* __restrict__ pts, float* __restrict__ warped,
+                    IndexMap im, int B, int P, int W, int bulk, float* __restrict__ pts, float* __restrict__ warped,
                     float* __restrict__ ray, float* __restrict__ center) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* sw = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* es = smem + (size_t)NB * S_BLOCK + warp * 32;
     float* s_c = smem + (size_t)NB * S_BLOCK + (FWD_WARPS + 1) * 32;
     const int b = blockIdx.y;
     LaneBias lb;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)NB * S_BLOCK + (FWD_WARPS + 1) * 32 + 4);
+    weights_issue(sw, wpack, NB, bar, bulk);
     load_lane_bias(lb, code_bias, B, b, lane);                            // in flight while the weights arrive
-    load_weights_smem(sw, wpack, NB);
     const bool is_center = warp == FWD_WARPS;
     const int p = is_center ? P : blockIdx.x * FWD_WARPS + warp;          // local row of the [grid ; centre] list
     const bool active = is_center || p < P;
@@ -269,7 +295,7 @@ nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ c
         }
         if (lane < 3 && (!is_center || blockIdx.x == 0)) pts[((int64_t)b * (P + 1) + p) * 3 + lane] = sel3(x, lane);
     }
-    __syncthreads();                                                      // weights in shared memory
+    weights_arrive(bar, bulk);                                            // weights in shared memory
     if (active) {
         const int n = list_index(im, p);
         const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
@@ -651,14 +677,33 @@ nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, int ipc, 
     const float* const* P = T.p + blk * 12;
     const float *Wc = P[10], *bc = P[11];
     float* wp = wpack + (size_t)blk * BLOCK_FLOATS;
-    // (1) row scales g/||v|| and the effective embedded-coordinate columns
-    for (int r = warp; r < 2 * HID; r += nwarp) {
-        const int part = r >> 7, j = r & 127;
-        const int emb = part == 0 ? EA : EB, ld = emb + DF;
-        const float* v = P[part * 5 + 0] + (size_t)j * ld;
-        const float scale = P[part * 5 + 1][j] / sqrtf(row_norm2(v, ld, lane));
-        if (lane == 0) s_scale[r] = scale;
-        if (writer && lane < emb) wp[(part == 0 ? OFF_W1A + j * SA : OFF_W1B + j * EB) + lane] = v[lane] * scale;
+    if (nimg <= 0 && !writer) return;          // fewer images than splits: nothing to do here
+    // (1) row scales g/||v|| and the effective embedded-coordinate columns.  A warp's rows are taken four at a time with
+    // all their loads issued before the first norm (one global-memory round trip per four rows, not per row)
+    constexpr int RB = 4;
+    static_assert((2 * HID) % (RB * (PACK_THREADS / 32)) == 0, "rows per warp");
+    for (int r0 = warp; r0 < 2 * HID; r0 += RB * nwarp) {
+        float t[RB][5], gsc[RB];
+#pragma unroll
+        for (int a = 0; a < RB; ++a) {
+            const int r = r0 + a * nwarp, part = r >> 7, j = r & 127;
+            const int ld = (part == 0 ? EA : EB) + DF;
+            const float* v = P[part * 5 + 0] + (size_t)j * ld;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { const int c = lane + 32 * i; t[a][i] = c < ld ? v[c] : 0.f; }
+            gsc[a] = P[part * 5 + 1][j];
+        }
+#pragma unroll
+        for (int a = 0; a < RB; ++a) {
+            const int r = r0 + a * nwarp, part = r >> 7, j = r & 127;
+            const int emb = part == 0 ? EA : EB;
+            float n2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) n2 += t[a][i] * t[a][i];
+            const float scale = gsc[a] / sqrtf(warp_sum(n2));
+            if (lane == 0) s_scale[r] = scale;
+            if (writer && lane < emb) wp[(part == 0 ? OFF_W1A + j * SA : OFF_W1B + j * EB) + lane] = t[a][0] * scale;
+        }
     }
     if (writer) {   // output layers: copies
         for (int i = tid; i < HID; i += PACK_THREADS) wp[OFF_W2A + i] = P[3][i];
@@ -667,36 +712,60 @@ nvp_pack_fwd_kernel(PtrTable T, const float* __restrict__ code, int B, int ipc, 
         if (tid < 3) wp[OFF_B2B + tid] = P[9][tid];
     }
     // (2) code_b[img][k] = code + b_c + W_c code      (nvp_ndr.py:382): warp per output, lanes over m
-    for (int o = warp; o < nimg * DF; o += nwarp) {
-        const int li = o / DF, k = o % DF;
-        const float* c = code + (size_t)(img0 + li) * DF;
-        const float* w = Wc + (size_t)k * DF;
-        float a = 0.f;
+    for (int o0 = warp; o0 < nimg * DF; o0 += RB * nwarp) {
+        float wv[RB][DF / 32], cv[RB][DF / 32];
 #pragma unroll
-        for (int m = lane; m < DF; m += 32) a += w[m] * c[m];
-        a = warp_sum(a);
-        if (lane == 0) {
-            a += c[k] + bc[k];
-            s_cb[li * LDC + k] = a;
-            cb_out[((size_t)blk * B + img0 + li) * DF + k] = a;
+        for (int a = 0; a < RB; ++a) {
+            const int o = o0 + a * nwarp;
+            const bool on = o < nimg * DF;
+            const int li = on ? o / DF : 0, k = on ? o % DF : 0;
+            const float* c = code + (size_t)(img0 + li) * DF;
+            const float* w = Wc + (size_t)k * DF;
+#pragma unroll
+            for (int q = 0; q < DF / 32; ++q) { wv[a][q] = w[lane + 32 * q]; cv[a][q] = c[lane + 32 * q]; }
+        }
+#pragma unroll
+        for (int a = 0; a < RB; ++a) {
+            const int o = o0 + a * nwarp;
+            if (o < nimg * DF) {
+                const int li = o / DF, k = o % DF;
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < DF / 32; ++q) acc += wv[a][q] * cv[a][q];
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    acc += code[(size_t)(img0 + li) * DF + k] + bc[k];
+                    s_cb[li * LDC + k] = acc;
+                    cb_out[((size_t)blk * B + img0 + li) * DF + k] = acc;
+                }
+            }
         }
     }
     __syncthreads();
-    // (3) per-image first-layer biases: warp per (part, j), lanes over the latent axis, loop over images
-    for (int r = warp; r < 2 * HID; r += nwarp) {
-        const int part = r >> 7, j = r & 127;
-        const int emb = part == 0 ? EA : EB, ld = emb + DF;
-        const float* v = P[part * 5 + 0] + (size_t)j * ld + emb;
-        float vl[DF / 32];
+    // (3) per-image first-layer biases: warp per (part, j), lanes over the latent axis, loop over images (rows four at a time
+    // as above)
+    for (int r0 = warp; r0 < 2 * HID; r0 += RB * nwarp) {
+        float vl[RB][DF / 32], b0[RB];
 #pragma unroll
-        for (int q = 0; q < DF / 32; ++q) vl[q] = v[lane + 32 * q];
-        const float b0 = P[part * 5 + 2][j], scale = s_scale[r];
-        for (int li = 0; li < nimg; ++li) {
-            float a = 0.f;
+        for (int a = 0; a < RB; ++a) {
+            const int r = r0 + a * nwarp, part = r >> 7, j = r & 127;
+            const int emb = part == 0 ? EA : EB, ld = emb + DF;
+            const float* v = P[part * 5 + 0] + (size_t)j * ld + emb;
 #pragma unroll
-            for (int q = 0; q < DF / 32; ++q) a += vl[q] * s_cb[li * LDC + lane + 32 * q];
-            a = warp_sum(a);
-            if (lane == 0) code_bias[((size_t)(blk * 2 + part) * B + img0 + li) * HID + j] = b0 + scale * a;
+            for (int q = 0; q < DF / 32; ++q) vl[a][q] = v[lane + 32 * q];
+            b0[a] = P[part * 5 + 2][j];
+        }
+#pragma unroll
+        for (int a = 0; a < RB; ++a) {
+            const int r = r0 + a * nwarp, part = r >> 7, j = r & 127;
+            const float scale = s_scale[r];
+            for (int li = 0; li < nimg; ++li) {
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < DF / 32; ++q) acc += vl[a][q] * s_cb[li * LDC + lane + 32 * q];
+                acc = warp_sum(acc);
+                if (lane == 0) code_bias[((size_t)(blk * 2 + part) * B + img0 + li) * HID + j] = b0[a] + scale * acc;
+            }
         }
     }
 }
@@ -860,7 +929,7 @@ extern "C" int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, cons
     const int64_t cap = (int64_t)niw_num_sms() * 2;
     if (blocks > cap) blocks = cap;
     niw::note_launch(), nvp_fwd_kernel<<<(unsigned)blocks, FWD_WARPS * 32, FWD_SMEM, niw_stream(stream)>>>(
-        wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, out);
+        wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, ((uintptr_t)wpack & 15) == 0 ? 1 : 0, out);
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -877,7 +946,8 @@ extern "C" int niw_nvp_rays_fwd(const float* wpack, const float* code_bias, cons
     NIW_CUDA(cudaFuncSetAttribute(nvp_rays_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RAYS_SMEM));
     const dim3 grid((unsigned)((P + FWD_WARPS - 1) / FWD_WARPS), (unsigned)B);
     niw::note_launch(), nvp_rays_fwd_kernel<<<grid, (FWD_WARPS + 1) * 32, RAYS_SMEM, niw_stream(stream)>>>(
-        wpack, code_bias, intr, pose_init, ray_idx, idx_start, make_bands(alpha_ratio), im, B, P, W, pts, warped, ray, center);
+        wpack, code_bias, intr, pose_init, ray_idx, idx_start, make_bands(alpha_ratio), im, B, P, W,
+        ((uintptr_t)wpack & 15) == 0 ? 1 : 0, pts, warped, ray, center);
     NIW_LAUNCH_CHECK();
     return 0;
 }

@@ -188,8 +188,10 @@ class _NvpWarp(torch.autograd.Function):
         B, Pt = pts.shape[0], pts.shape[1]
         d_w = torch.empty_like(wpack)
         d_cb = torch.empty_like(code_bias)
+        ov = backward_overlap                   # engine: the MLP weight-gradient pass is running on another stream
         _lib.check(_lib.load().niw_nvp_warp_bwd(_p(wpack), _p(code_bias), _p(pts), ctx.alpha, B, Pt, *ctx.im,
-                                                _p(d_out.contiguous()), _p(d_w), _p(d_cb), 0, _stream()))
+                                                _p(d_out.contiguous()), _p(d_w), _p(d_cb),
+                                                int(ov.side_ctas) if ov is not None and ov.used else 0, _stream()))
         return d_w, d_cb, None, None, None
 
 

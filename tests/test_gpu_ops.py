@@ -321,6 +321,42 @@ def test_nvp_vs_oracle_large(F):
         assert rel_l2(p[k].grad, q[k].grad) < 3e-3, k
 
 
+@pytest.mark.parametrize("max_ctas,Pt", [(1, 700), (3, 700), (2, 37), (7, 333)])
+def test_nvp_backward_on_a_capped_grid_runs_rounds(F, max_ctas, Pt):
+    """csrc/nvp.cu nvp_bwd_kernel with the CTA budget the engine's backward overlap leaves it (``max_ctas``): every warp
+    takes one point per round, the records of a round are summed into per-thread register accumulators after one barrier
+    (two record buffers alternate), the per-image bias sums are flushed when a CTA's point range crosses an image
+    boundary.  Odd and even round counts, the 32-round cap (more CTAs than the budget), partial last rounds: gradients
+    equal the oracle's."""
+    import types
+    B = 3
+    p_cpu = syn.nvp_params(5)
+    code_cpu = syn.latent_codes(6, B)
+    pts_cpu = torch.randn(B, Pt, 1, 3, generator=torch.Generator().manual_seed(7)) * 0.7
+    q = {k: v.clone().requires_grad_(True) for k, v in p_cpu.items()}
+    cg = code_cpu.clone().requires_grad_(True)
+    ref = ora.nvp_warp(q, cg, pts_cpu, 0.3)
+    w = torch.rand(ref.shape, generator=torch.Generator().manual_seed(8)) - 0.5
+    (ref * w).sum().backward()
+    p = {k: v.to(DEV).requires_grad_(True) for k, v in p_cpu.items()}
+    code = code_cpu.to(DEV).requires_grad_(True)
+    wpack, code_bias = _nvp_pack(p, code)
+    out = F.nvp_warp(wpack, code_bias, pts_cpu[:, :, 0].to(DEV), 0.3)
+    saved = F.backward_overlap
+    F.backward_overlap = types.SimpleNamespace(side_ctas=max_ctas, used=True)
+    try:
+        (out * w[:, :, 0].to(DEV)).sum().backward()
+    finally:
+        F.backward_overlap = saved
+    assert rel_l2(code.grad, cg.grad) < 2e-3
+    for k in q:
+        if q[k].numel() == 1:
+            # a scalar bias gradient is a sum of O(1) terms over all points that may cancel to ~1e-4: absolute bound
+            assert abs(float(p[k].grad) - float(q[k].grad)) <= 5e-5 + 3e-3 * abs(float(q[k].grad)), k
+        else:
+            assert rel_l2(p[k].grad, q[k].grad) < 3e-3, k
+
+
 @pytest.mark.parametrize("alpha", [0.05, 0.4])
 def test_nvp_ray_shards_and_shared_centre_equal_the_full_list(F, alpha):
     """The warp of a per-image list [grid rows (P) ; centre rows (P)] must not change when (a) the rays are split
