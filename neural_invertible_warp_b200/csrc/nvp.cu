@@ -5,16 +5,20 @@
 //   weight_norm first layers reference model/nvp/nvp_ndr.py:291-292,335-336
 // The reference issues ~900 tiny ATen launches per call (plus as many again in backward).  Here:
 //
-//   nvp_pack_fwd_kernel   (3 CTAs)  weight-norm resolution w = g v/||v||, code projection
+//   nvp_pack_fwd_kernel   (3 x 16 CTAs) weight-norm resolution w = g v/||v||, code projection
 //                                   code_b = W_c code + b_c + code, and the per-image first-layer
 //                                   biases b_0 + w[:, emb:] code_b  ->  wpack, code_bias
 //   nvp_fwd_kernel        one WARP per point, lanes = hidden units (4 each): all three coupling
-//                         blocks, weights of all blocks resident in shared memory
-//   nvp_bwd_kernel        one warp per point, forward recomputed; weight gradients are
-//                         accumulated in registers over the warp's points (block-outer order),
-//                         reduced across the CTA in shared memory and flushed with one atomic
-//                         per weight per CTA
-//   nvp_pack_bwd_kernel   (3 CTAs)  back through the biases, the code projector and weight-norm,
+//                         blocks; the weights of all blocks arrive in shared memory by bulk async
+//                         copies while the warp loads its point and its image's biases
+//   nvp_rays_fwd_kernel   the same with the un-warped grid point computed from the pixel index in
+//                         front and ray = warped grid - warped centre behind (one launch for the
+//                         train-mode ray generation; opt-in, see functional.fused_warped_rays)
+//   nvp_bwd_kernel        one warp per point and round, forward recomputed; the weight gradients
+//                         (outer products dpre (x) e) are deferred to a per-round pass in which
+//                         every thread adds the round's records into register accumulators for its
+//                         fixed slice of the weight image; one global atomic per weight per CTA
+//   nvp_pack_bwd_kernel   (3 x 16 CTAs) back through the biases, the code projector and weight-norm,
 //                                   accumulating straight into the parameters' .grad buffers
 #include "common.cuh"
 #include "tc_ptx.cuh"

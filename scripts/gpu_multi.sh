@@ -1,3 +1,5 @@
+#!/bin/bash
+# Multi-GPU bench lines: scripts/gpu_multi.sh <N> <config>... (run under gpurun --gpus N); c2 also writes per-rank timelines
 N=${1:-2}; shift
 for cfg in "$@"; do
   extra=""; [ "$cfg" = "c2" ] && extra="--timeline gpurun_out/r3x_tl_n${N}"
