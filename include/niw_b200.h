@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NIW_ABI_VERSION 4
+#define NIW_ABI_VERSION 5
 
 #define NIW_E_BADARG   (-1)  /* null pointer / non-positive size */
 #define NIW_E_UNSUPP   (-2)  /* shape or option outside what the kernels implement */
@@ -104,7 +104,8 @@ int niw_nvp_pack_bwd(const float* const* params, float* const* grads, const floa
  * built, n < idx_split ? n + idx_offset : n + idx_offset + idx_jump (the embedder's annealing quirk, embedder.py:46-49,
  * is keyed on it).  Identity: (0, Pt, 0).  A ray shard passes its first ray's index in the global per-image list. */
 /* (max_ctas of the backward: 0 = one CTA per SM; > 0 caps the grid, each warp then walks more points -- for callers that
- * run it next to another kernel, e.g. niw_nerf_bwd_dw on a second stream) */
+ * run it next to another kernel, e.g. niw_nerf_bwd_dw on a second stream; wpack must be 16-byte aligned: the weight images
+ * move as bulk copies / 128-bit vectors, NIW_E_BADARG otherwise) */
 int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                      int B, int Pt, int idx_offset, int idx_split, int idx_jump, float* out, void* stream);
 int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,

@@ -18,7 +18,7 @@ NIW_PREC_BF16X3 = 2
 NIW_NERF_PREPACKED = 2
 NIW_NERF_PARAMS = 530052
 NIW_NVP_BLOCK_FLOATS = ((128 * 27 + 128 + 1 + 128 * 13 + 3 * 128 + 3) + 3) // 4 * 4   # 5636, include/niw_b200.h
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # name -> (restype, argtypes); mirrors include/niw_b200.h one to one
 SIGNATURES = {

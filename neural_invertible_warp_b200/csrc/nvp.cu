@@ -105,24 +105,20 @@ __device__ __forceinline__ void load_weights_smem(float* sw, const float* __rest
 }
 
 // the forward kernels' form: all blocks' weights with one thread's bulk async copies (TMA engine, one mbarrier) while the
-// other threads compute their points' inputs; `bulk` = 0 (wpack not 16-byte aligned) keeps the copy loop.  Every thread
-// calls weights_arrive() before its first read.
-__device__ __forceinline__ void weights_issue(float* sw, const float* __restrict__ wpack, int nblocks, uint64_t* bar, int bulk) {
-    if (bulk) {
-        if (threadIdx.x == 0) {
-            niw::ptx::mbar_init(bar, 1);
-            niw::ptx::fence_mbar_init();
-            niw::ptx::mbar_arrive_expect_tx(bar, (uint32_t)(nblocks * S_BLOCK * sizeof(float)));
-            for (int b = 0; b < nblocks; ++b)
-                niw::ptx::bulk_g2s(sw + (size_t)b * S_BLOCK, wpack + (size_t)b * S_BLOCK, (uint32_t)(S_BLOCK * sizeof(float)), bar);
-        }
-    } else {
-        load_weights_smem(sw, wpack, nblocks);
+// other threads compute their points' inputs (wpack is 16-byte aligned: the launchers check).  Every thread calls
+// weights_arrive() before its first read.
+__device__ __forceinline__ void weights_issue(float* sw, const float* __restrict__ wpack, int nblocks, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        niw::ptx::mbar_init(bar, 1);
+        niw::ptx::fence_mbar_init();
+        niw::ptx::mbar_arrive_expect_tx(bar, (uint32_t)(nblocks * S_BLOCK * sizeof(float)));
+        for (int b = 0; b < nblocks; ++b)
+            niw::ptx::bulk_g2s(sw + (size_t)b * S_BLOCK, wpack + (size_t)b * S_BLOCK, (uint32_t)(S_BLOCK * sizeof(float)), bar);
     }
 }
-__device__ __forceinline__ void weights_arrive(uint64_t* bar, int bulk) {
-    __syncthreads();                                  // the barrier's initialisation / the copy loop's stores
-    if (bulk) niw::ptx::mbar_wait(bar, 0);
+__device__ __forceinline__ void weights_arrive(uint64_t* bar) {
+    __syncthreads();                                  // the barrier's initialisation
+    niw::ptx::mbar_wait(bar, 0);
 }
 
 // embedding of D coordinates into e[D*(1+2NF)], computed cooperatively: lane i < D*NF evaluates
@@ -207,13 +203,13 @@ static_assert((FWD_SMEM - 8) % 8 == 0, "mbarrier alignment");
 
 __global__ void __launch_bounds__(FWD_WARPS * 32)
 nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ pts,
-               Bands bw, IndexMap im, int B, int Pt, int bulk, float* __restrict__ out) {
+               Bands bw, IndexMap im, int B, int Pt, float* __restrict__ out) {
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* es = smem + (size_t)NB * S_BLOCK + warp * 32;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)NB * S_BLOCK + FWD_WARPS * 32);
-    weights_issue(sw, wpack, NB, bar, bulk);
+    weights_issue(sw, wpack, NB, bar);
     const int64_t total = (int64_t)B * Pt;
     int64_t t = (int64_t)blockIdx.x * FWD_WARPS + warp;
     LaneBias lb;
@@ -222,7 +218,7 @@ nvp_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_b
         load_lane_bias(lb, code_bias, B, (int)(t / Pt), lane);
         x[0] = pts[t * 3]; x[1] = pts[t * 3 + 1]; x[2] = pts[t * 3 + 2];
     }
-    weights_arrive(bar, bulk);
+    weights_arrive(bar);
     while (t < total) {
         const int n = list_index(im, (int)(t % Pt));
         const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
@@ -252,7 +248,7 @@ static_assert((RAYS_SMEM - 8) % 8 == 0, "mbarrier alignment");
 __global__ void __launch_bounds__((FWD_WARPS + 1) * 32)
 nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ code_bias, const float* __restrict__ intr,
                     const float* __restrict__ pose_init, const int64_t* __restrict__ ray_idx, int64_t idx_start, Bands bw,
-                    IndexMap im, int B, int P, int W, int bulk, float* __restrict__ pts, float* __restrict__ warped,
+                    IndexMap im, int B, int P, int W, float* __restrict__ pts, float* __restrict__ warped,
                     float* __restrict__ ray, float* __restrict__ center) {
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;
@@ -262,7 +258,7 @@ nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ c
     const int b = blockIdx.y;
     LaneBias lb;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)NB * S_BLOCK + (FWD_WARPS + 1) * 32 + 4);
-    weights_issue(sw, wpack, NB, bar, bulk);
+    weights_issue(sw, wpack, NB, bar);
     load_lane_bias(lb, code_bias, B, b, lane);                            // in flight while the weights arrive
     const bool is_center = warp == FWD_WARPS;
     const int p = is_center ? P : blockIdx.x * FWD_WARPS + warp;          // local row of the [grid ; centre] list
@@ -299,7 +295,7 @@ nvp_rays_fwd_kernel(const float* __restrict__ wpack, const float* __restrict__ c
         }
         if (lane < 3 && (!is_center || blockIdx.x == 0)) pts[((int64_t)b * (P + 1) + p) * 3 + lane] = sel3(x, lane);
     }
-    weights_arrive(bar, bulk);                                            // weights in shared memory
+    weights_arrive(bar);                                            // weights in shared memory
     if (active) {
         const int n = list_index(im, p);
         const float sa = quirk_scale<2>(bw, n), sb = quirk_scale<1>(bw, n);
@@ -926,6 +922,7 @@ extern "C" int niw_nvp_pack_bwd(const float* const* params, float* const* grads,
 extern "C" int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, const float* pts, float alpha_ratio,
                                 int B, int Pt, int idx_offset, int idx_split, int idx_jump, float* out, void* stream) {
     NIW_CHECK_ARG(wpack && code_bias && pts && out && B > 0 && Pt > 0 && idx_offset >= 0 && idx_split >= 0 && idx_jump >= 0);
+    NIW_CHECK_ARG(((uintptr_t)wpack & 15) == 0);          // the weight images move as 128-bit vectors / bulk copies
     const IndexMap im{idx_offset, idx_split, idx_jump};
     const int64_t total = (int64_t)B * Pt;
     NIW_CUDA(cudaFuncSetAttribute(nvp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
@@ -933,7 +930,7 @@ extern "C" int niw_nvp_warp_fwd(const float* wpack, const float* code_bias, cons
     const int64_t cap = (int64_t)niw_num_sms() * 2;
     if (blocks > cap) blocks = cap;
     niw::note_launch(), nvp_fwd_kernel<<<(unsigned)blocks, FWD_WARPS * 32, FWD_SMEM, niw_stream(stream)>>>(
-        wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, ((uintptr_t)wpack & 15) == 0 ? 1 : 0, out);
+        wpack, code_bias, pts, make_bands(alpha_ratio), im, B, Pt, out);
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -945,13 +942,12 @@ extern "C" int niw_nvp_rays_fwd(const float* wpack, const float* code_bias, cons
                                 int idx_offset, int idx_split, int idx_jump, float* pts, float* warped, float* ray,
                                 float* center, void* stream) {
     NIW_CHECK_ARG(wpack && code_bias && intr && pts && ray && center && B > 0 && P > 0 && H > 0 && W > 0 && idx_offset >= 0 &&
-                  idx_split >= 0 && idx_jump >= 0);
+                  idx_split >= 0 && idx_jump >= 0 && ((uintptr_t)wpack & 15) == 0);
     const IndexMap im{idx_offset, idx_split, idx_jump};
     NIW_CUDA(cudaFuncSetAttribute(nvp_rays_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RAYS_SMEM));
     const dim3 grid((unsigned)((P + FWD_WARPS - 1) / FWD_WARPS), (unsigned)B);
     niw::note_launch(), nvp_rays_fwd_kernel<<<grid, (FWD_WARPS + 1) * 32, RAYS_SMEM, niw_stream(stream)>>>(
-        wpack, code_bias, intr, pose_init, ray_idx, idx_start, make_bands(alpha_ratio), im, B, P, W,
-        ((uintptr_t)wpack & 15) == 0 ? 1 : 0, pts, warped, ray, center);
+        wpack, code_bias, intr, pose_init, ray_idx, idx_start, make_bands(alpha_ratio), im, B, P, W, pts, warped, ray, center);
     NIW_LAUNCH_CHECK();
     return 0;
 }
@@ -960,7 +956,7 @@ extern "C" int niw_nvp_warp_bwd(const float* wpack, const float* code_bias, cons
                                 int B, int Pt, int idx_offset, int idx_split, int idx_jump, const float* d_out,
                                 float* d_wpack, float* d_code_bias, int max_ctas, void* stream) {
     NIW_CHECK_ARG(wpack && code_bias && pts && d_out && d_wpack && d_code_bias && B > 0 && Pt > 0 && idx_offset >= 0 &&
-                  idx_split >= 0 && idx_jump >= 0 && max_ctas >= 0);
+                  idx_split >= 0 && idx_jump >= 0 && max_ctas >= 0 && ((uintptr_t)wpack & 15) == 0);
     const IndexMap im{idx_offset, idx_split, idx_jump};
     cudaStream_t st = niw_stream(stream);
     NIW_CUDA(cudaMemsetAsync(d_wpack, 0, sizeof(float) * NB * BLOCK_FLOATS, st));
