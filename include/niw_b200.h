@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NIW_ABI_VERSION 5
+#define NIW_ABI_VERSION 6
 
 #define NIW_E_BADARG   (-1)  /* null pointer / non-positive size */
 #define NIW_E_UNSUPP   (-2)  /* shape or option outside what the kernels implement */
@@ -164,6 +164,21 @@ int niw_composite_bwd(const float* ray, const float* rgb_s, const float* sigma, 
                       const float* prob, const float* trans, int64_t R, int N, float bg,
                       const float* d_rgb, const float* d_depth, const float* d_opacity,
                       float* d_rgb_s, float* d_sigma, float* d_ray, void* stream);
+/* (a9 + f1) the compositor with the loss head of model/nerf.py:276-288 (model/base.py:209-211 MSE_loss) in its epilogue:
+ * the warp that composited ray r = b P + p gathers image[b, :, pixel] (image [B,3,H,W]; pixel = ray_idx[p], or idx_start + p
+ * when ray_idx is NULL), writes d_unit [R,3] = 2 (rgb - gt) / (3 R) and the kernel leaves loss = mean((rgb - gt)^2) (summed
+ * in block order by the last block to finish: deterministic).  scratch: niw_composite_mse_scratch_floats() floats, zeroed
+ * once by the caller before the first call and owned by one stream of calls.  N in {64,128,192,256} (NIW_E_UNSUPP else).
+ * Backward: d_rgb of niw_composite_bwd becomes d_rgb (may be NULL) + d_loss[0] * d_unit, d_loss a device scalar. */
+int niw_composite_mse_scratch_floats(void);
+int niw_composite_fwd_mse(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                          int64_t R, int N, float bg, float* rgb, float* depth, float* opacity, float* prob, float* trans,
+                          const float* image, const int64_t* ray_idx, int64_t idx_start, int B, int P, int H, int W,
+                          float* d_unit, float* scratch, float* loss, void* stream);
+int niw_composite_bwd_mse(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                          const float* prob, const float* trans, int64_t R, int N, float bg,
+                          const float* d_rgb, const float* d_depth, const float* d_opacity, const float* d_unit,
+                          const float* d_loss, float* d_rgb_s, float* d_sigma, float* d_ray, void* stream);
 
 /* ---- (a6+a7+a8) NeRF.forward_samples   model/nerf.py:416-456, model/barf.py:256-268, camera.py:517-521
  * x = center + depth*ray, view = normalize(ray), BARF-weighted positional encoding (L=10 / 4),

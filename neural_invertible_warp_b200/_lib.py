@@ -18,7 +18,7 @@ NIW_PREC_BF16X3 = 2
 NIW_NERF_PREPACKED = 2
 NIW_NERF_PARAMS = 530052
 NIW_NVP_BLOCK_FLOATS = ((128 * 27 + 128 + 1 + 128 * 13 + 3 * 128 + 3) + 3) // 4 * 4   # 5636, include/niw_b200.h
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # name -> (restype, argtypes); mirrors include/niw_b200.h one to one
 SIGNATURES = {
@@ -42,6 +42,11 @@ SIGNATURES = {
     "niw_sample_pdf_merge": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     "niw_composite_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P, _P]),
     "niw_composite_bwd": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "niw_composite_mse_scratch_floats": (_c.c_int, []),
+    "niw_composite_fwd_mse": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P,
+                                         _P, _P, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
+    "niw_composite_bwd_mse": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int64, _c.c_int, _c.c_float, _P, _P, _P, _P, _P,
+                                         _P, _P, _P, _P]),
     "niw_nerf_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
     "niw_nerf_fwd": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_int, _P, _c.c_float, _c.c_float, _c.c_int, _c.c_int, _P,
                                 _c.c_size_t, _P, _P, _P]),

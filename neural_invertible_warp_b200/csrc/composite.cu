@@ -128,15 +128,85 @@ composite_bwd_kernel(const float* __restrict__ ray, const float* __restrict__ rg
 }
 
 // ---- fast kernels: N = 32 * CH ---------------------------------------------------------------------------
+// Loss head in the compositor's epilogue (reference model/nerf.py:276-288, model/base.py:209-211):
+// the warp that has composited ray r = b P + p also gathers the ground-truth pixel image[b, :, ray_idx[p]], writes
+// d_unit[r] = 2 scale (rgb - gt) (the loss gradient for a unit upstream gradient) and adds its squared error to the block's
+// sum; the blocks leave partial sums and the LAST block to finish (ticket) adds them in index order and writes the loss --
+// deterministic, nothing to zero per call (the ticket resets itself; `ticket` is zero before the first call).
+struct MseEpilogue {
+    const float* image;         // [B,3,HW] or nullptr: no loss head
+    const int64_t* ray_idx;     // [P] or nullptr (pixel = idx_start + p)
+    int64_t idx_start;
+    int P, HW;
+    float scale;                // 1 / (3 R)
+    float* d_unit;              // [R,3]
+    float* partial;             // [gridDim.x]
+    unsigned int* ticket;
+    float* loss;
+};
+
+// lanes 0..2 of the warp fetch the ground-truth channel early (index load -> pixel load: two dependent round trips that
+// overlap the ray's sample loads)
+__device__ __forceinline__ float mse_fetch(const MseEpilogue& e, int64_t r, int lane) {
+    if (!e.image || lane >= 3) return 0.f;
+    const int b = (int)(r / e.P), p = (int)(r % e.P);
+    const int64_t pix = e.ray_idx ? e.ray_idx[p] : e.idx_start + p;
+    return e.image[((int64_t)b * 3 + lane) * e.HW + pix];
+}
+// every lane passes its channel of the composited colour (lane c < 3 holds channel c); returns the ray's squared error in lane 0
+__device__ __forceinline__ float mse_ray(const MseEpilogue& e, int64_t r, int lane, float mine, float gt) {
+    float sq = 0.f;
+    if (lane < 3) {
+        const float diff = mine - gt;
+        e.d_unit[r * 3 + lane] = 2.f * e.scale * diff;
+        sq = diff * diff;
+    }
+    sq += __shfl_down_sync(0xffffffffu, sq, 1) + __shfl_down_sync(0xffffffffu, sq, 2);
+    return sq;                  // lane 0: all three channels
+}
+// end of kernel: block sum of the warps' errors, partial[], ticket, ordered final sum by the last block
+__device__ __forceinline__ void mse_finish(const MseEpilogue& e, float warp_err, int lane, int warp) {
+    __shared__ float red[WARPS];
+    __shared__ bool last;
+    if (lane == 0) red[warp] = warp_err;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) v += red[w];
+        e.partial[blockIdx.x] = v;
+        __threadfence();
+        last = atomicAdd(e.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    float v = 0.f;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(e.partial + i);
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) t += red[w];
+        *e.loss = t * e.scale;
+        *e.ticket = 0u;
+    }
+}
+
 template <int CH>
 __global__ void __launch_bounds__(WARPS * 32)
 composite_fwd_vec_kernel(const float* __restrict__ ray, const float* __restrict__ rgb_s, const float* __restrict__ sigma,
                          const float* __restrict__ depth_s, int64_t R, float bg, float* __restrict__ rgb,
                          float* __restrict__ depth, float* __restrict__ opacity, float* __restrict__ prob,
-                         float* __restrict__ trans) {
+                         float* __restrict__ trans, MseEpilogue mse) {
     constexpr int N = 32 * CH;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float warp_err = 0.f;
     for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
+        const float gt = mse_fetch(mse, r, lane);
         float sg[CH], d[CH], c[3 * CH];
         vload<CH>(sigma + r * N + lane * CH, sg);
         vload<CH>(depth_s + r * N + lane * CH, d);
@@ -165,12 +235,14 @@ composite_fwd_vec_kernel(const float* __restrict__ ray, const float* __restrict_
         if (prob) vstore<CH>(prob + r * N + lane * CH, w);
         if (trans) vstore<CH>(trans + r * N + lane * CH, T);
         a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b); a_d = warp_sum(a_d); a_o = warp_sum(a_o);
+        if (bg >= 0.f) { float k = bg * (1.f - a_o); a_r += k; a_g += k; a_b += k; }     // (all lanes hold the sums)
         if (lane == 0) {
-            if (bg >= 0.f) { float k = bg * (1.f - a_o); a_r += k; a_g += k; a_b += k; }
             rgb[r * 3] = a_r; rgb[r * 3 + 1] = a_g; rgb[r * 3 + 2] = a_b;
             depth[r] = a_d; opacity[r] = a_o;
         }
+        if (mse.image) warp_err += mse_ray(mse, r, lane, lane == 0 ? a_r : (lane == 1 ? a_g : a_b), gt);
     }
+    if (mse.image) mse_finish(mse, warp_err, lane, warp);
 }
 
 template <int CH>
@@ -179,9 +251,12 @@ composite_bwd_vec_kernel(const float* __restrict__ ray, const float* __restrict_
                          const float* __restrict__ depth_s, const float* __restrict__ prob,
                          const float* __restrict__ trans, int64_t R, float bg, const float* __restrict__ d_rgb,
                          const float* __restrict__ d_depth, const float* __restrict__ d_opacity,
-                         float* __restrict__ d_rgb_s, float* __restrict__ d_sigma, float* __restrict__ d_ray) {
+                         float* __restrict__ d_rgb_s, float* __restrict__ d_sigma, float* __restrict__ d_ray,
+                         const float* __restrict__ d_unit, const float* __restrict__ d_loss) {
     constexpr int N = 32 * CH;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // loss head of the forward's epilogue: d_rgb += d_loss * d_unit (d_loss: the upstream gradient of the scalar loss)
+    const float gl = d_unit ? d_loss[0] : 0.f;
     for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
         float sg[CH], d[CH], c[3 * CH], T[CH], w[CH];
         vload<CH>(sigma + r * N + lane * CH, sg);
@@ -191,7 +266,8 @@ composite_bwd_vec_kernel(const float* __restrict__ ray, const float* __restrict_
         if (prob) vload<CH>(prob + r * N + lane * CH, w);
         const float rx = ray[r * 3], ry = ray[r * 3 + 1], rz = ray[r * 3 + 2];
         const float len = sqrtf(rx * rx + ry * ry + rz * rz);
-        const float gr = d_rgb ? d_rgb[r * 3] : 0.f, gg = d_rgb ? d_rgb[r * 3 + 1] : 0.f, gb = d_rgb ? d_rgb[r * 3 + 2] : 0.f;
+        float gr = d_rgb ? d_rgb[r * 3] : 0.f, gg = d_rgb ? d_rgb[r * 3 + 1] : 0.f, gb = d_rgb ? d_rgb[r * 3 + 2] : 0.f;
+        if (d_unit) { gr += gl * d_unit[r * 3]; gg += gl * d_unit[r * 3 + 1]; gb += gl * d_unit[r * 3 + 2]; }
         const float gd = d_depth ? d_depth[r] : 0.f;
         float go = d_opacity ? d_opacity[r] : 0.f;
         if (bg >= 0.f) go -= bg * (gr + gg + gb);
@@ -239,14 +315,18 @@ inline unsigned grid_vec(K kernel, int64_t R) {
 
 }  // namespace
 
-extern "C" int niw_composite_fwd(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
-                                 int64_t R, int N, float bg, float* rgb, float* depth, float* opacity, float* prob,
-                                 float* trans, void* stream) {
-    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && rgb && depth && opacity && R > 0 && N > 0);
-    cudaStream_t st = niw_stream(stream);
+// scratch of the loss-head variant: [0] the ticket (unsigned, zero before the first call), [1 ..] per-block partial sums
+constexpr int MSE_SCRATCH_FLOATS = 4096;
+
+static int composite_fwd_launch(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s, int64_t R, int N,
+                                float bg, float* rgb, float* depth, float* opacity, float* prob, float* trans,
+                                const MseEpilogue& mse, cudaStream_t st) {
     const bool al = niw_aligned16(rgb_s) && niw_aligned16(sigma) && niw_aligned16(depth_s) && niw_aligned16(prob) && niw_aligned16(trans);
+    const bool vec = al && (N == 64 || N == 128 || N == 192 || N == 256);
+    if (mse.image && !vec) return NIW_E_UNSUPP;         // the loss head rides on the vector kernels only
     niw::note_launch();
-#define NIW_FWD(CH) composite_fwd_vec_kernel<CH><<<grid_vec(composite_fwd_vec_kernel<CH>, R), WARPS * 32, 0, st>>>(ray, rgb_s, sigma, depth_s, R, bg, rgb, depth, opacity, prob, trans)
+#define NIW_FWD(CH) do { unsigned g = grid_vec(composite_fwd_vec_kernel<CH>, R); if (g > MSE_SCRATCH_FLOATS - 1) g = MSE_SCRATCH_FLOATS - 1; \
+        composite_fwd_vec_kernel<CH><<<g, WARPS * 32, 0, st>>>(ray, rgb_s, sigma, depth_s, R, bg, rgb, depth, opacity, prob, trans, mse); } while (0)
     if (al && N == 64) NIW_FWD(2);
     else if (al && N == 128) NIW_FWD(4);
     else if (al && N == 192) NIW_FWD(6);
@@ -257,16 +337,38 @@ extern "C" int niw_composite_fwd(const float* ray, const float* rgb_s, const flo
     return 0;
 }
 
-extern "C" int niw_composite_bwd(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
-                                 const float* prob, const float* trans, int64_t R, int N, float bg,
-                                 const float* d_rgb, const float* d_depth, const float* d_opacity, float* d_rgb_s,
-                                 float* d_sigma, float* d_ray, void* stream) {
-    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && trans && d_rgb_s && d_sigma && R > 0 && N > 0);   // prob may be NULL
-    cudaStream_t st = niw_stream(stream);
+extern "C" int niw_composite_fwd(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                                 int64_t R, int N, float bg, float* rgb, float* depth, float* opacity, float* prob,
+                                 float* trans, void* stream) {
+    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && rgb && depth && opacity && R > 0 && N > 0);
+    return composite_fwd_launch(ray, rgb_s, sigma, depth_s, R, N, bg, rgb, depth, opacity, prob, trans, MseEpilogue{}, niw_stream(stream));
+}
+
+extern "C" int niw_composite_mse_scratch_floats(void) { return MSE_SCRATCH_FLOATS; }
+
+extern "C" int niw_composite_fwd_mse(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                                     int64_t R, int N, float bg, float* rgb, float* depth, float* opacity, float* prob,
+                                     float* trans, const float* image, const int64_t* ray_idx, int64_t idx_start, int B, int P,
+                                     int H, int W, float* d_unit, float* scratch, float* loss, void* stream) {
+    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && rgb && depth && opacity && R > 0 && N > 0);
+    NIW_CHECK_ARG(image && d_unit && scratch && loss && B > 0 && P > 0 && H > 0 && W > 0 && (int64_t)B * P == R);
+    MseEpilogue mse;
+    mse.image = image; mse.ray_idx = ray_idx; mse.idx_start = idx_start; mse.P = P; mse.HW = H * W;
+    mse.scale = 1.0f / (float)(R * 3); mse.d_unit = d_unit; mse.partial = scratch + 1;
+    mse.ticket = reinterpret_cast<unsigned int*>(scratch); mse.loss = loss;
+    return composite_fwd_launch(ray, rgb_s, sigma, depth_s, R, N, bg, rgb, depth, opacity, prob, trans, mse, niw_stream(stream));
+}
+
+static int composite_bwd_launch(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                                const float* prob, const float* trans, int64_t R, int N, float bg,
+                                const float* d_rgb, const float* d_depth, const float* d_opacity, float* d_rgb_s,
+                                float* d_sigma, float* d_ray, const float* d_unit, const float* d_loss, cudaStream_t st) {
     const bool al = niw_aligned16(rgb_s) && niw_aligned16(sigma) && niw_aligned16(depth_s) && niw_aligned16(prob) &&
                     niw_aligned16(trans) && niw_aligned16(d_rgb_s) && niw_aligned16(d_sigma);
+    const bool vec = al && (N == 64 || N == 128 || N == 192 || N == 256);
+    if (d_unit && !vec) return NIW_E_UNSUPP;
     niw::note_launch();
-#define NIW_BWD(CH) composite_bwd_vec_kernel<CH><<<grid_vec(composite_bwd_vec_kernel<CH>, R), WARPS * 32, 0, st>>>(ray, rgb_s, sigma, depth_s, prob, trans, R, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma, d_ray)
+#define NIW_BWD(CH) composite_bwd_vec_kernel<CH><<<grid_vec(composite_bwd_vec_kernel<CH>, R), WARPS * 32, 0, st>>>(ray, rgb_s, sigma, depth_s, prob, trans, R, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma, d_ray, d_unit, d_loss)
     if (al && N == 64) NIW_BWD(2);
     else if (al && N == 128) NIW_BWD(4);
     else if (al && N == 192) NIW_BWD(6);
@@ -275,4 +377,22 @@ extern "C" int niw_composite_bwd(const float* ray, const float* rgb_s, const flo
 #undef NIW_BWD
     NIW_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int niw_composite_bwd(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                                 const float* prob, const float* trans, int64_t R, int N, float bg,
+                                 const float* d_rgb, const float* d_depth, const float* d_opacity, float* d_rgb_s,
+                                 float* d_sigma, float* d_ray, void* stream) {
+    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && trans && d_rgb_s && d_sigma && R > 0 && N > 0);   // prob may be NULL
+    return composite_bwd_launch(ray, rgb_s, sigma, depth_s, prob, trans, R, N, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma,
+                                d_ray, nullptr, nullptr, niw_stream(stream));
+}
+
+extern "C" int niw_composite_bwd_mse(const float* ray, const float* rgb_s, const float* sigma, const float* depth_s,
+                                     const float* prob, const float* trans, int64_t R, int N, float bg,
+                                     const float* d_rgb, const float* d_depth, const float* d_opacity, const float* d_unit,
+                                     const float* d_loss, float* d_rgb_s, float* d_sigma, float* d_ray, void* stream) {
+    NIW_CHECK_ARG(ray && rgb_s && sigma && depth_s && trans && d_rgb_s && d_sigma && R > 0 && N > 0 && d_unit && d_loss);
+    return composite_bwd_launch(ray, rgb_s, sigma, depth_s, prob, trans, R, N, bg, d_rgb, d_depth, d_opacity, d_rgb_s, d_sigma,
+                                d_ray, d_unit, d_loss, niw_stream(stream));
 }

@@ -353,6 +353,120 @@ def composite(ray, rgb_samples, density_samples, depth_samples, bgcolor=None, wa
 
 
 # --------------------------------------------------------------------------------------------
+# compositor with the loss head in its epilogue
+# --------------------------------------------------------------------------------------------
+
+class MseTarget:
+    """What the rendered colours of the coming ``composite`` calls will be compared with (model/nerf.py:276-288):
+    ``image`` [B,3,H,W] and the pixel subset ``ray_idx`` (or None: pixels idx_start ..).  A Graph's ``forward`` sets it
+    (``functional.mse_target``) for a train-mode render; ``composite_mse`` then leaves each call's loss here, and the
+    Graph's ``compute_loss`` picks it up by the identity of the colour tensor it is about to compare."""
+
+    def __init__(self, image, ray_idx=None, idx_start=0):
+        self.image, self.ray_idx, self.idx_start = _f32(image, "image"), ray_idx, int(idx_start)
+        self.losses = []
+
+    def put(self, rgb, loss):
+        self.losses.append((rgb, loss))
+
+    def take(self, rgb):
+        for t, loss in self.losses:
+            if t is rgb:
+                return loss
+        return None
+
+
+mse_target = None
+# NIW_FUSED_LOSS=0: the loss head stays a kernel of its own (niw_mse_gather) -- the parity partner of the fused form
+fused_loss = os.environ.get("NIW_FUSED_LOSS", "1") != "0"
+_mse_scratch = {}
+
+
+def _mse_scratch_for(dev):
+    """Ticket + per-block partial sums of niw_composite_fwd_mse: zeroed once, then kept (the ticket resets itself)."""
+    key = (dev.type, dev.index)
+    buf = _mse_scratch.get(key)
+    if buf is None:
+        buf = torch.zeros(_lib.load().niw_composite_mse_scratch_floats(), device=dev)
+        if not torch.cuda.is_current_stream_capturing():     # (memory of a graph's private pool must not outlive the graph)
+            _mse_scratch[key] = buf
+    return buf
+
+
+def composite_mse_supported(N):
+    return fused_loss and int(N) in (64, 128, 192, 256)
+
+
+class _CompositeMse(torch.autograd.Function):
+    """_Composite + the MSE against the gathered ground-truth pixels in the same two launches: the forward kernel also
+    writes the loss and d_unit = d loss / d rgb, the backward kernel adds d_loss * d_unit to the incoming d_rgb."""
+
+    @staticmethod
+    def forward(ctx, ray, rgb_s, sigma, depth_s, bg, want_prob, image, ray_idx, idx_start, B, P):
+        lib = _lib.load()
+        ray, rgb_s, sigma, depth_s = _f32(ray, "ray"), _f32(rgb_s, "rgb_samples"), _f32(sigma, "density_samples"), \
+            _f32(depth_s, "depth_samples")
+        R, N = sigma.shape
+        dev = ray.device
+        H, W = image.shape[-2:]
+        rgb = torch.empty(R, 3, device=dev)
+        depth = torch.empty(R, device=dev)
+        opacity = torch.empty(R, device=dev)
+        loss = torch.empty((), device=dev)
+        d_unit = torch.empty(R, 3, device=dev)
+        ctx.set_materialize_grads(False)
+        need_grad = any(ctx.needs_input_grad[:3])
+        prob = torch.empty(R, N, device=dev) if want_prob else None
+        trans = torch.empty(R, N, device=dev) if need_grad else None
+        with _timed("composite_fwd"):
+            _lib.check(lib.niw_composite_fwd_mse(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), R, N, float(bg), _p(rgb),
+                                                 _p(depth), _p(opacity), _p(prob), _p(trans), _p(image), _p(ray_idx),
+                                                 int(idx_start), int(B), int(P), int(H), int(W), _p(d_unit),
+                                                 _p(_mse_scratch_for(dev)), _p(loss), _stream()))
+        if need_grad:
+            ctx.save_for_backward(ray, rgb_s, sigma, depth_s, trans, d_unit, *([prob] if want_prob else []))
+        ctx.bg = float(bg)
+        if prob is None:
+            prob = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(prob)
+        return rgb, depth, opacity, prob, loss
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_depth, d_opacity, _d_prob, d_loss):
+        ray, rgb_s, sigma, depth_s, trans, d_unit, *rest = ctx.saved_tensors
+        prob = rest[0] if rest else None
+        none = (None,) * 11
+        if d_rgb is None and d_depth is None and d_opacity is None and d_loss is None:
+            return none
+        R, N = sigma.shape
+        d_rgb_s = torch.empty_like(rgb_s)
+        d_sigma = torch.empty_like(sigma)
+        d_ray = torch.empty_like(ray)
+        c = lambda t: None if t is None else t.contiguous()
+        d_rgb, d_depth, d_opacity = c(d_rgb), c(d_depth), c(d_opacity)
+        lib = _lib.load()
+        with _timed("composite_bwd"):
+            if d_loss is None:
+                _lib.check(lib.niw_composite_bwd(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), _p(prob), _p(trans), R, N, ctx.bg,
+                                                 _p(d_rgb), _p(d_depth), _p(d_opacity), _p(d_rgb_s), _p(d_sigma), _p(d_ray),
+                                                 _stream()))
+            else:
+                d_loss = _f32(d_loss, "d_loss")
+                _lib.check(lib.niw_composite_bwd_mse(_p(ray), _p(rgb_s), _p(sigma), _p(depth_s), _p(prob), _p(trans), R, N,
+                                                     ctx.bg, _p(d_rgb), _p(d_depth), _p(d_opacity), _p(d_unit), _p(d_loss),
+                                                     _p(d_rgb_s), _p(d_sigma), _p(d_ray), _stream()))
+        return (d_ray, d_rgb_s, d_sigma) + (None,) * 8
+
+
+def composite_mse(ray, rgb_samples, density_samples, depth_samples, target, B, P, bgcolor=None, want_prob=True):
+    """``composite`` plus mean((rgb - image[:, :, ray_idx])**2) of ``target`` (an ``MseTarget``) from the same kernel:
+    -> rgb [R,3], depth [R], opacity [R], prob [R,N], loss [] (R = B P rays, image by image)."""
+    bg = -1.0 if bgcolor is None else float(bgcolor)
+    return _CompositeMse.apply(ray, rgb_samples, density_samples, depth_samples, bg, bool(want_prob), target.image,
+                               _idx(target.ray_idx, ray.device), target.idx_start, int(B), int(P))
+
+
+# --------------------------------------------------------------------------------------------
 # positional encoding + MLP
 # --------------------------------------------------------------------------------------------
 

@@ -11,6 +11,7 @@ resampling and second pass) that ``Graph.render`` / ``render_local`` / ``render_
 Tensors cross this layer in the reference's shapes ([B,P,3], [B,P,N,1] ...); the kernels see them
 flattened over rays.
 """
+import contextlib
 import math
 
 import torch
@@ -241,10 +242,22 @@ class NeRFCore(nn.Module):
         (``want_prob=False``, used by the render pipeline when nothing samples from the weights: prob is None)."""
         B, P, N = density_samples.shape
         bg = opt.data.bgcolor if opt.nerf.setbg_opaque else None
-        rgb, depth, opacity, prob = F.composite(ray.reshape(B * P, 3), rgb_samples.reshape(B * P, N, 3),
-                                                density_samples.reshape(B * P, N), depth_samples.reshape(B * P, N), bg,
-                                                want_prob=want_prob)
-        return rgb.view(B, P, 3), depth.view(B, P, 1), opacity.view(B, P, 1), (prob.view(B, P, N, 1) if want_prob else None)
+        target = F.mse_target
+        if target is not None and F.composite_mse_supported(N) and target.image.shape[0] == B and \
+                (target.ray_idx is None or len(target.ray_idx) == P):
+            # train-mode render of a Graph that will compare these colours with the target's pixels (model/nerf.py:276-288):
+            # the loss comes out of the compositor's epilogue; ``compute_loss`` finds it by the identity of ``rgb``
+            rgb, depth, opacity, prob, loss = F.composite_mse(
+                ray.reshape(B * P, 3), rgb_samples.reshape(B * P, N, 3), density_samples.reshape(B * P, N),
+                depth_samples.reshape(B * P, N), target, B, P, bg, want_prob=want_prob)
+            rgb = rgb.view(B, P, 3)
+            target.put(rgb, loss)
+        else:
+            rgb, depth, opacity, prob = F.composite(ray.reshape(B * P, 3), rgb_samples.reshape(B * P, N, 3),
+                                                    density_samples.reshape(B * P, N), depth_samples.reshape(B * P, N), bg,
+                                                    want_prob=want_prob)
+            rgb = rgb.view(B, P, 3)
+        return rgb, depth.view(B, P, 1), opacity.view(B, P, 1), (prob.view(B, P, N, 1) if want_prob else None)
 
     def positional_encoding(self, opt, input, L):
         """model/nerf.py:476-483 (+ the BARF weighting of model/barf.py:256-268 in subclasses with
@@ -376,10 +389,37 @@ class RenderCore(nn.Module):
         B = len(var.idx)
         ray_idx = var.ray_idx if (opt.nerf.rand_rays and mode in ["train", "test-optim"]) else None
         image = var.image.view(B, 3, opt.H, opt.W)
+        # a train-mode render leaves the losses of its composite calls with the target it was given (``_loss_target``)
+        target = getattr(var, "_mse_target", None)
+        fused = (lambda rgb: target.take(rgb)) if target is not None and target.ray_idx is ray_idx else (lambda rgb: None)
         if opt.loss_weight.render is not None:
-            loss.render = F.mse_gather(var.rgb, image, ray_idx)
+            loss.render = fused(var.rgb)
+            if loss.render is None:
+                loss.render = F.mse_gather(var.rgb, image, ray_idx)
         if opt.loss_weight.render_fine is not None:
             if not opt.nerf.fine_sampling:
                 raise AssertionError("loss_weight.render_fine needs nerf.fine_sampling")
-            loss.render_fine = F.mse_gather(var.rgb_fine, image, ray_idx)
+            loss.render_fine = fused(var.rgb_fine)
+            if loss.render_fine is None:
+                loss.render_fine = F.mse_gather(var.rgb_fine, image, ray_idx)
         return loss
+
+    @contextlib.contextmanager
+    def _loss_target(self, opt, var, mode):
+        """Around the train-mode render of ``forward``: the compositor may compute the image loss of ``compute_loss``
+        (model/nerf.py:276-288) in its epilogue (functional.MseTarget).  Only when gradients are on and a render loss is
+        configured; ``var._mse_target`` carries the results to ``_image_losses``."""
+        var._mse_target = None
+        on = (F.fused_loss and mode in ["train", "test-optim"] and opt.nerf.rand_rays and torch.is_grad_enabled()
+              and (opt.loss_weight.render is not None or opt.loss_weight.render_fine is not None)
+              and var.get("image") is not None and var.get("ray_idx") is not None)
+        if not on:
+            yield
+            return
+        target = F.MseTarget(var.image.view(len(var.idx), 3, opt.H, opt.W), var.ray_idx)
+        saved, F.mse_target = F.mse_target, target
+        try:
+            yield
+        finally:
+            F.mse_target = saved
+        var._mse_target = target

@@ -24,7 +24,8 @@ class Graph(base.Graph):
         if opt.nerf.rand_rays and mode in ["train", "test-optim"]:
             pose = self.get_pose(opt, var, mode=mode)
             var.ray_idx = torch.randperm(opt.H * opt.W, device=opt.device)[:opt.nerf.rand_rays // batch_size]
-            ret = self.render(opt, pose, intr=var.intr, ray_idx=var.ray_idx, mode=mode)
+            with self._loss_target(opt, var, mode):     # the image loss of compute_loss rides in the compositor's epilogue
+                ret = self.render(opt, pose, intr=var.intr, ray_idx=var.ray_idx, mode=mode)
         elif mode == "render_train":
             ind = np.random.choice(len(var.idx))
             pose = self.get_pose(opt, var, mode=mode, ind=ind)

@@ -34,11 +34,13 @@ class Graph(base.Graph):
                 # the aligned test POSE (barf_inn_dtu.py:546-564) and the unpack raises; the evident intent -- the BARF
                 # test-time refinement (barf_inn_dtu.py:468-483), rendering the drawn pixels from that pose -- is implemented
                 pose_w2c = self.get_pose(opt, var, mode=mode)
-                ret = self.render(opt, pose_w2c, intr=var.intr, ray_idx=var.ray_idx, mode=mode, depth_range=depth_range)
+                with self._loss_target(opt, var, mode):
+                    ret = self.render(opt, pose_w2c, intr=var.intr, ray_idx=var.ray_idx, mode=mode, depth_range=depth_range)
                 var.update(ret)
                 return var
             ray, center, grid_3d = self.get_pose(opt, var, mode=mode, iter=iter)
-            ret = self.render_local(opt, ray, center, intr=var.intr, mode=mode, depth_range=depth_range)
+            with self._loss_target(opt, var, mode):     # the image losses ride in the compositors' epilogues
+                ret = self.render_local(opt, ray, center, intr=var.intr, mode=mode, depth_range=depth_range)
             ret.update(grid_local=grid_3d, center_local=center, grid_init=self.pose_net.grid_init,
                        center_init=self.pose_net.center_init)
         else:

@@ -46,14 +46,16 @@ class Graph(base.Graph):
                 # warp kernels of get_pose run (same draws, same values; only the launch order differs)
                 pre = self.prefetch_render(opt, batch_size, len(var.ray_idx)) if not opt.camera.ndc else None
                 ray, center, grid_3D, alpha_ratio = self.get_pose(opt, var, mode=mode, iter=iter)
-                ret = self._render_local(opt, ray, center, intr=var.intr, mode=mode, prefetched=pre)
+                with self._loss_target(opt, var, mode):     # the image loss rides in the compositor's epilogue
+                    ret = self._render_local(opt, ray, center, intr=var.intr, mode=mode, prefetched=pre)
                 # the un-warped points were generated inside get_pose (one kernel instead of the
                 # reference's two full-frame grids, nerf_inn_llff.py:519 and barf_inn_llff.py:325)
                 ret.update(grid_3D=grid_3D, center=center, grid_cam=var.grid_cam, center_cam=var.center_cam,
                            inn_posenc_alpha=alpha_ratio)
             else:
                 pose = self.get_pose(opt, var, mode=mode)
-                ret = self.render(opt, pose, intr=var.intr, ray_idx=var.ray_idx, mode=mode)
+                with self._loss_target(opt, var, mode):
+                    ret = self.render(opt, pose, intr=var.intr, ray_idx=var.ray_idx, mode=mode)
         elif mode == "render_train":
             ind = np.random.choice(len(var.idx))
             ray, center = self.get_pose(opt, var, mode=mode, ind=ind)

@@ -492,6 +492,60 @@ def test_mse_gather(F):
     torch.testing.assert_close(x.grad.cpu(), rgb.grad * 3, rtol=1e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize("B,P,N,with_idx,bg", [(3, 50, 128, True, None), (2, 37, 64, False, 1.0), (4, 5000, 128, True, None),
+                                                  (1, 9, 192, True, 0.5)])
+def test_composite_with_the_loss_head_in_its_epilogue(F, B, P, N, with_idx, bg):
+    """niw_composite_fwd_mse / _bwd_mse (model/nerf.py:276-288 + 458-474 in one forward and one backward
+    launch) against the oracle's composite followed by its MSE over the gathered pixels, and against the two-kernel
+    form (composite -> mse_gather): same colours (bit for bit), same loss, same gradients with upstream gradients on the
+    loss AND on rgb / depth; repeated calls (the ticket of the block-ordered final sum resets itself)."""
+    gen = torch.Generator().manual_seed(B * 1000 + P)
+    H, W = 60, 100
+    R = B * P
+    image = torch.rand(B, 3, H, W, generator=gen)
+    idx = torch.randperm(H * W, generator=gen)[:P] if with_idx else None
+    ray = torch.randn(R, 3, generator=gen)
+    rgb_s = torch.rand(R, N, 3, generator=gen)
+    sigma = torch.rand(R, N, generator=gen) * 3
+    depth_s = (torch.rand(R, N, generator=gen) * 0.1 + 0.01).cumsum(-1)
+    w_rgb, w_depth = torch.randn(R, 3, generator=gen), torch.randn(R, generator=gen)
+
+    def total(rgb, depth, loss):
+        return 0.7 * loss + (rgb * w_rgb.to(rgb.device)).sum() * 1e-3 + (depth * w_depth.to(rgb.device)).sum() * 1e-3
+
+    # oracle (CPU, fp32)
+    a = [t.clone().requires_grad_(True) for t in (ray, rgb_s, sigma)]
+    o_rgb, o_depth, o_op, _ = ora.composite(a[0].view(B, P, 3), a[1].view(B, P, N, 3), a[2].view(B, P, N),
+                                            depth_s.view(B, P, N, 1), bgcolor=bg)
+    gt = ora.gather_pixels(image, idx) if with_idx else image.view(B, 3, H * W).permute(0, 2, 1)[:, :P]
+    o_loss = ora.mse(o_rgb, gt)
+    total(o_rgb.reshape(R, 3), o_depth.reshape(R), o_loss).backward()
+
+    outs = {}
+    for fused in (False, True):
+        g = [t.to(DEV).requires_grad_(True) for t in (ray, rgb_s, sigma)]
+        for rep in range(2 if fused else 1):
+            for t in g:
+                t.grad = None
+            if fused:
+                target = F.MseTarget(image.to(DEV), None if idx is None else idx.to(DEV))
+                rgb, depth, op, _, loss = F.composite_mse(g[0], g[1], g[2], depth_s.to(DEV), target, B, P, bgcolor=bg,
+                                                          want_prob=False)
+            else:
+                rgb, depth, op, _ = F.composite(g[0], g[1], g[2], depth_s.to(DEV), bgcolor=bg, want_prob=False)
+                loss = F.mse_gather(rgb.view(B, P, 3), image.to(DEV), None if idx is None else idx.to(DEV))
+            total(rgb, depth, loss).backward()
+            torch.cuda.synchronize()
+        outs[fused] = (rgb.detach(), depth.detach(), op.detach(), loss.detach(), [t.grad.clone() for t in g])
+    f, u = outs[True], outs[False]
+    assert torch.equal(f[0], u[0]) and torch.equal(f[1], u[1]) and torch.equal(f[2], u[2])
+    torch.testing.assert_close(f[3], u[3], rtol=2e-6, atol=1e-9)
+    torch.testing.assert_close(f[3].cpu(), o_loss.detach(), rtol=1e-5, atol=1e-8)
+    for gf, gu, go in zip(f[4], u[4], a):
+        assert rel_l2(gf, gu) < 1e-6
+        assert rel_l2(gf, go.grad) < 3e-4
+
+
 def test_sample_pixels_is_a_permutation_prefix(F):
     """niw_sample_pixels: k distinct indices in range, the full draw (k = n) is a permutation, successive calls
     differ (device counter), marginals are uniform to sampling error."""
