@@ -63,9 +63,11 @@ class Graph(nerf_inn_llff.Graph):
                 or opt.warp_latent.enc_type != "l2fbarf":      # (other encodings build a new code tensor per call)
             return
         cur = torch.cuda.current_stream()
-        side = getattr(self, "_side_stream", None)
+        # (a stream of its own: on the render side stream the depth samples and the MLP weight pack of ``prefetch_render``
+        # would queue behind this pack instead of running beside it)
+        side = getattr(self, "_pose_stream", None)
         if side is None:
-            side = self._side_stream = torch.cuda.Stream()
+            side = self._pose_stream = torch.cuda.Stream()
         side.wait_stream(cur)
         self.warp_mlp.prepack(self._latent(opt), side)
 
